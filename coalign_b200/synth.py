@@ -1,0 +1,166 @@
+"""Synthetic OPV2V/DAIR-shape inputs and random-init weights (no dataset / checkpoint is reachable).
+
+Follows SURVEY.md 8(d).  numpy/torch-CPU only; used by bench.py, smoke(), the tests and the
+golden generator so that every side sees byte-identical inputs from a seed.
+"""
+from __future__ import annotations
+
+import copy
+import math
+from typing import Dict, List
+
+import numpy as np
+import torch
+
+# model.args of opencood/hypes_yaml/opv2v/lidar_only_with_noise/coalign/pointpillar_coalign.yaml:94-126
+# (+ grid_size as injected by yaml_utils.load_point_pillar_params, yaml_utils.py:113-119)
+OPV2V_ARGS = {
+    "voxel_size": [0.4, 0.4, 4],
+    "lidar_range": [-140.8, -40, -3, 140.8, 40, 1],
+    "anchor_number": 2,
+    "pillar_vfe": {"use_norm": True, "with_distance": False, "use_absolute_xyz": True, "num_filters": [64]},
+    "point_pillar_scatter": {"num_features": 64},
+    "base_bev_backbone": {"layer_nums": [3, 5, 8], "layer_strides": [2, 2, 2], "num_filters": [64, 128, 256],
+                          "upsample_strides": [1, 2, 4], "num_upsample_filter": [128, 128, 128]},
+    "fusion_method": "att",
+    "att": {"feat_dim": [64, 128, 256]},
+    "shrink_header": {"kernal_size": [3], "stride": [1], "padding": [1], "dim": [256], "input_dim": 384},
+    "dir_args": {"dir_offset": 0.7853, "num_bins": 2, "anchor_yaw": [0, 90]},
+}
+# preprocess section of the same yaml (:47-56)
+OPV2V_PRE = {"max_points_per_voxel": 32, "max_voxel_train": 32000, "max_voxel_test": 70000, "max_cav": 5}
+
+
+def make_args(lidar_range=None, voxel_size=None, base=None):
+    """Copy of the yaml model.args with `grid_size` injected like load_point_pillar_params does."""
+    a = copy.deepcopy(base or OPV2V_ARGS)
+    if lidar_range is not None:
+        a["lidar_range"] = list(lidar_range)
+    if voxel_size is not None:
+        a["voxel_size"] = list(voxel_size)
+    r, v = a["lidar_range"], a["voxel_size"]
+    g = (np.array(r[3:6]) - np.array(r[0:3])) / np.array(v)
+    a["point_pillar_scatter"]["grid_size"] = np.round(g).astype(np.int64)
+    return a
+
+
+def opv2v_args():
+    return make_args()
+
+
+def dairv2x_args():
+    """dairv2x/lidar_only_with_noise/coalign/pointpillar_coalign.yaml:52,57."""
+    return make_args([-100.8, -40, -3.5, 100.8, 40, 1.5], [0.4, 0.4, 5])
+
+
+# ------------------------------------------------------------------------------------------
+# weights
+# ------------------------------------------------------------------------------------------
+def _bn(sd, prefix, c, g):
+    sd[prefix + ".weight"] = torch.empty(c).uniform_(0.6, 1.4, generator=g)
+    sd[prefix + ".bias"] = torch.empty(c).normal_(0.0, 0.1, generator=g)
+    sd[prefix + ".running_mean"] = torch.empty(c).normal_(0.0, 0.2, generator=g)
+    sd[prefix + ".running_var"] = torch.empty(c).uniform_(0.5, 1.5, generator=g)
+    sd[prefix + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+
+
+def _conv(shape, g, fan):
+    return torch.empty(*shape).normal_(0.0, math.sqrt(2.0 / fan), generator=g)
+
+
+def random_state_dict(args, seed=0) -> Dict[str, torch.Tensor]:
+    """Random weights with the reference's state_dict key names and shapes, with
+    non-trivial BatchNorm statistics so that BN-folding mistakes show up."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    nf = args["pillar_vfe"]["num_filters"][0]
+    sd["pillar_vfe.pfn_layers.0.linear.weight"] = torch.empty(nf, 10).normal_(0.0, 0.3, generator=g)
+    _bn(sd, "pillar_vfe.pfn_layers.0.norm", nf, g)
+    bb = args["base_bev_backbone"]
+    inpl = bb.get("inplanes", 64)
+    for li, (nb, st, pl) in enumerate(zip(bb["layer_nums"], bb["layer_strides"], bb["num_filters"])):
+        for k in range(nb):
+            p = f"backbone.resnet.layer{li}.{k}"
+            cin = inpl if k == 0 else pl
+            sd[p + ".conv1.weight"] = _conv((pl, cin, 3, 3), g, 9 * cin)
+            _bn(sd, p + ".bn1", pl, g)
+            sd[p + ".conv2.weight"] = _conv((pl, pl, 3, 3), g, 9 * pl * 2)
+            _bn(sd, p + ".bn2", pl, g)
+            if k == 0 and (st != 1 or inpl != pl):
+                sd[p + ".downsample.0.weight"] = _conv((pl, cin, 1, 1), g, cin * 2)
+                _bn(sd, p + ".downsample.1", pl, g)
+        inpl = pl
+    for i, (s, cu) in enumerate(zip(bb["upsample_strides"], bb["num_upsample_filter"])):
+        ci = bb["num_filters"][i]
+        sd[f"backbone.deblocks.{i}.0.weight"] = _conv((ci, cu, s, s), g, ci)
+        _bn(sd, f"backbone.deblocks.{i}.1", cu, g)
+    out_c = sum(bb["num_upsample_filter"])
+    if "shrink_header" in args:
+        sh = args["shrink_header"]
+        cin = sh["input_dim"]
+        for li, (ks, dim) in enumerate(zip(sh["kernal_size"], sh["dim"])):
+            p = f"shrink_conv.layers.{li}.double_conv"
+            sd[p + ".0.weight"] = _conv((dim, cin, ks, ks), g, ks * ks * cin)
+            sd[p + ".0.bias"] = torch.empty(dim).normal_(0.0, 0.1, generator=g)
+            sd[p + ".2.weight"] = _conv((dim, dim, 3, 3), g, 9 * dim)
+            sd[p + ".2.bias"] = torch.empty(dim).normal_(0.0, 0.1, generator=g)
+            cin = dim
+        out_c = sh["dim"][-1]
+    an = args["anchor_number"]
+    heads = [("cls_head", an), ("reg_head", 7 * an)]
+    if "dir_args" in args:
+        heads.append(("dir_head", args["dir_args"]["num_bins"] * an))
+    for name, co in heads:
+        sd[name + ".weight"] = _conv((co, out_c, 1, 1), g, out_c)
+        sd[name + ".bias"] = torch.empty(co).normal_(0.0, 0.1, generator=g)
+    return sd
+
+
+# ------------------------------------------------------------------------------------------
+# point clouds and poses
+# ------------------------------------------------------------------------------------------
+def lidar_cloud(rng: np.random.Generator, n_points: int, lidar_range, sigma=35.0) -> np.ndarray:
+    """LiDAR-like cloud in the agent's own frame: r = |N(0,sigma)|+2, azimuth U(0,2pi),
+    z uniform strictly inside the z range, intensity U(0,1).  float32 (P,4)."""
+    r = np.abs(rng.normal(0.0, sigma, n_points)) + 2.0
+    az = rng.uniform(0.0, 2 * np.pi, n_points)
+    zlo, zhi = lidar_range[2], lidar_range[5]
+    z = rng.uniform(zlo + 0.025 * (zhi - zlo), zhi - 0.1 * (zhi - zlo), n_points)
+    pts = np.stack([r * np.cos(az), r * np.sin(az), z, rng.uniform(0, 1, n_points)], axis=1)
+    return pts.astype(np.float32)
+
+
+def _pose_matrix(pose):
+    x, y, z, roll, yaw, pitch = [float(v) for v in pose]
+    cy, sy = math.cos(math.radians(yaw)), math.sin(math.radians(yaw))
+    cr, sr = math.cos(math.radians(roll)), math.sin(math.radians(roll))
+    cp, sp = math.cos(math.radians(pitch)), math.sin(math.radians(pitch))
+    rz = np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1.0]])
+    ry = np.array([[cp, 0, -sp], [0, 1.0, 0], [sp, 0, cp]])
+    rx = np.array([[1.0, 0, 0], [0, cr, sr], [0, -sr, cr]])
+    m = np.identity(4)
+    m[:3, :3] = rz @ ry @ rx
+    m[:3, 3] = (x, y, z)
+    return m
+
+
+def make_scene(seed: int, n_agents: int, n_points: int, lidar_range, max_cav=5, pose_noise=False,
+               spread=50.0, sigma=35.0):
+    """One scene: per-agent clouds (own frame, proj_first=false) + pairwise_t_matrix (L,L,4,4) f64
+    with [i,j] = T_j^-1 T_i (transformation_utils.py:22-67), identity padded."""
+    rng = np.random.default_rng(seed)
+    clouds = [lidar_cloud(rng, n_points, lidar_range, sigma) for _ in range(n_agents)]
+    poses = [np.zeros(6)]
+    for _ in range(1, n_agents):
+        poses.append(np.array([rng.uniform(-spread, spread), rng.uniform(-spread, spread), 0, 0,
+                               rng.uniform(-180, 180), 0]))
+    if pose_noise:      # pose_utils.py:43-73 noise model, N(0,0.2 m) / N(0,0.2 deg)
+        poses = [p + np.array([rng.normal(0, 0.2), rng.normal(0, 0.2), 0, 0, rng.normal(0, 0.2), 0])
+                 for p in poses]
+    ts = [_pose_matrix(p) for p in poses]
+    pw = np.tile(np.eye(4), (max_cav, max_cav, 1, 1))
+    for i in range(n_agents):
+        for j in range(n_agents):
+            if i != j:
+                pw[i, j] = np.linalg.solve(ts[j], ts[i])
+    return {"points": clouds, "poses": poses, "pairwise_t_matrix": pw}

@@ -1,0 +1,48 @@
+"""Inputs of the golden cases (shared by tests/golden/gen_golden.py and the tests).
+
+Deterministic from seeds: synthetic scenes (coalign_b200.synth) -> oracle voxelizer -> reference-format
+batch dict.  No reference import here, so it runs on the GPU box too.
+"""
+import numpy as np
+
+from coalign_b200 import synth
+from oracle import voxelize_np as V
+
+SMALL_RANGE = [-11.2, -4.8, -3, 11.2, 4.8, 1]      # -> nx=56, ny=24 (levels 28x12, 14x6, 7x3: odd sizes covered)
+SMALL_VOXEL = [0.4, 0.4, 4]
+
+
+def small_args(fusion_method="att"):
+    a = synth.make_args(SMALL_RANGE, SMALL_VOXEL)
+    a["fusion_method"] = fusion_method
+    return a
+
+
+def scenes_to_batch(scenes, lidar_range, voxel_size, max_pts=32, max_voxels=70000):
+    per_agent, pws = [], []
+    for sc in scenes:
+        for pts in sc["points"]:
+            per_agent.append(V.voxelize_c(pts, lidar_range, voxel_size, max_pts, max_voxels))
+        pws.append(sc["pairwise_t_matrix"])
+    vf, vc, vn = V.collate(per_agent)
+    return {"voxel_features": vf, "voxel_coords": vc, "voxel_num_points": vn,
+            "record_len": np.asarray([len(sc["points"]) for sc in scenes], np.int64),
+            "pairwise_t_matrix": np.stack(pws)}
+
+
+def small_case_scenes(record_len, seed0, n_points=1800):
+    return [synth.make_scene(seed0 + b, n, n_points, SMALL_RANGE, max_cav=5, pose_noise=True,
+                             spread=5.0, sigma=5.0) for b, n in enumerate(record_len)]
+
+
+def small_case_inputs(record_len, seed0, n_points=1800):
+    return scenes_to_batch(small_case_scenes(record_len, seed0, n_points), SMALL_RANGE, SMALL_VOXEL)
+
+
+def to_torch_batch(inp):
+    import torch
+    return {"processed_lidar": {"voxel_features": torch.from_numpy(inp["voxel_features"]),
+                                "voxel_coords": torch.from_numpy(inp["voxel_coords"]),
+                                "voxel_num_points": torch.from_numpy(inp["voxel_num_points"])},
+            "record_len": torch.from_numpy(inp["record_len"]),
+            "pairwise_t_matrix": torch.from_numpy(inp["pairwise_t_matrix"])}
