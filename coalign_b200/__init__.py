@@ -1,0 +1,25 @@
+"""coalign_b200 - B200-native (sm_100a) implementation of CoAlign's per-frame hot path.
+
+    import coalign_b200; coalign_b200.register()      # then: model.core_method: point_pillar_coalign_b200
+
+See DESIGN.md / INTEGRATION.md.  The CUDA library is mandatory; nothing here falls back to CPU.
+"""
+import os
+
+__all__ = ["register", "PointPillarCoalignB200"]
+PLUGIN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "opencood_plugin")
+
+
+def register():
+    """Make `opencood.models.point_pillar_coalign_b200` importable for train_utils.create_model without
+    touching the reference tree (extends the package search path of opencood.models)."""
+    import opencood.models as m
+    if PLUGIN_DIR not in list(m.__path__):
+        m.__path__.append(PLUGIN_DIR)
+
+
+def __getattr__(name):
+    if name == "PointPillarCoalignB200":
+        from .model import PointPillarCoalignB200
+        return PointPillarCoalignB200
+    raise AttributeError(name)

@@ -1,0 +1,86 @@
+"""ctypes binding of libcoalign_b200.so (include/coalign_b200.h).  No fallback: a missing library or a
+non-B200 device raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libcoalign_b200.so")
+
+CB_MAX_KSTEPS = 168
+CB_MAX_AGENTS = 64
+CB_OUT_PF, CB_OUT_PS, CB_OUT_UPSAMPLE, CB_OUT_HEADS = 0, 1, 2, 3
+
+
+class KStep(C.Structure):
+    _fields_ = [("row_off", C.c_int32), ("w_k", C.c_int32), ("col", C.c_uint16), ("a_sel", C.c_uint16)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("a_ptr", C.c_void_p * 2), ("a_rows", C.c_int64 * 2), ("a_pitch", C.c_int32 * 2),
+        ("w_ptr", C.c_void_p), ("w_rows", C.c_int32), ("w_k_total", C.c_int32),
+        ("n_img", C.c_int32), ("Hp", C.c_int32), ("Wp", C.c_int32),
+        ("n_total", C.c_int32), ("block_n", C.c_int32),
+        ("bias", C.c_void_p), ("cout_mod", C.c_int32), ("relu", C.c_int32),
+        ("residual", C.c_void_p), ("res_pitch", C.c_int32), ("res_lo_off", C.c_int64),
+        ("out", C.c_void_p), ("out_pitch", C.c_int32), ("out_ch_off", C.c_int32), ("out_lo_off", C.c_int64),
+        ("out_mode", C.c_int32), ("up_k", C.c_int32), ("out_Hp", C.c_int32), ("out_Wp", C.c_int32),
+        ("out_plane_rows", C.c_int64),
+        ("head_out", C.c_void_p * 3), ("head_c0", C.c_int32 * 3), ("head_cn", C.c_int32 * 3), ("n_heads", C.c_int32),
+        ("n_ksteps", C.c_int32), ("ksteps", KStep * CB_MAX_KSTEPS),
+    ]
+
+
+EXPORTS = {
+    "cb_version": (C.c_int, []),
+    "cb_device_check": (C.c_int, []),
+    "cb_voxelize_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    "cb_voxelize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "cb_pfn_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
+    "cb_points_to_canvas": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "cb_conv_gemm": (C.c_int, [C.POINTER(ConvDesc), C.c_int, C.c_void_p]),
+    "cb_conv_gemm_simt": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
+    "cb_normalize_affine": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p,
+                                      C.c_void_p]),
+    "cb_warp_att_fuse": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
+    "cb_nchw_to_layout": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64,
+                                    C.c_void_p]),
+    "cb_layout_to_nchw": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+def load(check_device: bool = False):
+    """Load the CUDA library (raises if it was not built).  With check_device, also require sm_100."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing - run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(coalign_b200 has no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    if check_device:
+        rc = _lib.cb_device_check()
+        if rc != 0:
+            raise RuntimeError(f"coalign_b200 needs a B200 (sm_100) CUDA device, cb_device_check() = {rc}")
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        kind = "cudaError" if rc > 0 else "argument/driver error"
+        raise RuntimeError(f"libcoalign_b200 {what} failed: {kind} {rc}")

@@ -1,0 +1,246 @@
+// Implicit-GEMM convolution on Blackwell tensor cores (sm_100a): TMA -> shared (SWIZZLE_128B) ->
+// tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> tcgen05.ld epilogue.  Persistent, warp specialised:
+//   warp 0 : TMA producer (one elected thread)       warp 1 : MMA issuer (one elected thread)
+//   warp 2 : TMEM allocator                          warps 4..7 : epilogue (TMEM lane quarter = warp%4)
+// GEMM rows are flattened zero-padded output pixels (PF layout), so every filter tap is a constant row
+// shift of a plain 2-D TMA box; stride-2 convolutions read phase-split (PS) inputs the same way.
+// Replaces cuDNN conv2d/conv_transpose2d under
+//   /root/reference/opencood/models/sub_modules/resblock.py:53-69 (BasicBlock),
+//   base_bev_backbone_resnet.py:52-65,121-138 (deblocks), downsample_conv.py:18-24 (shrink header),
+//   point_pillar_baseline_multiscale.py:126-133 (heads).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <mutex>
+#include "conv_common.cuh"
+
+namespace cb {
+
+constexpr int BM = 128;       // GEMM rows per tile (= UMMA M, one TMEM lane per row)
+constexpr int BK = 64;        // K per pipeline stage: 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+
+template <int BN> struct TcCfg {
+    static constexpr int B_STAGE_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : (BN == 64 ? 6 : 8));
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;   // +1024: manual 1 KiB alignment
+    static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;    // double-buffered accumulator
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
+                    const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ ConvParams p,
+                    int m_tiles, int n_tiles) {
+    using Cfg = TcCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+    uint8_t* smem = smem_raw + pad;                       // 1 KiB aligned (SWIZZLE_128B atoms)
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int total_tiles = m_tiles * n_tiles;
+    const int nk = p.n_ksteps;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_a0);
+        prefetch_tmap(&tmap_a1);
+        prefetch_tmap(&tmap_w);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(&tmem_base_smem, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+                const int m0 = mt * BM, n0 = nt * BN;
+                for (int ks = 0; ks < nk; ++ks) {
+                    const cb_kstep st = p.ksteps[ks];
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sb = sa + A_STAGE_BYTES;
+                    tma_load_2d(sa, st.a_sel ? &tmap_a1 : &tmap_a0, &full_bar[stage], (int)st.col, m0 + st.row_off);
+                    tma_load_2d(sb, &tmap_w, &full_bar[stage], st.w_k, n0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty_bar[buf], acc_phase ^ 1);      // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * BN;
+                for (int ks = 0; ks < nk; ++ks) {
+                    mbar_wait(&full_bar[stage], phase);              // TMA bytes landed
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t sb = sa + A_STAGE_BYTES;
+                    const uint64_t adesc = make_sw128_desc(sa);
+                    const uint64_t bdesc = make_sw128_desc(sb);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // advance 32 B (=16 bf16) inside the 128 B swizzle row: +2 in the >>4 address field
+                        umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                  (ks > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);                  // frees the smem slot when MMAs retire
+                    if (ks == nk - 1) umma_commit(&tmem_full_bar[buf]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue
+        const int q4 = warp & 3;                                     // TMEM lane quarter of this warp
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+            const int n0 = nt * BN;
+            const int buf = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const long q = (long)mt * BM + q4 * 32 + lane;
+            const RowDest dst = decode_row(p, q, n0);
+            mbar_wait(&tmem_full_bar[buf], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + buf * BN + ((uint32_t)(q4 * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t r[32];
+                tmem_ld32(t_row + c, r);
+                tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                epilogue_chunk(p, dst, q, n0 + c, v);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------- host side
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_cuTensorMapEncodeTiled_v12000)ptr;
+    });
+    return fn;
+}
+
+// bf16 [rows][pitch] row-major; box = 64 columns x box_rows rows, 128-byte swizzle, zero OOB fill.
+static int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t pitch_elems, int box_rows) {
+    auto enc = get_encode();
+    if (!enc) return CB_ERR_DRIVER;
+    if (((uintptr_t)base & 15) || (pitch_elems * 2) % 16) return CB_ERR_ARG;
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)pitch_elems * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? CB_OK : CB_ERR_DRIVER;
+}
+
+template <int BN>
+static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const ConvParams& p,
+                  int m_tiles, int n_tiles, int max_ctas, cudaStream_t stream) {
+    using Cfg = TcCfg<BN>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::SMEM_BYTES);
+    });
+    if (attr_err != cudaSuccess) return (int)attr_err;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int grid = m_tiles * n_tiles;
+    int cap = max_ctas > 0 ? max_ctas : sms;
+    if (grid > cap) grid = cap;
+    conv_gemm_tc_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(a0, a1, w, p, m_tiles, n_tiles);
+    CB_CHECK_LAUNCH();
+    return CB_OK;
+}
+
+}  // namespace cb
+
+extern "C" int cb_conv_gemm(const cb_conv_desc* d, int max_ctas, void* stream) {
+    using namespace cb;
+    if (!d) return CB_ERR_ARG;
+    static thread_local ConvParams p;
+    int rc = fill_params(d, p);
+    if (rc) return rc;
+    for (int i = 0; i < d->n_ksteps; ++i) {
+        const cb_kstep& s = d->ksteps[i];
+        if (s.a_sel > 1 || d->a_ptr[s.a_sel] == nullptr) return CB_ERR_ARG;
+        if (s.col % 8 || s.col + 64 > d->a_pitch[s.a_sel]) return CB_ERR_ARG;
+        if (s.w_k % 8 || s.w_k < 0 || s.w_k + 64 > d->w_k_total) return CB_ERR_ARG;
+    }
+    CUtensorMap ta0, ta1, tw;
+    rc = make_tmap(&ta0, d->a_ptr[0], d->a_rows[0], d->a_pitch[0], d->a_pitch[0], BM);
+    if (rc) return rc;
+    if (d->a_ptr[1]) {
+        rc = make_tmap(&ta1, d->a_ptr[1], d->a_rows[1], d->a_pitch[1], d->a_pitch[1], BM);
+        if (rc) return rc;
+    } else {
+        ta1 = ta0;
+    }
+    rc = make_tmap(&tw, d->w_ptr, d->w_rows, d->w_k_total, d->w_k_total, d->block_n);
+    if (rc) return rc;
+    const int m_tiles = (int)((p.rows_total + BM - 1) / BM);
+    const int n_tiles = d->n_total / d->block_n;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (d->block_n) {
+        case 32: return launch<32>(ta0, ta1, tw, p, m_tiles, n_tiles, max_ctas, st);
+        case 64: return launch<64>(ta0, ta1, tw, p, m_tiles, n_tiles, max_ctas, st);
+        case 128: return launch<128>(ta0, ta1, tw, p, m_tiles, n_tiles, max_ctas, st);
+        case 256: return launch<256>(ta0, ta1, tw, p, m_tiles, n_tiles, max_ctas, st);
+    }
+    return CB_ERR_ARG;
+}

@@ -1,0 +1,78 @@
+// Layout helpers: dense NCHW float32 <-> PF / PS bf16 (tests, debugging, interop) + library probes.
+#include "common.cuh"
+#include "../../include/coalign_b200.h"
+
+namespace cb {
+
+__device__ __forceinline__ long layout_row(int ps, int n_img, int H, int W, int n, int h, int w) {
+    if (!ps) return ((long)n * (H + 2) + h + 1) * (W + 2) + w + 1;
+    const int Hq = (H + 1) / 2 + 2, Wq = (W + 1) / 2 + 2;
+    const int ph = (h & 1) * 2 + (w & 1);
+    return (long)ph * n_img * Hq * Wq + ((long)n * Hq + (h >> 1) + 1) * Wq + (w >> 1) + 1;
+}
+
+__global__ void nchw_to_layout_kernel(const float* __restrict__ src, int N, int C, int H, int W, int ps,
+                                      __nv_bfloat16* __restrict__ dst, long lo_off) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;      // over (n,h,w,c), c fastest
+    const long total = (long)N * H * W * C;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    long t = i / C;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    const float v = src[(((long)n * C + c) * H + h) * W + w];
+    const long row = layout_row(ps, N, H, W, n, h, w);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    dst[row * C + c] = hi;
+    if (lo_off) dst[lo_off + row * C + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+__global__ void layout_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, long lo_off, int ps, int N, int C, int H,
+                                      int W, int pitch, int ch_off, float* __restrict__ dst) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;      // over (n,c,h,w), w fastest
+    const long total = (long)N * C * H * W;
+    if (i >= total) return;
+    const int w = (int)(i % W);
+    long t = i / W;
+    const int h = (int)(t % H); t /= H;
+    const int c = (int)(t % C);
+    const int n = (int)(t / C);
+    const long row = layout_row(ps, N, H, W, n, h, w);
+    float v = __bfloat162float(src[row * pitch + ch_off + c]);
+    if (lo_off) v += __bfloat162float(src[lo_off + row * pitch + ch_off + c]);
+    dst[i] = v;
+}
+
+}  // namespace cb
+
+extern "C" int cb_version(void) { return 100; }
+
+extern "C" int cb_device_check(void) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -3;
+    int major = 0, minor = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    return (major == 10 && minor == 0) ? 0 : -4;
+}
+
+extern "C" int cb_nchw_to_layout(const float* src, int n, int c, int h, int w, int to_ps, void* dst, int64_t lo_off,
+                                 void* stream) {
+    const long total = (long)n * c * h * w;
+    if (total <= 0) return CB_ERR_ARG;
+    cb::nchw_to_layout_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        src, n, c, h, w, to_ps, (__nv_bfloat16*)dst, (long)lo_off);
+    CB_CHECK_LAUNCH();
+    return CB_OK;
+}
+
+extern "C" int cb_layout_to_nchw(const void* src, int64_t lo_off, int from_ps, int n, int c, int h, int w, int pitch,
+                                 int ch_off, float* dst, void* stream) {
+    const long total = (long)n * c * h * w;
+    if (total <= 0) return CB_ERR_ARG;
+    cb::layout_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)src, (long)lo_off, from_ps, n, c, h, w, pitch, ch_off, dst);
+    CB_CHECK_LAUNCH();
+    return CB_OK;
+}

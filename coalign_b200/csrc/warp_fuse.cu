@@ -1,0 +1,193 @@
+// Fused multi-agent feature warp + per-pixel ego-row attention (A10..A13) for sm_100a.
+// One pass over the N agent maps: for every output pixel a warp bilinearly samples each agent's map at
+// the affine-transformed location (F.affine_grid + F.grid_sample semantics: bilinear, zero padding,
+// align_corners=False), forms the ego-row scaled-dot-product scores, soft-maxes over agents and writes
+// the weighted sum.  HBM-bound: channels are innermost so every tap is a coalesced 128-byte read and the
+// warped copies are never materialised.  Reference lines: include/coalign_b200.h.
+#include "common.cuh"
+#include "../../include/coalign_b200.h"
+
+namespace cb {
+
+constexpr int FUSE_MAX_AGENTS = 8;
+constexpr int FUSE_MAX_CHUNKS = 4;     // C <= 256, 64 channels (2 per lane) per chunk
+
+struct FuseGeom {
+    int H, W, C, in_ps;
+    int Hp, Wp;            // PF dims of input (in_ps=0) / of each parity plane (in_ps=1)
+    long plane_rows;       // in_ps=1: rows per parity plane (= sum_agents*Hp*Wp)
+};
+
+__device__ __forceinline__ long in_row(const FuseGeom& g, int agent, int y, int x) {
+    if (!g.in_ps) return ((long)agent * g.Hp + y + 1) * g.Wp + x + 1;
+    const int ph = (y & 1) * 2 + (x & 1);
+    return (long)ph * g.plane_rows + ((long)agent * g.Hp + (y >> 1) + 1) * g.Wp + (x >> 1) + 1;
+}
+
+__global__ void normalize_affine_kernel(const double* __restrict__ pw, int n_scenes, int L, int H, int W, double ratio,
+                                        double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_scenes * L) return;
+    const int b = i / L, j = i - b * L;
+    const double* T = pw + (((long)b * L + 0) * L + j) * 16;           // pairwise[b][0][j] (ego row)
+    double* A = out + (long)i * 6;
+    // transformation_utils.py:84-89 (same operation order, float64)
+    A[0] = T[0];
+    A[1] = T[1] * H / W;
+    A[2] = T[3] / (1 * ratio * W) * 2;
+    A[3] = T[4] * W / H;
+    A[4] = T[5];
+    A[5] = T[7] / (1 * ratio * H) * 2;
+}
+
+template <int CHUNKS>
+__global__ void __launch_bounds__(256) warp_att_fuse_kernel(const __nv_bfloat16* __restrict__ feat, long in_lo_off,
+                                                            const double* __restrict__ affine,
+                                                            const int* __restrict__ agent_off, int n_scenes, int L,
+                                                            const FuseGeom g, int method,
+                                                            __nv_bfloat16* __restrict__ out, long out_lo_off) {
+    const int lane = threadIdx.x & 31;
+    const long gw = (long)blockIdx.x * 8 + (threadIdx.x >> 5), nw = (long)gridDim.x * 8;
+    const long total = (long)n_scenes * g.H * g.W;
+    const float inv_sqrt_c = (float)(1.0 / sqrt((double)g.C));
+    for (long pix = gw; pix < total; pix += nw) {
+        const int b = (int)(pix / (g.H * g.W));
+        const int rem = (int)(pix - (long)b * g.H * g.W);
+        const int h = rem / g.W, w = rem - h * g.W;
+        const int a0 = agent_off[b];
+        int n = agent_off[b + 1] - a0;
+        n = n < FUSE_MAX_AGENTS ? n : FUSE_MAX_AGENTS;
+        const double xs = (2.0 * w + 1.0) / g.W - 1.0;                  // affine_grid base grid, align_corners=False
+        const double ys = (2.0 * h + 1.0) / g.H - 1.0;
+        float x[FUSE_MAX_AGENTS][CHUNKS][2];
+        float score[FUSE_MAX_AGENTS];
+#pragma unroll
+        for (int j = 0; j < FUSE_MAX_AGENTS; ++j) {
+            if (j < n) {
+                const double* A = affine + ((long)b * L + j) * 6;
+                const float gx = (float)(A[0] * xs + A[1] * ys + A[2]);  // grid computed in f64, cast to f32
+                const float gy = (float)(A[3] * xs + A[4] * ys + A[5]);
+                const float ix = ((gx + 1.f) * g.W - 1.f) * 0.5f;        // grid_sample unnormalise
+                const float iy = ((gy + 1.f) * g.H - 1.f) * 0.5f;
+                const float fx0 = floorf(ix), fy0 = floorf(iy);
+                const float wx1 = ix - fx0, wy1 = iy - fy0, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+                // clamp before the int conversion so far-away (or non-finite) coordinates stay out of range
+                const int x0 = (int)fminf(fmaxf(fx0, -2.f), (float)g.W + 1.f);
+                const int y0 = (int)fminf(fmaxf(fy0, -2.f), (float)g.H + 1.f);
+#pragma unroll
+                for (int c = 0; c < CHUNKS; ++c) { x[j][c][0] = 0.f; x[j][c][1] = 0.f; }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
+                    const float wt = ((t & 1) ? wx1 : wx0) * ((t >> 1) ? wy1 : wy0);
+                    if (xx >= 0 && xx < g.W && yy >= 0 && yy < g.H) {
+                        const long row = in_row(g, a0 + j, yy, xx);
+                        const uint32_t* src = reinterpret_cast<const uint32_t*>(feat + row * g.C) + lane;
+#pragma unroll
+                        for (int c = 0; c < CHUNKS; ++c) {
+                            const uint32_t u = __ldg(src + 32 * c);
+                            float v0 = bf16_lo(u), v1 = bf16_hi(u);
+                            if (in_lo_off != 0) {
+                                const uint32_t ul = __ldg(reinterpret_cast<const uint32_t*>(feat + in_lo_off + row * g.C) + lane + 32 * c);
+                                v0 += bf16_lo(ul); v1 += bf16_hi(ul);
+                            }
+                            x[j][c][0] = fmaf(wt, v0, x[j][c][0]);
+                            x[j][c][1] = fmaf(wt, v1, x[j][c][1]);
+                        }
+                    }
+                }
+            }
+        }
+        float o[CHUNKS][2];
+        if (method == 1) {                                               // MaxFusion
+#pragma unroll
+            for (int c = 0; c < CHUNKS; ++c) { o[c][0] = x[0][c][0]; o[c][1] = x[0][c][1]; }
+#pragma unroll
+            for (int j = 1; j < FUSE_MAX_AGENTS; ++j)
+                if (j < n) {
+#pragma unroll
+                    for (int c = 0; c < CHUNKS; ++c) { o[c][0] = fmaxf(o[c][0], x[j][c][0]); o[c][1] = fmaxf(o[c][1], x[j][c][1]); }
+                }
+        } else {
+            float smax = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < FUSE_MAX_AGENTS; ++j) {
+                if (j < n) {
+                    float d = 0.f;
+#pragma unroll
+                    for (int c = 0; c < CHUNKS; ++c) d += x[0][c][0] * x[j][c][0] + x[0][c][1] * x[j][c][1];
+#pragma unroll
+                    for (int s = 16; s > 0; s >>= 1) d += __shfl_xor_sync(0xffffffffu, d, s);
+                    score[j] = d * inv_sqrt_c;                            // att_fuse.py:44
+                    smax = fmaxf(smax, score[j]);
+                }
+            }
+            float den = 0.f;
+#pragma unroll
+            for (int j = 0; j < FUSE_MAX_AGENTS; ++j)
+                if (j < n) { score[j] = expf(score[j] - smax); den += score[j]; }
+            const float inv = 1.f / den;
+#pragma unroll
+            for (int c = 0; c < CHUNKS; ++c) { o[c][0] = 0.f; o[c][1] = 0.f; }
+#pragma unroll
+            for (int j = 0; j < FUSE_MAX_AGENTS; ++j)
+                if (j < n) {
+                    const float wj = score[j] * inv;
+#pragma unroll
+                    for (int c = 0; c < CHUNKS; ++c) { o[c][0] = fmaf(wj, x[j][c][0], o[c][0]); o[c][1] = fmaf(wj, x[j][c][1], o[c][1]); }
+                }
+        }
+        const long orow = ((long)b * (g.H + 2) + h + 1) * (g.W + 2) + w + 1;   // PF output
+        uint32_t* dst = reinterpret_cast<uint32_t*>(out + orow * g.C) + lane;
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+            const uint32_t hi = pack_bf16(o[c][0], o[c][1]);
+            dst[32 * c] = hi;
+            if (out_lo_off != 0)
+                (reinterpret_cast<uint32_t*>(out + out_lo_off + orow * g.C) + lane)[32 * c] =
+                    pack_bf16(o[c][0] - bf16_lo(hi), o[c][1] - bf16_hi(hi));
+        }
+    }
+}
+
+}  // namespace cb
+
+extern "C" int cb_normalize_affine(const double* pairwise_t_matrix, int n_scenes, int max_cav, int H, int W,
+                                   double discrete_ratio, double* affine_out, void* stream) {
+    if (n_scenes < 1 || max_cav < 1) return CB_ERR_ARG;
+    const int n = n_scenes * max_cav;
+    cb::normalize_affine_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(pairwise_t_matrix, n_scenes, max_cav,
+                                                                                  H, W, discrete_ratio, affine_out);
+    CB_CHECK_LAUNCH();
+    return CB_OK;
+}
+
+extern "C" int cb_warp_att_fuse(const void* feat, int in_ps, int64_t in_lo_off, int sum_agents, const double* affine,
+                                const int32_t* agent_off, int n_scenes, int max_cav, int H, int W, int C, int method,
+                                void* out_pf, int64_t out_lo_off, void* stream) {
+    using namespace cb;
+    if (C % 64 != 0 || C < 64 || C > 64 * FUSE_MAX_CHUNKS || n_scenes < 1 || max_cav < 1 || sum_agents < 1)
+        return CB_ERR_ARG;
+    if (method != 0 && method != 1) return CB_ERR_ARG;
+    if (!feat || !out_pf || !affine || !agent_off) return CB_ERR_ARG;
+    FuseGeom g;
+    g.H = H; g.W = W; g.C = C; g.in_ps = in_ps;
+    g.Hp = in_ps ? (H + 1) / 2 + 2 : H + 2;
+    g.Wp = in_ps ? (W + 1) / 2 + 2 : W + 2;
+    g.plane_rows = (long)sum_agents * g.Hp * g.Wp;
+    const long total = (long)n_scenes * H * W;
+    long blocks = (total + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    cudaStream_t st = (cudaStream_t)stream;
+    const __nv_bfloat16* f = (const __nv_bfloat16*)feat;
+    __nv_bfloat16* o = (__nv_bfloat16*)out_pf;
+    switch (C / 64) {
+        case 1: warp_att_fuse_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(f, in_lo_off, affine, agent_off, n_scenes, max_cav, g, method, o, out_lo_off); break;
+        case 2: warp_att_fuse_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(f, in_lo_off, affine, agent_off, n_scenes, max_cav, g, method, o, out_lo_off); break;
+        case 3: warp_att_fuse_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(f, in_lo_off, affine, agent_off, n_scenes, max_cav, g, method, o, out_lo_off); break;
+        case 4: warp_att_fuse_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(f, in_lo_off, affine, agent_off, n_scenes, max_cav, g, method, o, out_lo_off); break;
+        default: return CB_ERR_ARG;
+    }
+    CB_CHECK_LAUNCH();
+    return CB_OK;
+}

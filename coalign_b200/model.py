@@ -1,0 +1,175 @@
+"""Drop-in nn.Module for the reference's model registry.
+
+`PointPillarCoalignB200` is the state_dict-compatible twin of
+/root/reference/opencood/models/point_pillar_baseline_multiscale.py:17-135 (class
+PointPillarBaselineMultiscale; `CoAlign` in point_pillar_coalign.py:9-10 is an empty subclass): same
+constructor argument (the yaml `model.args` dict), same parameter/buffer names and shapes (so reference
+checkpoints load with train_utils.load_saved_model), same `forward(data_dict)` input schema and output
+dict.  The forward itself runs entirely on our CUDA library - there is no PyTorch/CPU fallback:
+constructing the engine without the built library or without a B200 raises.
+
+Scope: inference / eval mode.  `.train()` forward raises NotImplementedError (training
+kernels are a later row of SURVEY 8f).
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+import torch.nn as nn
+
+
+class _PFN(nn.Module):                         # pillar_vfe.py:8-29 parameter container
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.linear = nn.Linear(cin, cout, bias=False)
+        self.norm = nn.BatchNorm1d(cout, eps=1e-3, momentum=0.01)
+
+
+class _PillarVFE(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        cin = 4 + (6 if cfg["use_absolute_xyz"] else 3) + (1 if cfg["with_distance"] else 0)
+        if not cfg["use_norm"] or cfg["with_distance"] or not cfg["use_absolute_xyz"] or len(cfg["num_filters"]) != 1:
+            raise NotImplementedError("B200 path implements the CoAlign PillarVFE config "
+                                      "(use_norm, use_absolute_xyz, no distance, one PFN layer)")
+        self.pfn_layers = nn.ModuleList([_PFN(cin, cfg["num_filters"][0])])
+
+
+class _BasicBlock(nn.Module):                  # resblock.py:23-51 parameter container
+    def __init__(self, cin, cout, stride, has_ds):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(cout)
+        self.conv2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(cout)
+        if has_ds:
+            self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), nn.BatchNorm2d(cout))
+
+
+class _ResNet(nn.Module):                      # resblock.py:135-210
+    def __init__(self, layer_nums, strides, filters, inplanes):
+        super().__init__()
+        for i, (nb, st, pl) in enumerate(zip(layer_nums, strides, filters)):
+            blocks = [_BasicBlock(inplanes, pl, st, st != 1 or inplanes != pl)]
+            blocks += [_BasicBlock(pl, pl, 1, False) for _ in range(1, nb)]
+            setattr(self, f"layer{i}", nn.Sequential(*blocks))
+            inplanes = pl
+        for m in self.modules():               # resblock.py:165-170
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+
+
+class _Backbone(nn.Module):                    # base_bev_backbone_resnet.py:15-86
+    def __init__(self, cfg):
+        super().__init__()
+        self.resnet = _ResNet(cfg["layer_nums"], cfg["layer_strides"], cfg["num_filters"], cfg.get("inplanes", 64))
+        self.deblocks = nn.ModuleList()
+        for cin, cout, s in zip(cfg["num_filters"], cfg["num_upsample_filter"], cfg["upsample_strides"]):
+            if s < 1:
+                raise NotImplementedError("fractional upsample strides are not used by CoAlign")
+            self.deblocks.append(nn.Sequential(nn.ConvTranspose2d(cin, cout, s, stride=s, bias=False),
+                                               nn.BatchNorm2d(cout, eps=1e-3, momentum=0.01), nn.ReLU()))
+
+
+class _DoubleConv(nn.Module):                  # downsample_conv.py:7-27
+    def __init__(self, cin, cout, k, s, p):
+        super().__init__()
+        self.double_conv = nn.Sequential(nn.Conv2d(cin, cout, k, s, p), nn.ReLU(inplace=True),
+                                         nn.Conv2d(cout, cout, 3, padding=1), nn.ReLU(inplace=True))
+
+
+class _Shrink(nn.Module):                      # downsample_conv.py:30-50
+    def __init__(self, cfg):
+        super().__init__()
+        self.layers = nn.ModuleList()
+        cin = cfg["input_dim"]
+        for k, d, s, p in zip(cfg["kernal_size"], cfg["dim"], cfg["stride"], cfg["padding"]):
+            self.layers.append(_DoubleConv(cin, d, k, s, p))
+            cin = d
+
+
+class PointPillarCoalignB200(nn.Module):
+    """core_method: point_pillar_coalign_b200 (registry rule: train_utils.py:127-146)."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.pillar_vfe = _PillarVFE(args["pillar_vfe"])
+        self.backbone = _Backbone(args["base_bev_backbone"])
+        self.fusion_net = nn.ModuleList()            # parameter-free (fusion_in_one.py:91-136)
+        out_c = sum(args["base_bev_backbone"]["num_upsample_filter"])
+        if "shrink_header" in args:
+            self.shrink_conv = _Shrink(args["shrink_header"])
+            out_c = args["shrink_header"]["dim"][-1]
+        an = args["anchor_number"]
+        self.cls_head = nn.Conv2d(out_c, an, 1)
+        self.reg_head = nn.Conv2d(out_c, 7 * an, 1)
+        if "dir_args" in args:
+            self.dir_head = nn.Conv2d(out_c, args["dir_args"]["num_bins"] * an, 1)
+        self.max_cav = int(args.get("max_cav", 5))
+        self.precise = bool(args.get("b200_precise", False))
+        self.block_n_cap = int(args.get("b200_block_n", 128))
+        self._engine = None
+        self._engine_key = None
+        if args.get("backbone_fix", False):
+            self.backbone_fix()
+
+    def backbone_fix(self):                          # point_pillar_baseline_multiscale.py:68-91
+        for name in ("pillar_vfe", "backbone", "shrink_conv", "cls_head", "reg_head"):
+            if hasattr(self, name):
+                for p in getattr(self, name).parameters():
+                    p.requires_grad = False
+
+    # ---- engine management: weights are packed once per (device, weights version, capacity)
+    def _weights_version(self):
+        return tuple(int(p._version) for p in self.parameters()) + tuple(int(b._version) for b in self.buffers())
+
+    def invalidate(self):
+        self._engine = None
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self.invalidate()
+        return r
+
+    def engine(self, n_agents: int, n_scenes: int):
+        from .engine import CoAlignEngine
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("PointPillarCoalignB200 runs on a B200 only: call .to('cuda') (no CPU fallback)")
+        key = (dev, self._weights_version())
+        e = self._engine
+        if e is None or self._engine_key != key or e.max_agents < n_agents or e.max_scenes < n_scenes:
+            cap_s = max(n_scenes, e.max_scenes if e is not None else 1)
+            cap_a = max(n_agents, e.max_agents if e is not None else 1, cap_s * self.max_cav)
+            self._engine = None
+            self._engine = CoAlignEngine(self.args, self.state_dict(), cap_a, cap_s, device=dev,
+                                         precise=self.precise, max_cav=self.max_cav, block_n_cap=self.block_n_cap)
+            self._engine_key = key
+        return self._engine
+
+    def forward(self, data_dict: Dict):
+        if self.training:
+            raise NotImplementedError("coalign_b200: training-mode forward/backward is not implemented yet "
+                                      "(inference path only; see DESIGN.md)")
+        pl = data_dict["processed_lidar"]
+        record_len = [int(v) for v in data_dict["record_len"].tolist()]
+        pw = data_dict["pairwise_t_matrix"]
+        if pw.shape[1] != self.max_cav:
+            self.max_cav = int(pw.shape[1])
+            self.invalidate()
+        eng = self.engine(sum(record_len), len(record_len))
+        vc = pl["voxel_coords"]
+        vn = pl["voxel_num_points"]
+        return eng.forward_voxels(pl["voxel_features"].float(), vc.int() if vc.dtype != torch.int32 else vc,
+                                  vn.int() if vn.dtype != torch.int32 else vn, record_len, pw)
+
+    @torch.no_grad()
+    def forward_points(self, points, pt_offset, record_len, pairwise_t_matrix, max_pts=32, max_voxels=70000):
+        """Extension of the boundary: raw clouds in, voxelisation fused on the GPU."""
+        if pairwise_t_matrix.shape[1] != self.max_cav:
+            self.max_cav = int(pairwise_t_matrix.shape[1])
+            self.invalidate()
+        eng = self.engine(sum(record_len), len(record_len))
+        return eng.forward_points(points, pt_offset, record_len, pairwise_t_matrix, max_pts, max_voxels)

@@ -1,0 +1,193 @@
+/* libcoalign_b200 - C ABI of the B200-native CoAlign hot path.
+ *
+ * This is the drop-in boundary below the reference's Python model
+ * (/root/reference/opencood/models/point_pillar_baseline_multiscale.py:93-135): every entry point
+ * replaces one stage of that forward (citations on each function).  Conventions:
+ *   - plain C: raw DEVICE pointers, sizes, a cudaStream_t passed as void*; no torch types;
+ *   - returns 0 on success, a positive cudaError_t, or a negative CB_ERR_* argument/driver error;
+ *   - never allocates and never synchronises: the caller owns inputs, outputs and workspaces,
+ *     all work is enqueued on `stream` (CUDA-graph capturable);
+ *   - no global state except the lazily resolved cuTensorMapEncodeTiled entry point and
+ *     per-kernel shared-memory attributes (idempotent, thread-safe).
+ *
+ * Activation layouts (bf16, channels innermost):
+ *   PF  "padded flat": [n][H+2][W+2][C]; the 1-pixel halo is zero and is never written.
+ *       A 3x3/s1 convolution is then a GEMM over the flattened padded pixel index with one
+ *       constant row shift per filter tap.
+ *   PS  "phase split": tensor (n,H,W,C) stored as 4 parity planes [(h&1)*2+(w&1)][n][Ho+2][Wo+2][C],
+ *       Ho=ceil(H/2), Wo=ceil(W/2) (each plane PF-padded).  Input format of the stride-2 convs:
+ *       every tap of a 3x3/s2 (or 1x1/s2) convolution becomes (plane, constant row shift).
+ *   "precise" mode keeps a second bf16 plane (lo = x - bf16(x)) at element offset `lo_off` behind
+ *   the hi plane and evaluates hi*hi + lo*hi + hi*lo (fp32-class accuracy on bf16 tensor cores).
+ */
+#ifndef COALIGN_B200_H
+#define COALIGN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB_MAX_KSTEPS 168
+#define CB_MAX_AGENTS 64
+
+/* --------------------------------------------------------------------------------------------
+ * cb_version / cb_device_check
+ * ------------------------------------------------------------------------------------------ */
+int cb_version(void);
+/* 0 when the current device is sm_100 (B200); negative otherwise.  The Python side raises - there is
+ * no CPU or generic-GPU fallback. */
+int cb_device_check(void);
+
+/* --------------------------------------------------------------------------------------------
+ * A1/A2  voxelisation - replaces spconv VoxelGeneratorV2.generate / Point2VoxelCPU3d.point_to_voxel
+ * as called from /root/reference/opencood/data_utils/pre_processor/sp_voxel_preprocessor.py:62-85
+ * and the collate at :145-174 (agent index prepended to coords).
+ *
+ * points      : concatenated clouds, float32 [sum_P][4]; agent a owns rows [pt_offset[a], pt_offset[a+1])
+ * pt_offset   : HOST int32 [n_agents+1]
+ * range/vsize : HOST float32 [6]/[3]; grid: HOST int32 [3] = (nx,ny,nz)
+ * outputs (device), bit-exact with the serial generator:
+ *   voxels     float32 [cap][max_pts][4] zero padded     (cap >= min(sum_P, n_agents*max_voxels))
+ *   coords     int32   [cap][4] = [agent, z, y, x]
+ *   num_points int32   [cap]
+ *   n_voxels   int32   [n_agents+1]: per-agent counts, last = total
+ * workspace    : cb_voxelize_workspace_bytes(...) bytes, device
+ * ------------------------------------------------------------------------------------------ */
+size_t cb_voxelize_workspace_bytes(int n_agents, int sum_points, const int32_t* grid, int max_voxels);
+int cb_voxelize(const float* points, const int32_t* pt_offset, int n_agents,
+                const float* range, const float* vsize, const int32_t* grid,
+                int max_pts, int max_voxels,
+                float* voxels, int32_t* coords, int32_t* num_points, int32_t* n_voxels,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * A3+A4+A5  PillarVFE + PFNLayer + PointPillarScatter fused
+ *   /root/reference/opencood/models/sub_modules/pillar_vfe.py:31-53,105-155
+ *   /root/reference/opencood/models/sub_modules/point_pillar_scatter.py:15-72
+ * Reads reference-format voxel tensors, writes the BEV canvas in PS layout (the canvas is only ever
+ * consumed by stride-2 convolutions).  The canvas must have been zeroed by the caller.
+ *   w        float32 [64][10]  pfn_layers.0.linear.weight
+ *   scale/shift float32 [64]   folded eval BatchNorm1d (eps 1e-3)
+ *   vsize/center_off HOST float32 [3]: voxel size and (voxel/2 + range_min) rounded from double
+ *                              exactly like PillarVFE.__init__ (pillar_vfe.py:84-89)
+ *   canvas_agents: agent capacity the PS canvas was allocated for (plane stride), >= n_agents
+ *   n_voxels_dev: optional DEVICE int32* holding the number of valid rows (<= n_rows); NULL = n_rows
+ * ------------------------------------------------------------------------------------------ */
+int cb_pfn_scatter(const float* voxels, const int32_t* coords, const int32_t* num_points,
+                   int n_rows, const int32_t* n_voxels_dev, int max_pts,
+                   const float* w, const float* scale, const float* shift,
+                   const float* vsize, const float* center_off,
+                   int n_agents, int canvas_agents, int ny, int nx,
+                   void* canvas_ps, int64_t lo_off, void* stream);
+
+/* Same stages straight from raw points (A1..A5 fused; the (M,32,4) voxel tensor is never
+ * materialised).  Uses the same workspace as cb_voxelize. */
+int cb_points_to_canvas(const float* points, const int32_t* pt_offset, int n_agents,
+                        const float* range, const float* vsize, const int32_t* grid,
+                        int max_pts, int max_voxels,
+                        const float* w, const float* scale, const float* shift,
+                        const float* center_off, int canvas_agents, void* canvas_ps, int64_t lo_off,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * A6..A9  convolutions as implicit GEMMs on tcgen05 tensor cores (TMA-fed, TMEM accumulators)
+ *   BasicBlock / ResNetModified   /root/reference/opencood/models/sub_modules/resblock.py:53-69,212-221
+ *   deblocks (ConvTranspose k==s) /root/reference/opencood/models/sub_modules/base_bev_backbone_resnet.py:52-65,121-138
+ *   shrink header                 /root/reference/opencood/models/sub_modules/downsample_conv.py:18-24
+ *   heads                         /root/reference/opencood/models/point_pillar_baseline_multiscale.py:55-63,126-133
+ *
+ * One GEMM:  D[q][n] = sum_steps sum_{kk<64} A_sel[q + row_off][col + kk] * W[n][w_k + kk]
+ * over the flattened padded output-pixel index q (rows_total = n_img*Hp*Wp), followed by the epilogue
+ *   v = D + bias[n % cout_mod] (+ residual[q][n]) ; relu ; store.
+ * BatchNorm scale is folded into W by the host; `bias` carries the BN shift or the conv bias.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct cb_kstep {
+    int32_t row_off;  /* row shift (tap) + plane offset, in rows of the A tensor */
+    int32_t w_k;      /* K coordinate of the 64-wide weight block */
+    uint16_t col;     /* first input channel of the 64-wide block */
+    uint16_t a_sel;   /* which A tensor (0/1) */
+} cb_kstep;
+
+enum { CB_OUT_PF = 0, CB_OUT_PS = 1, CB_OUT_UPSAMPLE = 2, CB_OUT_HEADS = 3 };
+
+typedef struct cb_conv_desc {
+    /* A operands: bf16 [a_rows][a_pitch] (a_rows counts hi+lo planes in precise mode) */
+    const void* a_ptr[2];
+    int64_t a_rows[2];
+    int32_t a_pitch[2];
+    /* weights: bf16 [w_rows][w_k_total], K-major */
+    const void* w_ptr;
+    int32_t w_rows;
+    int32_t w_k_total;
+    /* GEMM row space */
+    int32_t n_img, Hp, Wp;     /* rows_total = n_img*Hp*Wp; interior = 1..Hp-2 x 1..Wp-2 */
+    int32_t n_total;           /* GEMM N (multiple of block_n) */
+    int32_t block_n;           /* 32, 64, 128 or 256 */
+    /* epilogue */
+    const float* bias;         /* [cout_mod] */
+    int32_t cout_mod;
+    int32_t relu;
+    const void* residual;      /* bf16 PF, same row space, or NULL */
+    int32_t res_pitch;
+    int64_t res_lo_off;        /* element offset of the lo plane (precise) */
+    void* out;
+    int32_t out_pitch;
+    int32_t out_ch_off;
+    int64_t out_lo_off;        /* 0 = bf16 mode; else precise: element offset of the lo plane */
+    int32_t out_mode;          /* CB_OUT_* */
+    int32_t up_k;              /* CB_OUT_UPSAMPLE: kernel==stride */
+    int32_t out_Hp, out_Wp;    /* padded dims of the destination (PS plane dims / upsample target) */
+    int64_t out_plane_rows;    /* CB_OUT_PS: rows per parity plane */
+    /* CB_OUT_HEADS: fp32 NCHW outputs, channel segments [c0, c0+cn) */
+    float* head_out[3];
+    int32_t head_c0[3];
+    int32_t head_cn[3];
+    int32_t n_heads;
+    /* K loop */
+    int32_t n_ksteps;
+    cb_kstep ksteps[CB_MAX_KSTEPS];
+} cb_conv_desc;
+
+/* tcgen05 path (the product).  max_ctas <= 0: one persistent CTA per SM. */
+int cb_conv_gemm(const cb_conv_desc* desc, int max_ctas, void* stream);
+/* Plain SIMT fp32-accumulate evaluation of the same descriptor: a validation kernel for the
+ * tensor-core path (tests only; never used by the model). */
+int cb_conv_gemm_simt(const cb_conv_desc* desc, void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * A10..A13  pose normalisation + affine feature warp + per-pixel ego-row attention, one kernel
+ *   normalize_pairwise_tfm  /root/reference/opencood/utils/transformation_utils.py:69-91
+ *   warp_affine_simple      /root/reference/opencood/models/sub_modules/torch_transformation_utils.py:322-331
+ *   AttFusion.forward       /root/reference/opencood/models/fuse_modules/fusion_in_one.py:96-136
+ *   ScaledDotProductAttention /root/reference/opencood/models/fuse_modules/att_fuse.py:43-47
+ *   regroup                 /root/reference/opencood/models/fuse_modules/fusion_in_one.py:21-24
+ *
+ * feat      : bf16, (sum_agents, H, W, C) in PF (in_ps=0) or PS (in_ps=1) layout; `sum_agents` is the
+ *             agent capacity of the buffer (PS plane stride)
+ * affine    : DEVICE float64 [n_scenes][max_cav][2][3] = normalised ego-row matrices (A_n = affine[b][0][n])
+ *             as produced by cb_normalize_affine
+ * agent_off : DEVICE int32 [n_scenes+1], prefix sums of record_len
+ * out       : bf16 PF (n_scenes, H, W, C)
+ * method    : 0 = attention ("att"), 1 = element-wise max ("max", MaxFusion fusion_in_one.py:83-86)
+ * ------------------------------------------------------------------------------------------ */
+int cb_normalize_affine(const double* pairwise_t_matrix, int n_scenes, int max_cav,
+                        int H, int W, double discrete_ratio, double* affine_out, void* stream);
+int cb_warp_att_fuse(const void* feat, int in_ps, int64_t in_lo_off, int sum_agents,
+                     const double* affine, const int32_t* agent_off, int n_scenes, int max_cav,
+                     int H, int W, int C, int method,
+                     void* out_pf, int64_t out_lo_off, void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * layout helpers (tests, debugging, interop): dense NCHW float32 <-> PF / PS bf16
+ * ------------------------------------------------------------------------------------------ */
+int cb_nchw_to_layout(const float* src, int n, int c, int h, int w, int to_ps,
+                      void* dst, int64_t lo_off, void* stream);
+int cb_layout_to_nchw(const void* src, int64_t lo_off, int from_ps, int n, int c, int h, int w,
+                      int pitch, int ch_off, float* dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COALIGN_B200_H */

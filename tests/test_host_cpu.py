@@ -1,0 +1,137 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol of include/coalign_b200.h, the ctypes
+descriptor mirrors the C struct, host-side weight packing / K-step logic, plugin registry contract."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ensure_lib():
+    from coalign_b200 import build
+    return build.build()
+
+
+def test_library_exports_every_declared_symbol():
+    path = _ensure_lib()
+    hdr = open(os.path.join(ROOT, "include", "coalign_b200.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|size_t)\s+(cb_\w+)\s*\(", hdr, flags=re.M))
+    assert len(declared) >= 12
+    lib = ctypes.CDLL(path)
+    for name in declared:
+        assert hasattr(lib, name), name
+    from coalign_b200 import _lib
+    assert set(_lib.EXPORTS) == declared
+    assert _lib.load().cb_version() == 100
+
+
+def test_ctypes_descriptor_matches_c_struct(tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "coalign_b200.h"\n'
+                   'int main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(cb_conv_desc), offsetof(cb_conv_desc, ksteps),'
+                   'offsetof(cb_conv_desc, head_out), offsetof(cb_conv_desc, out_plane_rows), sizeof(cb_kstep));return 0;}')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    vals = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    from coalign_b200._lib import ConvDesc, KStep
+    assert vals == [ctypes.sizeof(ConvDesc), ConvDesc.ksteps.offset, ConvDesc.head_out.offset,
+                    ConvDesc.out_plane_rows.offset, ctypes.sizeof(KStep)]
+
+
+def test_missing_gpu_fails_loudly():
+    from coalign_b200 import synth
+    from coalign_b200.model import PointPillarCoalignB200
+    from tests import golden_cases as G
+    m = PointPillarCoalignB200(G.small_args()).eval()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        m({"processed_lidar": {}, "record_len": torch.tensor([1]), "pairwise_t_matrix": torch.zeros(1, 5, 5, 4, 4)})
+    with pytest.raises(RuntimeError):
+        from coalign_b200.engine import CoAlignEngine
+        CoAlignEngine(G.small_args(), synth.random_state_dict(G.small_args(), 0), 1, 1)
+
+
+def test_state_dict_contract():
+    from coalign_b200 import synth
+    from coalign_b200.model import PointPillarCoalignB200
+    args = synth.opv2v_args()
+    m = PointPillarCoalignB200(args)
+    sd = synth.random_state_dict(args, 0)
+    assert set(m.state_dict()) == set(sd) and len(sd) == 244
+    assert sum(p.numel() for p in m.parameters()) == 12901524
+    m.load_state_dict(sd, strict=True)
+
+
+def test_weight_packing_is_a_gemm_restatement_of_conv():
+    """pack_conv_weight + tap shifts reproduce F.conv2d (the host logic behind the K-step tables)."""
+    from coalign_b200.engine import CoAlignEngine, pack_conv_weight
+    g = torch.Generator().manual_seed(0)
+    cin, cout, H, W = 64, 8, 5, 7
+    x = torch.randn(1, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g)
+    ref = torch.nn.functional.conv2d(x, w, padding=1)
+    Hp, Wp = H + 2, W + 2
+    xp = torch.zeros(Hp * Wp, cin)
+    xp.view(Hp, Wp, cin)[1:-1, 1:-1] = x[0].permute(1, 2, 0)
+    wp = pack_conv_weight(w, None).float()
+    out = torch.zeros(Hp * Wp, cout)
+    for (ro, col, wk, sel) in CoAlignEngine._steps_3x3_s1(cin, Wp):
+        rows = torch.arange(Hp * Wp) + ro
+        ok = (rows >= 0) & (rows < Hp * Wp)
+        a = torch.zeros(Hp * Wp, 64)
+        a[ok] = xp[rows[ok], col:col + 64]
+        out += a @ wp[:, wk:wk + 64].t()
+    got = out.view(Hp, Wp, cout)[1:-1, 1:-1].permute(2, 0, 1)
+    assert torch.allclose(got, ref[0], atol=1e-3)
+
+
+def _to_ps(x, n_cap):
+    """dense (N,C,H,W) -> PS rows [4*plane_rows, C] (include/coalign_b200.h layout)."""
+    N, C_, H, W = x.shape
+    Hq, Wq = (H + 1) // 2 + 2, (W + 1) // 2 + 2
+    plane_rows = n_cap * Hq * Wq
+    buf = torch.zeros(4 * plane_rows, C_)
+    for n in range(N):
+        for h in range(H):
+            for w in range(W):
+                ph = (h & 1) * 2 + (w & 1)
+                buf[ph * plane_rows + (n * Hq + (h >> 1) + 1) * Wq + (w >> 1) + 1] = x[n, :, h, w]
+    return buf, Hq, Wq, plane_rows
+
+
+@pytest.mark.parametrize("H,W", [(6, 8), (5, 7)])
+def test_stride2_phase_split_ksteps(H, W):
+    """K-step table of the k3/s2/p1 conv over a PS input == F.conv2d(stride=2) (+ the fused 1x1/s2 branch)."""
+    from coalign_b200.engine import Act, CoAlignEngine, pack_conv_weight
+    g = torch.Generator().manual_seed(1)
+    cin, cout, N, cap = 64, 4, 2, 3
+    x = torch.randn(N, cin, H, W, generator=g)
+    w3 = torch.randn(cout, cin, 3, 3, generator=g)
+    w1 = torch.randn(cout, cin, 1, 1, generator=g)
+    ref = torch.nn.functional.conv2d(x, w3, stride=2, padding=1) + torch.nn.functional.conv2d(x, w1, stride=2)
+    buf, Hq, Wq, plane_rows = _to_ps(x, cap)
+
+    class Src:                    # the attributes _steps_3x3_s2 reads from an Act
+        pass
+    src = Src()
+    src.plane_rows, src.Wp = plane_rows, Wq
+    steps = CoAlignEngine._steps_3x3_s2(cin, src) + CoAlignEngine._steps_1x1(cin, 0, 9 * cin)
+    wp = torch.cat([pack_conv_weight(w3, None), pack_conv_weight(w1, None)], 1).float()
+    rows_total = N * Hq * Wq
+    out = torch.zeros(rows_total, cout)
+    for (ro, col, wk, sel) in steps:
+        rows = torch.arange(rows_total) + ro
+        ok = (rows >= 0) & (rows < buf.shape[0])
+        a = torch.zeros(rows_total, 64)
+        a[ok] = buf[rows[ok], col:col + 64]
+        out += a @ wp[:, wk:wk + 64].t()
+    Ho, Wo = (H + 1) // 2, (W + 1) // 2
+    got = out.view(N, Hq, Wq, cout)[:, 1:Ho + 1, 1:Wo + 1].permute(0, 3, 1, 2)
+    assert torch.allclose(got, ref, atol=1e-3), (got - ref).abs().max()

@@ -1,0 +1,220 @@
+"""GPU parity tests: the CUDA path (through the C ABI / ctypes) against the CPU oracle and the golden
+vectors of the unmodified reference.  Run on the B200 box: pytest -m gpu."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from coalign_b200 import synth
+from tests import golden_cases as G
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+def assert_close(a, b, rtol, atol, what=""):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    err = np.abs(a - b)
+    tol = atol + rtol * np.abs(b)
+    bad = err > tol
+    assert not bad.any(), f"{what}: {bad.sum()}/{bad.size} out of tol, max err {err.max():.3e}, rel_l2 {rel_l2(a, b):.3e}"
+
+
+def make_engine(args, sd, n_agents, n_scenes, **kw):
+    from coalign_b200.engine import CoAlignEngine
+    return CoAlignEngine(args, sd, n_agents, n_scenes, device="cuda", **kw)
+
+
+def cuda_batch(inp):
+    return (torch.from_numpy(inp["voxel_features"]).cuda(), torch.from_numpy(inp["voxel_coords"]).cuda(),
+            torch.from_numpy(inp["voxel_num_points"]).cuda(), [int(v) for v in inp["record_len"]],
+            torch.from_numpy(inp["pairwise_t_matrix"]).cuda())
+
+
+def oracle_stages(args, sd, inp):
+    from oracle import coalign_oracle as O
+    st = {}
+    out = O.forward(sd, args, G.to_torch_batch(inp), st)
+    return out, st
+
+
+def engine_stages(eng, n_img, n_scenes):
+    s = {"canvas": eng.read_act(eng.canvas, n_img).cpu().numpy()}
+    for i in range(len(eng.levels)):
+        s[f"feat{i}"] = eng.read_act(eng.lvl[i]["out"], n_img).cpu().numpy()
+        s[f"fused{i}"] = eng.read_act(eng.lvl[i]["fused"], n_scenes).cpu().numpy()
+    s["decoded"] = eng.read_act(eng.cat, n_scenes).cpu().numpy()
+    s["shrunk"] = eng.read_act(eng.shrink_bufs[-1], n_scenes).cpu().numpy()
+    return s
+
+
+@pytest.mark.parametrize("name,fusion", [("model_small_att", "att"), ("model_small_single", "att"),
+                                         ("model_small_max", "max")])
+def test_precise_mode_matches_reference_golden(name, fusion):
+    """fp32-class path (bf16x3 split on tensor cores): heads within rtol 1e-3 of the reference's own outputs."""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    seed = int(g["seed"])
+    args = G.small_args(fusion)
+    sd = synth.random_state_dict(args, seed)
+    rl = [int(v) for v in g["record_len"]]
+    inp = G.small_case_inputs(rl, seed0=100 + seed)
+    eng = make_engine(args, sd, sum(rl), len(rl), precise=True)
+    out = eng.forward_voxels(*cuda_batch(inp))
+    torch.cuda.synchronize()
+    st = engine_stages(eng, sum(rl), len(rl))
+    for i in range(3):
+        assert_close(st[f"feat{i}"], g[f"feat{i}"], 1e-3, 1e-3, f"feat{i}")
+        assert_close(st[f"fused{i}"], g[f"fused{i}"], 1e-3, 1e-3, f"fused{i}")
+    assert_close(st["shrunk"], g["shrunk"], 1e-3, 1e-3, "shrunk")
+    for k in ("cls_preds", "reg_preds", "dir_preds"):
+        assert_close(out[k].cpu().numpy(), g[k], 1e-3, 1e-3, k)
+
+
+def test_bf16_mode_tensor_core_vs_simt_and_oracle():
+    """bf16 path: (1) tcgen05 kernel == SIMT evaluation of the same descriptors (same bf16 operands, fp32
+    accumulate) up to accumulation order; (2) drift vs the fp32 oracle stays at bf16 level."""
+    seed = 1
+    args = G.small_args("att")
+    sd = synth.random_state_dict(args, seed)
+    rl = [3, 2]
+    inp = G.small_case_inputs(rl, seed0=100 + seed)
+    ref_out, ref_st = oracle_stages(args, sd, inp)
+    res = {}
+    for simt in (True, False):
+        eng = make_engine(args, sd, 5, 2, precise=False, simt_conv=simt, use_graph=not simt)
+        out = eng.forward_voxels(*cuda_batch(inp))
+        torch.cuda.synchronize()
+        res[simt] = ({k: v.cpu().numpy() for k, v in out.items()}, engine_stages(eng, 5, 2))
+    # canvas: PFN is fp32 math rounded to bf16 once
+    assert_close(res[False][1]["canvas"], ref_st["canvas"].numpy(), 1e-2, 1e-2, "canvas")
+    for k in res[True][1]:
+        assert rel_l2(res[False][1][k], res[True][1][k]) < 2e-2, (k, rel_l2(res[False][1][k], res[True][1][k]))
+    for k in ("cls_preds", "reg_preds", "dir_preds"):
+        assert rel_l2(res[False][0][k], res[True][0][k]) < 2e-2, k
+        assert rel_l2(res[False][0][k], ref_out[k].numpy()) < 5e-2, (k, rel_l2(res[False][0][k], ref_out[k].numpy()))
+
+
+@pytest.mark.parametrize("block_n", [64, 128, 256])
+def test_conv_tile_shapes_agree(block_n):
+    seed = 2
+    args = G.small_args("att")
+    sd = synth.random_state_dict(args, seed)
+    rl = [2]
+    inp = G.small_case_inputs(rl, seed0=300)
+    outs = []
+    for bn, simt in ((block_n, False), (128, True)):
+        eng = make_engine(args, sd, 2, 1, precise=True, block_n_cap=bn, simt_conv=simt, use_graph=False)
+        o = eng.forward_voxels(*cuda_batch(inp))
+        torch.cuda.synchronize()
+        outs.append({k: v.cpu().numpy() for k, v in o.items()})
+    for k in outs[0]:
+        assert_close(outs[0][k], outs[1][k], 1e-3, 1e-3, k)
+
+
+def test_voxelize_bit_exact_and_fused_path():
+    """Integer pillar indices bit-exact with the serial generator restatement (oracle/voxelize.c);
+    fused points->canvas == voxels->canvas."""
+    from oracle import voxelize_np as V
+    args = G.small_args("att")
+    sd = synth.random_state_dict(args, 5)
+    eng = make_engine(args, sd, 4, 1, precise=True)
+    rng = np.random.default_rng(11)
+    clouds = [synth.lidar_cloud(rng, n, G.SMALL_RANGE, sigma=s) for n, s in ((3000, 5.0), (1, 5.0), (5000, 1.5), (257, 8.0))]
+    edge = np.array([[-11.2, -4.8, -3.0, 0.5], [11.2, 0, 0, 0.5], [0, 4.8, 0, 0.5], [0, 0, 1.0, 0.5],
+                     [0.4, 0.8, -1.0, 0.1], [11.199999, 4.799999, 0.999, 0.2], [-11.2000001, 0, 0, 0.3]], np.float32)
+    clouds[0] = np.concatenate([edge, clouds[0]])
+    off = np.concatenate([[0], np.cumsum([c.shape[0] for c in clouds])]).astype(np.int32)
+    pts = torch.from_numpy(np.concatenate(clouds)).cuda()
+    for max_pts, max_vox in ((32, 70000), (5, 70000), (32, 150)):
+        vox, crd, npt, nv = eng.voxelize(pts, off, max_pts, max_vox)
+        ref = V.collate([V.voxelize_c(c, G.SMALL_RANGE, G.SMALL_VOXEL, max_pts, max_vox) for c in clouds])
+        assert np.array_equal(crd.cpu().numpy(), ref[1]), (max_pts, max_vox)
+        assert np.array_equal(npt.cpu().numpy(), ref[2])
+        assert np.array_equal(vox.cpu().numpy(), ref[0])          # bit-exact incl. slot order and zero padding
+    # fused path: same canvas as the staged path
+    pw = torch.from_numpy(np.tile(np.eye(4), (1, 5, 5, 1, 1))).cuda()
+    vox, crd, npt, nv = eng.voxelize(pts, off, 32, 70000)
+    eng.forward_voxels(vox, crd, npt, [4], pw)
+    c1 = eng.read_act(eng.canvas, 4).cpu().numpy()
+    eng.forward_points(pts, off, [4], pw, 32, 70000)
+    c2 = eng.read_act(eng.canvas, 4).cpu().numpy()
+    assert np.array_equal(c1, c2)
+
+
+def test_warp_fuse_op_golden():
+    """A11/A12 op-level: fused warp+attention kernel vs the reference's AttFusion/MaxFusion on 64-channel maps."""
+    from coalign_b200 import _lib
+    from oracle import coalign_oracle as O
+    lib = _lib.load(True)
+    g = torch.Generator().manual_seed(3)
+    H, W, Cc = 9, 14, 64
+    x = torch.randn(5, Cc, H, W, generator=g)
+    aff = torch.zeros(2, 5, 5, 2, 3, dtype=torch.float64)
+    aff[..., 0, 0] = 1
+    aff[..., 1, 1] = 1
+    aff[0, 0, 1] = torch.tensor([[0.8, -0.5, 0.2], [0.6, 0.9, -0.3]])
+    aff[0, 0, 2] = torch.tensor([[-1.0, 0.05, 1.7], [0.02, -1.0, 0.4]])
+    aff[1, 0, 1] = torch.tensor([[1.0, 0, 5.0], [0, 1.0, 5.0]])     # fully out of view
+    sp = torch.cuda.current_stream().cuda_stream
+    for ps in (0, 1):
+        for method, name in ((0, "att"), (1, "max")):
+            ref = O.att_fusion(x, [3, 2], aff, name).numpy()
+            Hq, Wq = ((H + 1) // 2 + 2, (W + 1) // 2 + 2) if ps else (H + 2, W + 2)
+            rows = 5 * Hq * Wq * (4 if ps else 1)
+            buf = torch.zeros(2 * rows, Cc, dtype=torch.bfloat16, device="cuda")
+            xd = x.cuda().contiguous()
+            _lib.check(lib.cb_nchw_to_layout(xd.data_ptr(), 5, Cc, H, W, ps, buf.data_ptr(), rows * Cc, sp))
+            out = torch.zeros(2 * 2 * (H + 2) * (W + 2), Cc, dtype=torch.bfloat16, device="cuda")
+            affd = aff[:, 0].contiguous().cuda()
+            offd = torch.tensor([0, 3, 5], dtype=torch.int32, device="cuda")
+            _lib.check(lib.cb_warp_att_fuse(buf.data_ptr(), ps, rows * Cc, 5, affd.data_ptr(), offd.data_ptr(), 2, 5,
+                                            H, W, Cc, method, out.data_ptr(), 2 * (H + 2) * (W + 2) * Cc, sp))
+            dense = torch.empty(2, Cc, H, W, device="cuda")
+            _lib.check(lib.cb_layout_to_nchw(out.data_ptr(), 2 * (H + 2) * (W + 2) * Cc, 0, 2, Cc, H, W, Cc, 0,
+                                             dense.data_ptr(), sp))
+            torch.cuda.synchronize()
+            assert_close(dense.cpu().numpy(), ref, 1e-4, 1e-4, f"fuse ps={ps} {name}")
+
+
+def test_normalize_affine_matches_reference_golden():
+    from coalign_b200 import _lib
+    lib = _lib.load(True)
+    g = np.load(os.path.join(GOLD, "ops.npz"))
+    pw = torch.from_numpy(g["pairwise"][None].copy()).cuda()
+    out = torch.zeros(1, 5, 2, 3, dtype=torch.float64, device="cuda")
+    _lib.check(lib.cb_normalize_affine(pw.data_ptr(), 1, 5, 200, 704, 0.4, out.data_ptr(),
+                                       torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out.cpu().numpy(), g["affine_200_704"][:, 0], rtol=0, atol=1e-13)
+
+
+def test_plugin_through_reference_style_call():
+    """The nn.Module twin: state_dict round trip + forward(data_dict) with the reference batch schema."""
+    from coalign_b200.model import PointPillarCoalignB200
+    g = np.load(os.path.join(GOLD, "model_small_att.npz"))
+    seed = int(g["seed"])
+    args = G.small_args("att")
+    args["b200_precise"] = True
+    sd = synth.random_state_dict(args, seed)
+    m = PointPillarCoalignB200(args)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    inp = G.small_case_inputs([3, 2], seed0=100 + seed)
+    batch = G.to_torch_batch(inp)
+    batch = {"processed_lidar": {k: v.cuda() for k, v in batch["processed_lidar"].items()},
+             "record_len": batch["record_len"].cuda(), "pairwise_t_matrix": batch["pairwise_t_matrix"].cuda()}
+    with torch.no_grad():
+        out = m(batch)
+    for k in ("cls_preds", "reg_preds", "dir_preds"):
+        assert_close(out[k].cpu().numpy(), g[k], 1e-3, 1e-3, k)
+    with pytest.raises(NotImplementedError):
+        m.train()(batch)
