@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py - scenes/sec of the CoAlign hot path (5-agent OPV2V-shape scenes, 60k points/agent) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA library)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the reference algorithm on host cores
+
+A step = one pass of the hot path (raw point clouds + poses -> cls/reg/dir maps) over one batch of
+`--scenes-per-step` synthetic scenes per GPU.  N>1: one process per GPU (torchrun), scenes sharded, no data-path
+collective (weak scaling); timing = max over ranks.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_AGENTS = 5
+N_POINTS = 60000
+CONV_GFLOP_PER_SCENE = 81.0287 * N_AGENTS + 108.2065          # OPV2V forward, 2*MAC
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"],
+                "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_batches(n_batches, scenes_per_step, seed0):
+    from coalign_b200 import synth
+    args = synth.opv2v_args()
+    out = []
+    for b in range(n_batches):
+        scenes = [synth.make_scene(seed0 + b * scenes_per_step + s, N_AGENTS, N_POINTS, args["lidar_range"],
+                                   max_cav=5, pose_noise=True) for s in range(scenes_per_step)]
+        pts = np.concatenate([p for sc in scenes for p in sc["points"]]).astype(np.float32)
+        pw = np.stack([sc["pairwise_t_matrix"] for sc in scenes])
+        out.append((pts, pw, scenes))
+    return args, out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference algorithm on the host cores
+# ----------------------------------------------------------------------------------------------------------
+def cpu_scene_seconds(args, sd, scene, threads):
+    import torch
+    from oracle import coalign_oracle as O
+    from tests.golden_cases import scenes_to_batch, to_torch_batch
+    torch.set_num_threads(threads)
+    t0 = time.perf_counter()
+    inp = scenes_to_batch([scene], args["lidar_range"], args["voxel_size"], 32, 70000)      # oracle/voxelize.c
+    out = O.forward(sd, args, to_torch_batch(inp))
+    dt = time.perf_counter() - t0
+    return dt, out
+
+
+def run_reference(opt):
+    """--impl reference: per step one 5-agent 60k-pt scene through the CPU restatement (oracle/) of the reference's
+    PyTorch path, fp32, all host threads torch will use.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from coalign_b200 import synth
+    args, batches = make_batches(1, 1, seed0=0)
+    sd = synth.random_state_dict(args, 0)
+    threads = opt.cpu_threads or min(os.cpu_count() or 1, 64)
+    scene = batches[0][2][0]
+    for _ in range(opt.warmup):
+        cpu_scene_seconds(args, sd, scene, threads)
+    t0 = time.perf_counter()
+    for _ in range(opt.steps):
+        cpu_scene_seconds(args, sd, scene, threads)
+    dt = time.perf_counter() - t0
+    v = opt.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "scenes_per_sec", "value": v, "unit": "scenes/s", "n_gpus": opt.gpus,
+        "steps": opt.steps, "warmup": opt.warmup, "ms_per_step": dt / opt.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "OPV2V-shape 5-agent CoAlign scene, 60k pts/agent (BASELINE configs[2] shape)",
+                   "scenes_per_step": 1, "note": "CPU restatement of the reference PyTorch path (oracle/), "
+                   "voxelisation by oracle/voxelize.c"},
+        "cpu_baseline": {"value": v, "unit": "scenes/s", "cores": threads, "kind": "port",
+                         "sample": f"{opt.steps} x one 5-agent scene"},
+        "e2e": {"value": v, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------
+def run_ours(opt):
+    import torch
+    import torch.distributed as dist
+    from coalign_b200 import synth
+    from coalign_b200.engine import CoAlignEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = opt.scenes_per_step
+    NB = 8                                                   # rotating input batches (> L2 together with activations)
+    args, batches = make_batches(NB, B, seed0=1000 * rank)
+    sd = synth.random_state_dict(args, 0)
+    eng = CoAlignEngine(args, sd, B * N_AGENTS, B, device=f"cuda:{local}", precise=opt.precise,
+                        block_n_cap=opt.block_n)
+    rl = [N_AGENTS] * B
+    off = (np.arange(B * N_AGENTS + 1) * N_POINTS).astype(np.int32)
+    dev_pts = [torch.from_numpy(p).cuda() for p, _, _ in batches]
+    dev_pw = [torch.from_numpy(w).cuda() for _, w, _ in batches]
+    host_pts = [torch.from_numpy(p).pin_memory() for p, _, _ in batches]
+    host_pw = [torch.from_numpy(w).pin_memory() for _, w, _ in batches]
+    stage_pts = torch.empty_like(dev_pts[0])
+    stage_pw = torch.empty_like(dev_pw[0])
+    host_out = None
+
+    def step_resident(i):
+        return eng.forward_points(dev_pts[i % NB], off, rl, dev_pw[i % NB], 32, 70000, clone=False)
+
+    def step_e2e(i):
+        nonlocal host_out
+        stage_pts.copy_(host_pts[i % NB], non_blocking=True)
+        stage_pw.copy_(host_pw[i % NB], non_blocking=True)
+        out = eng.forward_points(stage_pts, off, rl, stage_pw, 32, 70000, clone=False)
+        if host_out is None:
+            host_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
+        for k, v in out.items():
+            host_out[k].copy_(v, non_blocking=True)
+        return out
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            dist.barrier()
+        return ms
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(step_resident, opt.steps, opt.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, opt.steps, opt.warmup)
+    torch.cuda.synchronize()
+
+    scenes_total = world * B * opt.steps
+    value = scenes_total / (ms * 1e-3)
+    e2e_value = scenes_total / (ms_e2e * 1e-3)
+    h2d = int(host_pts[0].numel() * 4 + host_pw[0].numel() * 8)
+    d2h = int(sum(v.numel() * 4 for v in host_out.values()))
+
+    # ---- roofline of the dominant kernel (conv GEMM on tcgen05), measured live with CUDA events per launch
+    roof, hbm_roofs, launches_per_step = None, [], 0
+    if rank == 0:
+        peaks = load_peaks()
+        ops = eng.build_descs(B * N_AGENTS, B)
+        sp = torch.cuda.current_stream().cuda_stream
+        n_conv = sum(1 for k, _ in ops if k == "conv")
+        launches_per_step = len(ops) + 1 + 4                   # + normalize_affine + pillar front-end (K1..K4)
+        reps = 5
+        tot = {"conv": 0.0, "fuse": 0.0}
+        evs = []
+        for r in range(reps + 1):
+            for kind, o in ops:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                eng._launch_ops([(kind, o)], B, sp)
+                b.record()
+                if r > 0:
+                    evs.append((kind, a, b))
+        torch.cuda.synchronize()
+        for kind, a, b in evs:
+            tot[kind] += a.elapsed_time(b) * 1e-3 / reps
+        conv_flop = CONV_GFLOP_PER_SCENE * 1e9 * B
+        ach = conv_flop / tot["conv"] / 1e12
+        roof = {"bound": "tensor", "kernel": "conv_gemm_tc_kernel<BN> (all %d conv GEMM launches of a step)" % n_conv,
+                "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
+                "peak_source": peaks["src"] + ", sustained figure (kernel timed inside a long step)",
+                "avg_launch_us": tot["conv"] / n_conv * 1e6, "flop_per_step": conv_flop, "traffic": None}
+        fuse_bytes = (N_AGENTS + 1) * 3942400 * 2 * B          # (N+1)*sum(C*H*W)*2 B, bf16
+        hbm_roofs.append({"kernel": "warp_att_fuse_kernel", "bound": "hbm", "achieved": fuse_bytes / tot["fuse"] / 1e9,
+                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": fuse_bytes / tot["fuse"] / 1e9 / peaks["hbm_gbs"],
+                          "traffic": None})
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): one scene through the oracle port
+    cpu = None
+    if rank == 0 and world == 1 and not opt.no_cpu_baseline:
+        threads = opt.cpu_threads or min(os.cpu_count() or 1, 64)
+        scene = batches[0][2][0]
+        cpu_scene_seconds(args, sd, scene, threads)             # warm-up
+        dts = [cpu_scene_seconds(args, sd, scene, threads)[0] for _ in range(2)]
+        cpu = {"value": 1.0 / float(np.median(dts)), "unit": "scenes/s", "cores": threads, "kind": "port",
+               "sample": "2 timed forwards of one 5-agent 60k-pt scene (1 warm-up), fp32, oracle/ restatement"}
+
+    if rank == 0:
+        line = {
+            "metric": "scenes_per_sec", "value": value, "unit": "scenes/s", "n_gpus": world, "steps": opt.steps,
+            "warmup": opt.warmup, "ms_per_step": ms / opt.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16x3 (fp32-class)" if opt.precise else "bf16", "data": "synthetic",
+            "config": {"workload": "OPV2V-shape 5-agent CoAlign multiscale fusion, 60k pts/agent, raw points + poses -> "
+                                   "cls/reg/dir maps (BASELINE configs[2] shape on each GPU)",
+                       "scenes_per_step": B, "agents_per_scene": N_AGENTS, "points_per_agent": N_POINTS,
+                       "canvas": "200x704", "parallelism": f"scenes sharded over {world} GPU(s), no data-path collective",
+                       "l2": f"{NB} rotating input batches; a step streams >1 GB of activations (> 126 MB L2)",
+                       "block_n_cap": opt.block_n},
+            "e2e": {"value": e2e_value, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / opt.steps},
+            "gpu_launches": launches_per_step * opt.steps,
+            "clocks": clocks, "roofline": roof, "roofline_hbm": hbm_roofs, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scenes-per-step", type=int, default=4,
+                    help="scenes per GPU per step (reference yaml train_params.batch_size = 4)")
+    ap.add_argument("--precise", action="store_true", help="bf16x3 split (fp32-class accuracy) instead of bf16")
+    ap.add_argument("--block-n", type=int, default=256)
+    ap.add_argument("--cpu-threads", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    opt = ap.parse_args()
+    if opt.warmup < 3 and opt.impl == "ours":
+        opt.warmup = 3
+    if opt.impl == "reference":
+        run_reference(opt)
+    else:
+        run_ours(opt)
+
+
+if __name__ == "__main__":
+    main()
