@@ -46,7 +46,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -121,10 +121,11 @@ def run_reference(opt):
     from coalign_b200 import synth
     args, batches = make_batches(1, 1, seed0=0)
     sd = synth.random_state_dict(args, 0)
-    threads = opt.cpu_threads or min(os.cpu_count() or 1, 64)
+    threads = opt.cpu_threads or min(os.cpu_count() or 1, 32)
     scene = batches[0][2][0]
-    for _ in range(opt.warmup):
+    for _ in range(min(opt.warmup, 2)):               # ~2 s per scene: keep the whole run within a few minutes
         cpu_scene_seconds(args, sd, scene, threads)
+    opt.steps = min(opt.steps, 30)
     t0 = time.perf_counter()
     for _ in range(opt.steps):
         cpu_scene_seconds(args, sd, scene, threads)
@@ -162,7 +163,7 @@ def run_ours(opt):
     args, batches = make_batches(NB, B, seed0=1000 * rank)
     sd = synth.random_state_dict(args, 0)
     eng = CoAlignEngine(args, sd, B * N_AGENTS, B, device=f"cuda:{local}", precise=opt.precise,
-                        block_n_cap=opt.block_n)
+                        block_n_cap=opt.block_n, pair=not opt.no_pair)
     rl = [N_AGENTS] * B
     off = (np.arange(B * N_AGENTS + 1) * N_POINTS).astype(np.int32)
     dev_pts = [torch.from_numpy(p).cuda() for p, _, _ in batches]
@@ -258,7 +259,7 @@ def run_ours(opt):
     # ---- CPU baseline beside it (rank 0, N=1 only): one scene through the oracle port
     cpu = None
     if rank == 0 and world == 1 and not opt.no_cpu_baseline:
-        threads = opt.cpu_threads or min(os.cpu_count() or 1, 64)
+        threads = opt.cpu_threads or min(os.cpu_count() or 1, 32)
         scene = batches[0][2][0]
         cpu_scene_seconds(args, sd, scene, threads)             # warm-up
         dts = [cpu_scene_seconds(args, sd, scene, threads)[0] for _ in range(2)]
@@ -275,7 +276,7 @@ def run_ours(opt):
                        "scenes_per_step": B, "agents_per_scene": N_AGENTS, "points_per_agent": N_POINTS,
                        "canvas": "200x704", "parallelism": f"scenes sharded over {world} GPU(s), no data-path collective",
                        "l2": f"{NB} rotating input batches; a step streams >1 GB of activations (> 126 MB L2)",
-                       "block_n_cap": opt.block_n},
+                       "block_n_cap": opt.block_n, "cta_pair": not opt.no_pair},
             "e2e": {"value": e2e_value, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / opt.steps},
             "gpu_launches": launches_per_step * opt.steps,
@@ -289,8 +290,8 @@ def run_ours(opt):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scenes-per-step", type=int, default=4,
                     help="scenes per GPU per step (reference yaml train_params.batch_size = 4)")
@@ -298,6 +299,7 @@ def main():
     ap.add_argument("--block-n", type=int, default=256)
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pair", action="store_true", help="single-CTA conv kernel instead of CTA pairs")
     opt = ap.parse_args()
     if opt.warmup < 3 and opt.impl == "ours":
         opt.warmup = 3

@@ -157,6 +157,152 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_co
     }
 }
 
+
+// ----------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a cluster of 2 CTAs computes a 256 x BN tile.  Each CTA stages its own 128
+// rows of A and HALF of the weight tile (BN/2 rows); the pair's tensor cores read both halves, so the shared-
+// memory traffic per MAC drops (the single-CTA kernel is smem-bandwidth bound: TMA writes + MMA reads > 128 B/clk).
+// Leader CTA (rank 0) issues every MMA; both CTAs run a TMA producer and an epilogue over their own TMEM lanes.
+// ----------------------------------------------------------------------------------------------------------
+template <int BN> struct Tc2Cfg {
+    static constexpr int B_STAGE_BYTES = (BN / 2) * BK * 2;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;        // per CTA
+    static constexpr int STAGES = (BN == 256) ? 6 : 8;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+    static constexpr int TMEM_COLS = 2 * BN;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
+                     const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ ConvParams p,
+                     int m_pairs, int n_tiles) {
+    using Cfg = Tc2Cfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];       // used in the leader CTA (both CTAs' TMA bytes land here)
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];      // per CTA; released by the leader's multicast commit
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];       // per CTA; multicast commit
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];      // leader's copy counts 8 epilogue warps (both CTAs)
+    __shared__ uint32_t tmem_base_smem;
+
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+    uint8_t* smem = smem_raw + pad;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int total_tiles = m_pairs * n_tiles;
+    const int nk = p.n_ksteps;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_a0);
+        prefetch_tmap(&tmap_a1);
+        prefetch_tmap(&tmap_w);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 8); }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc_2sm(&tmem_base_smem, Cfg::TMEM_COLS);
+        tmem_relinquish_2sm();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+                const int mp = tile / n_tiles, nt = tile - mp * n_tiles;
+                const int m0 = (mp * 2 + (int)rank) * BM, n0 = nt * BN + (int)rank * (BN / 2);
+                for (int ks = 0; ks < nk; ++ks) {
+                    const cb_kstep st = p.ksteps[ks];
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sb = sa + A_STAGE_BYTES;
+                    tma_load_2d_2sm(sa, st.a_sel ? &tmap_a1 : &tmap_a0, &full_bar[stage], (int)st.col, m0 + st.row_off);
+                    tma_load_2d_2sm(sb, &tmap_w, &full_bar[stage], st.w_k, n0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
+                const int buf = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty_bar[buf], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * BN;
+                for (int ks = 0; ks < nk; ++ks) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t sb = sa + A_STAGE_BYTES;
+                    const uint64_t adesc = make_sw128_desc(sa);
+                    const uint64_t bdesc = make_sw128_desc(sb);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        umma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                      (ks > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit_2sm(&empty_bar[stage]);
+                    if (ks == nk - 1) umma_commit_2sm(&tmem_full_bar[buf]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
+        const int q4 = warp & 3;
+        int it = 0;
+        for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
+            const int mp = tile / n_tiles, nt = tile - mp * n_tiles;
+            const int n0 = nt * BN;
+            const int buf = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const long q = (long)(mp * 2 + (int)rank) * BM + q4 * 32 + lane;
+            const RowDest dst = decode_row(p, q, n0);
+            mbar_wait(&tmem_full_bar[buf], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + buf * BN + ((uint32_t)(q4 * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t r[32];
+                tmem_ld32(t_row + c, r);
+                tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                epilogue_chunk(p, dst, q, n0 + c, v);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[buf], 0);      // leader's barrier
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
 // ---------------------------------------------------------------------------------------- host side
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -208,9 +354,33 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
     return CB_OK;
 }
 
+
+template <int BN>
+static int launch2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const ConvParams& p,
+                   int m_tiles, int n_tiles, int max_clusters, cudaStream_t stream) {
+    using Cfg = Tc2Cfg<BN>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(conv_gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::SMEM_BYTES);
+    });
+    if (attr_err != cudaSuccess) return (int)attr_err;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int m_pairs = (m_tiles + 1) / 2;
+    int clusters = m_pairs * n_tiles;
+    int cap = max_clusters > 0 ? max_clusters : sms / 2;
+    if (clusters > cap) clusters = cap;
+    conv_gemm_tc2_kernel<BN><<<2 * clusters, 256, Cfg::SMEM_BYTES, stream>>>(a0, a1, w, p, m_pairs, n_tiles);
+    CB_CHECK_LAUNCH();
+    return CB_OK;
+}
+
 }  // namespace cb
 
-extern "C" int cb_conv_gemm(const cb_conv_desc* d, int max_ctas, void* stream) {
+static int conv_gemm_impl(const cb_conv_desc* d, int max_ctas, void* stream, bool pair) {
     using namespace cb;
     if (!d) return CB_ERR_ARG;
     static thread_local ConvParams p;
@@ -231,11 +401,20 @@ extern "C" int cb_conv_gemm(const cb_conv_desc* d, int max_ctas, void* stream) {
     } else {
         ta1 = ta0;
     }
-    rc = make_tmap(&tw, d->w_ptr, d->w_rows, d->w_k_total, d->w_k_total, d->block_n);
+    if (pair && (d->block_n < 64 || d->w_rows < d->block_n)) pair = false;      // heads (N=32) stay single-CTA
+    rc = make_tmap(&tw, d->w_ptr, d->w_rows, d->w_k_total, d->w_k_total, pair ? d->block_n / 2 : d->block_n);
     if (rc) return rc;
     const int m_tiles = (int)((p.rows_total + BM - 1) / BM);
     const int n_tiles = d->n_total / d->block_n;
     cudaStream_t st = (cudaStream_t)stream;
+    if (pair) {
+        switch (d->block_n) {
+            case 64: return launch2<64>(ta0, ta1, tw, p, m_tiles, n_tiles, max_ctas, st);
+            case 128: return launch2<128>(ta0, ta1, tw, p, m_tiles, n_tiles, max_ctas, st);
+            case 256: return launch2<256>(ta0, ta1, tw, p, m_tiles, n_tiles, max_ctas, st);
+        }
+        return CB_ERR_ARG;
+    }
     switch (d->block_n) {
         case 32: return launch<32>(ta0, ta1, tw, p, m_tiles, n_tiles, max_ctas, st);
         case 64: return launch<64>(ta0, ta1, tw, p, m_tiles, n_tiles, max_ctas, st);
@@ -243,4 +422,12 @@ extern "C" int cb_conv_gemm(const cb_conv_desc* d, int max_ctas, void* stream) {
         case 256: return launch<256>(ta0, ta1, tw, p, m_tiles, n_tiles, max_ctas, st);
     }
     return CB_ERR_ARG;
+}
+
+extern "C" int cb_conv_gemm(const cb_conv_desc* d, int max_ctas, void* stream) {
+    return conv_gemm_impl(d, max_ctas, stream, false);
+}
+
+extern "C" int cb_conv_gemm_pair(const cb_conv_desc* d, int max_clusters, void* stream) {
+    return conv_gemm_impl(d, max_clusters, stream, true);
 }

@@ -1,19 +1,23 @@
 // Pillar front-end on sm_100a: deterministic voxelisation (A1/A2), PillarVFE+PFN (A3/A4) and
 // PointPillarScatter (A5), either staged through reference-format voxel tensors or fused
-// points -> canvas.  HBM-bound integer/byte work: coalesced 16-byte point loads, one warp per pillar,
-// 128-byte canvas-cell stores.  See include/coalign_b200.h for the reference lines each entry replaces.
+// points -> canvas.  HBM-bound integer/byte work: coalesced 16-byte point loads, 8 lanes per pillar
+// (16-byte stores, 128 B per canvas cell).  See include/coalign_b200.h for the reference lines.
 //
 // Determinism: spconv's generator is serial (voxel id = order of first appearance, a voxel keeps its
 // first `max_pts` points, new voxels are refused after `max_voxels`).  We reproduce it bit-exactly with
-//   K1  cell id per point, atomicMin(first point index per cell), per-cell count
-//   K2  one CTA per agent: ordered scan over "leader" points (first[cell]==i) -> voxel ids, CSR offsets
-//   K3  CSR fill (arbitrary order inside a cell)
-//   K4  one warp per voxel: rank the cell's point indices, keep the `max_pts` smallest in order.
+//   K1   cell id per point, atomicMin(first point index per cell), per-cell count
+//   K2a  per 1024-point chunk: number of "leader" points (first[cell]==i) and sum of their cell counts
+//   K2b  per agent: exclusive scan of the chunk totals
+//   K2c  per chunk: ordered in-block scan + chunk prefix -> voxel ids, CSR offsets
+//   K3   CSR fill (arbitrary order inside a cell)
+//   K4   8 lanes per voxel: rank the cell's point indices, keep the `max_pts` smallest in order.
 #include <limits.h>
 #include "common.cuh"
 #include "../../include/coalign_b200.h"
 
 namespace cb {
+
+constexpr int CHUNK = 1024;       // points per scan chunk (256 threads x 4)
 
 struct AgentOffsets { int n_agents; int off[CB_MAX_AGENTS + 1]; };
 
@@ -27,7 +31,8 @@ struct VoxWs {            // workspace carve-up (device pointers)
     int* cellid;          // [sum_P]
     int* list;            // [sum_P]
     int* nvox;            // [n_agents+1]
-    int ncell, vcap;
+    int2* chunk_tot;      // [n_agents][max_chunks]  (leaders, points) per chunk, then exclusive prefixes
+    int ncell, vcap, max_chunks;
 };
 
 struct Geom { float r0, r1, r2, v0, v1, v2; int gx, gy, gz; };
@@ -35,7 +40,7 @@ struct Geom { float r0, r1, r2, v0, v1, v2; int gx, gy, gz; };
 // PS canvas addressing (include/coalign_b200.h): 4 parity planes of PF-padded half-resolution maps
 struct CanvasGeom {
     int ny, nx, Hq, Wq;   // Hq = ceil(ny/2)+2, Wq = ceil(nx/2)+2  (padded plane dims)
-    long plane_rows;      // n_agents*Hq*Wq
+    long plane_rows;      // canvas_agents*Hq*Wq
 };
 __device__ __forceinline__ long canvas_row(const CanvasGeom& c, int a, int y, int x) {
     const int ph = (y & 1) * 2 + (x & 1);
@@ -70,64 +75,82 @@ __global__ void vox_assign_kernel(const float4* __restrict__ pts, const __grid_c
 }
 
 // K2 ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) vox_scan_kernel(const __grid_constant__ AgentOffsets ao, const VoxWs ws,
-                                                        int max_voxels) {
-    const int a = blockIdx.x;
+// Thread t of a chunk CTA owns points [4t, 4t+4) of the chunk: leader flags and their cell counts.
+__device__ __forceinline__ void chunk_flags(const AgentOffsets& ao, const VoxWs& ws, int a, int chunk, int (&cell)[4],
+                                            int (&lead)[4], int (&cnt)[4]) {
     const int p0 = ao.off[a], np = ao.off[a + 1] - p0;
     const int* first = ws.first + (long)a * ws.ncell;
     const int* count = ws.count + (long)a * ws.ncell;
-    int* cell2vox = ws.cell2vox + (long)a * ws.ncell;
-    int* vox_off = ws.vox_off + (long)a * (ws.vcap + 1);
-    int* vox_cell = ws.vox_cell + (long)a * ws.vcap;
-    __shared__ int s_warp_v[32], s_warp_c[32];
-    __shared__ int s_run_v, s_run_c;
-    if (threadIdx.x == 0) { s_run_v = 0; s_run_c = 0; vox_off[0] = 0; }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = 0; base < np; base += 1024) {
-        const int i = base + threadIdx.x;
-        int cell = -1, lead = 0, cnt = 0;
-        if (i < np) {
-            cell = ws.cellid[p0 + i];
-            if (cell >= 0 && first[cell] == i) { lead = 1; cnt = count[cell]; }
-        }
-        int v = lead, c = cnt;                                 // inclusive warp scans
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int tv = __shfl_up_sync(0xffffffffu, v, d), tc = __shfl_up_sync(0xffffffffu, c, d);
-            if (lane >= d) { v += tv; c += tc; }
-        }
-        if (lane == 31) { s_warp_v[warp] = v; s_warp_c[warp] = c; }
-        __syncthreads();
-        if (warp == 0) {
-            int wv = s_warp_v[lane], wc = s_warp_c[lane];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int tv = __shfl_up_sync(0xffffffffu, wv, d), tc = __shfl_up_sync(0xffffffffu, wc, d);
-                if (lane >= d) { wv += tv; wc += tc; }
-            }
-            s_warp_v[lane] = wv; s_warp_c[lane] = wc;          // inclusive over warps
-        }
-        __syncthreads();
-        const int pre_v = s_run_v + (warp ? s_warp_v[warp - 1] : 0) + v - lead;   // exclusive prefix
-        const int pre_c = s_run_c + (warp ? s_warp_c[warp - 1] : 0) + c - cnt;
-        if (lead) {
-            if (pre_v < max_voxels) {
-                cell2vox[cell] = pre_v;
-                vox_cell[pre_v] = cell;
-                vox_off[pre_v + 1] = pre_c + cnt;              // CSR end of this voxel == begin of the next
-            } else {
-                cell2vox[cell] = -1;                           // refused: max_voxels reached
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) { s_run_v += s_warp_v[31]; s_run_c += s_warp_c[31]; }
-        __syncthreads();
+    for (int j = 0; j < 4; ++j) {
+        const int i = chunk * CHUNK + threadIdx.x * 4 + j;
+        cell[j] = -1; lead[j] = 0; cnt[j] = 0;
+        if (i < np) cell[j] = ws.cellid[p0 + i];
     }
-    if (threadIdx.x == 0) ws.nvox[a] = s_run_v < max_voxels ? s_run_v : max_voxels;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = chunk * CHUNK + threadIdx.x * 4 + j;
+        if (cell[j] >= 0 && first[cell[j]] == i) { lead[j] = 1; cnt[j] = count[cell[j]]; }
+    }
 }
 
-__global__ void vox_total_kernel(const VoxWs ws, int n_agents, int* n_voxels_out) {
+// block scan of (v,c) over 256 threads: exclusive prefix of this thread and block totals
+__device__ __forceinline__ void block_scan2(int v, int c, int& ex_v, int& ex_c, int& tot_v, int& tot_c) {
+    __shared__ int s_v[8], s_c[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int iv = v, ic = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int tv = __shfl_up_sync(0xffffffffu, iv, d), tc = __shfl_up_sync(0xffffffffu, ic, d);
+        if (lane >= d) { iv += tv; ic += tc; }
+    }
+    if (lane == 31) { s_v[warp] = iv; s_c[warp] = ic; }
+    __syncthreads();
+    int pv = 0, pc = 0, tv = 0, tc = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        if (w < warp) { pv += s_v[w]; pc += s_c[w]; }
+        tv += s_v[w]; tc += s_c[w];
+    }
+    ex_v = pv + iv - v; ex_c = pc + ic - c;
+    tot_v = tv; tot_c = tc;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) vox_chunk_count_kernel(const __grid_constant__ AgentOffsets ao, const VoxWs ws) {
+    const int a = blockIdx.y, chunk = blockIdx.x;
+    int cell[4], lead[4], cnt[4];
+    chunk_flags(ao, ws, a, chunk, cell, lead, cnt);            // chunks past the agent's end yield zeros
+    int ev, ec, tv, tc;
+    block_scan2(lead[0] + lead[1] + lead[2] + lead[3], cnt[0] + cnt[1] + cnt[2] + cnt[3], ev, ec, tv, tc);
+    if (threadIdx.x == 0) ws.chunk_tot[(long)a * ws.max_chunks + chunk] = make_int2(tv, tc);
+}
+
+// one warp per agent: chunk totals -> exclusive prefixes; voxel count
+__global__ void vox_chunk_scan_kernel(const VoxWs ws, int max_voxels) {
+    const int a = blockIdx.x, lane = threadIdx.x;
+    int2* ct = ws.chunk_tot + (long)a * ws.max_chunks;
+    int run_v = 0, run_c = 0;
+    for (int base = 0; base < ws.max_chunks; base += 32) {
+        const int i = base + lane;
+        const int2 t = i < ws.max_chunks ? ct[i] : make_int2(0, 0);
+        int iv = t.x, ic = t.y;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int tv = __shfl_up_sync(0xffffffffu, iv, d), tc = __shfl_up_sync(0xffffffffu, ic, d);
+            if (lane >= d) { iv += tv; ic += tc; }
+        }
+        if (i < ws.max_chunks) ct[i] = make_int2(run_v + iv - t.x, run_c + ic - t.y);
+        run_v += __shfl_sync(0xffffffffu, iv, 31);
+        run_c += __shfl_sync(0xffffffffu, ic, 31);
+    }
+    if (lane == 0) {
+        ws.nvox[a] = run_v < max_voxels ? run_v : max_voxels;
+        ws.vox_off[(long)a * (ws.vcap + 1)] = 0;
+    }
+}
+
+__global__ void vox_total_kernel(const VoxWs ws, int n_agents, int* n_voxels_out, int* dirty_count) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         int t = 0;
         for (int a = 0; a < n_agents; ++a) {
@@ -136,6 +159,34 @@ __global__ void vox_total_kernel(const VoxWs ws, int n_agents, int* n_voxels_out
         }
         ws.nvox[n_agents] = t;
         if (n_voxels_out) n_voxels_out[n_agents] = t;
+        if (dirty_count) *dirty_count = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) vox_chunk_assign_kernel(const __grid_constant__ AgentOffsets ao, const VoxWs ws,
+                                                               int max_voxels) {
+    const int a = blockIdx.y, chunk = blockIdx.x;
+    int cell[4], lead[4], cnt[4];
+    chunk_flags(ao, ws, a, chunk, cell, lead, cnt);
+    int ev, ec, tv, tc;
+    block_scan2(lead[0] + lead[1] + lead[2] + lead[3], cnt[0] + cnt[1] + cnt[2] + cnt[3], ev, ec, tv, tc);
+    const int2 pre = ws.chunk_tot[(long)a * ws.max_chunks + chunk];
+    int pv = pre.x + ev, pc = pre.y + ec;
+    int* cell2vox = ws.cell2vox + (long)a * ws.ncell;
+    int* vox_off = ws.vox_off + (long)a * (ws.vcap + 1);
+    int* vox_cell = ws.vox_cell + (long)a * ws.vcap;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (lead[j]) {
+            if (pv < max_voxels) {
+                cell2vox[cell[j]] = pv;
+                vox_cell[pv] = cell[j];
+                vox_off[pv + 1] = pc + cnt[j];             // CSR end of this voxel == begin of the next
+            } else {
+                cell2vox[cell[j]] = -1;                    // refused: max_voxels reached
+            }
+            pv += 1; pc += cnt[j];
+        }
     }
 }
 
@@ -153,88 +204,84 @@ __global__ void vox_fill_kernel(const __grid_constant__ AgentOffsets ao, const V
 }
 
 // K4 helpers ----------------------------------------------------------------------------------
-// The `max_pts` smallest point indices of voxel (a,v), ascending, into s_sorted[]; returns the total count.
-__device__ __forceinline__ int voxel_sorted_points(const VoxWs& ws, const AgentOffsets& ao, int a, int v, int max_pts,
-                                                   int* s_sorted, int lane) {
-    const int* off = ws.vox_off + (long)a * (ws.vcap + 1);
-    const int beg = off[v], cnt = off[v + 1] - beg;
-    const int* lst = ws.list + ao.off[a] + beg;
-    for (int e0 = 0; e0 < cnt; e0 += 32) {
-        const int e = e0 + lane;
-        const int mine = e < cnt ? lst[e] : INT_MAX;
-        int rank = 0;
-        for (int m0 = 0; m0 < cnt; m0 += 32) {
-            const int other = (m0 + lane) < cnt ? lst[m0 + lane] : INT_MAX;
-#pragma unroll
-            for (int t = 0; t < 32; ++t) rank += (__shfl_sync(0xffffffffu, other, t) < mine) ? 1 : 0;
+// 8 lanes ("group") cooperate on one voxel.  sub = lane & 7.
+// The `max_pts` smallest point indices of the voxel, ascending, into s_sorted[].
+__device__ __forceinline__ void group_sorted_points(const int* __restrict__ lst, int cnt, int max_pts, int* s_sorted,
+                                                    int sub, unsigned gmask) {
+    if (cnt == 1) {
+        if (sub == 0) s_sorted[0] = lst[0];
+    } else {
+        for (int e = sub; e < cnt; e += 8) {
+            const int mine = lst[e];
+            int rank = 0;
+            for (int m = 0; m < cnt; ++m) rank += (lst[m] < mine) ? 1 : 0;
+            if (rank < max_pts) s_sorted[rank] = mine;
         }
-        if (e < cnt && rank < max_pts) s_sorted[rank] = mine;
     }
-    __syncwarp();
-    return cnt;
+    __syncwarp(gmask);
 }
 
-struct PfnRegs {                 // per-lane slice of the PFN parameters: channels 2*lane, 2*lane+1
-    float w[2][10], sc[2], sh[2];
+struct PfnParams {
+    const float* w; const float* scale; const float* shift;     // [64][10], [64], [64]
+    float vx, vy, vz, offx, offy, offz;                         // voxel size, voxel/2 + range_min
 };
-__device__ __forceinline__ void load_pfn(PfnRegs& r, const float* w, const float* scale, const float* shift, int lane) {
+
+struct PfnRegs { float w[8][10], sc[8], sh[8]; };               // channels 8*sub .. 8*sub+7
+__device__ __forceinline__ void load_pfn(PfnRegs& r, const PfnParams& pp, int sub) {
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < 8; ++c) {
 #pragma unroll
-        for (int j = 0; j < 10; ++j) r.w[c][j] = __ldg(w + (2 * lane + c) * 10 + j);
-        r.sc[c] = __ldg(scale + 2 * lane + c);
-        r.sh[c] = __ldg(shift + 2 * lane + c);
+        for (int j = 0; j < 10; ++j) r.w[c][j] = __ldg(pp.w + (8 * sub + c) * 10 + j);
+        r.sc[c] = __ldg(pp.scale + 8 * sub + c);
+        r.sh[c] = __ldg(pp.shift + 8 * sub + c);
     }
 }
 
-// PFN of one pillar held by one warp: lane k carries point slot k (valid iff k < n, n >= 1).
-// `off*` = voxel/2 + range_min.  Writes channels (2*lane, 2*lane+1) of canvas cell (a, cy, cx).
-__device__ __forceinline__ void pfn_pillar_store(float4 p, int n, int max_pts, int a, int cz, int cy, int cx,
-                                                 float vx, float vy, float vz, float offx, float offy, float offz,
-                                                 const PfnRegs& r, const CanvasGeom& cg, __nv_bfloat16* canvas,
-                                                 long lo_off, int lane) {
-    if (lane >= n) p = make_float4(0.f, 0.f, 0.f, 0.f);
-    float sx = p.x, sy = p.y, sz = p.z;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        sx += __shfl_xor_sync(0xffffffffu, sx, d);
-        sy += __shfl_xor_sync(0xffffffffu, sy, d);
-        sz += __shfl_xor_sync(0xffffffffu, sz, d);
-    }
+// PFN of one pillar by one 8-lane group: PointFn(k) returns slot k (k < n, n >= 1).  Every lane of the group walks
+// all n points (same addresses -> broadcast loads) and produces 8 of the 64 channels; one 16-byte store per lane.
+template <class PointFn>
+__device__ __forceinline__ void pfn_group_store(PointFn pt, int n, int max_pts, int a, int cz, int cy, int cx,
+                                                const PfnParams& pp, const PfnRegs& r, const CanvasGeom& cg,
+                                                __nv_bfloat16* canvas, long lo_off, int sub, long* dirty_slot) {
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    for (int k = 0; k < n; ++k) { const float4 p = pt(k); sx += p.x; sy += p.y; sz += p.z; }   // slot order
     const float fn = (float)n;
     const float mx = __fdiv_rn(sx, fn), my = __fdiv_rn(sy, fn), mz = __fdiv_rn(sz, fn);
     // pillar centre = coord*voxel + (voxel/2 + range_min)  (pillar_vfe.py:87-89,124-132), fp32, unfused
-    const float ctrx = __fadd_rn(__fmul_rn((float)cx, vx), offx);
-    const float ctry = __fadd_rn(__fmul_rn((float)cy, vy), offy);
-    const float ctrz = __fadd_rn(__fmul_rn((float)cz, vz), offz);
-    float f[10];
-    f[0] = p.x; f[1] = p.y; f[2] = p.z; f[3] = p.w;
-    f[4] = p.x - mx; f[5] = p.y - my; f[6] = p.z - mz;
-    f[7] = p.x - ctrx; f[8] = p.y - ctry; f[9] = p.z - ctrz;
-    float best0 = 0.f, best1 = 0.f;                  // ReLU outputs are >= 0
-    if (n < max_pts) {                               // zero-padded slots take part in the max (pillar_vfe.py:45-46)
-        best0 = fmaxf(r.sh[0], 0.f);
-        best1 = fmaxf(r.sh[1], 0.f);
-    }
-    for (int k = 0; k < n; ++k) {
-        float y0 = 0.f, y1 = 0.f;
+    const float ctrx = __fadd_rn(__fmul_rn((float)cx, pp.vx), pp.offx);
+    const float ctry = __fadd_rn(__fmul_rn((float)cy, pp.vy), pp.offy);
+    const float ctrz = __fadd_rn(__fmul_rn((float)cz, pp.vz), pp.offz);
+    float best[8];
 #pragma unroll
-        for (int j = 0; j < 10; ++j) {
-            const float fj = __shfl_sync(0xffffffffu, f[j], k);
-            y0 = fmaf(r.w[0][j], fj, y0);
-            y1 = fmaf(r.w[1][j], fj, y1);
+    for (int c = 0; c < 8; ++c) best[c] = (n < max_pts) ? fmaxf(r.sh[c], 0.f) : 0.f;   // zero-padded slots join the max
+    for (int k = 0; k < n; ++k) {
+        const float4 p = pt(k);
+        float f[10];
+        f[0] = p.x; f[1] = p.y; f[2] = p.z; f[3] = p.w;
+        f[4] = p.x - mx; f[5] = p.y - my; f[6] = p.z - mz;
+        f[7] = p.x - ctrx; f[8] = p.y - ctry; f[9] = p.z - ctrz;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float y = 0.f;
+#pragma unroll
+            for (int j = 0; j < 10; ++j) y = fmaf(r.w[c][j], f[j], y);
+            best[c] = fmaxf(best[c], fmaf(y, r.sc[c], r.sh[c]));       // ReLU folded into the max (best >= 0)
         }
-        best0 = fmaxf(best0, fmaf(y0, r.sc[0], r.sh[0]));
-        best1 = fmaxf(best1, fmaf(y1, r.sc[1], r.sh[1]));
     }
     const long row = canvas_row(cg, a, cy, cx);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(canvas + row * 64) + lane;
-    const uint32_t hi = pack_bf16(best0, best1);
-    *dst = hi;
+    uint4 hi;
+    hi.x = pack_bf16(best[0], best[1]); hi.y = pack_bf16(best[2], best[3]);
+    hi.z = pack_bf16(best[4], best[5]); hi.w = pack_bf16(best[6], best[7]);
+    reinterpret_cast<uint4*>(canvas + row * 64)[sub] = hi;
     if (lo_off != 0) {
-        uint32_t* dl = reinterpret_cast<uint32_t*>(canvas + lo_off + row * 64) + lane;
-        *dl = pack_bf16(best0 - bf16_lo(hi), best1 - bf16_hi(hi));
+        uint4 lo;
+        lo.x = pack_bf16(best[0] - bf16_lo(hi.x), best[1] - bf16_hi(hi.x));
+        lo.y = pack_bf16(best[2] - bf16_lo(hi.y), best[3] - bf16_hi(hi.y));
+        lo.z = pack_bf16(best[4] - bf16_lo(hi.z), best[5] - bf16_hi(hi.z));
+        lo.w = pack_bf16(best[6] - bf16_lo(hi.w), best[7] - bf16_hi(hi.w));
+        reinterpret_cast<uint4*>(canvas + lo_off + row * 64)[sub] = lo;
     }
+    if (dirty_slot && sub == 0) *dirty_slot = row;
 }
 
 // K4a: emit reference-format voxel tensors --------------------------------------------------------
@@ -242,80 +289,107 @@ __global__ void __launch_bounds__(256) vox_emit_kernel(const float4* __restrict_
                                                        const __grid_constant__ AgentOffsets ao, const VoxWs ws,
                                                        const Geom g, int max_pts, float4* __restrict__ voxels,
                                                        int4* __restrict__ coords, int* __restrict__ num_points) {
-    __shared__ int s_sorted[8][32];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int gw = blockIdx.x * 8 + wib, nw = gridDim.x * 8;
+    __shared__ int s_sorted[32][32];
+    const int lane = threadIdx.x & 31, sub = lane & 7, grp = threadIdx.x >> 3;
+    const unsigned gmask = 0xFFu << (lane & 24);
+    const int gg = blockIdx.x * 32 + grp, ng = gridDim.x * 32;
     int base = 0;
     for (int a = 0; a < ao.n_agents; ++a) {
         const int nv = ws.nvox[a];
-        for (int v = gw; v < nv; v += nw) {
-            const int cnt = voxel_sorted_points(ws, ao, a, v, max_pts, s_sorted[wib], lane);
+        const int* off = ws.vox_off + (long)a * (ws.vcap + 1);
+        for (int v = gg; v < nv; v += ng) {
+            const int beg = off[v], cnt = off[v + 1] - beg;
+            group_sorted_points(ws.list + ao.off[a] + beg, cnt, max_pts, s_sorted[grp], sub, gmask);
             const int n = cnt < max_pts ? cnt : max_pts;
-            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (lane < n) p = __ldg(pts + ao.off[a] + s_sorted[wib][lane]);
             const long row = base + v;
-            if (lane < max_pts) voxels[row * max_pts + lane] = p;
-            if (lane == 0) {
+            for (int k = sub; k < max_pts; k += 8) {
+                float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k < n) p = __ldg(pts + ao.off[a] + s_sorted[grp][k]);
+                voxels[row * max_pts + k] = p;
+            }
+            if (sub == 0) {
                 const int cell = ws.vox_cell[(long)a * ws.vcap + v];
                 const int x = cell % g.gx, y = (cell / g.gx) % g.gy, z = cell / (g.gx * g.gy);
                 coords[row] = make_int4(a, z, y, x);
                 num_points[row] = n;
             }
-            __syncwarp();
+            __syncwarp(gmask);
         }
         base += nv;
     }
 }
 
 // K4b: fused PFN + scatter straight from the CSR lists -------------------------------------------
-__global__ void __launch_bounds__(256) vox_pfn_kernel(const float4* __restrict__ pts,
+__global__ void __launch_bounds__(256, 2) vox_pfn_kernel(const float4* __restrict__ pts,
                                                       const __grid_constant__ AgentOffsets ao, const VoxWs ws,
-                                                      const Geom g, int max_pts, const float* __restrict__ w,
-                                                      const float* __restrict__ scale, const float* __restrict__ shift,
-                                                      float offx, float offy, float offz,
-                                                      const CanvasGeom cg, __nv_bfloat16* canvas, long lo_off) {
-    __shared__ int s_sorted[8][32];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int gw = blockIdx.x * 8 + wib, nw = gridDim.x * 8;
+                                                      const Geom g, int max_pts, const PfnParams pp, const CanvasGeom cg,
+                                                      __nv_bfloat16* canvas, long lo_off, long* dirty_rows) {
+    __shared__ int s_sorted[32][32];
+    const int lane = threadIdx.x & 31, sub = lane & 7, grp = threadIdx.x >> 3;
+    const unsigned gmask = 0xFFu << (lane & 24);
+    const int gg = blockIdx.x * 32 + grp, ng = gridDim.x * 32;
     PfnRegs r;
-    load_pfn(r, w, scale, shift, lane);
+    load_pfn(r, pp, sub);
+    int base = 0;
     for (int a = 0; a < ao.n_agents; ++a) {
         const int nv = ws.nvox[a];
-        for (int v = gw; v < nv; v += nw) {
-            const int cnt = voxel_sorted_points(ws, ao, a, v, max_pts, s_sorted[wib], lane);
+        const int* off = ws.vox_off + (long)a * (ws.vcap + 1);
+        const float4* ap = pts + ao.off[a];
+        for (int v = gg; v < nv; v += ng) {
+            const int beg = off[v], cnt = off[v + 1] - beg;
+            group_sorted_points(ws.list + ao.off[a] + beg, cnt, max_pts, s_sorted[grp], sub, gmask);
             const int n = cnt < max_pts ? cnt : max_pts;
-            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (lane < n) p = __ldg(pts + ao.off[a] + s_sorted[wib][lane]);
             const int cell = ws.vox_cell[(long)a * ws.vcap + v];
             const int x = cell % g.gx, y = (cell / g.gx) % g.gy, z = cell / (g.gx * g.gy);
-            pfn_pillar_store(p, n, max_pts, a, z, y, x, g.v0, g.v1, g.v2, offx, offy, offz, r, cg, canvas, lo_off, lane);
-            __syncwarp();
+            const int* srt = s_sorted[grp];
+            pfn_group_store([&](int k) { return __ldg(ap + srt[k]); }, n, max_pts, a, z, y, x, pp, r, cg, canvas, lo_off,
+                            sub, dirty_rows ? dirty_rows + base + v : nullptr);
+            __syncwarp(gmask);
         }
+        base += nv;
     }
 }
 
 // PFN + scatter from reference-format voxel tensors ----------------------------------------------
-__global__ void __launch_bounds__(256) pfn_scatter_kernel(const float4* __restrict__ voxels,
+__global__ void __launch_bounds__(256, 2) pfn_scatter_kernel(const float4* __restrict__ voxels,
                                                           const int4* __restrict__ coords,
                                                           const int* __restrict__ num_points, int n_rows,
                                                           const int* __restrict__ n_rows_dev, int max_pts,
-                                                          const float* __restrict__ w, const float* __restrict__ scale,
-                                                          const float* __restrict__ shift, float vx, float vy, float vz,
-                                                          float offx, float offy, float offz, const CanvasGeom cg,
-                                                          int n_agents, __nv_bfloat16* canvas, long lo_off) {
-    const int lane = threadIdx.x & 31;
-    const int gw = blockIdx.x * 8 + (threadIdx.x >> 5), nw = gridDim.x * 8;
+                                                          const PfnParams pp, const CanvasGeom cg, int n_agents,
+                                                          __nv_bfloat16* canvas, long lo_off, long* dirty_rows,
+                                                          int* dirty_count) {
+    const int lane = threadIdx.x & 31, sub = lane & 7, grp = threadIdx.x >> 3;
+    const int gg = blockIdx.x * 32 + grp, ng = gridDim.x * 32;
     PfnRegs r;
-    load_pfn(r, w, scale, shift, lane);
+    load_pfn(r, pp, sub);
     const int rows = n_rows_dev ? min(n_rows, *n_rows_dev) : n_rows;
-    for (int v = gw; v < rows; v += nw) {
+    if (dirty_count && blockIdx.x == 0 && threadIdx.x == 0) *dirty_count = rows;
+    for (int v = gg; v < rows; v += ng) {
         const int4 c = __ldg(coords + v);                     // [agent, z, y, x]
         int n = __ldg(num_points + v);
         n = n < max_pts ? n : max_pts;
-        if (n < 1 || c.x < 0 || c.x >= n_agents || c.z < 0 || c.z >= cg.ny || c.w < 0 || c.w >= cg.nx) continue;
-        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lane < n) p = __ldg(voxels + (long)v * max_pts + lane);
-        pfn_pillar_store(p, n, max_pts, c.x, c.y, c.z, c.w, vx, vy, vz, offx, offy, offz, r, cg, canvas, lo_off, lane);
+        const bool ok = !(n < 1 || c.x < 0 || c.x >= n_agents || c.z < 0 || c.z >= cg.ny || c.w < 0 || c.w >= cg.nx);
+        if (!ok) { if (dirty_rows && sub == 0) dirty_rows[v] = -1; continue; }
+        const float4* vp = voxels + (long)v * max_pts;
+        pfn_group_store([&](int k) { return __ldg(vp + k); }, n, max_pts, c.x, c.y, c.z, c.w, pp, r, cg, canvas, lo_off,
+                        sub, dirty_rows ? dirty_rows + v : nullptr);
+    }
+}
+
+// zero the canvas cells written by the previous frame (instead of a full-canvas memset)
+__global__ void __launch_bounds__(256) canvas_clear_kernel(__nv_bfloat16* canvas, long lo_off,
+                                                           const long* __restrict__ dirty_rows,
+                                                           const int* __restrict__ dirty_count, int capacity) {
+    const int sub = threadIdx.x & 7;
+    const int gg = blockIdx.x * 32 + (threadIdx.x >> 3), ng = gridDim.x * 32;
+    int n = *dirty_count;
+    n = n < capacity ? n : capacity;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = gg; i < n; i += ng) {
+        const long row = dirty_rows[i];
+        if (row < 0) continue;
+        reinterpret_cast<uint4*>(canvas + row * 64)[sub] = z;
+        if (lo_off != 0) reinterpret_cast<uint4*>(canvas + lo_off + row * 64)[sub] = z;
     }
 }
 
@@ -325,46 +399,48 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 static int carve(VoxWs& ws, void* base, size_t bytes, int n_agents, int sum_points, const int32_t* grid, int max_voxels,
                  size_t* clear_bytes, size_t* total_bytes) {
     const long ncell = (long)grid[0] * grid[1] * grid[2];
-    const int vcap = max_voxels < sum_points ? max_voxels : (sum_points > 0 ? sum_points : 1);
+    const int sp = sum_points > 0 ? sum_points : 1;
+    const int vcap = max_voxels < sp ? max_voxels : sp;
+    const int max_chunks = (sp + CHUNK - 1) / CHUNK;          // upper bound for any single agent
     uint8_t* p = (uint8_t*)base;
     size_t o = 0;
-    auto take = [&](size_t n_int) { void* r = p ? p + o : nullptr; o += align256(n_int * 4); return (int*)r; };
-    ws.first = take((size_t)n_agents * ncell);
+    auto take = [&](size_t n_bytes) { void* r = p ? p + o : nullptr; o += align256(n_bytes); return r; };
+    ws.first = (int*)take((size_t)n_agents * ncell * 4);
     size_t o_first_end = o;
-    ws.count = take((size_t)n_agents * ncell);
-    ws.cursor = take((size_t)n_agents * vcap);
+    ws.count = (int*)take((size_t)n_agents * ncell * 4);
+    ws.cursor = (int*)take((size_t)n_agents * vcap * 4);
     size_t o_clear_end = o;
-    ws.cell2vox = take((size_t)n_agents * ncell);
-    ws.vox_off = take((size_t)n_agents * (vcap + 1));
-    ws.vox_cell = take((size_t)n_agents * vcap);
-    ws.cellid = take((size_t)(sum_points > 0 ? sum_points : 1));
-    ws.list = take((size_t)(sum_points > 0 ? sum_points : 1));
-    ws.nvox = take((size_t)n_agents + 1);
+    ws.cell2vox = (int*)take((size_t)n_agents * ncell * 4);
+    ws.vox_off = (int*)take((size_t)n_agents * (vcap + 1) * 4);
+    ws.vox_cell = (int*)take((size_t)n_agents * vcap * 4);
+    ws.cellid = (int*)take((size_t)sp * 4);
+    ws.list = (int*)take((size_t)sp * 4);
+    ws.nvox = (int*)take(((size_t)n_agents + 1) * 4);
+    ws.chunk_tot = (int2*)take((size_t)n_agents * max_chunks * 8);
     ws.ncell = (int)ncell;
     ws.vcap = vcap;
+    ws.max_chunks = max_chunks;
     if (clear_bytes) { clear_bytes[0] = o_first_end; clear_bytes[1] = o_clear_end - o_first_end; }
     if (total_bytes) *total_bytes = o;
     if (p && o > bytes) return CB_ERR_ARG;
     return CB_OK;
 }
 
-static size_t ws_bytes(int n_agents, int sum_points, const int32_t* grid, int max_voxels) {
-    VoxWs ws;
-    size_t total = 0;
-    carve(ws, nullptr, 0, n_agents, sum_points, grid, max_voxels, nullptr, &total);
-    return total;
-}
-
 // Shared front half (K1..K3).  pt_offset is a HOST array.
 static int run_front(const float* points, const int32_t* pt_offset, int n_agents, const float* range,
                      const float* vsize, const int32_t* grid, int max_pts, int max_voxels, void* workspace,
-                     size_t workspace_bytes, cudaStream_t st, AgentOffsets& ao, VoxWs& ws, Geom& g) {
+                     size_t workspace_bytes, cudaStream_t st, AgentOffsets& ao, VoxWs& ws, Geom& g, int* n_voxels_out,
+                     int* dirty_count) {
     if (n_agents < 1 || n_agents > CB_MAX_AGENTS || max_pts < 1 || max_pts > 32 || max_voxels < 1) return CB_ERR_ARG;
     if (!workspace || ((uintptr_t)points & 15)) return CB_ERR_ARG;
     ao.n_agents = n_agents;
     for (int i = 0; i <= n_agents; ++i) ao.off[i] = pt_offset[i];
     if (ao.off[0] != 0) return CB_ERR_ARG;
-    for (int i = 0; i < n_agents; ++i) if (ao.off[i + 1] < ao.off[i]) return CB_ERR_ARG;
+    int max_np = 0;
+    for (int i = 0; i < n_agents; ++i) {
+        if (ao.off[i + 1] < ao.off[i]) return CB_ERR_ARG;
+        if (ao.off[i + 1] - ao.off[i] > max_np) max_np = ao.off[i + 1] - ao.off[i];
+    }
     const int total = ao.off[n_agents];
     size_t clr[2];
     int rc = carve(ws, workspace, workspace_bytes, n_agents, total, grid, max_voxels, clr, nullptr);
@@ -379,28 +455,48 @@ static int run_front(const float* points, const int32_t* pt_offset, int n_agents
         vox_assign_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float4*)points, ao, g, ws);
         CB_CHECK_LAUNCH();
     }
-    vox_scan_kernel<<<n_agents, 1024, 0, st>>>(ao, ws, max_voxels);
+    const dim3 cgrid((unsigned)ws.max_chunks, (unsigned)n_agents);
+    vox_chunk_count_kernel<<<cgrid, 256, 0, st>>>(ao, ws);
+    CB_CHECK_LAUNCH();
+    vox_chunk_scan_kernel<<<n_agents, 32, 0, st>>>(ws, max_voxels);
+    CB_CHECK_LAUNCH();
+    vox_total_kernel<<<1, 32, 0, st>>>(ws, n_agents, n_voxels_out, dirty_count);
     CB_CHECK_LAUNCH();
     if (total > 0) {
+        const dim3 agrid((unsigned)((max_np + CHUNK - 1) / CHUNK), (unsigned)n_agents);
+        vox_chunk_assign_kernel<<<agrid, 256, 0, st>>>(ao, ws, max_voxels);
+        CB_CHECK_LAUNCH();
         vox_fill_kernel<<<(total + 255) / 256, 256, 0, st>>>(ao, ws);
         CB_CHECK_LAUNCH();
     }
     return CB_OK;
 }
 
-static CanvasGeom make_canvas_geom(int n_agents, int ny, int nx) {
+static CanvasGeom make_canvas_geom(int canvas_agents, int ny, int nx) {
     CanvasGeom cg;
     cg.ny = ny; cg.nx = nx;
     cg.Hq = (ny + 1) / 2 + 2;
     cg.Wq = (nx + 1) / 2 + 2;
-    cg.plane_rows = (long)n_agents * cg.Hq * cg.Wq;
+    cg.plane_rows = (long)canvas_agents * cg.Hq * cg.Wq;
     return cg;
+}
+
+static PfnParams make_pfn(const float* w, const float* scale, const float* shift, const float* vsize,
+                          const float* center_off) {
+    PfnParams pp;
+    pp.w = w; pp.scale = scale; pp.shift = shift;
+    pp.vx = vsize[0]; pp.vy = vsize[1]; pp.vz = vsize[2];
+    pp.offx = center_off[0]; pp.offy = center_off[1]; pp.offz = center_off[2];
+    return pp;
 }
 
 }  // namespace cb
 
 extern "C" size_t cb_voxelize_workspace_bytes(int n_agents, int sum_points, const int32_t* grid, int max_voxels) {
-    return cb::ws_bytes(n_agents, sum_points, grid, max_voxels);
+    cb::VoxWs ws;
+    size_t total = 0;
+    cb::carve(ws, nullptr, 0, n_agents, sum_points, grid, max_voxels, nullptr, &total);
+    return total;
 }
 
 extern "C" int cb_voxelize(const float* points, const int32_t* pt_offset, int n_agents, const float* range,
@@ -411,10 +507,8 @@ extern "C" int cb_voxelize(const float* points, const int32_t* pt_offset, int n_
     cudaStream_t st = (cudaStream_t)stream;
     AgentOffsets ao; VoxWs ws; Geom g;
     int rc = run_front(points, pt_offset, n_agents, range, vsize, grid, max_pts, max_voxels, workspace,
-                       workspace_bytes, st, ao, ws, g);
+                       workspace_bytes, st, ao, ws, g, n_voxels, nullptr);
     if (rc) return rc;
-    vox_total_kernel<<<1, 32, 0, st>>>(ws, n_agents, n_voxels);
-    CB_CHECK_LAUNCH();
     vox_emit_kernel<<<148 * 4, 256, 0, st>>>((const float4*)points, ao, ws, g, max_pts, (float4*)voxels,
                                              (int4*)coords, num_points);
     CB_CHECK_LAUNCH();
@@ -425,18 +519,19 @@ extern "C" int cb_points_to_canvas(const float* points, const int32_t* pt_offset
                                    const float* vsize, const int32_t* grid, int max_pts, int max_voxels,
                                    const float* w, const float* scale, const float* shift,
                                    const float* center_off, int canvas_agents, void* canvas_ps,
-                                   int64_t lo_off, void* workspace, size_t workspace_bytes, void* stream) {
+                                   int64_t lo_off, int64_t* dirty_rows, int32_t* dirty_count,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
     using namespace cb;
-    if (grid[2] != 1 || !canvas_ps || canvas_agents < n_agents) return CB_ERR_ARG;       // PointPillarScatter asserts nz == 1 (point_pillar_scatter.py:13)
+    if (grid[2] != 1 || !canvas_ps || canvas_agents < n_agents) return CB_ERR_ARG;   // nz == 1 (point_pillar_scatter.py:13)
     cudaStream_t st = (cudaStream_t)stream;
     AgentOffsets ao; VoxWs ws; Geom g;
     int rc = run_front(points, pt_offset, n_agents, range, vsize, grid, max_pts, max_voxels, workspace,
-                       workspace_bytes, st, ao, ws, g);
+                       workspace_bytes, st, ao, ws, g, nullptr, dirty_count);
     if (rc) return rc;
     const CanvasGeom cg = make_canvas_geom(canvas_agents, grid[1], grid[0]);
-    vox_pfn_kernel<<<148 * 4, 256, 0, st>>>((const float4*)points, ao, ws, g, max_pts, w, scale, shift,
-                                            center_off[0], center_off[1], center_off[2], cg,
-                                            (__nv_bfloat16*)canvas_ps, (long)lo_off);
+    const PfnParams pp = make_pfn(w, scale, shift, vsize, center_off);
+    vox_pfn_kernel<<<148 * 4, 256, 0, st>>>((const float4*)points, ao, ws, g, max_pts, pp, cg,
+                                            (__nv_bfloat16*)canvas_ps, (long)lo_off, (long*)dirty_rows);
     CB_CHECK_LAUNCH();
     return CB_OK;
 }
@@ -444,17 +539,27 @@ extern "C" int cb_points_to_canvas(const float* points, const int32_t* pt_offset
 extern "C" int cb_pfn_scatter(const float* voxels, const int32_t* coords, const int32_t* num_points, int n_rows,
                               const int32_t* n_voxels_dev, int max_pts, const float* w, const float* scale,
                               const float* shift, const float* vsize, const float* center_off, int n_agents,
-                              int canvas_agents, int ny, int nx, void* canvas_ps, int64_t lo_off, void* stream) {
+                              int canvas_agents, int ny, int nx, void* canvas_ps, int64_t lo_off,
+                              int64_t* dirty_rows, int32_t* dirty_count, void* stream) {
     using namespace cb;
     if (max_pts < 1 || max_pts > 32 || n_agents < 1 || canvas_agents < n_agents || !canvas_ps) return CB_ERR_ARG;
     if (n_rows <= 0) return CB_OK;
     const CanvasGeom cg = make_canvas_geom(canvas_agents, ny, nx);
-    const float offx = center_off[0], offy = center_off[1], offz = center_off[2];
-    int blocks = (n_rows + 7) / 8;
+    const PfnParams pp = make_pfn(w, scale, shift, vsize, center_off);
+    int blocks = (n_rows + 31) / 32;
     if (blocks > 148 * 8) blocks = 148 * 8;
     pfn_scatter_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
-        (const float4*)voxels, (const int4*)coords, num_points, n_rows, n_voxels_dev, max_pts, w, scale, shift,
-        vsize[0], vsize[1], vsize[2], offx, offy, offz, cg, n_agents, (__nv_bfloat16*)canvas_ps, (long)lo_off);
+        (const float4*)voxels, (const int4*)coords, num_points, n_rows, n_voxels_dev, max_pts, pp, cg, n_agents,
+        (__nv_bfloat16*)canvas_ps, (long)lo_off, (long*)dirty_rows, dirty_count);
+    CB_CHECK_LAUNCH();
+    return CB_OK;
+}
+
+extern "C" int cb_canvas_clear(void* canvas_ps, int64_t lo_off, const int64_t* dirty_rows, const int32_t* dirty_count,
+                               int capacity, void* stream) {
+    if (!canvas_ps || !dirty_rows || !dirty_count || capacity < 1) return CB_ERR_ARG;
+    cb::canvas_clear_kernel<<<148 * 4, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)canvas_ps, (long)lo_off,
+                                                                       (const long*)dirty_rows, dirty_count, capacity);
     CB_CHECK_LAUNCH();
     return CB_OK;
 }

@@ -96,7 +96,7 @@ def pack_conv_weight(w: torch.Tensor, scale: Optional[torch.Tensor]) -> torch.Te
 class CoAlignEngine:
     def __init__(self, args: dict, state_dict: Dict[str, torch.Tensor], max_agents: int, max_scenes: int,
                  device="cuda", precise: bool = False, max_cav: int = 5, block_n_cap: int = 128,
-                 use_graph: bool = True, simt_conv: bool = False):
+                 use_graph: bool = True, simt_conv: bool = False, pair: bool = True):
         self.lib = _lib.load(check_device=True)
         self.args = args
         self.device = torch.device(device)
@@ -105,6 +105,7 @@ class CoAlignEngine:
         self.block_n_cap = int(block_n_cap)
         self.use_graph = use_graph
         self.simt_conv = simt_conv            # validation only: evaluate the descriptors with the SIMT kernel
+        self.pair = pair                      # CTA-pair (cta_group::2) conv kernel
         nx, ny, nz = [int(v) for v in args["point_pillar_scatter"]["grid_size"]]
         if nz != 1:
             raise ValueError("PointPillarScatter requires nz == 1")
@@ -232,6 +233,10 @@ class CoAlignEngine:
         self.pairwise = torch.zeros(NS, self.max_cav, self.max_cav, 4, 4, dtype=torch.float64, device=dev)
         self.agent_off = torch.zeros(NS + 1, dtype=torch.int32, device=dev)
         self._vox_ws = None
+        self._dirty_cap = self.max_agents * self.nx * self.ny      # one slot per canvas cell: cannot overflow
+        self.dirty_rows = torch.zeros(self._dirty_cap, dtype=torch.int64, device=dev)
+        self.dirty_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.pts_buf = None
 
     # ------------------------------------------------------------------ descriptors
     def _expand(self, steps, lo_rows, k_hi):
@@ -383,6 +388,8 @@ class CoAlignEngine:
             if kind == "conv":
                 if self.simt_conv:
                     _lib.check(lib.cb_conv_gemm_simt(C.byref(o), stream_ptr), "cb_conv_gemm_simt")
+                elif self.pair:
+                    _lib.check(lib.cb_conv_gemm_pair(C.byref(o), 0, stream_ptr), "cb_conv_gemm_pair")
                 else:
                     _lib.check(lib.cb_conv_gemm(C.byref(o), 0, stream_ptr), "cb_conv_gemm")
             else:
@@ -394,28 +401,31 @@ class CoAlignEngine:
                                                 self.max_cav, h, w, c, self.method, dst.ptr, dst.lo_off, stream_ptr),
                            "cb_warp_att_fuse")
 
-    def _backbone(self, record_len: Tuple[int, ...]):
-        """Everything after the canvas: affine normalisation, encoder, fusion, decoder, shrink, heads."""
+    def _run_backbone(self, ent, n_scenes: int, stream_ptr: int):
+        _lib.check(self.lib.cb_normalize_affine(self.pairwise.data_ptr(), n_scenes, self.max_cav, self.ny, self.nx,
+                                                float(self.voxel_size[0]), self.affine.data_ptr(), stream_ptr),
+                   "cb_normalize_affine")
+        self._launch_ops(ent["ops"], n_scenes, stream_ptr)
+
+    def _graphed(self, key, record_len: Tuple[int, ...], front=None):
+        """Run (front-end +) backbone for this batch signature; captured into a CUDA graph on first use."""
         n_img, n_scenes = sum(record_len), len(record_len)
-        sig = record_len
-        ent = self._graphs.get(sig)
+        ent = self._graphs.get(key)
         if ent is None:
             ent = {"ops": self.build_descs(n_img, n_scenes), "graph": None}
-            self._graphs[sig] = ent
+            self._graphs[key] = ent
         cur = torch.cuda.current_stream(self.device)
 
         def run(stream_ptr):
-            _lib.check(self.lib.cb_normalize_affine(self.pairwise.data_ptr(), n_scenes, self.max_cav, self.ny, self.nx,
-                                                    float(self.voxel_size[0]), self.affine.data_ptr(), stream_ptr),
-                       "cb_normalize_affine")
-            self._launch_ops(ent["ops"], n_scenes, stream_ptr)
+            if front is not None:
+                front(stream_ptr)
+            self._run_backbone(ent, n_scenes, stream_ptr)
 
         if not self.use_graph:
             run(cur.cuda_stream)
             return
         if ent["graph"] is None:
-            # warm-up launch outside capture (sets function attributes, resolves the driver entry point)
-            run(cur.cuda_stream)
+            run(cur.cuda_stream)          # warm-up outside capture (function attributes, driver entry point)
             cur.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=self._stream):
@@ -463,14 +473,29 @@ class CoAlignEngine:
         if vf.dim() != 3 or vf.shape[2] != 4 or vf.shape[1] > 32:
             raise ValueError("voxel_features must be (M, max_pts<=32, 4)")
         sp = torch.cuda.current_stream(self.device).cuda_stream
-        self.canvas.zero_()
+        track = vf.shape[0] <= self._dirty_cap
+        self._clear_canvas(sp)
         _lib.check(self.lib.cb_pfn_scatter(vf.data_ptr(), vc.data_ptr(), vn.data_ptr(), vf.shape[0], None,
                                            vf.shape[1], self.pfn_w.data_ptr(), self.pfn_scale.data_ptr(),
                                            self.pfn_shift.data_ptr(), self._vsize_f.ctypes.data,
                                            self._center_off_f.ctypes.data, n_img, self.canvas.n_cap, self.ny, self.nx,
-                                           self.canvas.ptr, self.canvas.lo_off, sp), "cb_pfn_scatter")
-        self._backbone(record_len)
+                                           self.canvas.ptr, self.canvas.lo_off,
+                                           self.dirty_rows.data_ptr() if track else None,
+                                           self.dirty_count.data_ptr() if track else None, sp), "cb_pfn_scatter")
+        if not track:
+            self._canvas_untracked = True
+        self._graphed(("bb", record_len), record_len)
         return self._outputs(len(record_len), clone)
+
+    def _clear_canvas(self, stream_ptr: int):
+        """Zero what the previous frame wrote: sparse (dirty-row list) when tracked, full memset otherwise."""
+        if getattr(self, "_canvas_untracked", False):
+            self.canvas.zero_()
+            self.dirty_count.zero_()
+            self._canvas_untracked = False
+            return
+        _lib.check(self.lib.cb_canvas_clear(self.canvas.ptr, self.canvas.lo_off, self.dirty_rows.data_ptr(),
+                                            self.dirty_count.data_ptr(), self._dirty_cap, stream_ptr), "cb_canvas_clear")
 
     def _ws(self, n_agents: int, sum_points: int, max_voxels: int):
         need = self.lib.cb_voxelize_workspace_bytes(n_agents, sum_points, self._grid_i.ctypes.data, max_voxels)
@@ -486,20 +511,35 @@ class CoAlignEngine:
         record_len = tuple(int(v) for v in record_len)
         self._set_scene_meta(record_len, pairwise)
         n_img = sum(record_len)
-        po = np.asarray(pt_offset, np.int32)
+        po = np.ascontiguousarray(pt_offset, dtype=np.int32)
         if po.shape[0] != n_img + 1:
             raise ValueError("pt_offset must have sum(record_len)+1 entries")
-        pts = points.contiguous()
-        ws = self._ws(n_img, int(po[-1]), max_voxels)
-        sp = torch.cuda.current_stream(self.device).cuda_stream
-        self.canvas.zero_()
-        _lib.check(self.lib.cb_points_to_canvas(pts.data_ptr(), po.ctypes.data, n_img, self._range_f.ctypes.data,
-                                                self._vsize_f.ctypes.data, self._grid_i.ctypes.data, max_pts,
-                                                max_voxels, self.pfn_w.data_ptr(), self.pfn_scale.data_ptr(),
-                                                self.pfn_shift.data_ptr(), self._center_off_f.ctypes.data,
-                                                self.canvas.n_cap, self.canvas.ptr, self.canvas.lo_off,
-                                                ws.data_ptr(), ws.numel(), sp), "cb_points_to_canvas")
-        self._backbone(record_len)
+        total = int(po[-1])
+        if points.dtype != torch.float32 or points.dim() != 2 or points.shape[1] != 4 or points.shape[0] < total:
+            raise TypeError("points must be float32 (sum_P, 4)")
+        if self.pts_buf is None or self.pts_buf.shape[0] < total:
+            self.pts_buf = torch.empty(max(total, 1), 4, dtype=torch.float32, device=self.device)
+            self._graphs = {k: v for k, v in self._graphs.items() if k[0] != "pts"}
+        if points.data_ptr() != self.pts_buf.data_ptr():
+            self.pts_buf[:total].copy_(points[:total], non_blocking=True)     # static address for the graph
+        ws = self._ws(n_img, total, max_voxels)
+        if getattr(self, "_canvas_untracked", False):
+            self._clear_canvas(torch.cuda.current_stream(self.device).cuda_stream)     # full memset, outside the graph
+        po_keep = po.copy()
+
+        def front(stream_ptr):
+            self._clear_canvas(stream_ptr)
+            _lib.check(self.lib.cb_points_to_canvas(self.pts_buf.data_ptr(), po_keep.ctypes.data, n_img,
+                                                    self._range_f.ctypes.data, self._vsize_f.ctypes.data,
+                                                    self._grid_i.ctypes.data, max_pts, max_voxels,
+                                                    self.pfn_w.data_ptr(), self.pfn_scale.data_ptr(),
+                                                    self.pfn_shift.data_ptr(), self._center_off_f.ctypes.data,
+                                                    self.canvas.n_cap, self.canvas.ptr, self.canvas.lo_off,
+                                                    self.dirty_rows.data_ptr(), self.dirty_count.data_ptr(),
+                                                    ws.data_ptr(), ws.numel(), stream_ptr), "cb_points_to_canvas")
+
+        key = ("pts", record_len, tuple(int(v) for v in po), int(max_pts), int(max_voxels), ws.data_ptr())
+        self._graphed(key, record_len, front)
         return self._outputs(len(record_len), clone)
 
     @torch.no_grad()

@@ -73,6 +73,7 @@ int cb_voxelize(const float* points, const int32_t* pt_offset, int n_agents,
  *   vsize/center_off HOST float32 [3]: voxel size and (voxel/2 + range_min) rounded from double
  *                              exactly like PillarVFE.__init__ (pillar_vfe.py:84-89)
  *   canvas_agents: agent capacity the PS canvas was allocated for (plane stride), >= n_agents
+ *   dirty_rows/dirty_count: optional DEVICE outputs for cb_canvas_clear (may be NULL)
  *   n_voxels_dev: optional DEVICE int32* holding the number of valid rows (<= n_rows); NULL = n_rows
  * ------------------------------------------------------------------------------------------ */
 int cb_pfn_scatter(const float* voxels, const int32_t* coords, const int32_t* num_points,
@@ -80,7 +81,8 @@ int cb_pfn_scatter(const float* voxels, const int32_t* coords, const int32_t* nu
                    const float* w, const float* scale, const float* shift,
                    const float* vsize, const float* center_off,
                    int n_agents, int canvas_agents, int ny, int nx,
-                   void* canvas_ps, int64_t lo_off, void* stream);
+                   void* canvas_ps, int64_t lo_off,
+                   int64_t* dirty_rows, int32_t* dirty_count, void* stream);
 
 /* Same stages straight from raw points (A1..A5 fused; the (M,32,4) voxel tensor is never
  * materialised).  Uses the same workspace as cb_voxelize. */
@@ -89,7 +91,14 @@ int cb_points_to_canvas(const float* points, const int32_t* pt_offset, int n_age
                         int max_pts, int max_voxels,
                         const float* w, const float* scale, const float* shift,
                         const float* center_off, int canvas_agents, void* canvas_ps, int64_t lo_off,
+                        int64_t* dirty_rows, int32_t* dirty_count,
                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Sparse canvas reset: zero the cells listed in dirty_rows[0..*dirty_count) (DEVICE arrays written by the two
+ * entry points above when their dirty_rows/dirty_count arguments are non-NULL: one canvas row per pillar, -1 =
+ * skipped).  Replaces the full-canvas memset between frames (the canvas is ~80 % zeros). */
+int cb_canvas_clear(void* canvas_ps, int64_t lo_off, const int64_t* dirty_rows, const int32_t* dirty_count,
+                    int capacity, void* stream);
 
 /* --------------------------------------------------------------------------------------------
  * A6..A9  convolutions as implicit GEMMs on tcgen05 tensor cores (TMA-fed, TMEM accumulators)
@@ -152,6 +161,9 @@ typedef struct cb_conv_desc {
 
 /* tcgen05 path (the product).  max_ctas <= 0: one persistent CTA per SM. */
 int cb_conv_gemm(const cb_conv_desc* desc, int max_ctas, void* stream);
+/* Same GEMM on CTA pairs (tcgen05 cta_group::2, 256 x block_n tiles, cluster of 2): halves the weight-tile
+ * shared-memory traffic per MAC.  max_clusters <= 0: one cluster per SM pair.  block_n 32 falls back to cb_conv_gemm. */
+int cb_conv_gemm_pair(const cb_conv_desc* desc, int max_clusters, void* stream);
 /* Plain SIMT fp32-accumulate evaluation of the same descriptor: a validation kernel for the
  * tensor-core path (tests only; never used by the model). */
 int cb_conv_gemm_simt(const cb_conv_desc* desc, void* stream);

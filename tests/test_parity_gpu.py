@@ -105,8 +105,9 @@ def test_bf16_mode_tensor_core_vs_simt_and_oracle():
         assert rel_l2(res[False][0][k], ref_out[k].numpy()) < 5e-2, (k, rel_l2(res[False][0][k], ref_out[k].numpy()))
 
 
-@pytest.mark.parametrize("block_n", [64, 128, 256])
-def test_conv_tile_shapes_agree(block_n):
+@pytest.mark.parametrize("block_n,pair", [(64, False), (128, False), (256, False), (64, True), (128, True), (256, True)])
+def test_conv_tile_shapes_agree(block_n, pair):
+    """Every tcgen05 tile shape, single-CTA and CTA-pair (cta_group::2), against the SIMT evaluation."""
     seed = 2
     args = G.small_args("att")
     sd = synth.random_state_dict(args, seed)
@@ -114,7 +115,7 @@ def test_conv_tile_shapes_agree(block_n):
     inp = G.small_case_inputs(rl, seed0=300)
     outs = []
     for bn, simt in ((block_n, False), (128, True)):
-        eng = make_engine(args, sd, 2, 1, precise=True, block_n_cap=bn, simt_conv=simt, use_graph=False)
+        eng = make_engine(args, sd, 2, 1, precise=True, block_n_cap=bn, simt_conv=simt, use_graph=False, pair=pair)
         o = eng.forward_voxels(*cuda_batch(inp))
         torch.cuda.synchronize()
         outs.append({k: v.cpu().numpy() for k, v in o.items()})

@@ -51,11 +51,11 @@ def small_case():
             print(f"  {k:10s} {stats(res[(precise, False)][k], res[(precise, True)][k])}")
 
 
-def full_case(n_agents=5, n_scenes=1, precise=False, block_n=128, n_points=60000, check=False):
+def full_case(n_agents=5, n_scenes=1, precise=False, block_n=128, n_points=60000, check=False, pair=True):
     args = synth.opv2v_args()
     sd = synth.random_state_dict(args, 0)
     rl = [n_agents] * n_scenes
-    eng = CoAlignEngine(args, sd, sum(rl), len(rl), precise=precise, block_n_cap=block_n, use_graph=False)
+    eng = CoAlignEngine(args, sd, sum(rl), len(rl), precise=precise, block_n_cap=block_n, use_graph=False, pair=pair)
     scenes = [synth.make_scene(s, n_agents, n_points, args["lidar_range"], pose_noise=True) for s in range(n_scenes)]
     pts = np.concatenate([p for sc in scenes for p in sc["points"]])
     off = np.arange(0, sum(rl) + 1, dtype=np.int32) * n_points
@@ -69,7 +69,7 @@ def full_case(n_agents=5, n_scenes=1, precise=False, block_n=128, n_points=60000
     import ctypes as C
     lib = eng.lib
     tot_flop, tot_t = 0.0, 0.0
-    print(f"=== full size: agents={n_agents} scenes={n_scenes} precise={precise} block_n_cap={block_n}")
+    print(f"=== full size: agents={n_agents} scenes={n_scenes} precise={precise} block_n_cap={block_n} pair={pair}")
     for kind, o in ops:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         reps = 5
@@ -94,20 +94,6 @@ def full_case(n_agents=5, n_scenes=1, precise=False, block_n=128, n_points=60000
             tot_t += t
     print(f"  conv total {tot_flop/1e9:.1f} GFLOP in {tot_t*1e3:.3f} ms -> {tot_flop/tot_t/1e12:.1f} TFLOP/s; "
           f"scenes/s (backbone only) = {n_scenes/tot_t:.1f}")
-    # front-end timing
-    for name, fn in (("points_to_canvas(+memset)", lambda: (eng.canvas.zero_(), _lib.check(lib.cb_points_to_canvas(
-            pts_d.data_ptr(), off.ctypes.data, sum(rl), eng._range_f.ctypes.data, eng._vsize_f.ctypes.data,
-            eng._grid_i.ctypes.data, 32, 70000, eng.pfn_w.data_ptr(), eng.pfn_scale.data_ptr(), eng.pfn_shift.data_ptr(),
-            eng._center_off_f.ctypes.data, eng.canvas.n_cap, eng.canvas.ptr, eng.canvas.lo_off,
-            eng._ws(sum(rl), int(off[-1]), 70000).data_ptr(), eng._ws(sum(rl), int(off[-1]), 70000).numel(), sp)))),):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        fn(); fn()
-        ev[0].record()
-        for _ in range(5):
-            fn()
-        ev[1].record()
-        torch.cuda.synchronize()
-        print(f"  {name}: {ev[0].elapsed_time(ev[1])/5*1e3:.1f} us")
     # whole forward, graph
     eng.use_graph = True
     for _ in range(3):
@@ -141,8 +127,9 @@ if __name__ == "__main__":
     if "small" in what:
         small_case()
     if "full" in what:
-        full_case(2, 1, precise=True, check=True)
-        full_case(5, 1, precise=False, check=True)
-        full_case(5, 1, precise=False, block_n=256)
-        full_case(5, 4, precise=False, block_n=128)
-        full_case(5, 4, precise=False, block_n=256)
+        full_case(5, 4, precise=False, block_n=256, pair=False)
+        full_case(5, 4, precise=False, block_n=256, pair=True, check=False)
+        full_case(5, 4, precise=False, block_n=128, pair=True)
+        full_case(5, 1, precise=False, block_n=256, pair=True)
+        full_case(5, 8, precise=False, block_n=256, pair=True)
+        full_case(2, 1, precise=True, block_n=256, pair=True, check=True)
