@@ -32,30 +32,30 @@ struct RowDest {
     int n, h, w;
 };
 
-// Decode GEMM row q (flattened padded pixel) and compute where its result goes.
-__device__ __forceinline__ RowDest decode_row(const ConvParams& p, long q, int n0) {
+// Decode GEMM row q (flattened padded pixel, < 2^31) and compute where its result goes.
+__device__ __forceinline__ RowDest decode_row(const ConvParams& p, long q64, int n0) {
     RowDest d;
     d.row = -1;
     d.n = d.h = d.w = 0;
-    if (q >= p.rows_total) return d;
-    const int plane = p.Hp * p.Wp;
-    const int n = (int)(q / plane);
-    const int rem = (int)(q - (long)n * plane);
-    const int hp = rem / p.Wp;
-    const int wp = rem - hp * p.Wp;
-    if (hp < 1 || hp > p.Hp - 2 || wp < 1 || wp > p.Wp - 2) return d;
-    const int h = hp - 1, w = wp - 1;
-    d.n = n; d.h = h; d.w = w;
+    if (q64 >= p.rows_total) return d;
+    const unsigned q = (unsigned)q64;
+    const unsigned plane = (unsigned)(p.Hp * p.Wp);
+    const unsigned n = q / plane;
+    const unsigned rem = q - n * plane;
+    const unsigned hp = rem / (unsigned)p.Wp;
+    const unsigned wp = rem - hp * (unsigned)p.Wp;
+    if (hp < 1u || hp > (unsigned)(p.Hp - 2) || wp < 1u || wp > (unsigned)(p.Wp - 2)) return d;
+    const int h = (int)hp - 1, w = (int)wp - 1;
+    d.n = (int)n; d.h = h; d.w = w;
     if (p.out_mode == CB_OUT_PF || p.out_mode == CB_OUT_HEADS) {
-        d.row = q;
+        d.row = q64;
     } else if (p.out_mode == CB_OUT_PS) {
         const int ph = (h & 1) * 2 + (w & 1);
-        d.row = (long)ph * p.out_plane_rows + (long)n * p.out_Hp * p.out_Wp + (long)((h >> 1) + 1) * p.out_Wp +
-                (w >> 1) + 1;
+        d.row = (long)ph * p.out_plane_rows + (long)((int)n * p.out_Hp + (h >> 1) + 1) * p.out_Wp + (w >> 1) + 1;
     } else {  // CB_OUT_UPSAMPLE: GEMM column block n0 selects the (a,b) sub-pixel
         const int ab = n0 / p.cout_mod;
         const int a = ab / p.up_k, b = ab - a * p.up_k;
-        d.row = (long)n * p.out_Hp * p.out_Wp + (long)(p.up_k * h + a + 1) * p.out_Wp + (p.up_k * w + b + 1);
+        d.row = (long)((int)n * p.out_Hp + p.up_k * h + a + 1) * p.out_Wp + (p.up_k * w + b + 1);
     }
     return d;
 }
@@ -133,6 +133,48 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const RowDes
             o4[t] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             l4[t] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
+    }
+}
+
+// bf16x2 pack with the ReLU folded into the conversion (low half = a, high half = b)
+__device__ __forceinline__ uint32_t pack_bf16_relu(float a, float b) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %2, %1;" : "=r"(d) : "f"(a), "f"(b));
+    return d;
+}
+
+// Fast epilogue of the tensor-core kernels (bf16 outputs, not the heads): bias from shared memory, residual
+// already prefetched into registers, ReLU fused into the bf16 conversion, four 16-byte stores.
+__device__ __forceinline__ void epilogue_chunk_fast(const ConvParams& p, const RowDest& d, int c_base,
+                                                    const float* __restrict__ s_bias, const uint4 (&res)[4],
+                                                    bool has_res, float (&v)[32]) {
+    if (d.row < 0) return;
+    const float4* b4 = reinterpret_cast<const float4*>(s_bias + c_base);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const float4 b = b4[t];
+        v[4 * t + 0] += b.x; v[4 * t + 1] += b.y; v[4 * t + 2] += b.z; v[4 * t + 3] += b.w;
+    }
+    if (has_res) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            v[8 * t + 0] += bf16_lo(res[t].x); v[8 * t + 1] += bf16_hi(res[t].x);
+            v[8 * t + 2] += bf16_lo(res[t].y); v[8 * t + 3] += bf16_hi(res[t].y);
+            v[8 * t + 4] += bf16_lo(res[t].z); v[8 * t + 5] += bf16_hi(res[t].z);
+            v[8 * t + 6] += bf16_lo(res[t].w); v[8 * t + 7] += bf16_hi(res[t].w);
+        }
+    }
+    uint4* o4 = reinterpret_cast<uint4*>(p.out + d.row * (long)p.out_pitch + p.out_ch_off + c_base);
+    if (p.relu) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            o4[t] = make_uint4(pack_bf16_relu(v[8 * t + 0], v[8 * t + 1]), pack_bf16_relu(v[8 * t + 2], v[8 * t + 3]),
+                               pack_bf16_relu(v[8 * t + 4], v[8 * t + 5]), pack_bf16_relu(v[8 * t + 6], v[8 * t + 7]));
+    } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            o4[t] = make_uint4(pack_bf16(v[8 * t + 0], v[8 * t + 1]), pack_bf16(v[8 * t + 2], v[8 * t + 3]),
+                               pack_bf16(v[8 * t + 4], v[8 * t + 5]), pack_bf16(v[8 * t + 6], v[8 * t + 7]));
     }
 }
 

@@ -11,6 +11,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <cstdlib>
 #include "conv_common.cuh"
 
 namespace cb {
@@ -28,23 +29,67 @@ template <int BN> struct TcCfg {
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;    // double-buffered accumulator
 };
 
+
+constexpr int TC_THREADS = 384;      // warps 0..3: producer / MMA / TMEM alloc / spare; warps 4..11: epilogue
+
+// Epilogue of one accumulator tile for one thread: row q (TMEM lane), columns [c_lo, c_hi) of the BN-wide tile.
 template <int BN>
-__global__ void __launch_bounds__(256, 1)
+__device__ __forceinline__ void epilogue_tile(const ConvParams& p, const float* s_bias, uint32_t t_row, long q, int n0,
+                                              int c_lo, int c_hi, uint32_t tfull_bar, uint32_t acc_phase, int dbg) {
+    const RowDest dst = decode_row(p, q, n0);
+    const bool fast = (p.out_lo_off == 0) && (p.out_mode != CB_OUT_HEADS) && (p.res_lo_off == 0);
+    const bool has_res = fast && p.residual != nullptr && dst.row >= 0;
+    uint4 rcur[4] = {}, rnext[4] = {};
+    const uint4* rptr = reinterpret_cast<const uint4*>(p.residual + q * (long)p.res_pitch + n0);
+    if (has_res) {                                       // residual of the first chunk: issued before the MMA is done
+#pragma unroll
+        for (int t = 0; t < 4; ++t) rcur[t] = __ldg(rptr + (c_lo >> 3) + t);
+    }
+    mbar_wait_a(tfull_bar, acc_phase);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = c_lo; c < c_hi; c += 32) {
+        if (has_res && c + 32 < c_hi) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) rnext[t] = __ldg(rptr + ((c + 32) >> 3) + t);
+        }
+        uint32_t r[32];
+        tmem_ld32(t_row + c, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (dbg & 1) {                                   // experiment: no epilogue math / stores
+            if (v[0] == 1.2345e-30f) p.out[0] = __float2bfloat16(v[1]);
+        } else if (fast) {
+            epilogue_chunk_fast(p, dst, (n0 + c) % p.cout_mod, s_bias, rcur, has_res, v);
+        } else {
+            epilogue_chunk(p, dst, q, n0 + c, v);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) rcur[t] = rnext[t];
+    }
+}
+
+template <int BN, int STAGES_OVR = 0>
+__global__ void __launch_bounds__(TC_THREADS, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
                     const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ ConvParams p,
-                    int m_tiles, int n_tiles) {
+                    int m_tiles, int n_tiles, int dbg) {
     using Cfg = TcCfg<BN>;
-    constexpr int STAGES = Cfg::STAGES;
+    constexpr int STAGES = STAGES_OVR ? STAGES_OVR : Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
     __shared__ __align__(8) uint64_t empty_bar[STAGES];
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(16) float s_bias[256];
 
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
     uint8_t* smem = smem_raw + pad;                       // 1 KiB aligned (SWIZZLE_128B atoms)
+    for (int i = threadIdx.x; i < 256; i += TC_THREADS) s_bias[i] = i < p.cout_mod ? p.bias[i] : 0.f;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -58,7 +103,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_co
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 8); }
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -70,80 +115,79 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_co
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
+    // loop-invariant shared addresses / descriptors for the two single-thread hot loops
+    const uint32_t smem_a0 = smem_u32(smem);
+    const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+    const uint32_t tfull0 = smem_u32(&tmem_full_bar[0]), tempty0 = smem_u32(&tmem_empty_bar[0]);
+
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
                 const int m0 = mt * BM, n0 = nt * BN;
                 for (int ks = 0; ks < nk; ++ks) {
                     const cb_kstep st = p.ksteps[ks];
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-                    uint8_t* sb = sa + A_STAGE_BYTES;
-                    tma_load_2d(sa, st.a_sel ? &tmap_a1 : &tmap_a0, &full_bar[stage], (int)st.col, m0 + st.row_off);
-                    tma_load_2d(sb, &tmap_w, &full_bar[stage], st.w_k, n0);
+                    const uint32_t fb = full0 + stage * 8;
+                    const uint32_t sa = smem_a0 + stage * Cfg::STAGE_BYTES;
+                    mbar_wait_a(empty0 + stage * 8, phase ^ 1);
+                    if ((dbg & 2) && ks > 0) {           // experiment: weights only (A left stale)
+                        mbar_expect_tx_a(fb, Cfg::B_STAGE_BYTES);
+                    } else {
+                        mbar_expect_tx_a(fb, Cfg::STAGE_BYTES);
+                        tma_load_2d_a(sa, st.a_sel ? &tmap_a1 : &tmap_a0, fb, (int)st.col, m0 + st.row_off);
+                    }
+                    tma_load_2d_a(sa + A_STAGE_BYTES, &tmap_w, fb, st.w_k, n0);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+            const uint64_t adesc0 = make_sw128_desc(smem_a0);
+            const uint64_t bdesc0 = make_sw128_desc(smem_a0 + A_STAGE_BYTES);
             int stage = 0; uint32_t phase = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int buf = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
-                mbar_wait(&tmem_empty_bar[buf], acc_phase ^ 1);      // epilogue drained this accumulator
+                mbar_wait_a(tempty0 + buf * 8, acc_phase ^ 1);       // epilogue drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * BN;
                 for (int ks = 0; ks < nk; ++ks) {
-                    mbar_wait(&full_bar[stage], phase);              // TMA bytes landed
+                    mbar_wait_a(full0 + stage * 8, phase);           // TMA bytes landed
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    const uint32_t sb = sa + A_STAGE_BYTES;
-                    const uint64_t adesc = make_sw128_desc(sa);
-                    const uint64_t bdesc = make_sw128_desc(sb);
+                    // descriptor start-address field is (addr >> 4): stage stride and the 32-byte K advance add linearly
+                    const uint64_t adesc = adesc0 + (uint64_t)(stage * (Cfg::STAGE_BYTES >> 4));
+                    const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (Cfg::STAGE_BYTES >> 4));
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // advance 32 B (=16 bf16) inside the 128 B swizzle row: +2 in the >>4 address field
                         umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
                                   (ks > 0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);                  // frees the smem slot when MMAs retire
-                    if (ks == nk - 1) umma_commit(&tmem_full_bar[buf]);
+                    umma_commit_a(empty0 + stage * 8);               // frees the smem slot when the MMAs retire
+                    if (ks == nk - 1) umma_commit_a(tfull0 + buf * 8);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp >= 4) {
-        // ------------------------------------------------------------------ epilogue
+        // ------------------------------------------------------------------ epilogue (8 warps)
         const int q4 = warp & 3;                                     // TMEM lane quarter of this warp
+        const int half = (warp - 4) >> 2;                            // column half of the tile
+        constexpr int CW = BN >= 64 ? BN / 2 : BN;                   // columns per warp (BN=32: half 1 idles)
+        const int c_lo = half * CW, c_hi = (BN >= 64 || half == 0) ? c_lo + CW : c_lo;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
-            const int n0 = nt * BN;
             const int buf = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const long q = (long)mt * BM + q4 * 32 + lane;
-            const RowDest dst = decode_row(p, q, n0);
-            mbar_wait(&tmem_full_bar[buf], acc_phase);
-            tc_fence_after();
             const uint32_t t_row = tmem_base + buf * BN + ((uint32_t)(q4 * 32) << 16);
-#pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
-                uint32_t r[32];
-                tmem_ld32(t_row + c, r);
-                tmem_ld_wait();
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                epilogue_chunk(p, dst, q, n0 + c, v);
-            }
+            epilogue_tile<BN>(p, s_bias, t_row, q, nt * BN, c_lo, c_hi, tfull0 + buf * 8, acc_phase, dbg);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
@@ -173,7 +217,7 @@ template <int BN> struct Tc2Cfg {
 };
 
 template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
                      const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ ConvParams p,
                      int m_pairs, int n_tiles) {
@@ -183,12 +227,14 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
     __shared__ __align__(8) uint64_t full_bar[STAGES];       // used in the leader CTA (both CTAs' TMA bytes land here)
     __shared__ __align__(8) uint64_t empty_bar[STAGES];      // per CTA; released by the leader's multicast commit
     __shared__ __align__(8) uint64_t tmem_full_bar[2];       // per CTA; multicast commit
-    __shared__ __align__(8) uint64_t tmem_empty_bar[2];      // leader's copy counts 8 epilogue warps (both CTAs)
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];      // leader's copy counts 16 epilogue warps (both CTAs)
     __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(16) float s_bias[256];
 
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
     uint8_t* smem = smem_raw + pad;
+    for (int i = threadIdx.x; i < 256; i += TC_THREADS) s_bias[i] = i < p.cout_mod ? p.bias[i] : 0.f;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -205,7 +251,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 8); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 16); }
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -217,79 +263,73 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
+    const uint32_t smem_a0 = smem_u32(smem);
+    const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+    const uint32_t tfull0 = smem_u32(&tmem_full_bar[0]), tempty0 = smem_u32(&tmem_empty_bar[0]);
+
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (both CTAs)
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
                 const int mp = tile / n_tiles, nt = tile - mp * n_tiles;
                 const int m0 = (mp * 2 + (int)rank) * BM, n0 = nt * BN + (int)rank * (BN / 2);
                 for (int ks = 0; ks < nk; ++ks) {
                     const cb_kstep st = p.ksteps[ks];
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-                    uint8_t* sb = sa + A_STAGE_BYTES;
-                    tma_load_2d_2sm(sa, st.a_sel ? &tmap_a1 : &tmap_a0, &full_bar[stage], (int)st.col, m0 + st.row_off);
-                    tma_load_2d_2sm(sb, &tmap_w, &full_bar[stage], st.w_k, n0);
+                    const uint32_t fb = (full0 + stage * 8) & 0xFEFFFFFFu;        // leader CTA's barrier
+                    const uint32_t sa = smem_a0 + stage * Cfg::STAGE_BYTES;
+                    mbar_wait_a(empty0 + stage * 8, phase ^ 1);
+                    if (leader) mbar_expect_tx_a(full0 + stage * 8, 2 * Cfg::STAGE_BYTES);
+                    tma_load_2d_2sm_a(sa, st.a_sel ? &tmap_a1 : &tmap_a0, fb, (int)st.col, m0 + st.row_off);
+                    tma_load_2d_2sm_a(sa + A_STAGE_BYTES, &tmap_w, fb, st.w_k, n0);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-        if (leader && lane == 0) {
+        if (leader && elect_one()) {
             constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
+            const uint64_t adesc0 = make_sw128_desc(smem_a0);
+            const uint64_t bdesc0 = make_sw128_desc(smem_a0 + A_STAGE_BYTES);
             int stage = 0; uint32_t phase = 0;
             int it = 0;
             for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
                 const int buf = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
-                mbar_wait(&tmem_empty_bar[buf], acc_phase ^ 1);
+                mbar_wait_a(tempty0 + buf * 8, acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * BN;
                 for (int ks = 0; ks < nk; ++ks) {
-                    mbar_wait(&full_bar[stage], phase);
+                    mbar_wait_a(full0 + stage * 8, phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    const uint32_t sb = sa + A_STAGE_BYTES;
-                    const uint64_t adesc = make_sw128_desc(sa);
-                    const uint64_t bdesc = make_sw128_desc(sb);
+                    const uint64_t adesc = adesc0 + (uint64_t)(stage * (Cfg::STAGE_BYTES >> 4));
+                    const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (Cfg::STAGE_BYTES >> 4));
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         umma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
                                       (ks > 0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit_2sm(&empty_bar[stage]);
-                    if (ks == nk - 1) umma_commit_2sm(&tmem_full_bar[buf]);
+                    umma_commit_2sm_a(empty0 + stage * 8);
+                    if (ks == nk - 1) umma_commit_2sm_a(tfull0 + buf * 8);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp >= 4) {
-        // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
+        // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows, 8 warps)
         const int q4 = warp & 3;
+        const int half = (warp - 4) >> 2;
+        constexpr int CW = BN / 2;
+        const int c_lo = half * CW, c_hi = c_lo + CW;
         int it = 0;
         for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
             const int mp = tile / n_tiles, nt = tile - mp * n_tiles;
-            const int n0 = nt * BN;
             const int buf = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const long q = (long)(mp * 2 + (int)rank) * BM + q4 * 32 + lane;
-            const RowDest dst = decode_row(p, q, n0);
-            mbar_wait(&tmem_full_bar[buf], acc_phase);
-            tc_fence_after();
             const uint32_t t_row = tmem_base + buf * BN + ((uint32_t)(q4 * 32) << 16);
-#pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
-                uint32_t r[32];
-                tmem_ld32(t_row + c, r);
-                tmem_ld_wait();
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                epilogue_chunk(p, dst, q, n0 + c, v);
-            }
+            epilogue_tile<BN>(p, s_bias, t_row, q, nt * BN, c_lo, c_hi, tfull0 + buf * 8, acc_phase, 0);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[buf], 0);      // leader's barrier
@@ -332,10 +372,39 @@ static int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t col
     return r == CUDA_SUCCESS ? CB_OK : CB_ERR_DRIVER;
 }
 
+static int dbg_flags() {
+    const char* e = getenv("CB_DEBUG");
+    return e ? atoi(e) : 0;
+}
+
+template <int BN, int ST>
+static int launch_st(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const ConvParams& p,
+                     int m_tiles, int n_tiles, int max_ctas, cudaStream_t stream) {
+    using Cfg = TcCfg<BN>;
+    constexpr int SMEM = ST * Cfg::STAGE_BYTES + 1024;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    });
+    if (attr_err != cudaSuccess) return (int)attr_err;
+    int grid = m_tiles * n_tiles;
+    int cap = max_ctas > 0 ? max_ctas : 148;
+    if (grid > cap) grid = cap;
+    conv_gemm_tc_kernel<BN, ST><<<grid, TC_THREADS, SMEM, stream>>>(a0, a1, w, p, m_tiles, n_tiles, dbg_flags() & 7);
+    CB_CHECK_LAUNCH();
+    return CB_OK;
+}
+
 template <int BN>
 static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const ConvParams& p,
                   int m_tiles, int n_tiles, int max_ctas, cudaStream_t stream) {
     using Cfg = TcCfg<BN>;
+    if (BN == 64) {                                       // experiment: stage-count sweep
+        const int f = dbg_flags();
+        if (f & 8) return launch_st<64, 3>(a0, a1, w, p, m_tiles, n_tiles, max_ctas, stream);
+        if (f & 16) return launch_st<64, 9>(a0, a1, w, p, m_tiles, n_tiles, max_ctas, stream);
+    }
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
@@ -349,7 +418,7 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
     int grid = m_tiles * n_tiles;
     int cap = max_ctas > 0 ? max_ctas : sms;
     if (grid > cap) grid = cap;
-    conv_gemm_tc_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(a0, a1, w, p, m_tiles, n_tiles);
+    conv_gemm_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(a0, a1, w, p, m_tiles, n_tiles, dbg_flags() & 7);
     CB_CHECK_LAUNCH();
     return CB_OK;
 }
@@ -373,7 +442,7 @@ static int launch2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorM
     int clusters = m_pairs * n_tiles;
     int cap = max_clusters > 0 ? max_clusters : sms / 2;
     if (clusters > cap) clusters = cap;
-    conv_gemm_tc2_kernel<BN><<<2 * clusters, 256, Cfg::SMEM_BYTES, stream>>>(a0, a1, w, p, m_pairs, n_tiles);
+    conv_gemm_tc2_kernel<BN><<<2 * clusters, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(a0, a1, w, p, m_pairs, n_tiles);
     CB_CHECK_LAUNCH();
     return CB_OK;
 }

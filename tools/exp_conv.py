@@ -1,0 +1,36 @@
+"""Conv-kernel experiments: time each conv launch of a B=4 step under CB_DEBUG variants (development aid)."""
+import os, sys, subprocess
+if len(sys.argv) > 1 and sys.argv[1] == "child":
+    import numpy as np, torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from coalign_b200 import synth
+    from coalign_b200.engine import CoAlignEngine
+    B = 4
+    args = synth.opv2v_args(); sd = synth.random_state_dict(args, 0); rl = [5] * B
+    eng = CoAlignEngine(args, sd, sum(rl), len(rl), precise=False, block_n_cap=256, use_graph=False, pair=False)
+    scenes = [synth.make_scene(s, 5, 60000, args["lidar_range"], pose_noise=True) for s in range(B)]
+    pts = torch.from_numpy(np.concatenate([p for sc in scenes for p in sc["points"]])).cuda()
+    off = np.arange(0, sum(rl) + 1, dtype=np.int32) * 60000
+    pw = torch.from_numpy(np.stack([sc["pairwise_t_matrix"] for sc in scenes])).cuda()
+    eng.forward_points(pts, off, rl, pw); torch.cuda.synchronize()
+    ops = eng.build_descs(sum(rl), len(rl)); sp = torch.cuda.current_stream().cuda_stream
+    seen = {}
+    for kind, o in ops:
+        if kind != "conv": continue
+        key = (o.n_img * (o.Hp - 2) * (o.Wp - 2), o.n_total, o.n_ksteps * 64, o.block_n, o.out_mode, bool(o.residual))
+        if key in seen: continue
+        for _ in range(2): eng._launch_ops([(kind, o)], B, sp)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5): eng._launch_ops([(kind, o)], B, sp)
+        e1.record(); torch.cuda.synchronize()
+        seen[key] = e0.elapsed_time(e1) / 5 * 1e3
+    print(" ".join(f"{v:7.1f}" for v in seen.values()))
+    if os.environ.get("CB_DEBUG", "0") == "0":
+        print("keys:", list(seen.keys()))
+else:
+    for name, flag in (("base", 0), ("no-epilogue", 1), ("no-A-loads", 2), ("no-epi+no-A", 3), ("L2-prefetch", 4),
+                       ("3-stages(bn64)", 8), ("9-stages(bn64)", 16), ("prefetch+9st", 20)):
+        env = dict(os.environ, CB_DEBUG=str(flag))
+        out = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
+        print(f"{name:16s}", out.stdout.strip().replace("\n", "\n                 "), out.stderr[-300:] if out.returncode else "", flush=True)
