@@ -178,6 +178,26 @@ __device__ __forceinline__ void epilogue_chunk_fast(const ConvParams& p, const R
     }
 }
 
+// Heads epilogue (CB_OUT_HEADS, one 32-column tile): fp32 NCHW stores, coalesced across the lanes of a warp
+// (consecutive lanes = consecutive pixels of the same channel plane).
+__device__ __forceinline__ void epilogue_heads_fast(const ConvParams& p, const RowDest& d, const float* __restrict__ s_bias,
+                                                    float (&v)[32]) {
+    if (d.row < 0) return;
+    const int W = p.Wp - 2;
+    const long HW = (long)(p.Hp - 2) * W;
+    const long pix = (long)d.h * W + d.w;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        if (s < p.n_heads) {
+            const int c0 = p.head_c0[s], cn = p.head_cn[s];
+            float* base = p.head_out[s] + (long)d.n * cn * HW + pix - (long)c0 * HW;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j >= c0 && j < c0 + cn) base[(long)j * HW] = v[j] + s_bias[j];
+        }
+    }
+}
+
 inline int fill_params(const cb_conv_desc* d, ConvParams& p) {
     if (d->n_ksteps < 1 || d->n_ksteps > CB_MAX_KSTEPS) return CB_ERR_ARG;
     if (d->block_n != 32 && d->block_n != 64 && d->block_n != 128 && d->block_n != 256) return CB_ERR_ARG;

@@ -21,14 +21,23 @@ constexpr int BK = 64;        // K per pipeline stage: 64 bf16 = 128 B = one swi
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 
+// A pipeline stage holds KPS consecutive K-steps (each: 128x64 A tile + BNx64 weight tile).  Small-N tiles have
+// little tensor work per K-step, so several K-steps share one barrier round trip (wait / expect_tx / commit).
 template <int BN> struct TcCfg {
     static constexpr int B_STAGE_BYTES = BN * BK * 2;
-    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : (BN == 64 ? 6 : 8));
+    static constexpr int KSTEP_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int KPS = (BN == 256) ? 1 : (BN == 128 ? 2 : (BN == 64 ? 3 : 2));
+    static constexpr int STAGE_BYTES = KPS * KSTEP_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : (BN == 64 ? 3 : 5));
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;   // +1024: manual 1 KiB alignment
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;    // double-buffered accumulator
 };
 
+
+template <int BN, int KPS_OVR> struct TcCfgK : TcCfg<BN> {
+    static constexpr int KPS = KPS_OVR ? KPS_OVR : TcCfg<BN>::KPS;
+    static constexpr int STAGE_BYTES = KPS * TcCfg<BN>::KSTEP_BYTES;
+};
 
 constexpr int TC_THREADS = 384;      // warps 0..3: producer / MMA / TMEM alloc / spare; warps 4..11: epilogue
 
@@ -63,6 +72,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const float* 
             if (v[0] == 1.2345e-30f) p.out[0] = __float2bfloat16(v[1]);
         } else if (fast) {
             epilogue_chunk_fast(p, dst, (n0 + c) % p.cout_mod, s_bias, rcur, has_res, v);
+        } else if (p.out_mode == CB_OUT_HEADS && BN == 32 && !p.relu && p.residual == nullptr) {
+            epilogue_heads_fast(p, dst, s_bias, v);
         } else {
             epilogue_chunk(p, dst, q, n0 + c, v);
         }
@@ -71,13 +82,13 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const float* 
     }
 }
 
-template <int BN, int STAGES_OVR = 0>
+template <int BN, int KPS_OVR = 0, int STAGES_OVR = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
                     const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ ConvParams p,
                     int m_tiles, int n_tiles, int dbg) {
-    using Cfg = TcCfg<BN>;
-    constexpr int STAGES = STAGES_OVR ? STAGES_OVR : Cfg::STAGES;
+    using Cfg = TcCfgK<BN, KPS_OVR>;
+    constexpr int STAGES = STAGES_OVR ? STAGES_OVR : TcCfg<BN>::STAGES;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
     __shared__ __align__(8) uint64_t empty_bar[STAGES];
@@ -127,18 +138,20 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_co
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
                 const int m0 = mt * BM, n0 = nt * BN;
-                for (int ks = 0; ks < nk; ++ks) {
-                    const cb_kstep st = p.ksteps[ks];
+                for (int ks = 0; ks < nk; ks += Cfg::KPS) {
+                    const int cnt = (nk - ks) < Cfg::KPS ? (nk - ks) : Cfg::KPS;
                     const uint32_t fb = full0 + stage * 8;
-                    const uint32_t sa = smem_a0 + stage * Cfg::STAGE_BYTES;
                     mbar_wait_a(empty0 + stage * 8, phase ^ 1);
-                    if ((dbg & 2) && ks > 0) {           // experiment: weights only (A left stale)
-                        mbar_expect_tx_a(fb, Cfg::B_STAGE_BYTES);
-                    } else {
-                        mbar_expect_tx_a(fb, Cfg::STAGE_BYTES);
-                        tma_load_2d_a(sa, st.a_sel ? &tmap_a1 : &tmap_a0, fb, (int)st.col, m0 + st.row_off);
+                    mbar_expect_tx_a(fb, (uint32_t)cnt * Cfg::KSTEP_BYTES);
+#pragma unroll
+                    for (int j = 0; j < Cfg::KPS; ++j) {
+                        if (j < cnt) {
+                            const cb_kstep st = p.ksteps[ks + j];
+                            const uint32_t sa = smem_a0 + stage * Cfg::STAGE_BYTES + j * Cfg::KSTEP_BYTES;
+                            tma_load_2d_a(sa, st.a_sel ? &tmap_a1 : &tmap_a0, fb, (int)st.col, m0 + st.row_off);
+                            tma_load_2d_a(sa + A_STAGE_BYTES, &tmap_w, fb, st.w_k, n0);
+                        }
                     }
-                    tma_load_2d_a(sa + A_STAGE_BYTES, &tmap_w, fb, st.w_k, n0);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -157,19 +170,26 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_co
                 mbar_wait_a(tempty0 + buf * 8, acc_phase ^ 1);       // epilogue drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * BN;
-                for (int ks = 0; ks < nk; ++ks) {
+                for (int ks = 0; ks < nk; ks += Cfg::KPS) {
+                    const int cnt = (nk - ks) < Cfg::KPS ? (nk - ks) : Cfg::KPS;
                     mbar_wait_a(full0 + stage * 8, phase);           // TMA bytes landed
                     tc_fence_after();
-                    // descriptor start-address field is (addr >> 4): stage stride and the 32-byte K advance add linearly
+                    // descriptor start-address field is (addr >> 4): stage / K-step strides and the 32-byte K advance add linearly
                     const uint64_t adesc = adesc0 + (uint64_t)(stage * (Cfg::STAGE_BYTES >> 4));
                     const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (Cfg::STAGE_BYTES >> 4));
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                  (ks > 0 || k > 0) ? 1u : 0u);
+                    for (int j = 0; j < Cfg::KPS; ++j) {
+                        if (j < cnt) {
+#pragma unroll
+                            for (int k = 0; k < BK / UMMA_K; ++k) {
+                                umma_bf16(d_tmem, adesc + (uint64_t)(j * (Cfg::KSTEP_BYTES >> 4) + 2 * k),
+                                          bdesc + (uint64_t)(j * (Cfg::KSTEP_BYTES >> 4) + 2 * k), idesc,
+                                          (ks > 0 || j > 0 || k > 0) ? 1u : 0u);
+                            }
+                        }
                     }
                     umma_commit_a(empty0 + stage * 8);               // frees the smem slot when the MMAs retire
-                    if (ks == nk - 1) umma_commit_a(tfull0 + buf * 8);
+                    if (ks + Cfg::KPS >= nk) umma_commit_a(tfull0 + buf * 8);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -377,21 +397,21 @@ static int dbg_flags() {
     return e ? atoi(e) : 0;
 }
 
-template <int BN, int ST>
+template <int BN, int KPS, int ST>
 static int launch_st(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const ConvParams& p,
                      int m_tiles, int n_tiles, int max_ctas, cudaStream_t stream) {
-    using Cfg = TcCfg<BN>;
-    constexpr int SMEM = ST * Cfg::STAGE_BYTES + 1024;
+    constexpr int SMEM = ST * KPS * TcCfg<BN>::KSTEP_BYTES + 1024;
+    static_assert(SMEM <= 227 * 1024, "stage configuration exceeds shared memory");
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        attr_err = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, KPS, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     });
     if (attr_err != cudaSuccess) return (int)attr_err;
     int grid = m_tiles * n_tiles;
     int cap = max_ctas > 0 ? max_ctas : 148;
     if (grid > cap) grid = cap;
-    conv_gemm_tc_kernel<BN, ST><<<grid, TC_THREADS, SMEM, stream>>>(a0, a1, w, p, m_tiles, n_tiles, dbg_flags() & 7);
+    conv_gemm_tc_kernel<BN, KPS, ST><<<grid, TC_THREADS, SMEM, stream>>>(a0, a1, w, p, m_tiles, n_tiles, dbg_flags() & 7);
     CB_CHECK_LAUNCH();
     return CB_OK;
 }
@@ -400,10 +420,15 @@ template <int BN>
 static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const ConvParams& p,
                   int m_tiles, int n_tiles, int max_ctas, cudaStream_t stream) {
     using Cfg = TcCfg<BN>;
-    if (BN == 64) {                                       // experiment: stage-count sweep
-        const int f = dbg_flags();
-        if (f & 8) return launch_st<64, 3>(a0, a1, w, p, m_tiles, n_tiles, max_ctas, stream);
-        if (f & 16) return launch_st<64, 9>(a0, a1, w, p, m_tiles, n_tiles, max_ctas, stream);
+    {                                                     // experiment: K-steps-per-stage / stage-count variants
+        const int f = dbg_flags() >> 3;
+        if (BN == 64 && f == 1) return launch_st<64, 1, 9>(a0, a1, w, p, m_tiles, n_tiles, max_ctas, stream);
+        if (BN == 64 && f == 2) return launch_st<64, 2, 4>(a0, a1, w, p, m_tiles, n_tiles, max_ctas, stream);
+        if (BN == 64 && f == 3) return launch_st<64, 4, 2>(a0, a1, w, p, m_tiles, n_tiles, max_ctas, stream);
+        if (BN == 128 && f == 1) return launch_st<128, 1, 6>(a0, a1, w, p, m_tiles, n_tiles, max_ctas, stream);
+        if (BN == 128 && f == 2) return launch_st<128, 3, 2>(a0, a1, w, p, m_tiles, n_tiles, max_ctas, stream);
+        if (BN == 128 && f == 3) return launch_st<128, 2, 3>(a0, a1, w, p, m_tiles, n_tiles, max_ctas, stream);
+        if (BN == 256 && f == 2) return launch_st<256, 2, 2>(a0, a1, w, p, m_tiles, n_tiles, max_ctas, stream);
     }
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;

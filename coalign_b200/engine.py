@@ -105,7 +105,8 @@ class CoAlignEngine:
         self.block_n_cap = int(block_n_cap)
         self.use_graph = use_graph
         self.simt_conv = simt_conv            # validation only: evaluate the descriptors with the SIMT kernel
-        self.pair = pair                      # CTA-pair (cta_group::2) conv kernel
+        self.pair = pair                      # CTA-pair (cta_group::2) conv kernel ...
+        self.pair_min_bn = 256                # ... for tiles at least this wide (measured: narrower tiles are faster single-CTA)
         nx, ny, nz = [int(v) for v in args["point_pillar_scatter"]["grid_size"]]
         if nz != 1:
             raise ValueError("PointPillarScatter requires nz == 1")
@@ -388,7 +389,7 @@ class CoAlignEngine:
             if kind == "conv":
                 if self.simt_conv:
                     _lib.check(lib.cb_conv_gemm_simt(C.byref(o), stream_ptr), "cb_conv_gemm_simt")
-                elif self.pair:
+                elif self.pair and o.block_n >= self.pair_min_bn:
                     _lib.check(lib.cb_conv_gemm_pair(C.byref(o), 0, stream_ptr), "cb_conv_gemm_pair")
                 else:
                     _lib.check(lib.cb_conv_gemm(C.byref(o), 0, stream_ptr), "cb_conv_gemm")

@@ -116,6 +116,7 @@ def test_conv_tile_shapes_agree(block_n, pair):
     outs = []
     for bn, simt in ((block_n, False), (128, True)):
         eng = make_engine(args, sd, 2, 1, precise=True, block_n_cap=bn, simt_conv=simt, use_graph=False, pair=pair)
+        eng.pair_min_bn = 64            # exercise the CTA-pair kernel at every tile width
         o = eng.forward_voxels(*cuda_batch(inp))
         torch.cuda.synchronize()
         outs.append({k: v.cpu().numpy() for k, v in o.items()})

@@ -29,8 +29,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     if os.environ.get("CB_DEBUG", "0") == "0":
         print("keys:", list(seen.keys()))
 else:
-    for name, flag in (("base", 0), ("no-epilogue", 1), ("no-A-loads", 2), ("no-epi+no-A", 3), ("L2-prefetch", 4),
-                       ("3-stages(bn64)", 8), ("9-stages(bn64)", 16), ("prefetch+9st", 20)):
+    for name, flag in (("base", 0), ("no-epilogue", 1),):
         env = dict(os.environ, CB_DEBUG=str(flag))
         out = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
-        print(f"{name:16s}", out.stdout.strip().replace("\n", "\n                 "), out.stderr[-300:] if out.returncode else "", flush=True)
+        print(f"{name:30s}", out.stdout.strip().replace("\n", "\n                 "), out.stderr[-300:] if out.returncode else "", flush=True)
