@@ -27,7 +27,7 @@ struct VoxWs {            // workspace carve-up (device pointers)
     int* cursor;          // [n_agents][vcap]
     int* cell2vox;        // [n_agents][ncell]
     int* vox_off;         // [n_agents][vcap+1]
-    int* vox_cell;        // [n_agents][vcap]
+    int4* vox_meta;       // [n_agents][vcap]   {CSR begin, point count, cell, first point index}
     int* cellid;          // [sum_P]
     int* list;            // [sum_P]
     int* nvox;            // [n_agents+1]
@@ -127,27 +127,24 @@ __global__ void __launch_bounds__(256) vox_chunk_count_kernel(const __grid_const
 }
 
 // one warp per agent: chunk totals -> exclusive prefixes; voxel count
-__global__ void vox_chunk_scan_kernel(const VoxWs ws, int max_voxels) {
+__global__ void vox_chunk_scan_kernel(const VoxWs ws, int n_chunks, int max_voxels) {
     const int a = blockIdx.x, lane = threadIdx.x;
     int2* ct = ws.chunk_tot + (long)a * ws.max_chunks;
     int run_v = 0, run_c = 0;
-    for (int base = 0; base < ws.max_chunks; base += 32) {
+    for (int base = 0; base < n_chunks; base += 32) {
         const int i = base + lane;
-        const int2 t = i < ws.max_chunks ? ct[i] : make_int2(0, 0);
+        const int2 t = i < n_chunks ? ct[i] : make_int2(0, 0);
         int iv = t.x, ic = t.y;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int tv = __shfl_up_sync(0xffffffffu, iv, d), tc = __shfl_up_sync(0xffffffffu, ic, d);
             if (lane >= d) { iv += tv; ic += tc; }
         }
-        if (i < ws.max_chunks) ct[i] = make_int2(run_v + iv - t.x, run_c + ic - t.y);
+        if (i < n_chunks) ct[i] = make_int2(run_v + iv - t.x, run_c + ic - t.y);
         run_v += __shfl_sync(0xffffffffu, iv, 31);
         run_c += __shfl_sync(0xffffffffu, ic, 31);
     }
-    if (lane == 0) {
-        ws.nvox[a] = run_v < max_voxels ? run_v : max_voxels;
-        ws.vox_off[(long)a * (ws.vcap + 1)] = 0;
-    }
+    if (lane == 0) ws.nvox[a] = run_v < max_voxels ? run_v : max_voxels;
 }
 
 __global__ void vox_total_kernel(const VoxWs ws, int n_agents, int* n_voxels_out, int* dirty_count) {
@@ -174,14 +171,14 @@ __global__ void __launch_bounds__(256) vox_chunk_assign_kernel(const __grid_cons
     int pv = pre.x + ev, pc = pre.y + ec;
     int* cell2vox = ws.cell2vox + (long)a * ws.ncell;
     int* vox_off = ws.vox_off + (long)a * (ws.vcap + 1);
-    int* vox_cell = ws.vox_cell + (long)a * ws.vcap;
+    int4* vox_meta = ws.vox_meta + (long)a * ws.vcap;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         if (lead[j]) {
             if (pv < max_voxels) {
                 cell2vox[cell[j]] = pv;
-                vox_cell[pv] = cell[j];
-                vox_off[pv + 1] = pc + cnt[j];             // CSR end of this voxel == begin of the next
+                vox_off[pv] = pc;                           // CSR begin (used by the fill kernel)
+                vox_meta[pv] = make_int4(pc, cnt[j], cell[j], chunk * CHUNK + (int)threadIdx.x * 4 + j);
             } else {
                 cell2vox[cell[j]] = -1;                    // refused: max_voxels reached
             }
@@ -206,10 +203,10 @@ __global__ void vox_fill_kernel(const __grid_constant__ AgentOffsets ao, const V
 // K4 helpers ----------------------------------------------------------------------------------
 // 8 lanes ("group") cooperate on one voxel.  sub = lane & 7.
 // The `max_pts` smallest point indices of the voxel, ascending, into s_sorted[].
-__device__ __forceinline__ void group_sorted_points(const int* __restrict__ lst, int cnt, int max_pts, int* s_sorted,
-                                                    int sub, unsigned gmask) {
+__device__ __forceinline__ void group_sorted_points(const int* __restrict__ lst, int cnt, int first_idx, int max_pts,
+                                                    int* s_sorted, int sub, unsigned gmask) {
     if (cnt == 1) {
-        if (sub == 0) s_sorted[0] = lst[0];
+        if (sub == 0) s_sorted[0] = first_idx;              // the leader itself: no list access
     } else {
         for (int e = sub; e < cnt; e += 8) {
             const int mine = lst[e];
@@ -296,10 +293,11 @@ __global__ void __launch_bounds__(256) vox_emit_kernel(const float4* __restrict_
     int base = 0;
     for (int a = 0; a < ao.n_agents; ++a) {
         const int nv = ws.nvox[a];
-        const int* off = ws.vox_off + (long)a * (ws.vcap + 1);
+        const int4* meta = ws.vox_meta + (long)a * ws.vcap;
         for (int v = gg; v < nv; v += ng) {
-            const int beg = off[v], cnt = off[v + 1] - beg;
-            group_sorted_points(ws.list + ao.off[a] + beg, cnt, max_pts, s_sorted[grp], sub, gmask);
+            const int4 m = meta[v];
+            const int cnt = m.y;
+            group_sorted_points(ws.list + ao.off[a] + m.x, cnt, m.w, max_pts, s_sorted[grp], sub, gmask);
             const int n = cnt < max_pts ? cnt : max_pts;
             const long row = base + v;
             for (int k = sub; k < max_pts; k += 8) {
@@ -308,7 +306,7 @@ __global__ void __launch_bounds__(256) vox_emit_kernel(const float4* __restrict_
                 voxels[row * max_pts + k] = p;
             }
             if (sub == 0) {
-                const int cell = ws.vox_cell[(long)a * ws.vcap + v];
+                const int cell = m.z;
                 const int x = cell % g.gx, y = (cell / g.gx) % g.gy, z = cell / (g.gx * g.gy);
                 coords[row] = make_int4(a, z, y, x);
                 num_points[row] = n;
@@ -333,13 +331,16 @@ __global__ void __launch_bounds__(256, 2) vox_pfn_kernel(const float4* __restric
     int base = 0;
     for (int a = 0; a < ao.n_agents; ++a) {
         const int nv = ws.nvox[a];
-        const int* off = ws.vox_off + (long)a * (ws.vcap + 1);
+        const int4* meta = ws.vox_meta + (long)a * ws.vcap;
         const float4* ap = pts + ao.off[a];
+        int4 m_next = gg < nv ? __ldg(meta + gg) : make_int4(0, 0, 0, 0);
         for (int v = gg; v < nv; v += ng) {
-            const int beg = off[v], cnt = off[v + 1] - beg;
-            group_sorted_points(ws.list + ao.off[a] + beg, cnt, max_pts, s_sorted[grp], sub, gmask);
+            const int4 m = m_next;
+            if (v + ng < nv) m_next = __ldg(meta + v + ng);       // software prefetch of the next voxel's metadata
+            const int cnt = m.y;
+            group_sorted_points(ws.list + ao.off[a] + m.x, cnt, m.w, max_pts, s_sorted[grp], sub, gmask);
             const int n = cnt < max_pts ? cnt : max_pts;
-            const int cell = ws.vox_cell[(long)a * ws.vcap + v];
+            const int cell = m.z;
             const int x = cell % g.gx, y = (cell / g.gx) % g.gy, z = cell / (g.gx * g.gy);
             const int* srt = s_sorted[grp];
             pfn_group_store([&](int k) { return __ldg(ap + srt[k]); }, n, max_pts, a, z, y, x, pp, r, cg, canvas, lo_off,
@@ -412,7 +413,7 @@ static int carve(VoxWs& ws, void* base, size_t bytes, int n_agents, int sum_poin
     size_t o_clear_end = o;
     ws.cell2vox = (int*)take((size_t)n_agents * ncell * 4);
     ws.vox_off = (int*)take((size_t)n_agents * (vcap + 1) * 4);
-    ws.vox_cell = (int*)take((size_t)n_agents * vcap * 4);
+    ws.vox_meta = (int4*)take((size_t)n_agents * vcap * 16);
     ws.cellid = (int*)take((size_t)sp * 4);
     ws.list = (int*)take((size_t)sp * 4);
     ws.nvox = (int*)take(((size_t)n_agents + 1) * 4);
@@ -455,16 +456,16 @@ static int run_front(const float* points, const int32_t* pt_offset, int n_agents
         vox_assign_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float4*)points, ao, g, ws);
         CB_CHECK_LAUNCH();
     }
-    const dim3 cgrid((unsigned)ws.max_chunks, (unsigned)n_agents);
+    const int n_chunks = max_np > 0 ? (max_np + CHUNK - 1) / CHUNK : 1;
+    const dim3 cgrid((unsigned)n_chunks, (unsigned)n_agents);
     vox_chunk_count_kernel<<<cgrid, 256, 0, st>>>(ao, ws);
     CB_CHECK_LAUNCH();
-    vox_chunk_scan_kernel<<<n_agents, 32, 0, st>>>(ws, max_voxels);
+    vox_chunk_scan_kernel<<<n_agents, 32, 0, st>>>(ws, n_chunks, max_voxels);
     CB_CHECK_LAUNCH();
     vox_total_kernel<<<1, 32, 0, st>>>(ws, n_agents, n_voxels_out, dirty_count);
     CB_CHECK_LAUNCH();
     if (total > 0) {
-        const dim3 agrid((unsigned)((max_np + CHUNK - 1) / CHUNK), (unsigned)n_agents);
-        vox_chunk_assign_kernel<<<agrid, 256, 0, st>>>(ao, ws, max_voxels);
+        vox_chunk_assign_kernel<<<cgrid, 256, 0, st>>>(ao, ws, max_voxels);
         CB_CHECK_LAUNCH();
         vox_fill_kernel<<<(total + 255) / 256, 256, 0, st>>>(ao, ws);
         CB_CHECK_LAUNCH();
@@ -530,7 +531,7 @@ extern "C" int cb_points_to_canvas(const float* points, const int32_t* pt_offset
     if (rc) return rc;
     const CanvasGeom cg = make_canvas_geom(canvas_agents, grid[1], grid[0]);
     const PfnParams pp = make_pfn(w, scale, shift, vsize, center_off);
-    vox_pfn_kernel<<<148 * 4, 256, 0, st>>>((const float4*)points, ao, ws, g, max_pts, pp, cg,
+    vox_pfn_kernel<<<148 * 8, 256, 0, st>>>((const float4*)points, ao, ws, g, max_pts, pp, cg,
                                             (__nv_bfloat16*)canvas_ps, (long)lo_off, (long*)dirty_rows);
     CB_CHECK_LAUNCH();
     return CB_OK;

@@ -160,66 +160,77 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
     v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
 }
 
-template <int LPP>
-__global__ void __launch_bounds__(256) warp_att_fuse_v8_kernel(const __nv_bfloat16* __restrict__ feat, long in_lo_off,
+// 32-bit row index of pixel (agent,y,x) inside the PF / PS buffer (rows < 2^31 by construction)
+__device__ __forceinline__ int in_row_i(const FuseGeom& g, int plane_rows, int agent, int y, int x) {
+    if (!g.in_ps) return (agent * g.Hp + y + 1) * g.Wp + x + 1;
+    const int ph = (y & 1) * 2 + (x & 1);
+    return ph * plane_rows + (agent * g.Hp + (y >> 1) + 1) * g.Wp + (x >> 1) + 1;
+}
+
+template <int LPP, int MAXN>
+__global__ void __launch_bounds__(256, (MAXN <= 5 ? 3 : 2)) warp_att_fuse_v8_kernel(const __nv_bfloat16* __restrict__ feat, long in_lo_off,
                                                                const double* __restrict__ affine,
                                                                const int* __restrict__ agent_off, int n_scenes, int L,
                                                                const FuseGeom g, int method,
                                                                __nv_bfloat16* __restrict__ out, long out_lo_off) {
     constexpr int PPW = 32 / LPP;                          // pixels per warp
     const int lane = threadIdx.x & 31, sub = lane % LPP, pin = lane / LPP;
-    const long gw = (long)blockIdx.x * 8 + (threadIdx.x >> 5), nw = (long)gridDim.x * 8;
-    const long total = (long)n_scenes * g.H * g.W;
+    const int gw = blockIdx.x * 8 + (threadIdx.x >> 5), nw = gridDim.x * 8;
+    const int HW = g.H * g.W;
+    const int total = n_scenes * HW;
+    const int plane_rows = (int)g.plane_rows;
     const float inv_sqrt_c = (float)(1.0 / sqrt((double)g.C));
-    for (long pix0 = gw * PPW; pix0 < total; pix0 += nw * PPW) {
-        const long pix = pix0 + pin;
+    const uint4* feat4 = reinterpret_cast<const uint4*>(feat);
+    const uint4* featl4 = reinterpret_cast<const uint4*>(feat + in_lo_off);
+    const bool has_lo = in_lo_off != 0;
+    for (int pix0 = gw * PPW; pix0 < total; pix0 += nw * PPW) {
+        const int pix = pix0 + pin;
         const bool live = pix < total;
-        const long pc = live ? pix : total - 1;             // clamp: idle lanes mirror a valid pixel, stores masked
-        const int b = (int)(pc / (g.H * g.W));
-        const int rem = (int)(pc - (long)b * g.H * g.W);
+        const int pc = live ? pix : total - 1;              // idle lanes mirror a valid pixel, stores masked
+        const int b = pc / HW;
+        const int rem = pc - b * HW;
         const int h = rem / g.W, w = rem - h * g.W;
         const int a0 = agent_off[b];
         int n = agent_off[b + 1] - a0;
-        n = n < FUSE_MAX_AGENTS ? n : FUSE_MAX_AGENTS;
-        const double xs = (2.0 * w + 1.0) / g.W - 1.0;
+        n = n < MAXN ? n : MAXN;
+        const double xs = (2.0 * w + 1.0) / g.W - 1.0;      // affine_grid base grid, align_corners=False
         const double ys = (2.0 * h + 1.0) / g.H - 1.0;
-        float x[FUSE_MAX_AGENTS][8];
+        float x[MAXN][8];
 #pragma unroll
-        for (int j = 0; j < FUSE_MAX_AGENTS; ++j) {
+        for (int j = 0; j < MAXN; ++j) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) x[j][c] = 0.f;
             if (j < n) {
-                const double* A = affine + ((long)b * L + j) * 6;
-                const float gx = (float)(A[0] * xs + A[1] * ys + A[2]);
+                const double* A = affine + (b * L + j) * 6;
+                const float gx = (float)(A[0] * xs + A[1] * ys + A[2]);   // grid in f64, cast to f32 (reference `.to(src)`)
                 const float gy = (float)(A[3] * xs + A[4] * ys + A[5]);
-                const float ix = ((gx + 1.f) * g.W - 1.f) * 0.5f;
+                const float ix = ((gx + 1.f) * g.W - 1.f) * 0.5f;         // grid_sample unnormalise
                 const float iy = ((gy + 1.f) * g.H - 1.f) * 0.5f;
                 const float fx0 = floorf(ix), fy0 = floorf(iy);
-                const float wx1 = ix - fx0, wy1 = iy - fy0, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+                const float wx1 = ix - fx0, wy1 = iy - fy0;
+                // clamp before the int conversion so far-away (or non-finite) coordinates stay out of range
                 const int x0 = (int)fminf(fmaxf(fx0, -2.f), (float)g.W + 1.f);
                 const int y0 = (int)fminf(fmaxf(fy0, -2.f), (float)g.H + 1.f);
-                uint4 u[4], ul[4];
-                float wt[4];
+                // branch-free taps: out-of-range taps get weight 0 and a clamped (valid) address
+                const float wxa = (x0 >= 0 && x0 < g.W) ? 1.f - wx1 : 0.f, wxb = (x0 + 1 >= 0 && x0 + 1 < g.W) ? wx1 : 0.f;
+                const float wya = (y0 >= 0 && y0 < g.H) ? 1.f - wy1 : 0.f, wyb = (y0 + 1 >= 0 && y0 + 1 < g.H) ? wy1 : 0.f;
+                const int xa = min(max(x0, 0), g.W - 1), xb = min(max(x0 + 1, 0), g.W - 1);
+                const int ya = min(max(y0, 0), g.H - 1), yb = min(max(y0 + 1, 0), g.H - 1);
+                const int ag = a0 + j;
+                const int r00 = in_row_i(g, plane_rows, ag, ya, xa), r01 = in_row_i(g, plane_rows, ag, ya, xb);
+                const int r10 = in_row_i(g, plane_rows, ag, yb, xa), r11 = in_row_i(g, plane_rows, ag, yb, xb);
+                const float wt[4] = {wya * wxa, wya * wxb, wyb * wxa, wyb * wxb};
+                const int rr[4] = {r00, r01, r10, r11};
+                uint4 u[4];
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {                 // issue all tap loads first
-                    const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
-                    const bool ok = xx >= 0 && xx < g.W && yy >= 0 && yy < g.H;
-                    wt[t] = ok ? ((t & 1) ? wx1 : wx0) * ((t >> 1) ? wy1 : wy0) : 0.f;
-                    u[t] = make_uint4(0u, 0u, 0u, 0u);
-                    ul[t] = make_uint4(0u, 0u, 0u, 0u);
-                    if (ok) {
-                        const long row = in_row(g, a0 + j, yy, xx);
-                        u[t] = __ldg(reinterpret_cast<const uint4*>(feat + row * g.C) + sub);
-                        if (in_lo_off != 0) ul[t] = __ldg(reinterpret_cast<const uint4*>(feat + in_lo_off + row * g.C) + sub);
-                    }
-                }
+                for (int t = 0; t < 4; ++t) u[t] = __ldg(feat4 + (size_t)rr[t] * LPP + sub);   // row pitch C = 8*LPP
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     float v[8];
                     unpack8(u[t], v);
-                    if (in_lo_off != 0) {
+                    if (has_lo) {
                         float vl[8];
-                        unpack8(ul[t], vl);
+                        unpack8(__ldg(featl4 + (size_t)rr[t] * LPP + sub), vl);
 #pragma unroll
                         for (int c = 0; c < 8; ++c) v[c] += vl[c];
                     }
@@ -233,35 +244,35 @@ __global__ void __launch_bounds__(256) warp_att_fuse_v8_kernel(const __nv_bfloat
 #pragma unroll
             for (int c = 0; c < 8; ++c) o[c] = x[0][c];
 #pragma unroll
-            for (int j = 1; j < FUSE_MAX_AGENTS; ++j)
+            for (int j = 1; j < MAXN; ++j)
                 if (j < n) {
 #pragma unroll
                     for (int c = 0; c < 8; ++c) o[c] = fmaxf(o[c], x[j][c]);
                 }
         } else {
-            float score[FUSE_MAX_AGENTS];
+            float score[MAXN];
             float smax = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < FUSE_MAX_AGENTS; ++j) {
+            for (int j = 0; j < MAXN; ++j) {
                 if (j < n) {
                     float d = 0.f;
 #pragma unroll
                     for (int c = 0; c < 8; ++c) d = fmaf(x[0][c], x[j][c], d);
 #pragma unroll
-                    for (int s = LPP / 2; s > 0; s >>= 1) d += __shfl_xor_sync(0xffffffffu, d, s);
+                    for (int sft = LPP / 2; sft > 0; sft >>= 1) d += __shfl_xor_sync(0xffffffffu, d, sft);
                     score[j] = d * inv_sqrt_c;
                     smax = fmaxf(smax, score[j]);
                 }
             }
             float den = 0.f;
 #pragma unroll
-            for (int j = 0; j < FUSE_MAX_AGENTS; ++j)
+            for (int j = 0; j < MAXN; ++j)
                 if (j < n) { score[j] = expf(score[j] - smax); den += score[j]; }
             const float inv = 1.f / den;
 #pragma unroll
             for (int c = 0; c < 8; ++c) o[c] = 0.f;
 #pragma unroll
-            for (int j = 0; j < FUSE_MAX_AGENTS; ++j)
+            for (int j = 0; j < MAXN; ++j)
                 if (j < n) {
                     const float wj = score[j] * inv;
 #pragma unroll
@@ -269,18 +280,18 @@ __global__ void __launch_bounds__(256) warp_att_fuse_v8_kernel(const __nv_bfloat
                 }
         }
         if (live) {
-            const long orow = ((long)b * (g.H + 2) + h + 1) * (g.W + 2) + w + 1;   // PF output
+            const int orow = (b * (g.H + 2) + h + 1) * (g.W + 2) + w + 1;   // PF output
             uint4 hi;
             hi.x = pack_bf16(o[0], o[1]); hi.y = pack_bf16(o[2], o[3]);
             hi.z = pack_bf16(o[4], o[5]); hi.w = pack_bf16(o[6], o[7]);
-            reinterpret_cast<uint4*>(out + orow * g.C)[sub] = hi;
+            reinterpret_cast<uint4*>(out)[(size_t)orow * LPP + sub] = hi;
             if (out_lo_off != 0) {
                 uint4 lo;
                 lo.x = pack_bf16(o[0] - bf16_lo(hi.x), o[1] - bf16_hi(hi.x));
                 lo.y = pack_bf16(o[2] - bf16_lo(hi.y), o[3] - bf16_hi(hi.y));
                 lo.z = pack_bf16(o[4] - bf16_lo(hi.z), o[5] - bf16_hi(hi.z));
                 lo.w = pack_bf16(o[6] - bf16_lo(hi.w), o[7] - bf16_hi(hi.w));
-                reinterpret_cast<uint4*>(out + out_lo_off + orow * g.C)[sub] = lo;
+                reinterpret_cast<uint4*>(out + out_lo_off)[(size_t)orow * LPP + sub] = lo;
             }
         }
     }
@@ -320,12 +331,17 @@ extern "C" int cb_warp_att_fuse(const void* feat, int in_ps, int64_t in_lo_off, 
     if (C == 64 || C == 128 || C == 256) {
         const int ppw = 256 / C;                                    // pixels per warp
         long nb = (total + 8L * ppw - 1) / (8L * ppw);
-        if (nb > 148 * 16) nb = 148 * 16;
+        if (nb > 148 * 24) nb = 148 * 24;
+        if ((long)sum_agents * g.Hp * g.Wp * (in_ps ? 4 : 1) >= (1L << 31) || total >= (1L << 31)) return CB_ERR_ARG;
+#define CB_FUSE_LAUNCH(LPP_, MAXN_) warp_att_fuse_v8_kernel<LPP_, MAXN_><<<(unsigned)nb, 256, 0, st>>>( \
+            f, in_lo_off, affine, agent_off, n_scenes, max_cav, g, method, o, out_lo_off)
+        const bool small = max_cav <= 5;
         switch (C) {
-            case 64: warp_att_fuse_v8_kernel<8><<<(unsigned)nb, 256, 0, st>>>(f, in_lo_off, affine, agent_off, n_scenes, max_cav, g, method, o, out_lo_off); break;
-            case 128: warp_att_fuse_v8_kernel<16><<<(unsigned)nb, 256, 0, st>>>(f, in_lo_off, affine, agent_off, n_scenes, max_cav, g, method, o, out_lo_off); break;
-            default: warp_att_fuse_v8_kernel<32><<<(unsigned)nb, 256, 0, st>>>(f, in_lo_off, affine, agent_off, n_scenes, max_cav, g, method, o, out_lo_off); break;
+            case 64: if (small) CB_FUSE_LAUNCH(8, 5); else CB_FUSE_LAUNCH(8, FUSE_MAX_AGENTS); break;
+            case 128: if (small) CB_FUSE_LAUNCH(16, 5); else CB_FUSE_LAUNCH(16, FUSE_MAX_AGENTS); break;
+            default: if (small) CB_FUSE_LAUNCH(32, 5); else CB_FUSE_LAUNCH(32, FUSE_MAX_AGENTS); break;
         }
+#undef CB_FUSE_LAUNCH
         CB_CHECK_LAUNCH();
         return CB_OK;
     }
