@@ -160,15 +160,12 @@ def run_reference(opt):
 def run_ours(opt):
     import torch
     import torch.distributed as dist
-    from coalign_b200 import synth
+    from coalign_b200 import dist_utils, synth
     from coalign_b200.engine import CoAlignEngine
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, local, world = dist_utils.world_info()
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dist_utils.init("nccl", device_id=torch.device("cuda", local))
     B = opt.scenes_per_step
     NB = 8                                                   # rotating input batches (> L2 together with activations)
     args, batches = make_batches(NB, B, seed0=1000 * rank)
@@ -218,9 +215,7 @@ def run_ours(opt):
             sampler.mark_end()
         ms = e0.elapsed_time(e1)
         if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            ms = dist_utils.max_over_ranks(ms, device="cuda")       # device time, max over ranks
             dist.barrier()
         return ms
 

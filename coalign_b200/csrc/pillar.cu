@@ -27,11 +27,13 @@ struct VoxWs {            // workspace carve-up (device pointers)
     int* cursor;          // [n_agents][vcap]
     int* cell2vox;        // [n_agents][ncell]
     int* vox_off;         // [n_agents][vcap+1]
-    int4* vox_meta;       // [n_agents][vcap]   {CSR begin, point count, cell, first point index}
+    int4* vox_meta;       // [n_agents][vcap]   {CSR begin, point count, x | y<<12 | z<<24, first point index}
     int* cellid;          // [sum_P]
     int* list;            // [sum_P]
     int* nvox;            // [n_agents+1]
     int2* chunk_tot;      // [n_agents][max_chunks]  (leaders, points) per chunk, then exclusive prefixes
+    int* perm;            // [n_agents][vcap]   voxel ids, single-point voxels first, multi-point voxels from the back
+    int* bucket;          // [n_agents][2]      atomic cursors of the two buckets
     int ncell, vcap, max_chunks;
 };
 
@@ -43,8 +45,8 @@ struct CanvasGeom {
     long plane_rows;      // canvas_agents*Hq*Wq
 };
 __device__ __forceinline__ long canvas_row(const CanvasGeom& c, int a, int y, int x) {
-    const int ph = (y & 1) * 2 + (x & 1);
-    return (long)ph * c.plane_rows + ((long)a * c.Hq + (y >> 1) + 1) * c.Wq + (x >> 1) + 1;
+    const int ph = (y & 1) * 2 + (x & 1);                                      // rows < 2^31 (checked on the host)
+    return (long)(ph * (int)c.plane_rows + (a * c.Hq + (y >> 1) + 1) * c.Wq + (x >> 1) + 1);
 }
 
 __device__ __forceinline__ int find_agent(const AgentOffsets& ao, int i) {
@@ -161,7 +163,7 @@ __global__ void vox_total_kernel(const VoxWs ws, int n_agents, int* n_voxels_out
 }
 
 __global__ void __launch_bounds__(256) vox_chunk_assign_kernel(const __grid_constant__ AgentOffsets ao, const VoxWs ws,
-                                                               int max_voxels) {
+                                                               const Geom g, int max_voxels) {
     const int a = blockIdx.y, chunk = blockIdx.x;
     int cell[4], lead[4], cnt[4];
     chunk_flags(ao, ws, a, chunk, cell, lead, cnt);
@@ -178,7 +180,13 @@ __global__ void __launch_bounds__(256) vox_chunk_assign_kernel(const __grid_cons
             if (pv < max_voxels) {
                 cell2vox[cell[j]] = pv;
                 vox_off[pv] = pc;                           // CSR begin (used by the fill kernel)
-                vox_meta[pv] = make_int4(pc, cnt[j], cell[j], chunk * CHUNK + (int)threadIdx.x * 4 + j);
+                const int cx = cell[j] % g.gx, cyz = cell[j] / g.gx;
+                const int cy = cyz % g.gy, cz = cyz / g.gy;
+                vox_meta[pv] = make_int4(pc, cnt[j], cx | (cy << 12) | (cz << 24), chunk * CHUNK + (int)threadIdx.x * 4 + j);
+                // processing order of the PFN kernel: uniform work per warp (1-point pillars first)
+                const int nv = ws.nvox[a];
+                if (cnt[j] == 1) ws.perm[(long)a * ws.vcap + atomicAdd(ws.bucket + 2 * a, 1)] = pv;
+                else ws.perm[(long)a * ws.vcap + nv - 1 - atomicAdd(ws.bucket + 2 * a + 1, 1)] = pv;
             } else {
                 cell2vox[cell[j]] = -1;                    // refused: max_voxels reached
             }
@@ -241,7 +249,9 @@ __device__ __forceinline__ void pfn_group_store(PointFn pt, int n, int max_pts, 
                                                 const PfnParams& pp, const PfnRegs& r, const CanvasGeom& cg,
                                                 __nv_bfloat16* canvas, long lo_off, int sub, long* dirty_slot) {
     float sx = 0.f, sy = 0.f, sz = 0.f;
-    for (int k = 0; k < n; ++k) { const float4 p = pt(k); sx += p.x; sy += p.y; sz += p.z; }   // slot order
+    float4 p0 = pt(0);
+    if (n == 1) { sx = p0.x; sy = p0.y; sz = p0.z; }
+    else for (int k = 0; k < n; ++k) { const float4 p = pt(k); sx += p.x; sy += p.y; sz += p.z; }   // slot order
     const float fn = (float)n;
     const float mx = __fdiv_rn(sx, fn), my = __fdiv_rn(sy, fn), mz = __fdiv_rn(sz, fn);
     // pillar centre = coord*voxel + (voxel/2 + range_min)  (pillar_vfe.py:87-89,124-132), fp32, unfused
@@ -252,7 +262,7 @@ __device__ __forceinline__ void pfn_group_store(PointFn pt, int n, int max_pts, 
 #pragma unroll
     for (int c = 0; c < 8; ++c) best[c] = (n < max_pts) ? fmaxf(r.sh[c], 0.f) : 0.f;   // zero-padded slots join the max
     for (int k = 0; k < n; ++k) {
-        const float4 p = pt(k);
+        const float4 p = k == 0 ? p0 : pt(k);
         float f[10];
         f[0] = p.x; f[1] = p.y; f[2] = p.z; f[3] = p.w;
         f[4] = p.x - mx; f[5] = p.y - my; f[6] = p.z - mz;
@@ -306,8 +316,7 @@ __global__ void __launch_bounds__(256) vox_emit_kernel(const float4* __restrict_
                 voxels[row * max_pts + k] = p;
             }
             if (sub == 0) {
-                const int cell = m.z;
-                const int x = cell % g.gx, y = (cell / g.gx) % g.gy, z = cell / (g.gx * g.gy);
+                const int x = m.z & 0xFFF, y = (m.z >> 12) & 0xFFF, z = (m.z >> 24) & 0xFF;
                 coords[row] = make_int4(a, z, y, x);
                 num_points[row] = n;
             }
@@ -332,20 +341,26 @@ __global__ void __launch_bounds__(256, 2) vox_pfn_kernel(const float4* __restric
     for (int a = 0; a < ao.n_agents; ++a) {
         const int nv = ws.nvox[a];
         const int4* meta = ws.vox_meta + (long)a * ws.vcap;
+        const int* perm = ws.perm + (long)a * ws.vcap;
         const float4* ap = pts + ao.off[a];
-        int4 m_next = gg < nv ? __ldg(meta + gg) : make_int4(0, 0, 0, 0);
-        for (int v = gg; v < nv; v += ng) {
-            const int4 m = m_next;
-            if (v + ng < nv) m_next = __ldg(meta + v + ng);       // software prefetch of the next voxel's metadata
+        for (int i = gg; i < nv; i += ng) {
+            const int v = perm[i];
+            const int4 m = __ldg(meta + v);
             const int cnt = m.y;
-            group_sorted_points(ws.list + ao.off[a] + m.x, cnt, m.w, max_pts, s_sorted[grp], sub, gmask);
             const int n = cnt < max_pts ? cnt : max_pts;
-            const int cell = m.z;
-            const int x = cell % g.gx, y = (cell / g.gx) % g.gy, z = cell / (g.gx * g.gy);
-            const int* srt = s_sorted[grp];
-            pfn_group_store([&](int k) { return __ldg(ap + srt[k]); }, n, max_pts, a, z, y, x, pp, r, cg, canvas, lo_off,
-                            sub, dirty_rows ? dirty_rows + base + v : nullptr);
-            __syncwarp(gmask);
+            const int x = m.z & 0xFFF, y = (m.z >> 12) & 0xFFF, z = (m.z >> 24) & 0xFF;
+            long* dslot = dirty_rows ? dirty_rows + base + v : nullptr;
+            if (cnt == 1) {                                        // the leader point itself, no list / ranking
+                const int idx = m.w;
+                pfn_group_store([&](int) { return __ldg(ap + idx); }, 1, max_pts, a, z, y, x, pp, r, cg, canvas, lo_off,
+                                sub, dslot);
+            } else {
+                group_sorted_points(ws.list + ao.off[a] + m.x, cnt, m.w, max_pts, s_sorted[grp], sub, gmask);
+                const int* srt = s_sorted[grp];
+                pfn_group_store([&](int k) { return __ldg(ap + srt[k]); }, n, max_pts, a, z, y, x, pp, r, cg, canvas,
+                                lo_off, sub, dslot);
+                __syncwarp(gmask);
+            }
         }
         base += nv;
     }
@@ -410,6 +425,7 @@ static int carve(VoxWs& ws, void* base, size_t bytes, int n_agents, int sum_poin
     size_t o_first_end = o;
     ws.count = (int*)take((size_t)n_agents * ncell * 4);
     ws.cursor = (int*)take((size_t)n_agents * vcap * 4);
+    ws.bucket = (int*)take((size_t)n_agents * 2 * 4);
     size_t o_clear_end = o;
     ws.cell2vox = (int*)take((size_t)n_agents * ncell * 4);
     ws.vox_off = (int*)take((size_t)n_agents * (vcap + 1) * 4);
@@ -418,6 +434,7 @@ static int carve(VoxWs& ws, void* base, size_t bytes, int n_agents, int sum_poin
     ws.list = (int*)take((size_t)sp * 4);
     ws.nvox = (int*)take(((size_t)n_agents + 1) * 4);
     ws.chunk_tot = (int2*)take((size_t)n_agents * max_chunks * 8);
+    ws.perm = (int*)take((size_t)n_agents * vcap * 4);
     ws.ncell = (int)ncell;
     ws.vcap = vcap;
     ws.max_chunks = max_chunks;
@@ -434,6 +451,7 @@ static int run_front(const float* points, const int32_t* pt_offset, int n_agents
                      int* dirty_count) {
     if (n_agents < 1 || n_agents > CB_MAX_AGENTS || max_pts < 1 || max_pts > 32 || max_voxels < 1) return CB_ERR_ARG;
     if (!workspace || ((uintptr_t)points & 15)) return CB_ERR_ARG;
+    if (grid[0] > 4096 || grid[1] > 4096 || grid[2] > 128) return CB_ERR_ARG;        // packed voxel coordinates
     ao.n_agents = n_agents;
     for (int i = 0; i <= n_agents; ++i) ao.off[i] = pt_offset[i];
     if (ao.off[0] != 0) return CB_ERR_ARG;
@@ -465,7 +483,7 @@ static int run_front(const float* points, const int32_t* pt_offset, int n_agents
     vox_total_kernel<<<1, 32, 0, st>>>(ws, n_agents, n_voxels_out, dirty_count);
     CB_CHECK_LAUNCH();
     if (total > 0) {
-        vox_chunk_assign_kernel<<<cgrid, 256, 0, st>>>(ao, ws, max_voxels);
+        vox_chunk_assign_kernel<<<cgrid, 256, 0, st>>>(ao, ws, g, max_voxels);
         CB_CHECK_LAUNCH();
         vox_fill_kernel<<<(total + 255) / 256, 256, 0, st>>>(ao, ws);
         CB_CHECK_LAUNCH();
