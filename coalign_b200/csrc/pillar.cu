@@ -10,7 +10,8 @@
 //   K2b  per agent: exclusive scan of the chunk totals
 //   K2c  per chunk: ordered in-block scan + chunk prefix -> voxel ids, CSR offsets
 //   K3   CSR fill (arbitrary order inside a cell)
-//   K4   8 lanes per voxel: rank the cell's point indices, keep the `max_pts` smallest in order.
+//   K3b  thread per point: rank inside its cell (points with a smaller index), regroup into voxel-slot order
+//   K4   8 lanes per voxel: emit reference-format tensors, or PFN + canvas store.
 #include <limits.h>
 #include "common.cuh"
 #include "../../include/coalign_b200.h"
@@ -32,8 +33,7 @@ struct VoxWs {            // workspace carve-up (device pointers)
     int* list;            // [sum_P]
     int* nvox;            // [n_agents+1]
     int2* chunk_tot;      // [n_agents][max_chunks]  (leaders, points) per chunk, then exclusive prefixes
-    int* perm;            // [n_agents][vcap]   voxel ids, single-point voxels first, multi-point voxels from the back
-    int* bucket;          // [n_agents][2]      atomic cursors of the two buckets
+    float4* vp;           // [sum_P]  points regrouped per voxel in slot order (first max_pts of each voxel)
     int ncell, vcap, max_chunks;
 };
 
@@ -183,10 +183,6 @@ __global__ void __launch_bounds__(256) vox_chunk_assign_kernel(const __grid_cons
                 const int cx = cell[j] % g.gx, cyz = cell[j] / g.gx;
                 const int cy = cyz % g.gy, cz = cyz / g.gy;
                 vox_meta[pv] = make_int4(pc, cnt[j], cx | (cy << 12) | (cz << 24), chunk * CHUNK + (int)threadIdx.x * 4 + j);
-                // processing order of the PFN kernel: uniform work per warp (1-point pillars first)
-                const int nv = ws.nvox[a];
-                if (cnt[j] == 1) ws.perm[(long)a * ws.vcap + atomicAdd(ws.bucket + 2 * a, 1)] = pv;
-                else ws.perm[(long)a * ws.vcap + nv - 1 - atomicAdd(ws.bucket + 2 * a + 1, 1)] = pv;
             } else {
                 cell2vox[cell[j]] = -1;                    // refused: max_voxels reached
             }
@@ -208,48 +204,57 @@ __global__ void vox_fill_kernel(const __grid_constant__ AgentOffsets ao, const V
     ws.list[ao.off[a] + ws.vox_off[(long)a * (ws.vcap + 1) + v] + pos] = i - ao.off[a];
 }
 
-// K4 helpers ----------------------------------------------------------------------------------
-// 8 lanes ("group") cooperate on one voxel.  sub = lane & 7.
-// The `max_pts` smallest point indices of the voxel, ascending, into s_sorted[].
-__device__ __forceinline__ void group_sorted_points(const int* __restrict__ lst, int cnt, int first_idx, int max_pts,
-                                                    int* s_sorted, int sub, unsigned gmask) {
-    if (cnt == 1) {
-        if (sub == 0) s_sorted[0] = first_idx;              // the leader itself: no list access
-    } else {
-        for (int e = sub; e < cnt; e += 8) {
-            const int mine = lst[e];
-            int rank = 0;
-            for (int m = 0; m < cnt; ++m) rank += (lst[m] < mine) ? 1 : 0;
-            if (rank < max_pts) s_sorted[rank] = mine;
-        }
+// K3b: thread per point: rank of the point inside its voxel (= number of same-cell points with a smaller index) and
+// regrouping into voxel-slot order.  Massively parallel, two dependent loads for 1-point voxels.
+__global__ void vox_rank_gather_kernel(const float4* __restrict__ pts, const __grid_constant__ AgentOffsets ao,
+                                       const VoxWs ws, int max_pts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ao.off[ao.n_agents]) return;
+    const int cell = ws.cellid[i];
+    if (cell < 0) return;
+    const int a = find_agent(ao, i);
+    const int v = ws.cell2vox[(long)a * ws.ncell + cell];
+    if (v < 0) return;
+    const int4 m = ws.vox_meta[(long)a * ws.vcap + v];           // {begin, count, xyz, first}
+    const int li = i - ao.off[a];
+    int rank = 0;
+    if (m.y > 1) {
+        const int* lst = ws.list + ao.off[a] + m.x;
+        for (int k = 0; k < m.y; ++k) rank += (lst[k] < li) ? 1 : 0;
     }
-    __syncwarp(gmask);
+    if (rank < max_pts) ws.vp[ao.off[a] + m.x + rank] = __ldg(pts + i);
 }
 
+// K4 helpers ----------------------------------------------------------------------------------
+// 8 lanes ("group") cooperate on one voxel.  sub = lane & 7.
 struct PfnParams {
     const float* w; const float* scale; const float* shift;     // [64][10], [64], [64]
     float vx, vy, vz, offx, offy, offz;                         // voxel size, voxel/2 + range_min
 };
 
-struct PfnRegs { float w[8][10], sc[8], sh[8]; };               // channels 8*sub .. 8*sub+7
-__device__ __forceinline__ void load_pfn(PfnRegs& r, const PfnParams& pp, int sub) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-#pragma unroll
-        for (int j = 0; j < 10; ++j) r.w[c][j] = __ldg(pp.w + (8 * sub + c) * 10 + j);
-        r.sc[c] = __ldg(pp.scale + 8 * sub + c);
-        r.sh[c] = __ldg(pp.shift + 8 * sub + c);
+// PFN parameters in shared memory, laid out for the 8-lanes-per-pillar mapping: lane `sub` owns channels
+// 8*sub .. 8*sub+7; s_w4[(j*8 + sub)*2 + h] = {W[8sub+4h+0..3][j]} so each (j) is two conflict-free LDS.128.
+struct PfnSmem { float4 w4[10 * 8 * 2]; float4 sc4[8 * 2]; float4 sh4[8 * 2]; };
+__device__ __forceinline__ void load_pfn_smem(PfnSmem& sm, const PfnParams& pp) {
+    float* w = reinterpret_cast<float*>(sm.w4);
+    float* sc = reinterpret_cast<float*>(sm.sc4);
+    float* sh = reinterpret_cast<float*>(sm.sh4);
+    for (int i = threadIdx.x; i < 640; i += blockDim.x) {
+        const int c = i / 10, j = i - c * 10;                 // pp.w is [64][10]
+        w[((j * 8 + (c >> 3)) * 2 + ((c >> 2) & 1)) * 4 + (c & 3)] = __ldg(pp.w + i);
     }
+    for (int c = threadIdx.x; c < 64; c += blockDim.x) { sc[c] = __ldg(pp.scale + c); sh[c] = __ldg(pp.shift + c); }
+    __syncthreads();
 }
 
 // PFN of one pillar by one 8-lane group: PointFn(k) returns slot k (k < n, n >= 1).  Every lane of the group walks
 // all n points (same addresses -> broadcast loads) and produces 8 of the 64 channels; one 16-byte store per lane.
 template <class PointFn>
 __device__ __forceinline__ void pfn_group_store(PointFn pt, int n, int max_pts, int a, int cz, int cy, int cx,
-                                                const PfnParams& pp, const PfnRegs& r, const CanvasGeom& cg,
+                                                const PfnParams& pp, const PfnSmem& sm, const CanvasGeom& cg,
                                                 __nv_bfloat16* canvas, long lo_off, int sub, long* dirty_slot) {
     float sx = 0.f, sy = 0.f, sz = 0.f;
-    float4 p0 = pt(0);
+    const float4 p0 = pt(0);
     if (n == 1) { sx = p0.x; sy = p0.y; sz = p0.z; }
     else for (int k = 0; k < n; ++k) { const float4 p = pt(k); sx += p.x; sy += p.y; sz += p.z; }   // slot order
     const float fn = (float)n;
@@ -258,22 +263,31 @@ __device__ __forceinline__ void pfn_group_store(PointFn pt, int n, int max_pts, 
     const float ctrx = __fadd_rn(__fmul_rn((float)cx, pp.vx), pp.offx);
     const float ctry = __fadd_rn(__fmul_rn((float)cy, pp.vy), pp.offy);
     const float ctrz = __fadd_rn(__fmul_rn((float)cz, pp.vz), pp.offz);
+    const float4 sc0 = sm.sc4[sub * 2], sc1 = sm.sc4[sub * 2 + 1], sh0 = sm.sh4[sub * 2], sh1 = sm.sh4[sub * 2 + 1];
+    const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+    const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
     float best[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) best[c] = (n < max_pts) ? fmaxf(r.sh[c], 0.f) : 0.f;   // zero-padded slots join the max
+    for (int c = 0; c < 8; ++c) best[c] = (n < max_pts) ? fmaxf(sh[c], 0.f) : 0.f;   // zero-padded slots join the max
     for (int k = 0; k < n; ++k) {
         const float4 p = k == 0 ? p0 : pt(k);
         float f[10];
         f[0] = p.x; f[1] = p.y; f[2] = p.z; f[3] = p.w;
         f[4] = p.x - mx; f[5] = p.y - my; f[6] = p.z - mz;
         f[7] = p.x - ctrx; f[8] = p.y - ctry; f[9] = p.z - ctrz;
+        float y[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float y = 0.f;
+        for (int c = 0; c < 8; ++c) y[c] = 0.f;
 #pragma unroll
-            for (int j = 0; j < 10; ++j) y = fmaf(r.w[c][j], f[j], y);
-            best[c] = fmaxf(best[c], fmaf(y, r.sc[c], r.sh[c]));       // ReLU folded into the max (best >= 0)
+        for (int j = 0; j < 10; ++j) {                        // same accumulation order (j = 0..9) for every channel
+            const float4 wa = sm.w4[(j * 8 + sub) * 2], wb = sm.w4[(j * 8 + sub) * 2 + 1];
+            y[0] = fmaf(wa.x, f[j], y[0]); y[1] = fmaf(wa.y, f[j], y[1]);
+            y[2] = fmaf(wa.z, f[j], y[2]); y[3] = fmaf(wa.w, f[j], y[3]);
+            y[4] = fmaf(wb.x, f[j], y[4]); y[5] = fmaf(wb.y, f[j], y[5]);
+            y[6] = fmaf(wb.z, f[j], y[6]); y[7] = fmaf(wb.w, f[j], y[7]);
         }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) best[c] = fmaxf(best[c], fmaf(y[c], sc[c], sh[c]));   // ReLU folded into the max
     }
     const long row = canvas_row(cg, a, cy, cx);
     uint4 hi;
@@ -292,92 +306,67 @@ __device__ __forceinline__ void pfn_group_store(PointFn pt, int n, int max_pts, 
 }
 
 // K4a: emit reference-format voxel tensors --------------------------------------------------------
-__global__ void __launch_bounds__(256) vox_emit_kernel(const float4* __restrict__ pts,
-                                                       const __grid_constant__ AgentOffsets ao, const VoxWs ws,
-                                                       const Geom g, int max_pts, float4* __restrict__ voxels,
+__global__ void __launch_bounds__(256) vox_emit_kernel(const __grid_constant__ AgentOffsets ao, const VoxWs ws,
+                                                       int max_pts, float4* __restrict__ voxels,
                                                        int4* __restrict__ coords, int* __restrict__ num_points) {
-    __shared__ int s_sorted[32][32];
     const int lane = threadIdx.x & 31, sub = lane & 7, grp = threadIdx.x >> 3;
-    const unsigned gmask = 0xFFu << (lane & 24);
     const int gg = blockIdx.x * 32 + grp, ng = gridDim.x * 32;
     int base = 0;
     for (int a = 0; a < ao.n_agents; ++a) {
         const int nv = ws.nvox[a];
         const int4* meta = ws.vox_meta + (long)a * ws.vcap;
+        const float4* vp = ws.vp + ao.off[a];
         for (int v = gg; v < nv; v += ng) {
             const int4 m = meta[v];
-            const int cnt = m.y;
-            group_sorted_points(ws.list + ao.off[a] + m.x, cnt, m.w, max_pts, s_sorted[grp], sub, gmask);
-            const int n = cnt < max_pts ? cnt : max_pts;
+            const int n = m.y < max_pts ? m.y : max_pts;
             const long row = base + v;
-            for (int k = sub; k < max_pts; k += 8) {
-                float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (k < n) p = __ldg(pts + ao.off[a] + s_sorted[grp][k]);
-                voxels[row * max_pts + k] = p;
-            }
+            for (int k = sub; k < max_pts; k += 8)
+                voxels[row * max_pts + k] = k < n ? vp[m.x + k] : make_float4(0.f, 0.f, 0.f, 0.f);
             if (sub == 0) {
-                const int x = m.z & 0xFFF, y = (m.z >> 12) & 0xFFF, z = (m.z >> 24) & 0xFF;
-                coords[row] = make_int4(a, z, y, x);
+                coords[row] = make_int4(a, (m.z >> 24) & 0xFF, (m.z >> 12) & 0xFFF, m.z & 0xFFF);
                 num_points[row] = n;
             }
-            __syncwarp(gmask);
         }
         base += nv;
     }
 }
 
-// K4b: fused PFN + scatter straight from the CSR lists -------------------------------------------
-__global__ void __launch_bounds__(256, 2) vox_pfn_kernel(const float4* __restrict__ pts,
-                                                      const __grid_constant__ AgentOffsets ao, const VoxWs ws,
-                                                      const Geom g, int max_pts, const PfnParams pp, const CanvasGeom cg,
-                                                      __nv_bfloat16* canvas, long lo_off, long* dirty_rows) {
-    __shared__ int s_sorted[32][32];
+// K4b: fused PFN + scatter from the regrouped points ----------------------------------------------
+__global__ void __launch_bounds__(256, 3) vox_pfn_kernel(const __grid_constant__ AgentOffsets ao, const VoxWs ws,
+                                                         int max_pts, const PfnParams pp, const CanvasGeom cg,
+                                                         __nv_bfloat16* canvas, long lo_off, long* dirty_rows) {
+    __shared__ PfnSmem r;
     const int lane = threadIdx.x & 31, sub = lane & 7, grp = threadIdx.x >> 3;
-    const unsigned gmask = 0xFFu << (lane & 24);
     const int gg = blockIdx.x * 32 + grp, ng = gridDim.x * 32;
-    PfnRegs r;
-    load_pfn(r, pp, sub);
+    load_pfn_smem(r, pp);
     int base = 0;
     for (int a = 0; a < ao.n_agents; ++a) {
         const int nv = ws.nvox[a];
         const int4* meta = ws.vox_meta + (long)a * ws.vcap;
-        const int* perm = ws.perm + (long)a * ws.vcap;
-        const float4* ap = pts + ao.off[a];
-        for (int i = gg; i < nv; i += ng) {
-            const int v = perm[i];
+        const float4* vp = ws.vp + ao.off[a];
+        for (int v = gg; v < nv; v += ng) {
             const int4 m = __ldg(meta + v);
-            const int cnt = m.y;
-            const int n = cnt < max_pts ? cnt : max_pts;
-            const int x = m.z & 0xFFF, y = (m.z >> 12) & 0xFFF, z = (m.z >> 24) & 0xFF;
-            long* dslot = dirty_rows ? dirty_rows + base + v : nullptr;
-            if (cnt == 1) {                                        // the leader point itself, no list / ranking
-                const int idx = m.w;
-                pfn_group_store([&](int) { return __ldg(ap + idx); }, 1, max_pts, a, z, y, x, pp, r, cg, canvas, lo_off,
-                                sub, dslot);
-            } else {
-                group_sorted_points(ws.list + ao.off[a] + m.x, cnt, m.w, max_pts, s_sorted[grp], sub, gmask);
-                const int* srt = s_sorted[grp];
-                pfn_group_store([&](int k) { return __ldg(ap + srt[k]); }, n, max_pts, a, z, y, x, pp, r, cg, canvas,
-                                lo_off, sub, dslot);
-                __syncwarp(gmask);
-            }
+            const int n = m.y < max_pts ? m.y : max_pts;
+            const float4* vpp = vp + m.x;
+            pfn_group_store([&](int k) { return vpp[k]; }, n, max_pts, a, (m.z >> 24) & 0xFF, (m.z >> 12) & 0xFFF,
+                            m.z & 0xFFF, pp, r, cg, canvas, lo_off, sub, dirty_rows ? dirty_rows + base + v : nullptr);
         }
         base += nv;
     }
 }
 
 // PFN + scatter from reference-format voxel tensors ----------------------------------------------
-__global__ void __launch_bounds__(256, 2) pfn_scatter_kernel(const float4* __restrict__ voxels,
+__global__ void __launch_bounds__(256, 3) pfn_scatter_kernel(const float4* __restrict__ voxels,
                                                           const int4* __restrict__ coords,
                                                           const int* __restrict__ num_points, int n_rows,
                                                           const int* __restrict__ n_rows_dev, int max_pts,
                                                           const PfnParams pp, const CanvasGeom cg, int n_agents,
                                                           __nv_bfloat16* canvas, long lo_off, long* dirty_rows,
                                                           int* dirty_count) {
+    __shared__ PfnSmem r;
     const int lane = threadIdx.x & 31, sub = lane & 7, grp = threadIdx.x >> 3;
     const int gg = blockIdx.x * 32 + grp, ng = gridDim.x * 32;
-    PfnRegs r;
-    load_pfn(r, pp, sub);
+    load_pfn_smem(r, pp);
     const int rows = n_rows_dev ? min(n_rows, *n_rows_dev) : n_rows;
     if (dirty_count && blockIdx.x == 0 && threadIdx.x == 0) *dirty_count = rows;
     for (int v = gg; v < rows; v += ng) {
@@ -425,7 +414,6 @@ static int carve(VoxWs& ws, void* base, size_t bytes, int n_agents, int sum_poin
     size_t o_first_end = o;
     ws.count = (int*)take((size_t)n_agents * ncell * 4);
     ws.cursor = (int*)take((size_t)n_agents * vcap * 4);
-    ws.bucket = (int*)take((size_t)n_agents * 2 * 4);
     size_t o_clear_end = o;
     ws.cell2vox = (int*)take((size_t)n_agents * ncell * 4);
     ws.vox_off = (int*)take((size_t)n_agents * (vcap + 1) * 4);
@@ -434,7 +422,7 @@ static int carve(VoxWs& ws, void* base, size_t bytes, int n_agents, int sum_poin
     ws.list = (int*)take((size_t)sp * 4);
     ws.nvox = (int*)take(((size_t)n_agents + 1) * 4);
     ws.chunk_tot = (int2*)take((size_t)n_agents * max_chunks * 8);
-    ws.perm = (int*)take((size_t)n_agents * vcap * 4);
+    ws.vp = (float4*)take((size_t)sp * 16);
     ws.ncell = (int)ncell;
     ws.vcap = vcap;
     ws.max_chunks = max_chunks;
@@ -487,6 +475,8 @@ static int run_front(const float* points, const int32_t* pt_offset, int n_agents
         CB_CHECK_LAUNCH();
         vox_fill_kernel<<<(total + 255) / 256, 256, 0, st>>>(ao, ws);
         CB_CHECK_LAUNCH();
+        vox_rank_gather_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float4*)points, ao, ws, max_pts);
+        CB_CHECK_LAUNCH();
     }
     return CB_OK;
 }
@@ -528,8 +518,7 @@ extern "C" int cb_voxelize(const float* points, const int32_t* pt_offset, int n_
     int rc = run_front(points, pt_offset, n_agents, range, vsize, grid, max_pts, max_voxels, workspace,
                        workspace_bytes, st, ao, ws, g, n_voxels, nullptr);
     if (rc) return rc;
-    vox_emit_kernel<<<148 * 4, 256, 0, st>>>((const float4*)points, ao, ws, g, max_pts, (float4*)voxels,
-                                             (int4*)coords, num_points);
+    vox_emit_kernel<<<148 * 4, 256, 0, st>>>(ao, ws, max_pts, (float4*)voxels, (int4*)coords, num_points);
     CB_CHECK_LAUNCH();
     return CB_OK;
 }
@@ -549,8 +538,8 @@ extern "C" int cb_points_to_canvas(const float* points, const int32_t* pt_offset
     if (rc) return rc;
     const CanvasGeom cg = make_canvas_geom(canvas_agents, grid[1], grid[0]);
     const PfnParams pp = make_pfn(w, scale, shift, vsize, center_off);
-    vox_pfn_kernel<<<148 * 8, 256, 0, st>>>((const float4*)points, ao, ws, g, max_pts, pp, cg,
-                                            (__nv_bfloat16*)canvas_ps, (long)lo_off, (long*)dirty_rows);
+    vox_pfn_kernel<<<148 * 4, 256, 0, st>>>(ao, ws, max_pts, pp, cg, (__nv_bfloat16*)canvas_ps, (long)lo_off,
+                                            (long*)dirty_rows);
     CB_CHECK_LAUNCH();
     return CB_OK;
 }
@@ -566,7 +555,7 @@ extern "C" int cb_pfn_scatter(const float* voxels, const int32_t* coords, const 
     const CanvasGeom cg = make_canvas_geom(canvas_agents, ny, nx);
     const PfnParams pp = make_pfn(w, scale, shift, vsize, center_off);
     int blocks = (n_rows + 31) / 32;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > 148 * 4) blocks = 148 * 4;
     pfn_scatter_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
         (const float4*)voxels, (const int4*)coords, num_points, n_rows, n_voxels_dev, max_pts, pp, cg, n_agents,
         (__nv_bfloat16*)canvas_ps, (long)lo_off, (long*)dirty_rows, dirty_count);
