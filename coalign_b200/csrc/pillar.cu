@@ -19,6 +19,7 @@
 namespace cb {
 
 constexpr int CHUNK = 1024;       // points per scan chunk (256 threads x 4)
+constexpr int NCLS = 5;           // pillar classes by point count: 1 | 2 | 3-4 | 5-8 | 9+
 
 struct AgentOffsets { int n_agents; int off[CB_MAX_AGENTS + 1]; };
 
@@ -34,6 +35,8 @@ struct VoxWs {            // workspace carve-up (device pointers)
     int* nvox;            // [n_agents+1]
     int2* chunk_tot;      // [n_agents][max_chunks]  (leaders, points) per chunk, then exclusive prefixes
     float4* vp;           // [sum_P]  points regrouped per voxel in slot order (first max_pts of each voxel)
+    int* perm;            // [n_agents][NCLS][vcap]  voxel ids bucketed by point-count class
+    int* bucket;          // [n_agents][NCLS]        bucket fill counters
     int ncell, vcap, max_chunks;
 };
 
@@ -174,8 +177,24 @@ __global__ void __launch_bounds__(256) vox_chunk_assign_kernel(const __grid_cons
     int* cell2vox = ws.cell2vox + (long)a * ws.ncell;
     int* vox_off = ws.vox_off + (long)a * (ws.vcap + 1);
     int4* vox_meta = ws.vox_meta + (long)a * ws.vcap;
+    const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
+        // processing order of the fused PFN kernel: pillars bucketed by point-count class (one atomic per warp and class)
+        const bool acc = lead[j] && pv < max_voxels;
+        const int cls = cnt[j] <= 1 ? 0 : (cnt[j] == 2 ? 1 : (cnt[j] <= 4 ? 2 : (cnt[j] <= 8 ? 3 : 4)));
+#pragma unroll
+        for (int c = 0; c < NCLS; ++c) {
+            const unsigned mask = __ballot_sync(0xffffffffu, acc && cls == c);
+            if (mask) {
+                const int leader = __ffs(mask) - 1;
+                int basep = 0;
+                if (lane == leader) basep = atomicAdd(ws.bucket + a * NCLS + c, __popc(mask));
+                basep = __shfl_sync(0xffffffffu, basep, leader);
+                if (acc && cls == c)
+                    ws.perm[((long)a * NCLS + c) * ws.vcap + basep + __popc(mask & ((1u << lane) - 1u))] = pv;
+            }
+        }
         if (lead[j]) {
             if (pv < max_voxels) {
                 cell2vox[cell[j]] = pv;
@@ -232,62 +251,61 @@ struct PfnParams {
     float vx, vy, vz, offx, offy, offz;                         // voxel size, voxel/2 + range_min
 };
 
-// PFN parameters in shared memory, laid out for the 8-lanes-per-pillar mapping: lane `sub` owns channels
-// 8*sub .. 8*sub+7; s_w4[(j*8 + sub)*2 + h] = {W[8sub+4h+0..3][j]} so each (j) is two conflict-free LDS.128.
-struct PfnSmem { float4 w4[10 * 8 * 2]; float4 sc4[8 * 2]; float4 sh4[8 * 2]; };
-__device__ __forceinline__ void load_pfn_smem(PfnSmem& sm, const PfnParams& pp) {
-    float* w = reinterpret_cast<float*>(sm.w4);
-    float* sc = reinterpret_cast<float*>(sm.sc4);
-    float* sh = reinterpret_cast<float*>(sm.sh4);
-    for (int i = threadIdx.x; i < 640; i += blockDim.x) {
-        const int c = i / 10, j = i - c * 10;                 // pp.w is [64][10]
-        w[((j * 8 + (c >> 3)) * 2 + ((c >> 2) & 1)) * 4 + (c & 3)] = __ldg(pp.w + i);
+struct PfnRegs { float w[8][10], sc[8], sh[8]; };               // channels 8*sub .. 8*sub+7
+__device__ __forceinline__ void load_pfn(PfnRegs& r, const PfnParams& pp, int sub) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+#pragma unroll
+        for (int j = 0; j < 10; ++j) r.w[c][j] = __ldg(pp.w + (8 * sub + c) * 10 + j);
+        r.sc[c] = __ldg(pp.scale + 8 * sub + c);
+        r.sh[c] = __ldg(pp.shift + 8 * sub + c);
     }
-    for (int c = threadIdx.x; c < 64; c += blockDim.x) { sc[c] = __ldg(pp.scale + c); sh[c] = __ldg(pp.shift + c); }
-    __syncthreads();
 }
 
-// PFN of one pillar by one 8-lane group: PointFn(k) returns slot k (k < n, n >= 1).  Every lane of the group walks
-// all n points (same addresses -> broadcast loads) and produces 8 of the 64 channels; one 16-byte store per lane.
+// Per-pillar geometry terms shared by both PFN mappings (pillar_vfe.py:118-132): mean over the valid slots
+// (slot order) and the pillar centre = coord*voxel + (voxel/2 + range_min), fp32, unfused like the reference.
+struct PillarTerms { float mx, my, mz, ctrx, ctry, ctrz; };
+template <class PointFn>
+__device__ __forceinline__ PillarTerms pillar_terms(PointFn pt, const float4& p0, int n, int cz, int cy, int cx,
+                                                    const PfnParams& pp) {
+    float sx = p0.x, sy = p0.y, sz = p0.z;
+    for (int k = 1; k < n; ++k) { const float4 p = pt(k); sx += p.x; sy += p.y; sz += p.z; }
+    const float fn = (float)n;
+    PillarTerms t;
+    t.mx = __fdiv_rn(sx, fn); t.my = __fdiv_rn(sy, fn); t.mz = __fdiv_rn(sz, fn);
+    t.ctrx = __fadd_rn(__fmul_rn((float)cx, pp.vx), pp.offx);
+    t.ctry = __fadd_rn(__fmul_rn((float)cy, pp.vy), pp.offy);
+    t.ctrz = __fadd_rn(__fmul_rn((float)cz, pp.vz), pp.offz);
+    return t;
+}
+__device__ __forceinline__ void point_features(const float4& p, const PillarTerms& t, float (&f)[10]) {
+    f[0] = p.x; f[1] = p.y; f[2] = p.z; f[3] = p.w;
+    f[4] = p.x - t.mx; f[5] = p.y - t.my; f[6] = p.z - t.mz;
+    f[7] = p.x - t.ctrx; f[8] = p.y - t.ctry; f[9] = p.z - t.ctrz;
+}
+
+// PFN of one pillar by one 8-lane group (staged path): PointFn(k) returns slot k (k < n, n >= 1).  Every lane walks
+// all n points (broadcast loads) and produces 8 of the 64 channels; one 16-byte store per lane.
 template <class PointFn>
 __device__ __forceinline__ void pfn_group_store(PointFn pt, int n, int max_pts, int a, int cz, int cy, int cx,
-                                                const PfnParams& pp, const PfnSmem& sm, const CanvasGeom& cg,
+                                                const PfnParams& pp, const PfnRegs& r, const CanvasGeom& cg,
                                                 __nv_bfloat16* canvas, long lo_off, int sub, long* dirty_slot) {
-    float sx = 0.f, sy = 0.f, sz = 0.f;
     const float4 p0 = pt(0);
-    if (n == 1) { sx = p0.x; sy = p0.y; sz = p0.z; }
-    else for (int k = 0; k < n; ++k) { const float4 p = pt(k); sx += p.x; sy += p.y; sz += p.z; }   // slot order
-    const float fn = (float)n;
-    const float mx = __fdiv_rn(sx, fn), my = __fdiv_rn(sy, fn), mz = __fdiv_rn(sz, fn);
-    // pillar centre = coord*voxel + (voxel/2 + range_min)  (pillar_vfe.py:87-89,124-132), fp32, unfused
-    const float ctrx = __fadd_rn(__fmul_rn((float)cx, pp.vx), pp.offx);
-    const float ctry = __fadd_rn(__fmul_rn((float)cy, pp.vy), pp.offy);
-    const float ctrz = __fadd_rn(__fmul_rn((float)cz, pp.vz), pp.offz);
-    const float4 sc0 = sm.sc4[sub * 2], sc1 = sm.sc4[sub * 2 + 1], sh0 = sm.sh4[sub * 2], sh1 = sm.sh4[sub * 2 + 1];
-    const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
-    const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+    const PillarTerms t = pillar_terms(pt, p0, n, cz, cy, cx, pp);
     float best[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) best[c] = (n < max_pts) ? fmaxf(sh[c], 0.f) : 0.f;   // zero-padded slots join the max
+    for (int c = 0; c < 8; ++c) best[c] = (n < max_pts) ? fmaxf(r.sh[c], 0.f) : 0.f;   // zero-padded slots join the max
     for (int k = 0; k < n; ++k) {
         const float4 p = k == 0 ? p0 : pt(k);
         float f[10];
-        f[0] = p.x; f[1] = p.y; f[2] = p.z; f[3] = p.w;
-        f[4] = p.x - mx; f[5] = p.y - my; f[6] = p.z - mz;
-        f[7] = p.x - ctrx; f[8] = p.y - ctry; f[9] = p.z - ctrz;
-        float y[8];
+        point_features(p, t, f);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) y[c] = 0.f;
+        for (int c = 0; c < 8; ++c) {
+            float y = 0.f;
 #pragma unroll
-        for (int j = 0; j < 10; ++j) {                        // same accumulation order (j = 0..9) for every channel
-            const float4 wa = sm.w4[(j * 8 + sub) * 2], wb = sm.w4[(j * 8 + sub) * 2 + 1];
-            y[0] = fmaf(wa.x, f[j], y[0]); y[1] = fmaf(wa.y, f[j], y[1]);
-            y[2] = fmaf(wa.z, f[j], y[2]); y[3] = fmaf(wa.w, f[j], y[3]);
-            y[4] = fmaf(wb.x, f[j], y[4]); y[5] = fmaf(wb.y, f[j], y[5]);
-            y[6] = fmaf(wb.z, f[j], y[6]); y[7] = fmaf(wb.w, f[j], y[7]);
+            for (int j = 0; j < 10; ++j) y = fmaf(r.w[c][j], f[j], y);
+            best[c] = fmaxf(best[c], fmaf(y, r.sc[c], r.sh[c]));       // ReLU folded into the max (best >= 0)
         }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) best[c] = fmaxf(best[c], fmaf(y[c], sc[c], sh[c]));   // ReLU folded into the max
     }
     const long row = canvas_row(cg, a, cy, cx);
     uint4 hi;
@@ -303,6 +321,57 @@ __device__ __forceinline__ void pfn_group_store(PointFn pt, int n, int max_pts, 
         reinterpret_cast<uint4*>(canvas + lo_off + row * 64)[sub] = lo;
     }
     if (dirty_slot && sub == 0) *dirty_slot = row;
+}
+
+// Fused path: ONE THREAD per pillar and channel half; the PFN parameters live in constant memory, so every FFMA
+// takes its weight as a constant-bank operand (no weight registers, no shared-memory traffic).  Pillars are visited
+// class by class (same point count inside a warp, see vox_chunk_assign_kernel) so warps do not diverge on n.
+__constant__ float c_pfn_w[64 * 10];
+__constant__ float c_pfn_sc[64];
+__constant__ float c_pfn_sh[64];
+
+template <int HALF, class PointFn>
+__device__ __forceinline__ void pfn_thread_store(PointFn pt, int n, int max_pts, int a, int cz, int cy, int cx,
+                                                 const PfnParams& pp, const CanvasGeom& cg, __nv_bfloat16* canvas,
+                                                 long lo_off, long* dirty_slot) {
+    const float4 p0 = pt(0);
+    const PillarTerms t = pillar_terms(pt, p0, n, cz, cy, cx, pp);
+    float best[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) best[c] = (n < max_pts) ? fmaxf(c_pfn_sh[HALF * 32 + c], 0.f) : 0.f;
+    for (int k = 0; k < n; ++k) {
+        const float4 p = k == 0 ? p0 : pt(k);
+        float f[10];
+        point_features(p, t, f);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            float y = 0.f;
+#pragma unroll
+            for (int j = 0; j < 10; ++j) y = fmaf(c_pfn_w[(HALF * 32 + c) * 10 + j], f[j], y);
+            best[c] = fmaxf(best[c], fmaf(y, c_pfn_sc[HALF * 32 + c], c_pfn_sh[HALF * 32 + c]));
+        }
+    }
+    const long row = canvas_row(cg, a, cy, cx);
+    uint4* dst = reinterpret_cast<uint4*>(canvas + row * 64 + HALF * 32);
+    uint32_t hi[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) hi[c] = pack_bf16(best[2 * c], best[2 * c + 1]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+    if (lo_off != 0) {
+        uint4* dl = reinterpret_cast<uint4*>(canvas + lo_off + row * 64 + HALF * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c = 4 * q + e;
+                lo[e] = pack_bf16(best[2 * c] - bf16_lo(hi[c]), best[2 * c + 1] - bf16_hi(hi[c]));
+            }
+            dl[q] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+    }
+    if (dirty_slot && HALF == 0) *dirty_slot = row;
 }
 
 // K4a: emit reference-format voxel tensors --------------------------------------------------------
@@ -331,42 +400,52 @@ __global__ void __launch_bounds__(256) vox_emit_kernel(const __grid_constant__ A
     }
 }
 
-// K4b: fused PFN + scatter from the regrouped points ----------------------------------------------
+// K4b: fused PFN + scatter from the regrouped points: thread per (pillar, channel half) -------------------
 __global__ void __launch_bounds__(256, 3) vox_pfn_kernel(const __grid_constant__ AgentOffsets ao, const VoxWs ws,
                                                          int max_pts, const PfnParams pp, const CanvasGeom cg,
                                                          __nv_bfloat16* canvas, long lo_off, long* dirty_rows) {
-    __shared__ PfnSmem r;
-    const int lane = threadIdx.x & 31, sub = lane & 7, grp = threadIdx.x >> 3;
-    const int gg = blockIdx.x * 32 + grp, ng = gridDim.x * 32;
-    load_pfn_smem(r, pp);
-    int base = 0;
-    for (int a = 0; a < ao.n_agents; ++a) {
-        const int nv = ws.nvox[a];
-        const int4* meta = ws.vox_meta + (long)a * ws.vcap;
-        const float4* vp = ws.vp + ao.off[a];
-        for (int v = gg; v < nv; v += ng) {
-            const int4 m = __ldg(meta + v);
-            const int n = m.y < max_pts ? m.y : max_pts;
-            const float4* vpp = vp + m.x;
-            pfn_group_store([&](int k) { return vpp[k]; }, n, max_pts, a, (m.z >> 24) & 0xFF, (m.z >> 12) & 0xFFF,
-                            m.z & 0xFFF, pp, r, cg, canvas, lo_off, sub, dirty_rows ? dirty_rows + base + v : nullptr);
+    __shared__ int s_base[CB_MAX_AGENTS + 1];
+    if (threadIdx.x == 0) {
+        int b = 0;
+        for (int a = 0; a < ao.n_agents; ++a) { s_base[a] = b; b += ws.nvox[a]; }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int half = warp & 1;                                     // even warps: channels 0-31, odd warps: 32-63
+    const int slot = (blockIdx.x * 4 + (warp >> 1)) * 32 + lane;   // pillar slot of this thread within a segment
+    const int nslot = gridDim.x * 4 * 32;
+    for (int c = 0; c < NCLS; ++c) {
+        for (int a = 0; a < ao.n_agents; ++a) {
+            const int cnt = ws.bucket[a * NCLS + c];
+            const int* perm = ws.perm + ((long)a * NCLS + c) * ws.vcap;
+            const int4* meta = ws.vox_meta + (long)a * ws.vcap;
+            const float4* vp = ws.vp + ao.off[a];
+            for (int i = slot; i < cnt; i += nslot) {
+                const int v = perm[i];
+                const int4 m = __ldg(meta + v);
+                const int n = m.y < max_pts ? m.y : max_pts;
+                const float4* vpp = vp + m.x;
+                const int cz = (m.z >> 24) & 0xFF, cy = (m.z >> 12) & 0xFFF, cx = m.z & 0xFFF;
+                long* dslot = dirty_rows ? dirty_rows + s_base[a] + v : nullptr;
+                if (half == 0) pfn_thread_store<0>([&](int k) { return vpp[k]; }, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dslot);
+                else           pfn_thread_store<1>([&](int k) { return vpp[k]; }, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dslot);
+            }
         }
-        base += nv;
     }
 }
 
 // PFN + scatter from reference-format voxel tensors ----------------------------------------------
-__global__ void __launch_bounds__(256, 3) pfn_scatter_kernel(const float4* __restrict__ voxels,
+__global__ void __launch_bounds__(256, 2) pfn_scatter_kernel(const float4* __restrict__ voxels,
                                                           const int4* __restrict__ coords,
                                                           const int* __restrict__ num_points, int n_rows,
                                                           const int* __restrict__ n_rows_dev, int max_pts,
                                                           const PfnParams pp, const CanvasGeom cg, int n_agents,
                                                           __nv_bfloat16* canvas, long lo_off, long* dirty_rows,
                                                           int* dirty_count) {
-    __shared__ PfnSmem r;
     const int lane = threadIdx.x & 31, sub = lane & 7, grp = threadIdx.x >> 3;
     const int gg = blockIdx.x * 32 + grp, ng = gridDim.x * 32;
-    load_pfn_smem(r, pp);
+    PfnRegs r;
+    load_pfn(r, pp, sub);
     const int rows = n_rows_dev ? min(n_rows, *n_rows_dev) : n_rows;
     if (dirty_count && blockIdx.x == 0 && threadIdx.x == 0) *dirty_count = rows;
     for (int v = gg; v < rows; v += ng) {
@@ -414,6 +493,7 @@ static int carve(VoxWs& ws, void* base, size_t bytes, int n_agents, int sum_poin
     size_t o_first_end = o;
     ws.count = (int*)take((size_t)n_agents * ncell * 4);
     ws.cursor = (int*)take((size_t)n_agents * vcap * 4);
+    ws.bucket = (int*)take((size_t)n_agents * NCLS * 4);
     size_t o_clear_end = o;
     ws.cell2vox = (int*)take((size_t)n_agents * ncell * 4);
     ws.vox_off = (int*)take((size_t)n_agents * (vcap + 1) * 4);
@@ -423,6 +503,7 @@ static int carve(VoxWs& ws, void* base, size_t bytes, int n_agents, int sum_poin
     ws.nvox = (int*)take(((size_t)n_agents + 1) * 4);
     ws.chunk_tot = (int2*)take((size_t)n_agents * max_chunks * 8);
     ws.vp = (float4*)take((size_t)sp * 16);
+    ws.perm = (int*)take((size_t)n_agents * NCLS * vcap * 4);
     ws.ncell = (int)ncell;
     ws.vcap = vcap;
     ws.max_chunks = max_chunks;
@@ -537,8 +618,13 @@ extern "C" int cb_points_to_canvas(const float* points, const int32_t* pt_offset
                        workspace_bytes, st, ao, ws, g, nullptr, dirty_count);
     if (rc) return rc;
     const CanvasGeom cg = make_canvas_geom(canvas_agents, grid[1], grid[0]);
+    if (cg.plane_rows * 4 >= (1L << 31)) return CB_ERR_ARG;
     const PfnParams pp = make_pfn(w, scale, shift, vsize, center_off);
-    vox_pfn_kernel<<<148 * 4, 256, 0, st>>>(ao, ws, max_pts, pp, cg, (__nv_bfloat16*)canvas_ps, (long)lo_off,
+    cudaError_t ce;
+    ce = cudaMemcpyToSymbolAsync(c_pfn_w, w, sizeof(float) * 640, 0, cudaMemcpyDeviceToDevice, st);     if (ce) return (int)ce;
+    ce = cudaMemcpyToSymbolAsync(c_pfn_sc, scale, sizeof(float) * 64, 0, cudaMemcpyDeviceToDevice, st);  if (ce) return (int)ce;
+    ce = cudaMemcpyToSymbolAsync(c_pfn_sh, shift, sizeof(float) * 64, 0, cudaMemcpyDeviceToDevice, st);  if (ce) return (int)ce;
+    vox_pfn_kernel<<<148 * 3, 256, 0, st>>>(ao, ws, max_pts, pp, cg, (__nv_bfloat16*)canvas_ps, (long)lo_off,
                                             (long*)dirty_rows);
     CB_CHECK_LAUNCH();
     return CB_OK;
