@@ -177,24 +177,15 @@ __global__ void __launch_bounds__(256) vox_chunk_assign_kernel(const __grid_cons
     int* cell2vox = ws.cell2vox + (long)a * ws.ncell;
     int* vox_off = ws.vox_off + (long)a * (ws.vcap + 1);
     int4* vox_meta = ws.vox_meta + (long)a * ws.vcap;
-    const int lane = threadIdx.x & 31;
+    // processing order of the fused PFN kernel: pillars bucketed by point-count class.  Positions are claimed with
+    // shared-memory atomics inside the CTA and ONE global atomic per class and CTA.
+    __shared__ int s_cnt[NCLS], s_gbase[NCLS];
+    if (threadIdx.x < NCLS) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    int lpos[4], lcls[4], lpv[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        // processing order of the fused PFN kernel: pillars bucketed by point-count class (one atomic per warp and class)
-        const bool acc = lead[j] && pv < max_voxels;
-        const int cls = cnt[j] <= 1 ? 0 : (cnt[j] == 2 ? 1 : (cnt[j] <= 4 ? 2 : (cnt[j] <= 8 ? 3 : 4)));
-#pragma unroll
-        for (int c = 0; c < NCLS; ++c) {
-            const unsigned mask = __ballot_sync(0xffffffffu, acc && cls == c);
-            if (mask) {
-                const int leader = __ffs(mask) - 1;
-                int basep = 0;
-                if (lane == leader) basep = atomicAdd(ws.bucket + a * NCLS + c, __popc(mask));
-                basep = __shfl_sync(0xffffffffu, basep, leader);
-                if (acc && cls == c)
-                    ws.perm[((long)a * NCLS + c) * ws.vcap + basep + __popc(mask & ((1u << lane) - 1u))] = pv;
-            }
-        }
+        lpos[j] = -1; lcls[j] = 0; lpv[j] = pv;
         if (lead[j]) {
             if (pv < max_voxels) {
                 cell2vox[cell[j]] = pv;
@@ -202,12 +193,21 @@ __global__ void __launch_bounds__(256) vox_chunk_assign_kernel(const __grid_cons
                 const int cx = cell[j] % g.gx, cyz = cell[j] / g.gx;
                 const int cy = cyz % g.gy, cz = cyz / g.gy;
                 vox_meta[pv] = make_int4(pc, cnt[j], cx | (cy << 12) | (cz << 24), chunk * CHUNK + (int)threadIdx.x * 4 + j);
+                lcls[j] = cnt[j] <= 1 ? 0 : (cnt[j] == 2 ? 1 : (cnt[j] <= 4 ? 2 : (cnt[j] <= 8 ? 3 : 4)));
+                lpos[j] = atomicAdd(&s_cnt[lcls[j]], 1);
             } else {
                 cell2vox[cell[j]] = -1;                    // refused: max_voxels reached
             }
             pv += 1; pc += cnt[j];
         }
     }
+    __syncthreads();
+    if (threadIdx.x < NCLS && s_cnt[threadIdx.x] > 0)
+        s_gbase[threadIdx.x] = atomicAdd(ws.bucket + a * NCLS + threadIdx.x, s_cnt[threadIdx.x]);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (lpos[j] >= 0) ws.perm[((long)a * NCLS + lcls[j]) * ws.vcap + s_gbase[lcls[j]] + lpos[j]] = lpv[j];
 }
 
 // K3 ------------------------------------------------------------------------------------------
@@ -374,63 +374,74 @@ __device__ __forceinline__ void pfn_thread_store(PointFn pt, int n, int max_pts,
     if (dirty_slot && HALF == 0) *dirty_slot = row;
 }
 
-// K4a: emit reference-format voxel tensors --------------------------------------------------------
+// K4a: emit reference-format voxel tensors (8 lanes per voxel, voxels of all agents flattened) ---------
 __global__ void __launch_bounds__(256) vox_emit_kernel(const __grid_constant__ AgentOffsets ao, const VoxWs ws,
                                                        int max_pts, float4* __restrict__ voxels,
                                                        int4* __restrict__ coords, int* __restrict__ num_points) {
-    const int lane = threadIdx.x & 31, sub = lane & 7, grp = threadIdx.x >> 3;
-    const int gg = blockIdx.x * 32 + grp, ng = gridDim.x * 32;
-    int base = 0;
-    for (int a = 0; a < ao.n_agents; ++a) {
-        const int nv = ws.nvox[a];
-        const int4* meta = ws.vox_meta + (long)a * ws.vcap;
-        const float4* vp = ws.vp + ao.off[a];
-        for (int v = gg; v < nv; v += ng) {
-            const int4 m = meta[v];
-            const int n = m.y < max_pts ? m.y : max_pts;
-            const long row = base + v;
-            for (int k = sub; k < max_pts; k += 8)
-                voxels[row * max_pts + k] = k < n ? vp[m.x + k] : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (sub == 0) {
-                coords[row] = make_int4(a, (m.z >> 24) & 0xFF, (m.z >> 12) & 0xFFF, m.z & 0xFFF);
-                num_points[row] = n;
-            }
-        }
-        base += nv;
-    }
-}
-
-// K4b: fused PFN + scatter from the regrouped points: thread per (pillar, channel half) -------------------
-__global__ void __launch_bounds__(256, 3) vox_pfn_kernel(const __grid_constant__ AgentOffsets ao, const VoxWs ws,
-                                                         int max_pts, const PfnParams pp, const CanvasGeom cg,
-                                                         __nv_bfloat16* canvas, long lo_off, long* dirty_rows) {
     __shared__ int s_base[CB_MAX_AGENTS + 1];
     if (threadIdx.x == 0) {
         int b = 0;
         for (int a = 0; a < ao.n_agents; ++a) { s_base[a] = b; b += ws.nvox[a]; }
+        s_base[ao.n_agents] = b;
     }
     __syncthreads();
+    const int total = s_base[ao.n_agents];
+    const int sub = threadIdx.x & 7, grp = threadIdx.x >> 3;
+    const int gg = blockIdx.x * 32 + grp, ng = gridDim.x * 32;
+    for (int row = gg; row < total; row += ng) {
+        int a = 0;
+        while (a + 1 < ao.n_agents && row >= s_base[a + 1]) ++a;
+        const int v = row - s_base[a];
+        const int4 m = ws.vox_meta[(long)a * ws.vcap + v];
+        const int n = m.y < max_pts ? m.y : max_pts;
+        const float4* vp = ws.vp + ao.off[a] + m.x;
+        for (int k = sub; k < max_pts; k += 8)
+            voxels[(long)row * max_pts + k] = k < n ? vp[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (sub == 0) {
+            coords[row] = make_int4(a, (m.z >> 24) & 0xFF, (m.z >> 12) & 0xFFF, m.z & 0xFFF);
+            num_points[row] = n;
+        }
+    }
+}
+
+// K4b: fused PFN + scatter from the regrouped points: thread per (pillar, channel half) -------------------
+// Work items are the pillars of all agents flattened class-major (class, agent, index): every thread of the grid has
+// work and the pillars of a warp share a point-count class.
+__global__ void __launch_bounds__(256, 3) vox_pfn_kernel(const __grid_constant__ AgentOffsets ao, const VoxWs ws,
+                                                         int max_pts, const PfnParams pp, const CanvasGeom cg,
+                                                         __nv_bfloat16* canvas, long lo_off, long* dirty_rows) {
+    __shared__ int s_base[CB_MAX_AGENTS + 1];                      // first output voxel row of each agent
+    __shared__ int s_seg[NCLS * CB_MAX_AGENTS + 1];                // prefix over (class, agent) segments
+    const int nseg = NCLS * ao.n_agents;
+    if (threadIdx.x == 0) {
+        int b = 0;
+        for (int a = 0; a < ao.n_agents; ++a) { s_base[a] = b; b += ws.nvox[a]; }
+        int t = 0;
+        for (int sgm = 0; sgm < nseg; ++sgm) {
+            s_seg[sgm] = t;
+            t += ws.bucket[(sgm % ao.n_agents) * NCLS + sgm / ao.n_agents];
+        }
+        s_seg[nseg] = t;
+    }
+    __syncthreads();
+    const int total = s_seg[nseg];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int half = warp & 1;                                     // even warps: channels 0-31, odd warps: 32-63
-    const int slot = (blockIdx.x * 4 + (warp >> 1)) * 32 + lane;   // pillar slot of this thread within a segment
+    const int slot = (blockIdx.x * 4 + (warp >> 1)) * 32 + lane;
     const int nslot = gridDim.x * 4 * 32;
-    for (int c = 0; c < NCLS; ++c) {
-        for (int a = 0; a < ao.n_agents; ++a) {
-            const int cnt = ws.bucket[a * NCLS + c];
-            const int* perm = ws.perm + ((long)a * NCLS + c) * ws.vcap;
-            const int4* meta = ws.vox_meta + (long)a * ws.vcap;
-            const float4* vp = ws.vp + ao.off[a];
-            for (int i = slot; i < cnt; i += nslot) {
-                const int v = perm[i];
-                const int4 m = __ldg(meta + v);
-                const int n = m.y < max_pts ? m.y : max_pts;
-                const float4* vpp = vp + m.x;
-                const int cz = (m.z >> 24) & 0xFF, cy = (m.z >> 12) & 0xFFF, cx = m.z & 0xFFF;
-                long* dslot = dirty_rows ? dirty_rows + s_base[a] + v : nullptr;
-                if (half == 0) pfn_thread_store<0>([&](int k) { return vpp[k]; }, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dslot);
-                else           pfn_thread_store<1>([&](int k) { return vpp[k]; }, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dslot);
-            }
-        }
+    for (int gidx = slot; gidx < total; gidx += nslot) {
+        int lo = 0, hi = nseg;                                     // largest seg with s_seg[seg] <= gidx
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_seg[mid] <= gidx) lo = mid; else hi = mid; }
+        const int c = lo / ao.n_agents, a = lo - c * ao.n_agents;
+        const int i = gidx - s_seg[lo];
+        const int v = ws.perm[((long)a * NCLS + c) * ws.vcap + i];
+        const int4 m = __ldg(ws.vox_meta + (long)a * ws.vcap + v);
+        const int n = m.y < max_pts ? m.y : max_pts;
+        const float4* vpp = ws.vp + ao.off[a] + m.x;
+        const int cz = (m.z >> 24) & 0xFF, cy = (m.z >> 12) & 0xFFF, cx = m.z & 0xFFF;
+        long* dslot = dirty_rows ? dirty_rows + s_base[a] + v : nullptr;
+        if (half == 0) pfn_thread_store<0>([&](int k) { return vpp[k]; }, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dslot);
+        else           pfn_thread_store<1>([&](int k) { return vpp[k]; }, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dslot);
     }
 }
 
