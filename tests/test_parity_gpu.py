@@ -222,3 +222,64 @@ def test_plugin_through_reference_style_call():
         assert_close(out[k].cpu().numpy(), g[k], 1e-3, 1e-3, k)
     with pytest.raises(NotImplementedError):
         m.train()(batch)
+
+
+def test_ragged_batches_and_empty_agent_same_engine():
+    """One engine, changing batch signatures (graph re-capture), an agent whose cloud is entirely out of range,
+    and a 1-point cloud: every result equals the oracle's."""
+    from oracle import coalign_oracle as O
+    args = G.small_args("att")
+    sd = synth.random_state_dict(args, 4)
+    eng = make_engine(args, sd, 8, 3, precise=True)
+    for case, (rl, seed0) in enumerate((([3, 2], 500), ([1, 5, 2], 600), ([2], 700), ([3, 2], 800))):
+        scenes = G.small_case_scenes(rl, seed0)
+        if case == 1:
+            scenes[1]["points"][2] = scenes[1]["points"][2] + np.array([1000, 0, 0, 0], np.float32)   # all out of range
+            scenes[1]["points"][3] = scenes[1]["points"][3][:1]                                       # single point
+        inp = G.scenes_to_batch(scenes, G.SMALL_RANGE, G.SMALL_VOXEL)
+        ref = O.forward(sd, args, G.to_torch_batch(inp))
+        pts = np.concatenate([p for sc in scenes for p in sc["points"]]).astype(np.float32)
+        off = np.concatenate([[0], np.cumsum([p.shape[0] for sc in scenes for p in sc["points"]])]).astype(np.int32)
+        pw = torch.from_numpy(inp["pairwise_t_matrix"]).cuda()
+        out_p = eng.forward_points(torch.from_numpy(pts).cuda(), off, rl, pw)
+        out_v = eng.forward_voxels(*cuda_batch(inp))
+        torch.cuda.synchronize()
+        for k in ref:
+            assert_close(out_p[k].cpu().numpy(), ref[k].numpy(), 1e-3, 1e-3, f"case{case} points {k}")
+            assert_close(out_v[k].cpu().numpy(), ref[k].numpy(), 1e-3, 1e-3, f"case{case} voxels {k}")
+
+
+def test_full_size_properties_opv2v():
+    """BASELINE-size (200x704 canvas, 60k points/agent) size-independent properties, no oracle needed:
+    (a) permuting the non-ego agents leaves the fused output unchanged; (b) N identical co-located copies of the
+    ego cloud give the single-agent result (uniform attention over identical vectors)."""
+    args = synth.opv2v_args()
+    sd = synth.random_state_dict(args, 0)
+    eng = make_engine(args, sd, 3, 1, precise=True)
+    sc = synth.make_scene(7, 3, 60000, args["lidar_range"], pose_noise=True)
+    P = 60000
+    off = np.array([0, P, 2 * P, 3 * P], np.int32)
+
+    def run(order, pw):
+        pts = torch.from_numpy(np.concatenate([sc["points"][i] for i in order])).cuda()
+        o = eng.forward_points(pts, off, [3], torch.from_numpy(pw[None]).cuda())
+        return {k: v.cpu().numpy() for k, v in o.items()}
+
+    pw = sc["pairwise_t_matrix"]
+    a = run([0, 1, 2], pw)
+    pw_sw = pw.copy()
+    perm = [0, 2, 1, 3, 4]
+    pw_sw = pw[np.ix_(perm, perm)]
+    b = run([0, 2, 1], pw_sw)
+    for k in a:
+        assert_close(b[k], a[k], 1e-3, 1e-3, f"permutation {k}")
+    # (b) three identical agents at the ego pose vs one agent
+    ident = np.tile(np.eye(4), (5, 5, 1, 1))
+    pts3 = torch.from_numpy(np.concatenate([sc["points"][0]] * 3)).cuda()
+    o3 = eng.forward_points(pts3, off, [3], torch.from_numpy(ident[None]).cuda())
+    o3 = {k: v.cpu().numpy() for k, v in o3.items()}
+    o1 = eng.forward_points(torch.from_numpy(sc["points"][0]).cuda(), np.array([0, P], np.int32), [1],
+                            torch.from_numpy(ident[None]).cuda())
+    for k in o3:
+        assert_close(o3[k], o1[k].cpu().numpy(), 1e-3, 1e-3, f"identical agents {k}")
+    assert all(np.isfinite(v).all() for v in o3.values())

@@ -5,7 +5,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from coalign_b200 import synth
     from coalign_b200.engine import CoAlignEngine
-    B = 4
+    B = int(os.environ.get("CB_B", "4"))
     args = synth.opv2v_args(); sd = synth.random_state_dict(args, 0); rl = [5] * B
     eng = CoAlignEngine(args, sd, sum(rl), len(rl), precise=False, block_n_cap=256, use_graph=False, pair=False)
     scenes = [synth.make_scene(s, 5, 60000, args["lidar_range"], pose_noise=True) for s in range(B)]
@@ -29,7 +29,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     if os.environ.get("CB_DEBUG", "0") == "0":
         print("keys:", list(seen.keys()))
 else:
-    for name, flag in (("base", 0), ("no-epilogue", 1),):
-        env = dict(os.environ, CB_DEBUG=str(flag))
+    for name, flag, b in (("B=4", 0, 4), ("B=2", 0, 2), ("B=1", 0, 1), ("B=6", 0, 6)):
+        env = dict(os.environ, CB_DEBUG=str(flag), CB_B=str(b))
         out = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
-        print(f"{name:30s}", out.stdout.strip().replace("\n", "\n                 "), out.stderr[-300:] if out.returncode else "", flush=True)
+        print(f"{name:8s}", out.stdout.strip().split("\n")[0], out.stderr[-300:] if out.returncode else "", flush=True)
