@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #define CB_OK 0
 #define CB_ERR_ARG (-1)
@@ -254,6 +255,32 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 // Instruction descriptor, kind::f16: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major both, N>>3 @17, M>>4 @24.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while their predecessor in the
+// stream is still draining: pdl_launch_dependents() lets the next kernel's CTAs take over SMs as ours retire, and
+// pdl_wait() blocks until the predecessor grid has completed and its memory is visible.  Everything a kernel does
+// before pdl_wait() must be independent of the predecessor (barrier init, TMEM alloc, weight/bias loads).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+}  // namespace cb
+
+namespace cb {
+// Host: launch `kernel` with the PDL attribute (falls back to a plain launch when disabled via CB_NO_PDL=1).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+    static const bool enabled = [] { const char* e = getenv("CB_NO_PDL"); return !(e && e[0] == '1'); }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = enabled ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 // ---------------------------------------------------------------- misc

@@ -121,9 +121,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_co
         tmem_alloc(&tmem_base_smem, Cfg::TMEM_COLS);
         tmem_relinquish();
     }
+    pdl_launch_dependents();          // the next kernel may start its own prologue as our CTAs retire
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();                       // predecessor grid complete: activations / residual readable, outputs writable
     const uint32_t tmem_base = tmem_base_smem;
 
     // loop-invariant shared addresses / descriptors for the two single-thread hot loops
@@ -278,9 +280,11 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
         tmem_alloc_2sm(&tmem_base_smem, Cfg::TMEM_COLS);
         tmem_relinquish_2sm();
     }
+    pdl_launch_dependents();
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
+    pdl_wait();
     const uint32_t tmem_base = tmem_base_smem;
 
     const uint32_t smem_a0 = smem_u32(smem);
@@ -411,8 +415,9 @@ static int launch_st(const CUtensorMap& a0, const CUtensorMap& a1, const CUtenso
     int grid = m_tiles * n_tiles;
     int cap = max_ctas > 0 ? max_ctas : 148;
     if (grid > cap) grid = cap;
-    conv_gemm_tc_kernel<BN, KPS, ST><<<grid, TC_THREADS, SMEM, stream>>>(a0, a1, w, p, m_tiles, n_tiles, dbg_flags() & 7);
-    CB_CHECK_LAUNCH();
+    cudaError_t le = launch_pdl(conv_gemm_tc_kernel<BN, KPS, ST>, dim3(grid), dim3(TC_THREADS), SMEM, stream, a0, a1, w, p,
+                                m_tiles, n_tiles, dbg_flags() & 7);
+    if (le != cudaSuccess) return (int)le;
     return CB_OK;
 }
 
@@ -443,8 +448,9 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
     int grid = m_tiles * n_tiles;
     int cap = max_ctas > 0 ? max_ctas : sms;
     if (grid > cap) grid = cap;
-    conv_gemm_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(a0, a1, w, p, m_tiles, n_tiles, dbg_flags() & 7);
-    CB_CHECK_LAUNCH();
+    cudaError_t le = launch_pdl(conv_gemm_tc_kernel<BN, 0, 0>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, stream, a0, a1,
+                                w, p, m_tiles, n_tiles, dbg_flags() & 7);
+    if (le != cudaSuccess) return (int)le;
     return CB_OK;
 }
 
@@ -467,8 +473,9 @@ static int launch2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorM
     int clusters = m_pairs * n_tiles;
     int cap = max_clusters > 0 ? max_clusters : sms / 2;
     if (clusters > cap) clusters = cap;
-    conv_gemm_tc2_kernel<BN><<<2 * clusters, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(a0, a1, w, p, m_pairs, n_tiles);
-    CB_CHECK_LAUNCH();
+    cudaError_t le = launch_pdl(conv_gemm_tc2_kernel<BN>, dim3(2 * clusters), dim3(TC_THREADS), Cfg::SMEM_BYTES, stream, a0,
+                                a1, w, p, m_pairs, n_tiles);
+    if (le != cudaSuccess) return (int)le;
     return CB_OK;
 }
 

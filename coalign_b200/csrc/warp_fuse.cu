@@ -174,6 +174,8 @@ __global__ void __launch_bounds__(256, (MAXN <= 5 ? 3 : 2)) warp_att_fuse_v8_ker
                                                                const FuseGeom g, int method,
                                                                __nv_bfloat16* __restrict__ out, long out_lo_off) {
     constexpr int PPW = 32 / LPP;                          // pixels per warp
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31, sub = lane % LPP, pin = lane / LPP;
     const int gw = blockIdx.x * 8 + (threadIdx.x >> 5), nw = gridDim.x * 8;
     const int HW = g.H * g.W;
@@ -333,8 +335,8 @@ extern "C" int cb_warp_att_fuse(const void* feat, int in_ps, int64_t in_lo_off, 
         long nb = (total + 8L * ppw - 1) / (8L * ppw);
         if (nb > 148 * 24) nb = 148 * 24;
         if ((long)sum_agents * g.Hp * g.Wp * (in_ps ? 4 : 1) >= (1L << 31) || total >= (1L << 31)) return CB_ERR_ARG;
-#define CB_FUSE_LAUNCH(LPP_, MAXN_) warp_att_fuse_v8_kernel<LPP_, MAXN_><<<(unsigned)nb, 256, 0, st>>>( \
-            f, in_lo_off, affine, agent_off, n_scenes, max_cav, g, method, o, out_lo_off)
+#define CB_FUSE_LAUNCH(LPP_, MAXN_) launch_pdl(warp_att_fuse_v8_kernel<LPP_, MAXN_>, dim3((unsigned)nb), dim3(256), 0, st, \
+            f, (long)in_lo_off, affine, agent_off, n_scenes, max_cav, g, method, o, (long)out_lo_off)
         const bool small = max_cav <= 5;
         switch (C) {
             case 64: if (small) CB_FUSE_LAUNCH(8, 5); else CB_FUSE_LAUNCH(8, FUSE_MAX_AGENTS); break;
