@@ -232,8 +232,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_co
 // ----------------------------------------------------------------------------------------------------------
 template <int BN> struct Tc2Cfg {
     static constexpr int B_STAGE_BYTES = (BN / 2) * BK * 2;
-    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;        // per CTA
-    static constexpr int STAGES = (BN == 256) ? 6 : 8;
+    static constexpr int KSTEP_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;        // per CTA and K-step
+    static constexpr int KPS = (BN == 256) ? 1 : 2;                          // K-steps per pipeline stage
+    static constexpr int STAGE_BYTES = KPS * KSTEP_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 6 : 4;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
     static constexpr int TMEM_COLS = 2 * BN;
 };
@@ -298,14 +300,20 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
             for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
                 const int mp = tile / n_tiles, nt = tile - mp * n_tiles;
                 const int m0 = (mp * 2 + (int)rank) * BM, n0 = nt * BN + (int)rank * (BN / 2);
-                for (int ks = 0; ks < nk; ++ks) {
-                    const cb_kstep st = p.ksteps[ks];
+                for (int ks = 0; ks < nk; ks += Cfg::KPS) {
+                    const int cnt = (nk - ks) < Cfg::KPS ? (nk - ks) : Cfg::KPS;
                     const uint32_t fb = (full0 + stage * 8) & 0xFEFFFFFFu;        // leader CTA's barrier
-                    const uint32_t sa = smem_a0 + stage * Cfg::STAGE_BYTES;
                     mbar_wait_a(empty0 + stage * 8, phase ^ 1);
-                    if (leader) mbar_expect_tx_a(full0 + stage * 8, 2 * Cfg::STAGE_BYTES);
-                    tma_load_2d_2sm_a(sa, st.a_sel ? &tmap_a1 : &tmap_a0, fb, (int)st.col, m0 + st.row_off);
-                    tma_load_2d_2sm_a(sa + A_STAGE_BYTES, &tmap_w, fb, st.w_k, n0);
+                    if (leader) mbar_expect_tx_a(full0 + stage * 8, 2u * (uint32_t)cnt * Cfg::KSTEP_BYTES);
+#pragma unroll
+                    for (int j = 0; j < Cfg::KPS; ++j) {
+                        if (j < cnt) {
+                            const cb_kstep st = p.ksteps[ks + j];
+                            const uint32_t sa = smem_a0 + stage * Cfg::STAGE_BYTES + j * Cfg::KSTEP_BYTES;
+                            tma_load_2d_2sm_a(sa, st.a_sel ? &tmap_a1 : &tmap_a0, fb, (int)st.col, m0 + st.row_off);
+                            tma_load_2d_2sm_a(sa + A_STAGE_BYTES, &tmap_w, fb, st.w_k, n0);
+                        }
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -324,18 +332,25 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
                 mbar_wait_a(tempty0 + buf * 8, acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * BN;
-                for (int ks = 0; ks < nk; ++ks) {
+                for (int ks = 0; ks < nk; ks += Cfg::KPS) {
+                    const int cnt = (nk - ks) < Cfg::KPS ? (nk - ks) : Cfg::KPS;
                     mbar_wait_a(full0 + stage * 8, phase);
                     tc_fence_after();
                     const uint64_t adesc = adesc0 + (uint64_t)(stage * (Cfg::STAGE_BYTES >> 4));
                     const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (Cfg::STAGE_BYTES >> 4));
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        umma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                      (ks > 0 || k > 0) ? 1u : 0u);
+                    for (int j = 0; j < Cfg::KPS; ++j) {
+                        if (j < cnt) {
+#pragma unroll
+                            for (int k = 0; k < BK / UMMA_K; ++k) {
+                                umma_bf16_2sm(d_tmem, adesc + (uint64_t)(j * (Cfg::KSTEP_BYTES >> 4) + 2 * k),
+                                              bdesc + (uint64_t)(j * (Cfg::KSTEP_BYTES >> 4) + 2 * k), idesc,
+                                              (ks > 0 || j > 0 || k > 0) ? 1u : 0u);
+                            }
+                        }
                     }
                     umma_commit_2sm_a(empty0 + stage * 8);
-                    if (ks == nk - 1) umma_commit_2sm_a(tfull0 + buf * 8);
+                    if (ks + Cfg::KPS >= nk) umma_commit_2sm_a(tfull0 + buf * 8);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -106,7 +107,7 @@ class CoAlignEngine:
         self.use_graph = use_graph
         self.simt_conv = simt_conv            # validation only: evaluate the descriptors with the SIMT kernel
         self.pair = pair                      # CTA-pair (cta_group::2) conv kernel ...
-        self.pair_min_bn = 256                # ... for tiles at least this wide (measured: narrower tiles are faster single-CTA)
+        self.pair_min_bn = int(os.environ.get('CB_PAIR_MIN_BN', '256'))   # ... for tiles at least this wide (measured)
         nx, ny, nz = [int(v) for v in args["point_pillar_scatter"]["grid_size"]]
         if nz != 1:
             raise ValueError("PointPillarScatter requires nz == 1")

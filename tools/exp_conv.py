@@ -7,7 +7,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     from coalign_b200.engine import CoAlignEngine
     B = int(os.environ.get("CB_B", "4"))
     args = synth.opv2v_args(); sd = synth.random_state_dict(args, 0); rl = [5] * B
-    eng = CoAlignEngine(args, sd, sum(rl), len(rl), precise=False, block_n_cap=256, use_graph=False, pair=False)
+    eng = CoAlignEngine(args, sd, sum(rl), len(rl), precise=False, block_n_cap=256, use_graph=False, pair=os.environ.get("CB_PAIR", "0") == "1")
     scenes = [synth.make_scene(s, 5, 60000, args["lidar_range"], pose_noise=True) for s in range(B)]
     pts = torch.from_numpy(np.concatenate([p for sc in scenes for p in sc["points"]])).cuda()
     off = np.arange(0, sum(rl) + 1, dtype=np.int32) * 60000
@@ -29,7 +29,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     if os.environ.get("CB_DEBUG", "0") == "0":
         print("keys:", list(seen.keys()))
 else:
-    for name, flag, b in (("B=4", 0, 4), ("B=2", 0, 2), ("B=1", 0, 1), ("B=6", 0, 6)):
-        env = dict(os.environ, CB_DEBUG=str(flag), CB_B=str(b))
+    for name, envs in (("single", {}), ("pair>=256", {"CB_PAIR": "1", "CB_PAIR_MIN_BN": "256"}),
+                       ("pair>=128", {"CB_PAIR": "1", "CB_PAIR_MIN_BN": "128"}), ("pair>=64", {"CB_PAIR": "1", "CB_PAIR_MIN_BN": "64"})):
+        env = dict(os.environ, CB_DEBUG="0", CB_B="4", **envs)
         out = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
-        print(f"{name:8s}", out.stdout.strip().split("\n")[0], out.stderr[-300:] if out.returncode else "", flush=True)
+        print(f"{name:10s}", out.stdout.strip().split("\n")[0], out.stderr[-300:] if out.returncode else "", flush=True)
