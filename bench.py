@@ -233,16 +233,17 @@ def run_ours(opt):
     h2d = int(host_pts[0].numel() * 4 + host_pw[0].numel() * 8)
     d2h = int(sum(v.numel() * 4 for v in host_out.values()))
 
-    # ---- roofline of the dominant kernel (conv GEMM on tcgen05), measured live with CUDA events per launch
+    # ---- roofline of the dominant kernel family (conv GEMM on tcgen05), measured live with CUDA events per launch
     roof, hbm_roofs, launches_per_step = None, [], 0
     if rank == 0:
         peaks = load_peaks()
         ops = eng.build_descs(B * N_AGENTS, B)
         sp = torch.cuda.current_stream().cuda_stream
         n_conv = sum(1 for k, _ in ops if k == "conv")
-        launches_per_step = len(ops) + 1 + 4                   # + normalize_affine + pillar front-end (K1..K4)
+        launches_per_step = len(ops) + 1 + 10                  # + normalize_affine + pillar front-end kernels
         reps = 5
         tot = {"conv": 0.0, "fuse": 0.0}
+        by_bn = {}
         evs = []
         for r in range(reps + 1):
             for kind, o in ops:
@@ -251,20 +252,48 @@ def run_ours(opt):
                 eng._launch_ops([(kind, o)], B, sp)
                 b.record()
                 if r > 0:
-                    evs.append((kind, a, b))
+                    evs.append((kind, o, a, b))
         torch.cuda.synchronize()
-        for kind, a, b in evs:
-            tot[kind] += a.elapsed_time(b) * 1e-3 / reps
+        for kind, o, a, b in evs:
+            t = a.elapsed_time(b) * 1e-3 / reps
+            tot[kind] += t
+            if kind == "conv":
+                rows = o.n_img * (o.Hp - 2) * (o.Wp - 2)
+                e = by_bn.setdefault(int(o.block_n), [0.0, 0.0, 0])
+                e[0] += t
+                e[1] += 2.0 * rows * o.n_total * o.n_ksteps * 64 / reps / (3 if opt.precise else 1)
+                e[2] += 1
         conv_flop = CONV_GFLOP_PER_SCENE * 1e9 * B
         ach = conv_flop / tot["conv"] / 1e12
-        roof = {"bound": "tensor", "kernel": "conv_gemm_tc_kernel<BN> (all %d conv GEMM launches of a step)" % n_conv,
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("conv_avg_dram_bytes_per_launch")
+        roof = {"bound": "tensor", "kernel": "conv_gemm_tc_kernel<BN> / conv_gemm_tc2_kernel<256> (all %d conv GEMM launches of a step)" % n_conv,
                 "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
                 "peak_source": peaks["src"] + ", sustained figure (kernel timed inside a long step)",
-                "avg_launch_us": tot["conv"] / n_conv * 1e6, "flop_per_step": conv_flop, "traffic": None}
+                "avg_launch_us": tot["conv"] / n_conv * 1e6, "flop_per_step": conv_flop, "traffic": traffic,
+                "traffic_note": "avg dram read+write bytes per conv launch, ncu --set full, profiles/r1_ncu_full_conv_current.csv (4 scenes/step)",
+                "by_tile_width": {str(bn): {"launches": v[2] // reps, "tflops": v[1] / v[0] / 1e12} for bn, v in sorted(by_bn.items())}}
         fuse_bytes = (N_AGENTS + 1) * 3942400 * 2 * B          # (N+1)*sum(C*H*W)*2 B, bf16
-        hbm_roofs.append({"kernel": "warp_att_fuse_kernel", "bound": "hbm", "achieved": fuse_bytes / tot["fuse"] / 1e9,
-                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": fuse_bytes / tot["fuse"] / 1e9 / peaks["hbm_gbs"],
-                          "traffic": None})
+        hbm_roofs.append({"kernel": "warp_att_fuse_v8_kernel (3 scales)", "bound": "hbm",
+                          "achieved": fuse_bytes / tot["fuse"] / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                          "frac": fuse_bytes / tot["fuse"] / 1e9 / peaks["hbm_gbs"], "traffic": None})
+        # pillar front-end: canvas clear + voxelise + PFN + scatter, SURVEY 8(d): P*16 + ny*nx*64*2 B per agent
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(2):
+            eng.run_front_only(off)
+        e0.record()
+        for _ in range(reps):
+            eng.run_front_only(off)
+        e1.record()
+        torch.cuda.synchronize()
+        t_front = e0.elapsed_time(e1) * 1e-3 / reps
+        pillar_bytes = B * N_AGENTS * (N_POINTS * 16 + 200 * 704 * 64 * 2)
+        hbm_roofs.append({"kernel": "pillar front-end (canvas_clear + vox_* + vox_pfn, 10 launches)", "bound": "hbm",
+                          "achieved": pillar_bytes / t_front / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                          "frac": pillar_bytes / t_front / 1e9 / peaks["hbm_gbs"], "us": t_front * 1e6, "traffic": None,
+                          "note": "algorithmic bytes count the full canvas; the sparse clear makes the real traffic smaller"})
 
     # ---- CPU baseline beside it (rank 0, N=1 only): one scene through the oracle port
     cpu = None

@@ -545,6 +545,23 @@ class CoAlignEngine:
         return self._outputs(len(record_len), clone)
 
     @torch.no_grad()
+    def run_front_only(self, pt_offset: Sequence[int], max_pts: int = 32, max_voxels: int = 70000):
+        """Measurement hook: the pillar front-end alone (canvas clear + voxelise + PFN + scatter) on `pts_buf`."""
+        po = np.ascontiguousarray(pt_offset, dtype=np.int32)
+        n_img = po.shape[0] - 1
+        ws = self._ws(n_img, int(po[-1]), max_voxels)
+        sp = torch.cuda.current_stream(self.device).cuda_stream
+        self._clear_canvas(sp)
+        _lib.check(self.lib.cb_points_to_canvas(self.pts_buf.data_ptr(), po.ctypes.data, n_img,
+                                                self._range_f.ctypes.data, self._vsize_f.ctypes.data,
+                                                self._grid_i.ctypes.data, max_pts, max_voxels,
+                                                self.pfn_w.data_ptr(), self.pfn_scale.data_ptr(),
+                                                self.pfn_shift.data_ptr(), self._center_off_f.ctypes.data,
+                                                self.canvas.n_cap, self.canvas.ptr, self.canvas.lo_off,
+                                                self.dirty_rows.data_ptr(), self.dirty_count.data_ptr(),
+                                                ws.data_ptr(), ws.numel(), sp), "cb_points_to_canvas")
+
+    @torch.no_grad()
     def voxelize(self, points, pt_offset: Sequence[int], max_pts: int = 32, max_voxels: int = 70000):
         """A1/A2 on the GPU, reference output format; returns (voxels, coords[a,z,y,x], num_points) trimmed."""
         po = np.asarray(pt_offset, np.int32)
