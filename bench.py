@@ -24,6 +24,8 @@ sys.path.insert(0, ROOT)
 N_AGENTS = 5
 N_POINTS = 60000
 CONV_GFLOP_PER_SCENE = 81.0287 * N_AGENTS + 108.2065          # OPV2V forward, 2*MAC
+WORKLOAD = ("OPV2V-shape 5-agent CoAlign multiscale fusion, 60k pts/agent, raw points + poses -> cls/reg/dir maps "
+            "(BASELINE configs[2] shape on each GPU)")
 
 
 def load_peaks():
@@ -146,9 +148,10 @@ def run_reference(opt):
         "impl": "reference", "metric": "scenes_per_sec", "value": v, "unit": "scenes/s", "n_gpus": opt.gpus,
         "steps": opt.steps, "warmup": opt.warmup, "ms_per_step": dt / opt.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "OPV2V-shape 5-agent CoAlign scene, 60k pts/agent (BASELINE configs[2] shape)",
-                   "scenes_per_step": 1, "note": "CPU restatement of the reference PyTorch path (oracle/), "
-                   "voxelisation by oracle/voxelize.c"},
+        "config": {"workload": WORKLOAD, "scenes_per_step": 1, "agents_per_scene": N_AGENTS,
+                   "points_per_agent": N_POINTS, "canvas": "200x704",
+                   "parallelism": "CPU only, rank 0; a step is a bounded sample (one scene) of the same workload",
+                   "note": "CPU restatement of the reference PyTorch path (oracle/), voxelisation by oracle/voxelize.c"},
         "cpu_baseline": {"value": v, "unit": "scenes/s", "cores": threads, "kind": "port",
                          "sample": f"{opt.steps} x one 5-agent scene"},
         "e2e": {"value": v, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -310,8 +313,7 @@ def run_ours(opt):
             "metric": "scenes_per_sec", "value": value, "unit": "scenes/s", "n_gpus": world, "steps": opt.steps,
             "warmup": opt.warmup, "ms_per_step": ms / opt.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16x3 (fp32-class)" if opt.precise else "bf16", "data": "synthetic",
-            "config": {"workload": "OPV2V-shape 5-agent CoAlign multiscale fusion, 60k pts/agent, raw points + poses -> "
-                                   "cls/reg/dir maps (BASELINE configs[2] shape on each GPU)",
+            "config": {"workload": WORKLOAD,
                        "scenes_per_step": B, "agents_per_scene": N_AGENTS, "points_per_agent": N_POINTS,
                        "canvas": "200x704", "parallelism": f"scenes sharded over {world} GPU(s), no data-path collective",
                        "l2": f"{NB} rotating input batches; a step streams >1 GB of activations (> 126 MB L2)",
