@@ -166,6 +166,7 @@ def run_ours(opt):
     from coalign_b200 import dist_utils, synth
     from coalign_b200.engine import CoAlignEngine
 
+    os.environ.setdefault("NCCL_DEBUG", "WARN")              # keep NCCL's version banner off stdout (one JSON line)
     rank, local, world = dist_utils.world_info()
     torch.cuda.set_device(local)
     dist_utils.init("nccl", device_id=torch.device("cuda", local))
@@ -323,7 +324,8 @@ def run_ours(opt):
             "gpu_launches": launches_per_step * opt.steps,
             "clocks": clocks, "roofline": roof, "roofline_hbm": hbm_roofs, "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
