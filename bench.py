@@ -246,14 +246,9 @@ def run_ours(opt):
         sampler.start()
     ms = timed(step_resident, opt.steps, opt.warmup, sampler if rank == 0 else None)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, host_out = run_e2e(opt.steps, opt.warmup)
-    torch.cuda.synchronize()
 
     scenes_total = world * B * opt.steps
     value = scenes_total / (ms * 1e-3)
-    e2e_value = scenes_total / (ms_e2e * 1e-3)
-    h2d = int(host_pts[0].numel() * 4 + host_pw[0].numel() * 8)
-    d2h = int(sum(v.numel() * 4 for v in host_out.values()))
 
     # ---- roofline of the dominant kernel family (conv GEMM on tcgen05), measured live with CUDA events per launch
     roof, hbm_roofs, launches_per_step = None, [], 0
@@ -316,6 +311,12 @@ def run_ours(opt):
                           "achieved": pillar_bytes / t_front / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                           "frac": pillar_bytes / t_front / 1e9 / peaks["hbm_gbs"], "us": t_front * 1e6, "traffic": None,
                           "note": "algorithmic bytes count the full canvas; the sparse clear makes the real traffic smaller"})
+
+    ms_e2e, host_out = run_e2e(opt.steps, opt.warmup)
+    torch.cuda.synchronize()
+    e2e_value = scenes_total / (ms_e2e * 1e-3)
+    h2d = int(host_pts[0].numel() * 4 + host_pw[0].numel() * 8)
+    d2h = int(sum(v.numel() * 4 for v in host_out.values()))
 
     # ---- CPU baseline beside it (rank 0, N=1 only): one scene through the oracle port
     cpu = None

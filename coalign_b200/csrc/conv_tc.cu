@@ -50,7 +50,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const float* 
                                               int c_lo, int c_hi, uint32_t tfull_bar, uint32_t acc_phase, int dbg) {
     const RowDest dst = decode_row(p, q, n0);
     const bool fast = (p.out_lo_off == 0) && (p.out_mode != CB_OUT_HEADS) && (p.res_lo_off == 0);
-    const bool has_res = fast && p.residual != nullptr && dst.row >= 0;
+    const bool has_res = fast && p.residual != nullptr && dst.row >= 0 && !(dbg & 4);
     uint4 rcur[4] = {}, rnext[4] = {};
     const uint4* rptr = reinterpret_cast<const uint4*>(p.residual + q * (long)p.res_pitch + n0);
     if (has_res) {                                       // residual of the first chunk: issued before the MMA is done
@@ -74,7 +74,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const float* 
         if (dbg & 1) {                                   // experiment: no epilogue math / stores
             if (v[0] == 1.2345e-30f) p.out[0] = __float2bfloat16(v[1]);
         } else if (fast) {
-            epilogue_chunk_fast(p, dst, (n0 + c) % p.cout_mod, s_bias, rcur, has_res, v);
+            epilogue_chunk_fast(p, dst, (n0 + c) % p.cout_mod, s_bias, rcur, has_res, v, dbg);
         } else if (p.out_mode == CB_OUT_HEADS && BN == 32 && !p.relu && p.residual == nullptr) {
             epilogue_heads_fast(p, dst, s_bias, v);
         } else {
