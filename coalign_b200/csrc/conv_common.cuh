@@ -144,11 +144,13 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float a, float b) {
 }
 
 // Fast epilogue of the tensor-core kernels (bf16 outputs, not the heads): bias from shared memory, residual
-// already prefetched into registers, ReLU fused into the bf16 conversion, four 16-byte stores.
-__device__ __forceinline__ void epilogue_chunk_fast(const ConvParams& p, const RowDest& d, int c_base,
+// already prefetched into registers, ReLU fused into the bf16 conversion.  The 32 rows x 64 B of the warp's chunk are
+// transposed through a 2 KB per-warp shared-memory stage so that every store instruction writes 8 rows x 64 B of full
+// sectors instead of 32 rows x 16 B (the scattered 16-byte stores cost 15-30 us per layer, profiles/r1_conv_analysis.md).
+__device__ __forceinline__ void epilogue_chunk_fast(const ConvParams& p, int drow, int c_base,
                                                     const float* __restrict__ s_bias, const uint4 (&res)[4],
-                                                    bool has_res, float (&v)[32], int dbg = 0) {
-    if (d.row < 0) return;
+                                                    bool has_res, float (&v)[32], uint4* __restrict__ stage, int lane,
+                                                    int dbg = 0) {
     const float4* b4 = reinterpret_cast<const float4*>(s_bias + c_base);
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
@@ -164,22 +166,27 @@ __device__ __forceinline__ void epilogue_chunk_fast(const ConvParams& p, const R
             v[8 * t + 6] += bf16_lo(res[t].w); v[8 * t + 7] += bf16_hi(res[t].w);
         }
     }
-    uint4* o4 = reinterpret_cast<uint4*>(p.out + d.row * (long)p.out_pitch + p.out_ch_off + c_base);
-    if (dbg & 2) {                                         // experiment: math but no stores
-        if (v[0] + v[9] + v[18] + v[27] == 1.2345e-30f) o4[0] = make_uint4(0, 0, 0, 0);
-        return;
-    }
-    if (p.relu) {
+    const int sw = (lane >> 1) & 3;                         // 16-byte chunk swizzle: conflict-free writes and reads
 #pragma unroll
-        for (int t = 0; t < 4; ++t)
-            o4[t] = make_uint4(pack_bf16_relu(v[8 * t + 0], v[8 * t + 1]), pack_bf16_relu(v[8 * t + 2], v[8 * t + 3]),
-                               pack_bf16_relu(v[8 * t + 4], v[8 * t + 5]), pack_bf16_relu(v[8 * t + 6], v[8 * t + 7]));
-    } else {
-#pragma unroll
-        for (int t = 0; t < 4; ++t)
-            o4[t] = make_uint4(pack_bf16(v[8 * t + 0], v[8 * t + 1]), pack_bf16(v[8 * t + 2], v[8 * t + 3]),
-                               pack_bf16(v[8 * t + 4], v[8 * t + 5]), pack_bf16(v[8 * t + 6], v[8 * t + 7]));
+    for (int t = 0; t < 4; ++t) {
+        uint4 u;
+        if (p.relu) u = make_uint4(pack_bf16_relu(v[8 * t + 0], v[8 * t + 1]), pack_bf16_relu(v[8 * t + 2], v[8 * t + 3]),
+                                   pack_bf16_relu(v[8 * t + 4], v[8 * t + 5]), pack_bf16_relu(v[8 * t + 6], v[8 * t + 7]));
+        else        u = make_uint4(pack_bf16(v[8 * t + 0], v[8 * t + 1]), pack_bf16(v[8 * t + 2], v[8 * t + 3]),
+                                   pack_bf16(v[8 * t + 4], v[8 * t + 5]), pack_bf16(v[8 * t + 6], v[8 * t + 7]));
+        stage[lane * 4 + (t ^ sw)] = u;
     }
+    __syncwarp();
+    const int j = lane & 3;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int R = it * 8 + (lane >> 2);
+        const uint4 val = stage[R * 4 + (j ^ ((R >> 1) & 3))];
+        const int dr = __shfl_sync(0xffffffffu, drow, R);
+        if (dr >= 0 && !(dbg & 2))
+            reinterpret_cast<uint4*>(p.out + (long)dr * p.out_pitch + p.out_ch_off + c_base)[j] = val;
+    }
+    __syncwarp();
 }
 
 // Heads epilogue (CB_OUT_HEADS, one 32-column tile): fp32 NCHW stores, coalesced across the lanes of a warp

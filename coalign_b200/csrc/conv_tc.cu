@@ -26,9 +26,9 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;
 template <int BN> struct TcCfg {
     static constexpr int B_STAGE_BYTES = BN * BK * 2;
     static constexpr int KSTEP_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int KPS = (BN == 256) ? 1 : (BN == 128 ? 2 : (BN == 64 ? 3 : 2));
+    static constexpr int KPS = (BN == 256) ? 1 : 2;
     static constexpr int STAGE_BYTES = KPS * KSTEP_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : (BN == 64 ? 3 : 5));
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : (BN == 64 ? 4 : 5));
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;   // +1024: manual 1 KiB alignment
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;    // double-buffered accumulator
 };
@@ -46,8 +46,9 @@ constexpr int W_PRODUCER = 8, W_MMA = 9, W_ALLOC = 10;
 
 // Epilogue of one accumulator tile for one thread: row q (TMEM lane), columns [c_lo, c_hi) of the BN-wide tile.
 template <int BN>
-__device__ __forceinline__ void epilogue_tile(const ConvParams& p, const float* s_bias, uint32_t t_row, long q, int n0,
-                                              int c_lo, int c_hi, uint32_t tfull_bar, uint32_t acc_phase, int dbg) {
+__device__ __forceinline__ void epilogue_tile(const ConvParams& p, const float* s_bias, uint4* stage, uint32_t t_row,
+                                              long q, int n0, int c_lo, int c_hi, uint32_t tfull_bar, uint32_t acc_phase,
+                                              int dbg) {
     const RowDest dst = decode_row(p, q, n0);
     const bool fast = (p.out_lo_off == 0) && (p.out_mode != CB_OUT_HEADS) && (p.res_lo_off == 0);
     const bool has_res = fast && p.residual != nullptr && dst.row >= 0 && !(dbg & 4);
@@ -74,7 +75,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const float* 
         if (dbg & 1) {                                   // experiment: no epilogue math / stores
             if (v[0] == 1.2345e-30f) p.out[0] = __float2bfloat16(v[1]);
         } else if (fast) {
-            epilogue_chunk_fast(p, dst, (n0 + c) % p.cout_mod, s_bias, rcur, has_res, v, dbg);
+            epilogue_chunk_fast(p, (int)dst.row, (n0 + c) % p.cout_mod, s_bias, rcur, has_res, v, stage,
+                                (int)(threadIdx.x & 31), dbg);
         } else if (p.out_mode == CB_OUT_HEADS && BN == 32 && !p.relu && p.residual == nullptr) {
             epilogue_heads_fast(p, dst, s_bias, v);
         } else {
@@ -99,6 +101,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_co
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
     __shared__ __align__(16) float s_bias[256];
+    __shared__ __align__(16) uint4 s_stage[8][128];       // per epilogue warp: 32 rows x 64 B transposition stage
 
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
@@ -212,7 +215,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_co
             const uint32_t acc_phase = (it >> 1) & 1;
             const long q = (long)mt * BM + q4 * 32 + lane;
             const uint32_t t_row = tmem_base + buf * BN + ((uint32_t)(q4 * 32) << 16);
-            epilogue_tile<BN>(p, s_bias, t_row, q, nt * BN, c_lo, c_hi, tfull0 + buf * 8, acc_phase, dbg);
+            epilogue_tile<BN>(p, s_bias, s_stage[warp], t_row, q, nt * BN, c_lo, c_hi, tfull0 + buf * 8, acc_phase, dbg);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
@@ -257,6 +260,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];      // leader's copy counts 16 epilogue warps (both CTAs)
     __shared__ uint32_t tmem_base_smem;
     __shared__ __align__(16) float s_bias[256];
+    __shared__ __align__(16) uint4 s_stage[8][128];
 
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
@@ -371,7 +375,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
             const uint32_t acc_phase = (it >> 1) & 1;
             const long q = (long)(mp * 2 + (int)rank) * BM + q4 * 32 + lane;
             const uint32_t t_row = tmem_base + buf * BN + ((uint32_t)(q4 * 32) << 16);
-            epilogue_tile<BN>(p, s_bias, t_row, q, nt * BN, c_lo, c_hi, tfull0 + buf * 8, acc_phase, 0);
+            epilogue_tile<BN>(p, s_bias, s_stage[warp], t_row, q, nt * BN, c_lo, c_hi, tfull0 + buf * 8, acc_phase, 0);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[buf], 0);      // leader's barrier
@@ -445,7 +449,7 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
     using Cfg = TcCfg<BN>;
     {                                                     // experiment: K-steps-per-stage / stage-count variants
         const int f = dbg_flags() >> 3;
-        if (BN == 64 && f == 1) return launch_st<64, 1, 9>(a0, a1, w, p, m_tiles, n_tiles, max_ctas, stream);
+        if (BN == 64 && f == 1) return launch_st<64, 1, 8>(a0, a1, w, p, m_tiles, n_tiles, max_ctas, stream);
         if (BN == 64 && f == 2) return launch_st<64, 2, 4>(a0, a1, w, p, m_tiles, n_tiles, max_ctas, stream);
         if (BN == 64 && f == 3) return launch_st<64, 4, 2>(a0, a1, w, p, m_tiles, n_tiles, max_ctas, stream);
         if (BN == 128 && f == 1) return launch_st<128, 1, 6>(a0, a1, w, p, m_tiles, n_tiles, max_ctas, stream);
