@@ -51,28 +51,21 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const float* 
                                               int dbg) {
     const RowDest dst = decode_row(p, q, n0);
     const bool fast = (p.out_lo_off == 0) && (p.out_mode != CB_OUT_HEADS) && (p.res_lo_off == 0);
-    const bool has_res = fast && p.residual != nullptr && !(dbg & 4);     // warp-uniform
-    const int lane = (int)(threadIdx.x & 31);
-    // Residual tile of the warp (32 consecutive GEMM rows x 64 B per chunk), loaded COALESCED: per instruction lane l
-    // fetches 16 B of row (it*8 + l/4) - 8 rows x 64 B of full sectors - and handed to the owning lane through the
-    // shared-memory stage right before use.  Issued one chunk ahead (the first one before the accumulator is ready).
-    const long q_warp = q - lane;                                        // GEMM row of lane 0
+    const bool has_res = fast && p.residual != nullptr && dst.row >= 0 && !(dbg & 4);
     uint4 rcur[4] = {}, rnext[4] = {};
-    auto load_res = [&](int c, uint4 (&dst4)[4]) {
+    const uint4* rptr = reinterpret_cast<const uint4*>(p.residual + q * (long)p.res_pitch + n0);
+    if (has_res) {                                       // residual of the first chunk: issued before the MMA is done
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const long qr = q_warp + it * 8 + (lane >> 2);
-            dst4[it] = make_uint4(0u, 0u, 0u, 0u);
-            if (qr < p.rows_total)
-                dst4[it] = __ldg(reinterpret_cast<const uint4*>(p.residual + qr * (long)p.res_pitch + n0 + c) + (lane & 3));
-        }
-    };
-    if (has_res) load_res(c_lo, rcur);
+        for (int t = 0; t < 4; ++t) rcur[t] = __ldg(rptr + (c_lo >> 3) + t);
+    }
     mbar_wait_a(tfull_bar, acc_phase);
     tc_fence_after();
 #pragma unroll 1
     for (int c = c_lo; c < c_hi; c += 32) {
-        if (has_res && c + 32 < c_hi) load_res(c + 32, rnext);
+        if (has_res && c + 32 < c_hi) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) rnext[t] = __ldg(rptr + ((c + 32) >> 3) + t);
+        }
         uint32_t r[32];
         tmem_ld32(t_row + c, r);
         tmem_ld_wait();
@@ -82,19 +75,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const float* 
         if (dbg & 1) {                                   // experiment: no epilogue math / stores
             if (v[0] == 1.2345e-30f) p.out[0] = __float2bfloat16(v[1]);
         } else if (fast) {
-            uint4 mine[4] = {};
-            if (has_res) {                               // transpose: (row it*8+l/4, chunk l%4) -> own row's 4 chunks
-#pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    const int R = it * 8 + (lane >> 2);
-                    stage[R * 4 + ((lane & 3) ^ ((R >> 1) & 3))] = rcur[it];
-                }
-                __syncwarp();
-#pragma unroll
-                for (int t = 0; t < 4; ++t) mine[t] = stage[lane * 4 + (t ^ ((lane >> 1) & 3))];
-                __syncwarp();
-            }
-            epilogue_chunk_fast(p, (int)dst.row, (n0 + c) % p.cout_mod, s_bias, mine, has_res, v, stage, lane, dbg);
+            epilogue_chunk_fast(p, (int)dst.row, (n0 + c) % p.cout_mod, s_bias, rcur, has_res, v, stage,
+                                (int)(threadIdx.x & 31), dbg);
         } else if (p.out_mode == CB_OUT_HEADS && BN == 32 && !p.relu && p.residual == nullptr) {
             epilogue_heads_fast(p, dst, s_bias, v);
         } else {
