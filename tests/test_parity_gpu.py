@@ -315,3 +315,34 @@ def test_pipelined_runner_matches_direct_forward():
     for a, b in zip(got, direct):
         for k in a:
             assert np.array_equal(a[k], b[k]), k
+
+
+def _full_size_case(args, n_agents, seed, pose_noise):
+    from oracle import coalign_oracle as O
+    torch.set_num_threads(min(32, os.cpu_count() or 1))
+    sd = synth.random_state_dict(args, 0)
+    sc = synth.make_scene(seed, n_agents, 60000, args["lidar_range"], pose_noise=pose_noise)
+    inp = G.scenes_to_batch([sc], args["lidar_range"], args["voxel_size"])
+    ref = O.forward(sd, args, G.to_torch_batch(inp))
+    pts = torch.from_numpy(np.concatenate(sc["points"])).cuda()
+    off = (np.arange(n_agents + 1) * 60000).astype(np.int32)
+    pw = torch.from_numpy(sc["pairwise_t_matrix"][None]).cuda()
+    res = {}
+    for precise in (True, False):
+        eng = make_engine(args, sd, n_agents, 1, precise=precise)
+        out = eng.forward_points(pts, off, [n_agents], pw)
+        res[precise] = {k: v.cpu().numpy() for k, v in out.items()}
+        del eng
+    for k in ref:
+        assert_close(res[True][k], ref[k].numpy(), 1e-3, 1e-3, f"precise {k}")
+        assert rel_l2(res[False][k], ref[k].numpy()) < 3e-2, (k, rel_l2(res[False][k], ref[k].numpy()))
+
+
+def test_full_size_opv2v_two_agents_vs_oracle():
+    """BASELINE configs[1]: OPV2V-shape 2-agent intermediate fusion, no pose noise, full 200x704 canvas, 60k points."""
+    _full_size_case(synth.opv2v_args(), 2, seed=11, pose_noise=False)
+
+
+def test_full_size_dairv2x_two_agents_pose_noise_vs_oracle():
+    """BASELINE configs[3]: DAIR-V2X shape (200x504 canvas, voxel z 5 m, odd 25x63 top level), 2 agents, pose noise."""
+    _full_size_case(synth.dairv2x_args(), 2, seed=12, pose_noise=True)
