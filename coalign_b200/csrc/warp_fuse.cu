@@ -200,6 +200,8 @@ __global__ void __launch_bounds__(256, 2) warp_att_fuse_v8_kernel(const __nv_bfl
         // Sampling taps: lane `sub` of the pixel's lane group evaluates agent j = sub (grid in f64, cast to f32 like the
         // reference's `.to(src)`), the other lanes fetch the 4 row indices / weights by shuffle - the coordinate math is
         // done once per (pixel, agent) instead of once per lane.
+        // all lanes of a pixel group share n; groups of one warp may differ -> shuffles use the group's lane mask
+        const unsigned gmask = LPP == 32 ? 0xffffffffu : (((1u << LPP) - 1u) << (pin * LPP));
         int my_r[4] = {0, 0, 0, 0};
         float my_w[4] = {0.f, 0.f, 0.f, 0.f};
         if (sub < n) {
@@ -229,8 +231,8 @@ __global__ void __launch_bounds__(256, 2) warp_att_fuse_v8_kernel(const __nv_bfl
         int rcur[4], rnext[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {                                      // agent 0 (always present)
-            rcur[t] = __shfl_sync(0xffffffffu, my_r[t], 0, LPP);
-            wcur[t] = __shfl_sync(0xffffffffu, my_w[t], 0, LPP);
+            rcur[t] = __shfl_sync(gmask, my_r[t], 0, LPP);
+            wcur[t] = __shfl_sync(gmask, my_w[t], 0, LPP);
             ucur[t] = __ldg(feat4 + (size_t)rcur[t] * LPP + sub);          // row pitch C = 8*LPP
         }
 #pragma unroll
@@ -241,8 +243,8 @@ __global__ void __launch_bounds__(256, 2) warp_att_fuse_v8_kernel(const __nv_bfl
                 if (j + 1 < MAXN && j + 1 < n) {                           // next agent's taps in flight during this one's math
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
-                        rnext[t] = __shfl_sync(0xffffffffu, my_r[t], j + 1, LPP);
-                        wnext[t] = __shfl_sync(0xffffffffu, my_w[t], j + 1, LPP);
+                        rnext[t] = __shfl_sync(gmask, my_r[t], j + 1, LPP);
+                        wnext[t] = __shfl_sync(gmask, my_w[t], j + 1, LPP);
                         unext[t] = __ldg(feat4 + (size_t)rnext[t] * LPP + sub);
                     }
                 }
@@ -283,7 +285,7 @@ __global__ void __launch_bounds__(256, 2) warp_att_fuse_v8_kernel(const __nv_bfl
 #pragma unroll
                     for (int c = 0; c < 8; ++c) d = fmaf(x[0][c], x[j][c], d);
 #pragma unroll
-                    for (int sft = LPP / 2; sft > 0; sft >>= 1) d += __shfl_xor_sync(0xffffffffu, d, sft);
+                    for (int sft = LPP / 2; sft > 0; sft >>= 1) d += __shfl_xor_sync(gmask, d, sft);
                     score[j] = d * inv_sqrt_c;
                     smax = fmaxf(smax, score[j]);
                 }
