@@ -168,7 +168,7 @@ __device__ __forceinline__ int in_row_i(const FuseGeom& g, int plane_rows, int a
 }
 
 template <int LPP, int MAXN>
-__global__ void __launch_bounds__(256, 2) warp_att_fuse_v8_kernel(const __nv_bfloat16* __restrict__ feat, long in_lo_off,
+__global__ void __launch_bounds__(256, (MAXN <= 5 ? 3 : 2)) warp_att_fuse_v8_kernel(const __nv_bfloat16* __restrict__ feat, long in_lo_off,
                                                                const double* __restrict__ affine,
                                                                const int* __restrict__ agent_off, int n_scenes, int L,
                                                                const FuseGeom g, int method,
@@ -197,72 +197,50 @@ __global__ void __launch_bounds__(256, 2) warp_att_fuse_v8_kernel(const __nv_bfl
         n = n < MAXN ? n : MAXN;
         const double xs = (2.0 * w + 1.0) / g.W - 1.0;      // affine_grid base grid, align_corners=False
         const double ys = (2.0 * h + 1.0) / g.H - 1.0;
-        // Sampling taps: lane `sub` of the pixel's lane group evaluates agent j = sub (grid in f64, cast to f32 like the
-        // reference's `.to(src)`), the other lanes fetch the 4 row indices / weights by shuffle - the coordinate math is
-        // done once per (pixel, agent) instead of once per lane.
         // all lanes of a pixel group share n; groups of one warp may differ -> shuffles use the group's lane mask
         const unsigned gmask = LPP == 32 ? 0xffffffffu : (((1u << LPP) - 1u) << (pin * LPP));
-        int my_r[4] = {0, 0, 0, 0};
-        float my_w[4] = {0.f, 0.f, 0.f, 0.f};
-        if (sub < n) {
-            const double* A = affine + (b * L + sub) * 6;
-            const float gx = (float)(A[0] * xs + A[1] * ys + A[2]);
-            const float gy = (float)(A[3] * xs + A[4] * ys + A[5]);
-            const float ix = ((gx + 1.f) * g.W - 1.f) * 0.5f;             // grid_sample unnormalise
-            const float iy = ((gy + 1.f) * g.H - 1.f) * 0.5f;
-            const float fx0 = floorf(ix), fy0 = floorf(iy);
-            const float wx1 = ix - fx0, wy1 = iy - fy0;
-            // clamp before the int conversion so far-away (or non-finite) coordinates stay out of range
-            const int x0 = (int)fminf(fmaxf(fx0, -2.f), (float)g.W + 1.f);
-            const int y0 = (int)fminf(fmaxf(fy0, -2.f), (float)g.H + 1.f);
-            // branch-free taps: out-of-range taps get weight 0 and a clamped (valid) address
-            const float wxa = (x0 >= 0 && x0 < g.W) ? 1.f - wx1 : 0.f, wxb = (x0 + 1 >= 0 && x0 + 1 < g.W) ? wx1 : 0.f;
-            const float wya = (y0 >= 0 && y0 < g.H) ? 1.f - wy1 : 0.f, wyb = (y0 + 1 >= 0 && y0 + 1 < g.H) ? wy1 : 0.f;
-            const int xa = min(max(x0, 0), g.W - 1), xb = min(max(x0 + 1, 0), g.W - 1);
-            const int ya = min(max(y0, 0), g.H - 1), yb = min(max(y0 + 1, 0), g.H - 1);
-            const int ag = a0 + sub;
-            my_r[0] = in_row_i(g, plane_rows, ag, ya, xa); my_r[1] = in_row_i(g, plane_rows, ag, ya, xb);
-            my_r[2] = in_row_i(g, plane_rows, ag, yb, xa); my_r[3] = in_row_i(g, plane_rows, ag, yb, xb);
-            my_w[0] = wya * wxa; my_w[1] = wya * wxb; my_w[2] = wyb * wxa; my_w[3] = wyb * wxb;
-        }
         float x[MAXN][8];
-        uint4 ucur[4], unext[4];
-        float wcur[4], wnext[4];
-        int rcur[4], rnext[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {                                      // agent 0 (always present)
-            rcur[t] = __shfl_sync(gmask, my_r[t], 0, LPP);
-            wcur[t] = __shfl_sync(gmask, my_w[t], 0, LPP);
-            ucur[t] = __ldg(feat4 + (size_t)rcur[t] * LPP + sub);          // row pitch C = 8*LPP
-        }
 #pragma unroll
         for (int j = 0; j < MAXN; ++j) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) x[j][c] = 0.f;
             if (j < n) {
-                if (j + 1 < MAXN && j + 1 < n) {                           // next agent's taps in flight during this one's math
+                const double* A = affine + (b * L + j) * 6;
+                const float gx = (float)(A[0] * xs + A[1] * ys + A[2]);   // grid in f64, cast to f32 (reference `.to(src)`)
+                const float gy = (float)(A[3] * xs + A[4] * ys + A[5]);
+                const float ix = ((gx + 1.f) * g.W - 1.f) * 0.5f;         // grid_sample unnormalise
+                const float iy = ((gy + 1.f) * g.H - 1.f) * 0.5f;
+                const float fx0 = floorf(ix), fy0 = floorf(iy);
+                const float wx1 = ix - fx0, wy1 = iy - fy0;
+                // clamp before the int conversion so far-away (or non-finite) coordinates stay out of range
+                const int x0 = (int)fminf(fmaxf(fx0, -2.f), (float)g.W + 1.f);
+                const int y0 = (int)fminf(fmaxf(fy0, -2.f), (float)g.H + 1.f);
+                // branch-free taps: out-of-range taps get weight 0 and a clamped (valid) address
+                const float wxa = (x0 >= 0 && x0 < g.W) ? 1.f - wx1 : 0.f, wxb = (x0 + 1 >= 0 && x0 + 1 < g.W) ? wx1 : 0.f;
+                const float wya = (y0 >= 0 && y0 < g.H) ? 1.f - wy1 : 0.f, wyb = (y0 + 1 >= 0 && y0 + 1 < g.H) ? wy1 : 0.f;
+                const int xa = min(max(x0, 0), g.W - 1), xb = min(max(x0 + 1, 0), g.W - 1);
+                const int ya = min(max(y0, 0), g.H - 1), yb = min(max(y0 + 1, 0), g.H - 1);
+                const int ag = a0 + j;
+                const int r00 = in_row_i(g, plane_rows, ag, ya, xa), r01 = in_row_i(g, plane_rows, ag, ya, xb);
+                const int r10 = in_row_i(g, plane_rows, ag, yb, xa), r11 = in_row_i(g, plane_rows, ag, yb, xb);
+                const float wt[4] = {wya * wxa, wya * wxb, wyb * wxa, wyb * wxb};
+                const int rr[4] = {r00, r01, r10, r11};
+                uint4 u[4];
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        rnext[t] = __shfl_sync(gmask, my_r[t], j + 1, LPP);
-                        wnext[t] = __shfl_sync(gmask, my_w[t], j + 1, LPP);
-                        unext[t] = __ldg(feat4 + (size_t)rnext[t] * LPP + sub);
-                    }
-                }
+                for (int t = 0; t < 4; ++t) u[t] = __ldg(feat4 + (size_t)rr[t] * LPP + sub);   // row pitch C = 8*LPP
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     float v[8];
-                    unpack8(ucur[t], v);
+                    unpack8(u[t], v);
                     if (has_lo) {
                         float vl[8];
-                        unpack8(__ldg(featl4 + (size_t)rcur[t] * LPP + sub), vl);
+                        unpack8(__ldg(featl4 + (size_t)rr[t] * LPP + sub), vl);
 #pragma unroll
                         for (int c = 0; c < 8; ++c) v[c] += vl[c];
                     }
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) x[j][c] = fmaf(wcur[t], v[c], x[j][c]);
+                    for (int c = 0; c < 8; ++c) x[j][c] = fmaf(wt[t], v[c], x[j][c]);
                 }
-#pragma unroll
-                for (int t = 0; t < 4; ++t) { ucur[t] = unext[t]; wcur[t] = wnext[t]; rcur[t] = rnext[t]; }
             }
         }
         float o[8];
