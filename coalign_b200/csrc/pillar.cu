@@ -331,10 +331,9 @@ __constant__ float c_pfn_sc[64];
 __constant__ float c_pfn_sh[64];
 
 template <int HALF, class PointFn>
-__device__ __forceinline__ void pfn_thread_store(PointFn pt, int n, int max_pts, int a, int cz, int cy, int cx,
-                                                 const PfnParams& pp, const CanvasGeom& cg, __nv_bfloat16* canvas,
+__device__ __forceinline__ void pfn_thread_store(PointFn pt, const float4 p0, int n, int max_pts, int a, int cz, int cy,
+                                                 int cx, const PfnParams& pp, const CanvasGeom& cg, __nv_bfloat16* canvas,
                                                  long lo_off, long* dirty_slot) {
-    const float4 p0 = pt(0);
     const PillarTerms t = pillar_terms(pt, p0, n, cz, cy, cx, pp);
     float best[32];
 #pragma unroll
@@ -429,19 +428,34 @@ __global__ void __launch_bounds__(256, 3) vox_pfn_kernel(const __grid_constant__
     const int half = warp & 1;                                     // even warps: channels 0-31, odd warps: 32-63
     const int slot = (blockIdx.x * 4 + (warp >> 1)) * 32 + lane;
     const int nslot = gridDim.x * 4 * 32;
-    for (int gidx = slot; gidx < total; gidx += nslot) {
+    // one pillar per thread and iteration; the next pillar's (perm -> metadata -> first point) chain is fetched while
+    // the current one is computed
+    struct Item { int a, v; int4 m; float4 p0; };
+    auto fetch = [&](int gidx) {
+        Item it;
         int lo = 0, hi = nseg;                                     // largest seg with s_seg[seg] <= gidx
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_seg[mid] <= gidx) lo = mid; else hi = mid; }
-        const int c = lo / ao.n_agents, a = lo - c * ao.n_agents;
-        const int i = gidx - s_seg[lo];
-        const int v = ws.perm[((long)a * NCLS + c) * ws.vcap + i];
-        const int4 m = __ldg(ws.vox_meta + (long)a * ws.vcap + v);
+        const int c = lo / ao.n_agents;
+        it.a = lo - c * ao.n_agents;
+        it.v = ws.perm[((long)it.a * NCLS + c) * ws.vcap + (gidx - s_seg[lo])];
+        it.m = __ldg(ws.vox_meta + (long)it.a * ws.vcap + it.v);
+        it.p0 = ws.vp[ao.off[it.a] + it.m.x];
+        return it;
+    };
+    Item cur;
+    if (slot < total) cur = fetch(slot);
+    for (int gidx = slot; gidx < total; gidx += nslot) {
+        Item nxt = cur;
+        if (gidx + nslot < total) nxt = fetch(gidx + nslot);
+        const int a = cur.a;
+        const int4 m = cur.m;
         const int n = m.y < max_pts ? m.y : max_pts;
         const float4* vpp = ws.vp + ao.off[a] + m.x;
         const int cz = (m.z >> 24) & 0xFF, cy = (m.z >> 12) & 0xFFF, cx = m.z & 0xFFF;
-        long* dslot = dirty_rows ? dirty_rows + s_base[a] + v : nullptr;
-        if (half == 0) pfn_thread_store<0>([&](int k) { return vpp[k]; }, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dslot);
-        else           pfn_thread_store<1>([&](int k) { return vpp[k]; }, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dslot);
+        long* dslot = dirty_rows ? dirty_rows + s_base[a] + cur.v : nullptr;
+        if (half == 0) pfn_thread_store<0>([&](int k) { return vpp[k]; }, cur.p0, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dslot);
+        else           pfn_thread_store<1>([&](int k) { return vpp[k]; }, cur.p0, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dslot);
+        cur = nxt;
     }
 }
 
