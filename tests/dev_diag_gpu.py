@@ -1,4 +1,5 @@
-"""GPU diagnostics (development aid): per-stage error tables and per-op timings.  Run under gpurun."""
+"""GPU diagnostics (development aid, lives under tests/ because it uses the oracle): per-stage error tables and
+per-op timings.  Run under gpurun: python tests/dev_diag_gpu.py [small] [full]."""
 import os
 import sys
 import time
