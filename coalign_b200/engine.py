@@ -97,8 +97,11 @@ def pack_conv_weight(w: torch.Tensor, scale: Optional[torch.Tensor]) -> torch.Te
 class CoAlignEngine:
     def __init__(self, args: dict, state_dict: Dict[str, torch.Tensor], max_agents: int, max_scenes: int,
                  device="cuda", precise: bool = False, max_cav: int = 5, block_n_cap: int = 128,
-                 use_graph: bool = True, simt_conv: bool = False, pair: bool = True):
-        self.lib = _lib.load(check_device=True)
+                 use_graph: bool = True, simt_conv: bool = False, pair: bool = True, plan_only: bool = False):
+        # plan_only: build weights, buffers and launch descriptors on any torch device WITHOUT loading the CUDA library;
+        # nothing can be launched.  Used by the CPU test that interprets the launch plan (tests/plan_interpreter.py).
+        self.plan_only = bool(plan_only)
+        self.lib = None if plan_only else _lib.load(check_device=True)
         self.args = args
         self.device = torch.device(device)
         self.precise = bool(precise)
@@ -145,7 +148,7 @@ class CoAlignEngine:
         self._pack_weights(state_dict)
         self._alloc()
         self._graphs: Dict[tuple, dict] = {}
-        self._stream = torch.cuda.Stream(device=self.device)
+        self._stream = None if self.plan_only else torch.cuda.Stream(device=self.device)
 
     # ------------------------------------------------------------------ weights
     def _pack_weights(self, sd):
@@ -257,6 +260,14 @@ class CoAlignEngine:
               out_ch_off: int = 0, up_k: int = 0, heads=None) -> ConvDesc:
         d = ConvDesc()
         lo_rows = [0, 0]
+        reg = self.__dict__.setdefault("_by_ptr", {})          # pointer -> owning object (plan interpreter / debugging)
+        for obj in list(a) + [out, residual]:
+            if obj is not None:
+                reg[obj.ptr] = obj
+        reg[pc.w.data_ptr()] = pc
+        reg[pc.bias.data_ptr()] = pc
+        for t, _cn in (heads or []):
+            reg[t.data_ptr()] = t
         for i, act in enumerate(a):
             if act is not None:
                 d.a_ptr[i] = act.ptr
@@ -385,6 +396,8 @@ class CoAlignEngine:
 
     # ------------------------------------------------------------------ launches
     def _launch_ops(self, ops, n_scenes: int, stream_ptr: int):
+        if self.plan_only:
+            raise RuntimeError("plan_only engine cannot launch (no CUDA library loaded)")
         lib = self.lib
         for kind, o in ops:
             if kind == "conv":

@@ -1,0 +1,37 @@
+"""CPU check of the host logic: the engine's launch plan (packed weights, PF/PS layouts, K-step tables, epilogue
+modes), executed by the reference interpreter in tests/plan_interpreter.py, reproduces the reference's golden
+outputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from coalign_b200 import synth
+from tests import golden_cases as G
+from tests import plan_interpreter as PI
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("name,fusion", [("model_small_att", "att"), ("model_small_max", "max")])
+def test_launch_plan_reproduces_reference_golden(name, fusion):
+    from coalign_b200.engine import CoAlignEngine
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    seed = int(g["seed"])
+    args = G.small_args(fusion)
+    sd = synth.random_state_dict(args, seed)
+    rl = [int(v) for v in g["record_len"]]
+    inp = G.small_case_inputs(rl, seed0=100 + seed)
+    eng = CoAlignEngine(args, sd, sum(rl), len(rl), device="cpu", precise=True, plan_only=True)
+    out = PI.run_plan(eng, sd, args, G.to_torch_batch(inp))
+    for i in range(3):
+        got = PI.act_to_nchw(eng.lvl[i]["out"], eng.lvl[i]["out"].n_cap)[:sum(rl)].numpy()
+        ref = g[f"feat{i}"]
+        assert np.abs(got - ref).max() <= 1e-3 * np.sqrt((ref * ref).mean()) + 1e-3 * np.abs(ref).max(), f"feat{i}"
+    for k in ("cls_preds", "reg_preds", "dir_preds"):
+        a, b = out[k].numpy().astype(np.float64), g[k].astype(np.float64)
+        err = np.abs(a - b)
+        assert (err <= 1e-3 * np.abs(b) + 1e-3 * np.sqrt((b * b).mean())).all(), (k, err.max())
+    with pytest.raises(RuntimeError):
+        eng._launch_ops([], 1, 0)
