@@ -246,13 +246,13 @@ template <int BN> struct Tc2Cfg {
     static constexpr int TMEM_COLS = 2 * BN;
 };
 
-template <int BN>
+template <int BN, int STAGES_OVR = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
                      const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ ConvParams p,
-                     int m_pairs, int n_tiles) {
+                     int m_pairs, int n_tiles, int dbg) {
     using Cfg = Tc2Cfg<BN>;
-    constexpr int STAGES = Cfg::STAGES;
+    constexpr int STAGES = STAGES_OVR ? STAGES_OVR : Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STAGES];       // used in the leader CTA (both CTAs' TMA bytes land here)
     __shared__ __align__(8) uint64_t empty_bar[STAGES];      // per CTA; released by the leader's multicast commit
@@ -319,6 +319,11 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
                             const uint32_t sa = smem_a0 + stage * Cfg::STAGE_BYTES + j * Cfg::KSTEP_BYTES;
                             tma_load_2d_2sm_a(sa, st.a_sel ? &tmap_a1 : &tmap_a0, fb, (int)st.col, m0 + st.row_off);
                             tma_load_2d_2sm_a(sa + A_STAGE_BYTES, &tmap_w, fb, st.w_k, n0);
+                            if ((dbg & 16) && tile + n_clusters < total_tiles) {   // experiment: L2 prefetch of the next tile's A box
+                                const int m1 = (((tile + n_clusters) / n_tiles) * 2 + (int)rank) * BM;
+                                asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+                                             ::"l"(st.a_sel ? &tmap_a1 : &tmap_a0), "r"((int)st.col), "r"(m1 + st.row_off) : "memory");
+                            }
                         }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -375,7 +380,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
             const uint32_t acc_phase = (it >> 1) & 1;
             const long q = (long)(mp * 2 + (int)rank) * BM + q4 * 32 + lane;
             const uint32_t t_row = tmem_base + buf * BN + ((uint32_t)(q4 * 32) << 16);
-            epilogue_tile<BN>(p, s_bias, s_stage[warp], t_row, q, nt * BN, c_lo, c_hi, tfull0 + buf * 8, acc_phase, 0);
+            epilogue_tile<BN>(p, s_bias, s_stage[warp], t_row, q, nt * BN, c_lo, c_hi, tfull0 + buf * 8, acc_phase, dbg & 7);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[buf], 0);      // leader's barrier
@@ -481,11 +486,15 @@ template <int BN>
 static int launch2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const ConvParams& p,
                    int m_tiles, int n_tiles, int max_clusters, cudaStream_t stream) {
     using Cfg = Tc2Cfg<BN>;
+    const int dbg = dbg_flags();
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(conv_gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        attr_err = cudaFuncSetAttribute(conv_gemm_tc2_kernel<BN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(conv_gemm_tc2_kernel<BN, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            Cfg::SMEM_BYTES);
     });
     if (attr_err != cudaSuccess) return (int)attr_err;
     int dev = 0, sms = 148;
@@ -495,8 +504,13 @@ static int launch2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorM
     int clusters = m_pairs * n_tiles;
     int cap = max_clusters > 0 ? max_clusters : sms / 2;
     if (clusters > cap) clusters = cap;
-    cudaError_t le = launch_pdl(conv_gemm_tc2_kernel<BN>, dim3(2 * clusters), dim3(TC_THREADS), Cfg::SMEM_BYTES, stream, a0,
-                                a1, w, p, m_pairs, n_tiles);
+    cudaError_t le;
+    if (dbg & 32)           // experiment: half the pipeline depth
+        le = launch_pdl(conv_gemm_tc2_kernel<BN, 3>, dim3(2 * clusters), dim3(TC_THREADS), Cfg::SMEM_BYTES, stream, a0, a1, w,
+                        p, m_pairs, n_tiles, dbg);
+    else
+        le = launch_pdl(conv_gemm_tc2_kernel<BN, 0>, dim3(2 * clusters), dim3(TC_THREADS), Cfg::SMEM_BYTES, stream, a0, a1, w,
+                        p, m_pairs, n_tiles, dbg);
     if (le != cudaSuccess) return (int)le;
     return CB_OK;
 }

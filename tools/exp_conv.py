@@ -29,9 +29,9 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     if os.environ.get("CB_DEBUG", "0") == "0":
         print("keys:", list(seen.keys()))
 else:
-    for name, envs in (("base", {}), ("no-epilogue", {"CB_DEBUG": "1"}), ("no-stores", {"CB_DEBUG": "2"}),
-                       ("no-residual", {"CB_DEBUG": "4"}), ("no-st+res", {"CB_DEBUG": "6"})):
+    for name, envs in (("pair base", {"CB_PAIR": "1"}), ("pair 3 stages", {"CB_PAIR": "1", "CB_DEBUG": "32"}),
+                       ("pair L2 prefetch", {"CB_PAIR": "1", "CB_DEBUG": "16"}), ("pair no-epilogue", {"CB_PAIR": "1", "CB_DEBUG": "1"})):
         env = dict(os.environ, CB_DEBUG="0", CB_B="4")
         env.update(envs)
         out = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
-        print(f"{name:12s}", out.stdout.strip().split("\n")[0], out.stderr[-300:] if out.returncode else "", flush=True)
+        print(f"{name:18s}", out.stdout.strip().split("\n")[0], out.stderr[-300:] if out.returncode else "", flush=True)
