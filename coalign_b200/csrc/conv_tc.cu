@@ -28,7 +28,7 @@ template <int BN> struct TcCfg {
     static constexpr int KSTEP_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int KPS = (BN == 256) ? 1 : 2;
     static constexpr int STAGE_BYTES = KPS * KSTEP_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : (BN == 64 ? 4 : 5));
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;   // +1024: manual 1 KiB alignment
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;    // double-buffered accumulator
 };
@@ -87,11 +87,90 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const float* 
     }
 }
 
+// PF-layout outputs: the half-tile (128 rows x GW columns) is assembled in shared memory (swizzled, conflict-free) and
+// written with ONE TMA store - no per-thread global stores on the LSU/L1 path at all.  Halo / out-of-range rows are
+// written as zeros, which is what the PF halo holds anyway.  `stage` = this column half's 16 KB buffer (1 KB aligned).
+template <int BN>
+__device__ __forceinline__ void epilogue_tile_tma(const ConvParams& p, const float* s_bias, uint4* stage,
+                                                  const CUtensorMap* tmap_out, uint32_t t_row, long q, int m0, int n0,
+                                                  int half, int q4, int lane, uint32_t tfull_bar, uint32_t acc_phase,
+                                                  bool& store_pending) {
+    constexpr int CW = BN / 2, GW = BN >= 128 ? 64 : 32, NG = CW / GW, CPG = GW / 32, CHR = GW / 8;
+    const RowDest dst = decode_row(p, q, n0);
+    const bool valid = dst.row >= 0;
+    const bool has_res = p.residual != nullptr && valid;
+    const uint4* rptr = reinterpret_cast<const uint4*>(p.residual + q * (long)p.res_pitch + n0 + half * CW);
+    uint4 rcur[4] = {}, rnext[4] = {};
+    if (has_res) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) rcur[t] = __ldg(rptr + t);
+    }
+    mbar_wait_a(tfull_bar, acc_phase);
+    tc_fence_after();
+    const int row_local = q4 * 32 + lane;
+    const bool issuer = (q4 == 0 && lane == 0);
+#pragma unroll 1
+    for (int gi = 0; gi < NG; ++gi) {
+        uint4 pk[CPG * 4];
+#pragma unroll
+        for (int cc = 0; cc < CPG; ++cc) {
+            const int ci = gi * CPG + cc;                        // 32-column chunk index inside this half
+            if (has_res && ci + 1 < NG * CPG) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) rnext[t] = __ldg(rptr + (ci + 1) * 4 + t);
+            }
+            uint32_t r[32];
+            tmem_ld32(t_row + half * CW + ci * 32, r);
+            tmem_ld_wait();
+            const float4* b4 = reinterpret_cast<const float4*>(s_bias + (n0 + half * CW + ci * 32) % p.cout_mod);
+            float v[32];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const float4 b = b4[t];
+                v[4 * t + 0] = __uint_as_float(r[4 * t + 0]) + b.x; v[4 * t + 1] = __uint_as_float(r[4 * t + 1]) + b.y;
+                v[4 * t + 2] = __uint_as_float(r[4 * t + 2]) + b.z; v[4 * t + 3] = __uint_as_float(r[4 * t + 3]) + b.w;
+            }
+            if (has_res) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    v[8 * t + 0] += bf16_lo(rcur[t].x); v[8 * t + 1] += bf16_hi(rcur[t].x);
+                    v[8 * t + 2] += bf16_lo(rcur[t].y); v[8 * t + 3] += bf16_hi(rcur[t].y);
+                    v[8 * t + 4] += bf16_lo(rcur[t].z); v[8 * t + 5] += bf16_hi(rcur[t].z);
+                    v[8 * t + 6] += bf16_lo(rcur[t].w); v[8 * t + 7] += bf16_hi(rcur[t].w);
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                uint4 u;
+                if (p.relu) u = make_uint4(pack_bf16_relu(v[8 * t + 0], v[8 * t + 1]), pack_bf16_relu(v[8 * t + 2], v[8 * t + 3]),
+                                           pack_bf16_relu(v[8 * t + 4], v[8 * t + 5]), pack_bf16_relu(v[8 * t + 6], v[8 * t + 7]));
+                else        u = make_uint4(pack_bf16(v[8 * t + 0], v[8 * t + 1]), pack_bf16(v[8 * t + 2], v[8 * t + 3]),
+                                           pack_bf16(v[8 * t + 4], v[8 * t + 5]), pack_bf16(v[8 * t + 6], v[8 * t + 7]));
+                pk[cc * 4 + t] = valid ? u : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) rcur[t] = rnext[t];
+        }
+        if (store_pending && issuer) tma_store_wait_read0();     // previous store of this half has read the stage
+        named_bar_sync(1 + half, 128);
+        const int sw = GW == 64 ? (row_local & 7) : ((row_local >> 1) & 3);   // SWIZZLE_128B / SWIZZLE_64B chunk XOR
+#pragma unroll
+        for (int k = 0; k < CPG * 4; ++k) stage[row_local * CHR + (k ^ sw)] = pk[k];
+        fence_proxy_async();                                     // generic-proxy writes -> visible to the TMA (async proxy)
+        named_bar_sync(1 + half, 128);
+        if (issuer) {
+            tma_store_2d(tmap_out, smem_u32(stage), p.out_ch_off + (n0 + half * CW + gi * GW) % p.cout_mod, m0);
+            tma_store_commit();
+        }
+        store_pending = true;
+    }
+}
+
 template <int BN, int KPS_OVR = 0, int STAGES_OVR = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
-                    const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ ConvParams p,
-                    int m_tiles, int n_tiles, int dbg) {
+                    const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out,
+                    const __grid_constant__ ConvParams p, int m_tiles, int n_tiles, int dbg, int use_tma) {
     using Cfg = TcCfgK<BN, KPS_OVR>;
     constexpr int STAGES = STAGES_OVR ? STAGES_OVR : TcCfg<BN>::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -101,7 +180,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_co
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
     __shared__ __align__(16) float s_bias[256];
-    __shared__ __align__(16) uint4 s_stage[8][128];       // per epilogue warp: 32 rows x 64 B transposition stage
+    __shared__ __align__(1024) uint4 s_stage[2][1024];    // per column half: 128 rows x 128 B epilogue stage (TMA store) /
+                                                          // per warp 2 KB slices for the transposed-STG path
 
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
@@ -117,6 +197,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_co
         prefetch_tmap(&tmap_a0);
         prefetch_tmap(&tmap_a1);
         prefetch_tmap(&tmap_w);
+        prefetch_tmap(&tmap_out);
     }
     if (warp == W_MMA && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -208,6 +289,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_co
         const int half = warp >> 2;                            // column half of the tile
         constexpr int CW = BN >= 64 ? BN / 2 : BN;                   // columns per warp (BN=32: half 1 idles)
         const int c_lo = half * CW, c_hi = (BN >= 64 || half == 0) ? c_lo + CW : c_lo;
+        bool store_pending = false;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
@@ -215,11 +297,17 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_co
             const uint32_t acc_phase = (it >> 1) & 1;
             const long q = (long)mt * BM + q4 * 32 + lane;
             const uint32_t t_row = tmem_base + buf * BN + ((uint32_t)(q4 * 32) << 16);
-            epilogue_tile<BN>(p, s_bias, s_stage[warp], t_row, q, nt * BN, c_lo, c_hi, tfull0 + buf * 8, acc_phase, dbg);
+            if (BN >= 64 && use_tma)
+                epilogue_tile_tma<(BN >= 64 ? BN : 64)>(p, s_bias, s_stage[half], &tmap_out, t_row, q, mt * BM, nt * BN, half,
+                                                       q4, lane, tfull0 + buf * 8, acc_phase, store_pending);
+            else
+                epilogue_tile<BN>(p, s_bias, &s_stage[0][0] + warp * 128, t_row, q, nt * BN, c_lo, c_hi, tfull0 + buf * 8,
+                                  acc_phase, dbg);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
         }
+        if (store_pending && q4 == 0 && lane == 0) tma_store_wait_all();
     }
     tc_fence_before();
     __syncthreads();
@@ -249,8 +337,8 @@ template <int BN> struct Tc2Cfg {
 template <int BN, int STAGES_OVR = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
-                     const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ ConvParams p,
-                     int m_pairs, int n_tiles, int dbg) {
+                     const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out,
+                     const __grid_constant__ ConvParams p, int m_pairs, int n_tiles, int dbg, int use_tma) {
     using Cfg = Tc2Cfg<BN>;
     constexpr int STAGES = STAGES_OVR ? STAGES_OVR : Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -260,7 +348,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];      // leader's copy counts 16 epilogue warps (both CTAs)
     __shared__ uint32_t tmem_base_smem;
     __shared__ __align__(16) float s_bias[256];
-    __shared__ __align__(16) uint4 s_stage[8][128];
+    __shared__ __align__(1024) uint4 s_stage[2][1024];
 
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
@@ -279,6 +367,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
         prefetch_tmap(&tmap_a0);
         prefetch_tmap(&tmap_a1);
         prefetch_tmap(&tmap_w);
+        prefetch_tmap(&tmap_out);
     }
     if (warp == W_MMA && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -373,6 +462,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
         const int half = warp >> 2;
         constexpr int CW = BN / 2;
         const int c_lo = half * CW, c_hi = c_lo + CW;
+        bool store_pending = false;
         int it = 0;
         for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
             const int mp = tile / n_tiles, nt = tile - mp * n_tiles;
@@ -380,11 +470,17 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
             const uint32_t acc_phase = (it >> 1) & 1;
             const long q = (long)(mp * 2 + (int)rank) * BM + q4 * 32 + lane;
             const uint32_t t_row = tmem_base + buf * BN + ((uint32_t)(q4 * 32) << 16);
-            epilogue_tile<BN>(p, s_bias, s_stage[warp], t_row, q, nt * BN, c_lo, c_hi, tfull0 + buf * 8, acc_phase, dbg & 7);
+            if (use_tma)
+                epilogue_tile_tma<BN>(p, s_bias, s_stage[half], &tmap_out, t_row, q, (mp * 2 + (int)rank) * BM, nt * BN, half,
+                                      q4, lane, tfull0 + buf * 8, acc_phase, store_pending);
+            else
+                epilogue_tile<BN>(p, s_bias, &s_stage[0][0] + warp * 128, t_row, q, nt * BN, c_lo, c_hi, tfull0 + buf * 8,
+                                  acc_phase, dbg & 7);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[buf], 0);      // leader's barrier
         }
+        if (store_pending && q4 == 0 && lane == 0) tma_store_wait_all();
     }
     tc_fence_before();
     cluster_sync_all();
@@ -409,16 +505,18 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 // bf16 [rows][pitch] row-major; box = 64 columns x box_rows rows, 128-byte swizzle, zero OOB fill.
-static int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t pitch_elems, int box_rows) {
+static int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t pitch_elems, int box_rows,
+                     int box_cols = 64) {
     auto enc = get_encode();
     if (!enc) return CB_ERR_DRIVER;
     if (((uintptr_t)base & 15) || (pitch_elems * 2) % 16) return CB_ERR_ARG;
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t gstr[1] = {(cuuint64_t)pitch_elems * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? CB_OK : CB_ERR_DRIVER;
 }
@@ -429,8 +527,8 @@ static int dbg_flags() {
 }
 
 template <int BN, int KPS, int ST>
-static int launch_st(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const ConvParams& p,
-                     int m_tiles, int n_tiles, int max_ctas, cudaStream_t stream) {
+static int launch_st(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& tout,
+                     int use_tma, const ConvParams& p, int m_tiles, int n_tiles, int max_ctas, cudaStream_t stream) {
     constexpr int SMEM = ST * KPS * TcCfg<BN>::KSTEP_BYTES + 1024;
     static_assert(SMEM <= 227 * 1024, "stage configuration exceeds shared memory");
     static std::once_flag once;
@@ -442,25 +540,25 @@ static int launch_st(const CUtensorMap& a0, const CUtensorMap& a1, const CUtenso
     int grid = m_tiles * n_tiles;
     int cap = max_ctas > 0 ? max_ctas : 148;
     if (grid > cap) grid = cap;
-    cudaError_t le = launch_pdl(conv_gemm_tc_kernel<BN, KPS, ST>, dim3(grid), dim3(TC_THREADS), SMEM, stream, a0, a1, w, p,
-                                m_tiles, n_tiles, dbg_flags() & 7);
+    cudaError_t le = launch_pdl(conv_gemm_tc_kernel<BN, KPS, ST>, dim3(grid), dim3(TC_THREADS), SMEM, stream, a0, a1, w, tout,
+                                p, m_tiles, n_tiles, dbg_flags() & 7, use_tma);
     if (le != cudaSuccess) return (int)le;
     return CB_OK;
 }
 
 template <int BN>
-static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const ConvParams& p,
-                  int m_tiles, int n_tiles, int max_ctas, cudaStream_t stream) {
+static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& tout, int use_tma,
+                  const ConvParams& p, int m_tiles, int n_tiles, int max_ctas, cudaStream_t stream) {
     using Cfg = TcCfg<BN>;
     {                                                     // experiment: K-steps-per-stage / stage-count variants
         const int f = dbg_flags() >> 3;
-        if (BN == 64 && f == 1) return launch_st<64, 1, 8>(a0, a1, w, p, m_tiles, n_tiles, max_ctas, stream);
-        if (BN == 64 && f == 2) return launch_st<64, 2, 4>(a0, a1, w, p, m_tiles, n_tiles, max_ctas, stream);
-        if (BN == 64 && f == 3) return launch_st<64, 4, 2>(a0, a1, w, p, m_tiles, n_tiles, max_ctas, stream);
-        if (BN == 128 && f == 1) return launch_st<128, 1, 6>(a0, a1, w, p, m_tiles, n_tiles, max_ctas, stream);
-        if (BN == 128 && f == 2) return launch_st<128, 3, 2>(a0, a1, w, p, m_tiles, n_tiles, max_ctas, stream);
-        if (BN == 128 && f == 3) return launch_st<128, 2, 3>(a0, a1, w, p, m_tiles, n_tiles, max_ctas, stream);
-        if (BN == 256 && f == 2) return launch_st<256, 2, 2>(a0, a1, w, p, m_tiles, n_tiles, max_ctas, stream);
+        if (BN == 64 && f == 1) return launch_st<64, 1, 8>(a0, a1, w, tout, use_tma, p, m_tiles, n_tiles, max_ctas, stream);
+        if (BN == 64 && f == 2) return launch_st<64, 2, 4>(a0, a1, w, tout, use_tma, p, m_tiles, n_tiles, max_ctas, stream);
+        if (BN == 64 && f == 3) return launch_st<64, 4, 2>(a0, a1, w, tout, use_tma, p, m_tiles, n_tiles, max_ctas, stream);
+        if (BN == 128 && f == 1) return launch_st<128, 1, 6>(a0, a1, w, tout, use_tma, p, m_tiles, n_tiles, max_ctas, stream);
+        if (BN == 128 && f == 2) return launch_st<128, 3, 2>(a0, a1, w, tout, use_tma, p, m_tiles, n_tiles, max_ctas, stream);
+        if (BN == 128 && f == 3) return launch_st<128, 2, 3>(a0, a1, w, tout, use_tma, p, m_tiles, n_tiles, max_ctas, stream);
+        if (BN == 256 && f == 2) return launch_st<256, 2, 2>(a0, a1, w, tout, use_tma, p, m_tiles, n_tiles, max_ctas, stream);
     }
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
@@ -476,15 +574,15 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
     int cap = max_ctas > 0 ? max_ctas : sms;
     if (grid > cap) grid = cap;
     cudaError_t le = launch_pdl(conv_gemm_tc_kernel<BN, 0, 0>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, stream, a0, a1,
-                                w, p, m_tiles, n_tiles, dbg_flags() & 7);
+                                w, tout, p, m_tiles, n_tiles, dbg_flags() & 7, use_tma);
     if (le != cudaSuccess) return (int)le;
     return CB_OK;
 }
 
 
 template <int BN>
-static int launch2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const ConvParams& p,
-                   int m_tiles, int n_tiles, int max_clusters, cudaStream_t stream) {
+static int launch2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& tout, int use_tma,
+                   const ConvParams& p, int m_tiles, int n_tiles, int max_clusters, cudaStream_t stream) {
     using Cfg = Tc2Cfg<BN>;
     const int dbg = dbg_flags();
     static std::once_flag once;
@@ -507,10 +605,10 @@ static int launch2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorM
     cudaError_t le;
     if (dbg & 32)           // experiment: half the pipeline depth
         le = launch_pdl(conv_gemm_tc2_kernel<BN, 3>, dim3(2 * clusters), dim3(TC_THREADS), Cfg::SMEM_BYTES, stream, a0, a1, w,
-                        p, m_pairs, n_tiles, dbg);
+                        tout, p, m_pairs, n_tiles, dbg, use_tma);
     else
         le = launch_pdl(conv_gemm_tc2_kernel<BN, 0>, dim3(2 * clusters), dim3(TC_THREADS), Cfg::SMEM_BYTES, stream, a0, a1, w,
-                        p, m_pairs, n_tiles, dbg);
+                        tout, p, m_pairs, n_tiles, dbg, use_tma);
     if (le != cudaSuccess) return (int)le;
     return CB_OK;
 }
@@ -544,19 +642,31 @@ static int conv_gemm_impl(const cb_conv_desc* d, int max_ctas, void* stream, boo
     const int m_tiles = (int)((p.rows_total + BM - 1) / BM);
     const int n_tiles = d->n_total / d->block_n;
     cudaStream_t st = (cudaStream_t)stream;
+    // PF-layout bf16 outputs go out through a TMA store (half-tile = 128 rows x 64 or 32 columns)
+    CUtensorMap tout = tw;
+    int use_tma = 0;
+    {
+        static const bool no_tma_store = [] { const char* e = getenv("CB_NO_TMA_STORE"); return e && e[0] == '1'; }();
+        if (!no_tma_store && d->out_mode == CB_OUT_PF && d->out_lo_off == 0 && d->res_lo_off == 0 && d->block_n >= 64 &&
+            !(dbg_flags() & 7)) {
+            rc = make_tmap(&tout, d->out, p.rows_total, d->out_pitch, d->out_pitch, BM, d->block_n >= 128 ? 64 : 32);
+            if (rc) return rc;
+            use_tma = 1;
+        }
+    }
     if (pair) {
         switch (d->block_n) {
-            case 64: return launch2<64>(ta0, ta1, tw, p, m_tiles, n_tiles, max_ctas, st);
-            case 128: return launch2<128>(ta0, ta1, tw, p, m_tiles, n_tiles, max_ctas, st);
-            case 256: return launch2<256>(ta0, ta1, tw, p, m_tiles, n_tiles, max_ctas, st);
+            case 64: return launch2<64>(ta0, ta1, tw, tout, use_tma, p, m_tiles, n_tiles, max_ctas, st);
+            case 128: return launch2<128>(ta0, ta1, tw, tout, use_tma, p, m_tiles, n_tiles, max_ctas, st);
+            case 256: return launch2<256>(ta0, ta1, tw, tout, use_tma, p, m_tiles, n_tiles, max_ctas, st);
         }
         return CB_ERR_ARG;
     }
     switch (d->block_n) {
-        case 32: return launch<32>(ta0, ta1, tw, p, m_tiles, n_tiles, max_ctas, st);
-        case 64: return launch<64>(ta0, ta1, tw, p, m_tiles, n_tiles, max_ctas, st);
-        case 128: return launch<128>(ta0, ta1, tw, p, m_tiles, n_tiles, max_ctas, st);
-        case 256: return launch<256>(ta0, ta1, tw, p, m_tiles, n_tiles, max_ctas, st);
+        case 32: return launch<32>(ta0, ta1, tw, tout, use_tma, p, m_tiles, n_tiles, max_ctas, st);
+        case 64: return launch<64>(ta0, ta1, tw, tout, use_tma, p, m_tiles, n_tiles, max_ctas, st);
+        case 128: return launch<128>(ta0, ta1, tw, tout, use_tma, p, m_tiles, n_tiles, max_ctas, st);
+        case 256: return launch<256>(ta0, ta1, tw, tout, use_tma, p, m_tiles, n_tiles, max_ctas, st);
     }
     return CB_ERR_ARG;
 }
