@@ -16,6 +16,8 @@ struct FuseGeom {
     int H, W, C, in_ps;
     int Hp, Wp;            // PF dims of input (in_ps=0) / of each parity plane (in_ps=1)
     long plane_rows;       // in_ps=1: rows per parity plane (= sum_agents*Hp*Wp)
+    double inv_W, inv_H;   // 1/W, 1/H for the base grid
+    float inv_sqrt_c;      // att_fuse.py:44 score scale
 };
 
 __device__ __forceinline__ long in_row(const FuseGeom& g, int agent, int y, int x) {
@@ -167,24 +169,27 @@ __device__ __forceinline__ int in_row_i(const FuseGeom& g, int plane_rows, int a
     return ph * plane_rows + (agent * g.Hp + (y >> 1) + 1) * g.Wp + (x >> 1) + 1;
 }
 
-template <int LPP, int MAXN>
+template <int LPP, int MAXN, bool HAS_LO>
 __global__ void __launch_bounds__(256, (MAXN <= 5 ? 3 : 2)) warp_att_fuse_v8_kernel(const __nv_bfloat16* __restrict__ feat, long in_lo_off,
                                                                const double* __restrict__ affine,
                                                                const int* __restrict__ agent_off, int n_scenes, int L,
                                                                const FuseGeom g, int method,
                                                                __nv_bfloat16* __restrict__ out, long out_lo_off) {
     constexpr int PPW = 32 / LPP;                          // pixels per warp
+    static_assert(LPP >= MAXN, "one lane of the pixel group per agent");
+    // tap records: per (warp, pixel of the warp, agent) 4 row indices (pre-multiplied by LPP) + 4 bilinear weights,
+    // computed once by lane `agent` of the pixel group and broadcast to the group's other lanes through shared memory
+    __shared__ __align__(16) uint4 s_tap[8][PPW][MAXN][2];
     pdl_launch_dependents();
     pdl_wait();
-    const int lane = threadIdx.x & 31, sub = lane % LPP, pin = lane / LPP;
-    const int gw = blockIdx.x * 8 + (threadIdx.x >> 5), nw = gridDim.x * 8;
+    const int lane = threadIdx.x & 31, sub = lane % LPP, pin = lane / LPP, wid = threadIdx.x >> 5;
+    const int gw = blockIdx.x * 8 + wid, nw = gridDim.x * 8;
     const int HW = g.H * g.W;
     const int total = n_scenes * HW;
     const int plane_rows = (int)g.plane_rows;
-    const float inv_sqrt_c = (float)(1.0 / sqrt((double)g.C));
+    const float inv_sqrt_c = g.inv_sqrt_c;
     const uint4* feat4 = reinterpret_cast<const uint4*>(feat);
     const uint4* featl4 = reinterpret_cast<const uint4*>(feat + in_lo_off);
-    const bool has_lo = in_lo_off != 0;
     for (int pix0 = gw * PPW; pix0 < total; pix0 += nw * PPW) {
         const int pix = pix0 + pin;
         const bool live = pix < total;
@@ -195,46 +200,55 @@ __global__ void __launch_bounds__(256, (MAXN <= 5 ? 3 : 2)) warp_att_fuse_v8_ker
         const int a0 = agent_off[b];
         int n = agent_off[b + 1] - a0;
         n = n < MAXN ? n : MAXN;
-        const double xs = (2.0 * w + 1.0) / g.W - 1.0;      // affine_grid base grid, align_corners=False
-        const double ys = (2.0 * h + 1.0) / g.H - 1.0;
-        // all lanes of a pixel group share n; groups of one warp may differ -> shuffles use the group's lane mask
-        const unsigned gmask = LPP == 32 ? 0xffffffffu : (((1u << LPP) - 1u) << (pin * LPP));
+        if (sub < n) {
+            const int j = sub;
+            const double xs = fma((double)(2 * w + 1), g.inv_W, -1.0);   // affine_grid base grid, align_corners=False
+            const double ys = fma((double)(2 * h + 1), g.inv_H, -1.0);
+            const double* A = affine + (b * L + j) * 6;
+            const float gx = (float)(A[0] * xs + A[1] * ys + A[2]);   // grid in f64, cast to f32 (reference `.to(src)`)
+            const float gy = (float)(A[3] * xs + A[4] * ys + A[5]);
+            const float ix = ((gx + 1.f) * g.W - 1.f) * 0.5f;         // grid_sample unnormalise
+            const float iy = ((gy + 1.f) * g.H - 1.f) * 0.5f;
+            const float fx0 = floorf(ix), fy0 = floorf(iy);
+            const float wx1 = ix - fx0, wy1 = iy - fy0;
+            // clamp before the int conversion so far-away (or non-finite) coordinates stay out of range
+            const int x0 = (int)fminf(fmaxf(fx0, -2.f), (float)g.W + 1.f);
+            const int y0 = (int)fminf(fmaxf(fy0, -2.f), (float)g.H + 1.f);
+            // branch-free taps: out-of-range taps get weight 0 and a clamped (valid) address
+            const float wxa = (x0 >= 0 && x0 < g.W) ? 1.f - wx1 : 0.f, wxb = (x0 + 1 >= 0 && x0 + 1 < g.W) ? wx1 : 0.f;
+            const float wya = (y0 >= 0 && y0 < g.H) ? 1.f - wy1 : 0.f, wyb = (y0 + 1 >= 0 && y0 + 1 < g.H) ? wy1 : 0.f;
+            const int xa = min(max(x0, 0), g.W - 1), xb = min(max(x0 + 1, 0), g.W - 1);
+            const int ya = min(max(y0, 0), g.H - 1), yb = min(max(y0 + 1, 0), g.H - 1);
+            const int ag = a0 + j;
+            uint4 rr, ww;
+            rr.x = in_row_i(g, plane_rows, ag, ya, xa) * LPP; rr.y = in_row_i(g, plane_rows, ag, ya, xb) * LPP;
+            rr.z = in_row_i(g, plane_rows, ag, yb, xa) * LPP; rr.w = in_row_i(g, plane_rows, ag, yb, xb) * LPP;
+            ww.x = __float_as_uint(wya * wxa); ww.y = __float_as_uint(wya * wxb);
+            ww.z = __float_as_uint(wyb * wxa); ww.w = __float_as_uint(wyb * wxb);
+            s_tap[wid][pin][j][0] = rr;
+            s_tap[wid][pin][j][1] = ww;
+        }
+        __syncwarp();
         float x[MAXN][8];
 #pragma unroll
         for (int j = 0; j < MAXN; ++j) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) x[j][c] = 0.f;
             if (j < n) {
-                const double* A = affine + (b * L + j) * 6;
-                const float gx = (float)(A[0] * xs + A[1] * ys + A[2]);   // grid in f64, cast to f32 (reference `.to(src)`)
-                const float gy = (float)(A[3] * xs + A[4] * ys + A[5]);
-                const float ix = ((gx + 1.f) * g.W - 1.f) * 0.5f;         // grid_sample unnormalise
-                const float iy = ((gy + 1.f) * g.H - 1.f) * 0.5f;
-                const float fx0 = floorf(ix), fy0 = floorf(iy);
-                const float wx1 = ix - fx0, wy1 = iy - fy0;
-                // clamp before the int conversion so far-away (or non-finite) coordinates stay out of range
-                const int x0 = (int)fminf(fmaxf(fx0, -2.f), (float)g.W + 1.f);
-                const int y0 = (int)fminf(fmaxf(fy0, -2.f), (float)g.H + 1.f);
-                // branch-free taps: out-of-range taps get weight 0 and a clamped (valid) address
-                const float wxa = (x0 >= 0 && x0 < g.W) ? 1.f - wx1 : 0.f, wxb = (x0 + 1 >= 0 && x0 + 1 < g.W) ? wx1 : 0.f;
-                const float wya = (y0 >= 0 && y0 < g.H) ? 1.f - wy1 : 0.f, wyb = (y0 + 1 >= 0 && y0 + 1 < g.H) ? wy1 : 0.f;
-                const int xa = min(max(x0, 0), g.W - 1), xb = min(max(x0 + 1, 0), g.W - 1);
-                const int ya = min(max(y0, 0), g.H - 1), yb = min(max(y0 + 1, 0), g.H - 1);
-                const int ag = a0 + j;
-                const int r00 = in_row_i(g, plane_rows, ag, ya, xa), r01 = in_row_i(g, plane_rows, ag, ya, xb);
-                const int r10 = in_row_i(g, plane_rows, ag, yb, xa), r11 = in_row_i(g, plane_rows, ag, yb, xb);
-                const float wt[4] = {wya * wxa, wya * wxb, wyb * wxa, wyb * wxb};
-                const int rr[4] = {r00, r01, r10, r11};
+                const uint4 rq = s_tap[wid][pin][j][0];
+                const uint4 wq = s_tap[wid][pin][j][1];
+                const float wt[4] = {__uint_as_float(wq.x), __uint_as_float(wq.y), __uint_as_float(wq.z), __uint_as_float(wq.w)};
+                const unsigned rr[4] = {rq.x, rq.y, rq.z, rq.w};
                 uint4 u[4];
 #pragma unroll
-                for (int t = 0; t < 4; ++t) u[t] = __ldg(feat4 + (size_t)rr[t] * LPP + sub);   // row pitch C = 8*LPP
+                for (int t = 0; t < 4; ++t) u[t] = __ldg(feat4 + (rr[t] + sub));   // row pitch C = 8*LPP
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     float v[8];
                     unpack8(u[t], v);
-                    if (has_lo) {
+                    if (HAS_LO) {
                         float vl[8];
-                        unpack8(__ldg(featl4 + (size_t)rr[t] * LPP + sub), vl);
+                        unpack8(__ldg(featl4 + (rr[t] + sub)), vl);
 #pragma unroll
                         for (int c = 0; c < 8; ++c) v[c] += vl[c];
                     }
@@ -243,45 +257,43 @@ __global__ void __launch_bounds__(256, (MAXN <= 5 ? 3 : 2)) warp_att_fuse_v8_ker
                 }
             }
         }
+        __syncwarp();                                        // tap records consumed; next iteration may overwrite
         float o[8];
-        if (method == 1) {
+        if (method == 1) {                                   // MaxFusion (branch-free over absent agents)
 #pragma unroll
             for (int c = 0; c < 8; ++c) o[c] = x[0][c];
 #pragma unroll
-            for (int j = 1; j < MAXN; ++j)
-                if (j < n) {
+            for (int j = 1; j < MAXN; ++j) {
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) o[c] = fmaxf(o[c], x[j][c]);
-                }
+                for (int c = 0; c < 8; ++c) o[c] = j < n ? fmaxf(o[c], x[j][c]) : o[c];
+            }
         } else {
+            // absent agents (j >= n) carry x = 0: their score is forced to -inf, so the warp stays converged and the
+            // group reductions can use full-mask shuffles
             float score[MAXN];
             float smax = -INFINITY;
 #pragma unroll
             for (int j = 0; j < MAXN; ++j) {
-                if (j < n) {
-                    float d = 0.f;
+                float d = 0.f;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) d = fmaf(x[0][c], x[j][c], d);
+                for (int c = 0; c < 8; ++c) d = fmaf(x[0][c], x[j][c], d);
 #pragma unroll
-                    for (int sft = LPP / 2; sft > 0; sft >>= 1) d += __shfl_xor_sync(gmask, d, sft);
-                    score[j] = d * inv_sqrt_c;
-                    smax = fmaxf(smax, score[j]);
-                }
+                for (int sft = LPP / 2; sft > 0; sft >>= 1) d += __shfl_xor_sync(0xffffffffu, d, sft);
+                score[j] = j < n ? d * inv_sqrt_c : -INFINITY;
+                smax = fmaxf(smax, score[j]);
             }
             float den = 0.f;
 #pragma unroll
-            for (int j = 0; j < MAXN; ++j)
-                if (j < n) { score[j] = expf(score[j] - smax); den += score[j]; }
+            for (int j = 0; j < MAXN; ++j) { score[j] = HAS_LO ? expf(score[j] - smax) : __expf(score[j] - smax); den += score[j]; }
             const float inv = 1.f / den;
 #pragma unroll
             for (int c = 0; c < 8; ++c) o[c] = 0.f;
 #pragma unroll
-            for (int j = 0; j < MAXN; ++j)
-                if (j < n) {
-                    const float wj = score[j] * inv;
+            for (int j = 0; j < MAXN; ++j) {
+                const float wj = score[j] * inv;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) o[c] = fmaf(wj, x[j][c], o[c]);
-                }
+                for (int c = 0; c < 8; ++c) o[c] = fmaf(wj, x[j][c], o[c]);
+            }
         }
         if (live) {
             const int orow = (b * (g.H + 2) + h + 1) * (g.W + 2) + w + 1;   // PF output
@@ -289,7 +301,7 @@ __global__ void __launch_bounds__(256, (MAXN <= 5 ? 3 : 2)) warp_att_fuse_v8_ker
             hi.x = pack_bf16(o[0], o[1]); hi.y = pack_bf16(o[2], o[3]);
             hi.z = pack_bf16(o[4], o[5]); hi.w = pack_bf16(o[6], o[7]);
             reinterpret_cast<uint4*>(out)[(size_t)orow * LPP + sub] = hi;
-            if (out_lo_off != 0) {
+            if (HAS_LO) {
                 uint4 lo;
                 lo.x = pack_bf16(o[0] - bf16_lo(hi.x), o[1] - bf16_hi(hi.x));
                 lo.y = pack_bf16(o[2] - bf16_lo(hi.y), o[3] - bf16_hi(hi.y));
@@ -326,6 +338,8 @@ extern "C" int cb_warp_att_fuse(const void* feat, int in_ps, int64_t in_lo_off, 
     g.Hp = in_ps ? (H + 1) / 2 + 2 : H + 2;
     g.Wp = in_ps ? (W + 1) / 2 + 2 : W + 2;
     g.plane_rows = (long)sum_agents * g.Hp * g.Wp;
+    g.inv_W = 1.0 / W; g.inv_H = 1.0 / H;
+    g.inv_sqrt_c = (float)(1.0 / sqrt((double)C));
     const long total = (long)n_scenes * H * W;
     long blocks = (total + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
@@ -336,9 +350,13 @@ extern "C" int cb_warp_att_fuse(const void* feat, int in_ps, int64_t in_lo_off, 
         const int ppw = 256 / C;                                    // pixels per warp
         long nb = (total + 8L * ppw - 1) / (8L * ppw);
         if (nb > 148 * 24) nb = 148 * 24;
-        if ((long)sum_agents * g.Hp * g.Wp * (in_ps ? 4 : 1) >= (1L << 31) || total >= (1L << 31)) return CB_ERR_ARG;
-#define CB_FUSE_LAUNCH(LPP_, MAXN_) launch_pdl(warp_att_fuse_v8_kernel<LPP_, MAXN_>, dim3((unsigned)nb), dim3(256), 0, st, \
-            f, (long)in_lo_off, affine, agent_off, n_scenes, max_cav, g, method, o, (long)out_lo_off)
+        if ((long)sum_agents * g.Hp * g.Wp * (in_ps ? 4 : 1) * (C / 8) >= (1L << 31) || total >= (1L << 31)) return CB_ERR_ARG;
+        if ((in_lo_off != 0) != (out_lo_off != 0)) return CB_ERR_ARG;   // hi/lo planes: both or neither
+#define CB_FUSE_LAUNCH(LPP_, MAXN_) do { if (in_lo_off != 0) \
+            launch_pdl(warp_att_fuse_v8_kernel<LPP_, MAXN_, true>, dim3((unsigned)nb), dim3(256), 0, st, \
+                       f, (long)in_lo_off, affine, agent_off, n_scenes, max_cav, g, method, o, (long)out_lo_off); \
+        else launch_pdl(warp_att_fuse_v8_kernel<LPP_, MAXN_, false>, dim3((unsigned)nb), dim3(256), 0, st, \
+                       f, (long)in_lo_off, affine, agent_off, n_scenes, max_cav, g, method, o, (long)out_lo_off); } while (0)
         const bool small = max_cav <= 5;
         switch (C) {
             case 64: if (small) CB_FUSE_LAUNCH(8, 5); else CB_FUSE_LAUNCH(8, FUSE_MAX_AGENTS); break;
