@@ -490,6 +490,206 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
     }
 }
 
+// ----------------------------------------------------------------------------------------------------------
+// Channel-major ("transposed") variant for Cout = 128 layers: the weight tile (128 output channels x 64) is the UMMA
+// A operand and a 256-pixel activation tile the B operand, so D^T[channel][pixel] (128 TMEM lanes x 256 columns)
+// accumulates 128 x 256 x 16 MACs per instruction instead of 128 x 128 x 16 - the pixel rows, which dominate the
+// shared-memory traffic, are read once per 256-wide instruction.  Same descriptors / K-step tables as above; only
+// the operand roles and the epilogue (TMEM lane = channel, so tiles are transposed back to pixel-major rows through
+// a 2 KB per-warp shared-memory stage) differ.
+// ----------------------------------------------------------------------------------------------------------
+constexpr int TP = 256;                                   // pixels per tile (UMMA N)
+struct TctCfg {
+    static constexpr int P_BYTES = TP * BK * 2;           // activation tile of one K-step
+    static constexpr int W_BYTES = 128 * BK * 2;          // weight tile of one K-step
+    static constexpr int KSTEP_BYTES = P_BYTES + W_BYTES;
+    static constexpr int STAGES = 4;
+    static constexpr int SMEM_BYTES = STAGES * KSTEP_BYTES + 1024;
+    static constexpr int TMEM_COLS = 2 * TP;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_gemm_tct_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
+                     const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ ConvParams p, int m_tiles) {
+    using Cfg = TctCfg;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(16) float s_bias[128];
+    __shared__ __align__(16) uint4 s_stage[8][128];       // per epilogue warp: 32 pixels x 64 B
+
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+    uint8_t* smem = smem_raw + pad;
+    for (int i = threadIdx.x; i < 128; i += TC_THREADS) s_bias[i] = p.bias[i];
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nk = p.n_ksteps;
+
+    if (warp == W_PRODUCER && lane == 0) {
+        prefetch_tmap(&tmap_a0);
+        prefetch_tmap(&tmap_a1);
+        prefetch_tmap(&tmap_w);
+    }
+    if (warp == W_MMA && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 8); }
+        fence_barrier_init();
+    }
+    if (warp == W_ALLOC) {
+        tmem_alloc(&tmem_base_smem, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    pdl_launch_dependents();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    pdl_wait();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    const uint32_t smem_p0 = smem_u32(smem);
+    const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+    const uint32_t tfull0 = smem_u32(&tmem_full_bar[0]), tempty0 = smem_u32(&tmem_empty_bar[0]);
+
+    if (warp == W_PRODUCER) {
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+                const int m0 = tile * TP;
+                for (int ks = 0; ks < nk; ++ks) {
+                    const uint32_t fb = full0 + stage * 8;
+                    mbar_wait_a(empty0 + stage * 8, phase ^ 1);
+                    mbar_expect_tx_a(fb, (uint32_t)Cfg::KSTEP_BYTES);
+                    const cb_kstep st = p.ksteps[ks];
+                    const uint32_t sa = smem_p0 + stage * Cfg::KSTEP_BYTES;
+                    tma_load_2d_a(sa, st.a_sel ? &tmap_a1 : &tmap_a0, fb, (int)st.col, m0 + st.row_off);
+                    tma_load_2d_a(sa + Cfg::P_BYTES, &tmap_w, fb, st.w_k, 0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == W_MMA) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, TP);          // M = channels, N = pixels
+            const uint64_t pdesc0 = make_sw128_desc(smem_p0);
+            const uint64_t wdesc0 = make_sw128_desc(smem_p0 + Cfg::P_BYTES);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait_a(tempty0 + buf * 8, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * TP;
+                for (int ks = 0; ks < nk; ++ks) {
+                    mbar_wait_a(full0 + stage * 8, phase);
+                    tc_fence_after();
+                    const uint64_t pdesc = pdesc0 + (uint64_t)(stage * (Cfg::KSTEP_BYTES >> 4));
+                    const uint64_t wdesc = wdesc0 + (uint64_t)(stage * (Cfg::KSTEP_BYTES >> 4));
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_bf16(d_tmem, wdesc + (uint64_t)(2 * k), pdesc + (uint64_t)(2 * k), idesc,
+                                  (ks > 0 || k > 0) ? 1u : 0u);
+                    umma_commit_a(empty0 + stage * 8);
+                    if (ks + 1 >= nk) umma_commit_a(tfull0 + buf * 8);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp < 8) {
+        // epilogue: warp -> channels [32*q4, +32) (TMEM lane quarter), pixel columns [128*half, +128) in 4 chunks of 32
+        const int q4 = warp & 3, half = warp >> 2;
+        const int ch = q4 * 32 + lane;
+        const float bias = s_bias[ch];
+        uint4* stage = s_stage[warp];
+        const uint16_t* stage16 = reinterpret_cast<const uint16_t*>(stage);
+        uint16_t* stage16w = reinterpret_cast<uint16_t*>(stage);
+        const int rsub = lane >> 2, csub = lane & 3;                 // row-in-8 / 16-byte chunk for the pixel-major accesses
+        const bool has_res = p.residual != nullptr;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const long pb0 = (long)tile * TP + half * 128;
+            const uint32_t t_row = tmem_base + buf * TP + half * 128 + ((uint32_t)(q4 * 32) << 16);
+            uint4 rcur[4] = {}, rnext[4] = {};
+            if (has_res) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const long q = pb0 + i * 8 + rsub;
+                    if (q < p.rows_total)
+                        rcur[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + q * (long)p.res_pitch + q4 * 32) + csub);
+                }
+            }
+            mbar_wait_a(tfull0 + buf * 8, acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int ci = 0; ci < 4; ++ci) {
+                const long pb = pb0 + ci * 32;
+                if (has_res && ci < 3) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const long q = pb + 32 + i * 8 + rsub;
+                        rnext[i] = make_uint4(0u, 0u, 0u, 0u);
+                        if (q < p.rows_total)
+                            rnext[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + q * (long)p.res_pitch + q4 * 32) + csub);
+                    }
+                }
+                const int drow = (int)decode_row(p, pb + lane, 0).row;       // destination row of pixel (pb + lane), -1 = halo
+                uint32_t r[32];
+                tmem_ld32(t_row + ci * 32, r);
+                float v[32];
+                if (has_res) {                                       // pixel-major residual -> this thread's channel column
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) stage[(i * 8 + rsub) * 4 + csub] = rcur[i];
+                    __syncwarp();
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        v[j] = __uint_as_float(r[j]) + bias + __uint_as_float((uint32_t)stage16[j * 32 + lane] << 16);
+                    __syncwarp();
+                } else {
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const uint32_t pk = p.relu ? pack_bf16_relu(v[j], v[j + 1]) : pack_bf16(v[j], v[j + 1]);
+                    stage16w[j * 32 + lane] = (uint16_t)(pk & 0xFFFFu);
+                    stage16w[(j + 1) * 32 + lane] = (uint16_t)(pk >> 16);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int R = i * 8 + rsub;
+                    const uint4 val = stage[R * 4 + csub];
+                    const int dr = __shfl_sync(0xffffffffu, drow, R);
+                    if (dr >= 0)
+                        reinterpret_cast<uint4*>(p.out + (long)dr * p.out_pitch + p.out_ch_off + q4 * 32)[csub] = val;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rcur[i] = rnext[i];
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == W_ALLOC) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
 // ---------------------------------------------------------------------------------------- host side
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -677,4 +877,50 @@ extern "C" int cb_conv_gemm(const cb_conv_desc* d, int max_ctas, void* stream) {
 
 extern "C" int cb_conv_gemm_pair(const cb_conv_desc* d, int max_clusters, void* stream) {
     return conv_gemm_impl(d, max_clusters, stream, true);
+}
+
+/* Channel-major tensor-core path for Cout = 128 layers (see conv_gemm_tct_kernel). */
+extern "C" int cb_conv_gemm_t(const cb_conv_desc* d, int max_ctas, void* stream) {
+    using namespace cb;
+    if (!d) return CB_ERR_ARG;
+    static thread_local ConvParams p;
+    int rc = fill_params(d, p);
+    if (rc) return rc;
+    if (d->n_total != 128 || d->cout_mod != 128 || d->w_rows < 128) return CB_ERR_ARG;
+    if (d->out_mode != CB_OUT_PF && d->out_mode != CB_OUT_PS) return CB_ERR_ARG;
+    if (d->out_lo_off != 0 || d->res_lo_off != 0) return CB_ERR_ARG;
+    if (p.rows_total >= (1L << 31) - 4 * TP) return CB_ERR_ARG;
+    for (int i = 0; i < d->n_ksteps; ++i) {
+        const cb_kstep& s = d->ksteps[i];
+        if (s.a_sel > 1 || d->a_ptr[s.a_sel] == nullptr) return CB_ERR_ARG;
+        if (s.col % 8 || s.col + 64 > d->a_pitch[s.a_sel]) return CB_ERR_ARG;
+        if (s.w_k % 8 || s.w_k < 0 || s.w_k + 64 > d->w_k_total) return CB_ERR_ARG;
+    }
+    CUtensorMap ta0, ta1, tw;
+    rc = make_tmap(&ta0, d->a_ptr[0], d->a_rows[0], d->a_pitch[0], d->a_pitch[0], TP);
+    if (rc) return rc;
+    if (d->a_ptr[1]) {
+        rc = make_tmap(&ta1, d->a_ptr[1], d->a_rows[1], d->a_pitch[1], d->a_pitch[1], TP);
+        if (rc) return rc;
+    } else {
+        ta1 = ta0;
+    }
+    rc = make_tmap(&tw, d->w_ptr, d->w_rows, d->w_k_total, d->w_k_total, 128);
+    if (rc) return rc;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(conv_gemm_tct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TctCfg::SMEM_BYTES);
+    });
+    if (attr_err != cudaSuccess) return (int)attr_err;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int m_tiles = (int)((p.rows_total + TP - 1) / TP);
+    int grid = m_tiles;
+    const int cap = max_ctas > 0 ? max_ctas : sms;
+    if (grid > cap) grid = cap;
+    cudaError_t le = launch_pdl(conv_gemm_tct_kernel, dim3(grid), dim3(TC_THREADS), TctCfg::SMEM_BYTES, (cudaStream_t)stream,
+                                ta0, ta1, tw, p, m_tiles);
+    return le == cudaSuccess ? CB_OK : (int)le;
 }

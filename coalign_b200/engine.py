@@ -110,6 +110,7 @@ class CoAlignEngine:
         self.use_graph = use_graph
         self.simt_conv = simt_conv            # validation only: evaluate the descriptors with the SIMT kernel
         self.pair = pair                      # CTA-pair (cta_group::2) conv kernel ...
+        self.chan_major = os.environ.get('CB_CHAN_MAJOR', '1') != '0'      # Cout=128 layers: channel-major 128x256 tiles
         self.pair_min_bn = int(os.environ.get('CB_PAIR_MIN_BN', '256'))   # ... for tiles at least this wide (measured)
         nx, ny, nz = [int(v) for v in args["point_pillar_scatter"]["grid_size"]]
         if nz != 1:
@@ -403,6 +404,9 @@ class CoAlignEngine:
             if kind == "conv":
                 if self.simt_conv:
                     _lib.check(lib.cb_conv_gemm_simt(C.byref(o), stream_ptr), "cb_conv_gemm_simt")
+                elif (self.chan_major and not self.precise and o.n_total == 128 and o.cout_mod == 128
+                      and o.out_mode in (CB_OUT_PF, CB_OUT_PS)):
+                    _lib.check(lib.cb_conv_gemm_t(C.byref(o), 0, stream_ptr), "cb_conv_gemm_t")
                 elif self.pair and o.block_n >= self.pair_min_bn:
                     _lib.check(lib.cb_conv_gemm_pair(C.byref(o), 0, stream_ptr), "cb_conv_gemm_pair")
                 else:

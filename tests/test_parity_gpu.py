@@ -124,6 +124,45 @@ def test_conv_tile_shapes_agree(block_n, pair):
         assert_close(outs[0][k], outs[1][k], 1e-3, 1e-3, k)
 
 
+def test_channel_major_conv_kernel_matches_pixel_major():
+    """cb_conv_gemm_t (Cout=128 layers, weights on the UMMA M side, 256-pixel tiles) against cb_conv_gemm on the same
+    descriptors: identical bf16 operands and fp32 accumulation, so the stages agree to accumulation order (a few bf16
+    roundings flip).  Small config: every K-step kind (stride 2 + fused downsample, residual, PS output); full-size
+    DAIR-V2X shape: odd 50x126 level, many tiles per CTA, partial last tile."""
+    seed = 4
+    args = G.small_args("att")
+    sd = synth.random_state_dict(args, seed)
+    inp = G.small_case_inputs([3, 2], seed0=100 + seed)
+    res = {}
+    for cm in (True, False):
+        eng = make_engine(args, sd, 5, 2, precise=False, use_graph=False)
+        eng.chan_major = cm
+        out = eng.forward_voxels(*cuda_batch(inp))
+        torch.cuda.synchronize()
+        res[cm] = ({k: v.cpu().numpy() for k, v in out.items()}, engine_stages(eng, 5, 2))
+    for k in res[True][1]:
+        assert rel_l2(res[True][1][k], res[False][1][k]) < 3e-3, (k, rel_l2(res[True][1][k], res[False][1][k]))
+    for k in res[True][0]:
+        assert rel_l2(res[True][0][k], res[False][0][k]) < 3e-3, k
+    args = synth.dairv2x_args()
+    sd = synth.random_state_dict(args, 0)
+    sc = synth.make_scene(21, 3, 60000, args["lidar_range"], pose_noise=True)
+    pts = torch.from_numpy(np.concatenate(sc["points"])).cuda()
+    off = (np.arange(4) * 60000).astype(np.int32)
+    pw = torch.from_numpy(sc["pairwise_t_matrix"][None]).cuda()
+    big = {}
+    for cm in (True, False):
+        eng = make_engine(args, sd, 3, 1, precise=False)
+        eng.chan_major = cm
+        out = eng.forward_points(pts, off, [3], pw)
+        big[cm] = ({k: v.cpu().numpy() for k, v in out.items()}, engine_stages(eng, 3, 1))
+        del eng
+    for k in big[True][1]:
+        assert rel_l2(big[True][1][k], big[False][1][k]) < 3e-3, (k, rel_l2(big[True][1][k], big[False][1][k]))
+    for k in big[True][0]:
+        assert rel_l2(big[True][0][k], big[False][0][k]) < 3e-3, k
+
+
 def test_voxelize_bit_exact_and_fused_path():
     """Integer pillar indices bit-exact with the serial generator restatement (oracle/voxelize.c);
     fused points->canvas == voxels->canvas."""
