@@ -51,6 +51,8 @@ EXPORTS = {
     "cb_conv_gemm": (C.c_int, [C.POINTER(ConvDesc), C.c_int, C.c_void_p]),
     "cb_conv_gemm_pair": (C.c_int, [C.POINTER(ConvDesc), C.c_int, C.c_void_p]),
     "cb_conv_gemm_t": (C.c_int, [C.POINTER(ConvDesc), C.c_int, C.c_void_p]),
+    "cb_conv_gemm_halo": (C.c_int, [C.POINTER(ConvDesc), C.c_int, C.c_void_p]),
+    "cb_conv_gemm_t_halo": (C.c_int, [C.POINTER(ConvDesc), C.c_int, C.c_void_p]),
     "cb_conv_gemm_simt": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "cb_normalize_affine": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p,
                                       C.c_void_p]),

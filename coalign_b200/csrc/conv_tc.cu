@@ -508,6 +508,90 @@ struct TctCfg {
     static constexpr int TMEM_COLS = 2 * TP;
 };
 
+// Epilogue of the channel-major kernels (one of the 8 epilogue warps): TMEM lane = output channel, so every 32-pixel
+// chunk is transposed back to pixel-major rows through the warp's 2 KB shared-memory stage.
+__device__ __forceinline__ void tct_epilogue(const ConvParams& p, const float* s_bias, uint4* stage, uint32_t tmem_base,
+                                             uint32_t tfull0, uint64_t* tmem_empty_bar, int m_tiles, int warp, int lane) {
+        // epilogue: warp -> channels [32*q4, +32) (TMEM lane quarter), pixel columns [128*half, +128) in 4 chunks of 32
+        const int q4 = warp & 3, half = warp >> 2;
+        const int ch = q4 * 32 + lane;
+        const float bias = s_bias[ch];
+        const uint16_t* stage16 = reinterpret_cast<const uint16_t*>(stage);
+        uint16_t* stage16w = reinterpret_cast<uint16_t*>(stage);
+        const int rsub = lane >> 2, csub = lane & 3;                 // row-in-8 / 16-byte chunk for the pixel-major accesses
+        const bool has_res = p.residual != nullptr;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const long pb0 = (long)tile * TP + half * 128;
+            const uint32_t t_row = tmem_base + buf * TP + half * 128 + ((uint32_t)(q4 * 32) << 16);
+            uint4 rcur[4] = {}, rnext[4] = {};
+            if (has_res) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const long q = pb0 + i * 8 + rsub;
+                    if (q < p.rows_total)
+                        rcur[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + q * (long)p.res_pitch + q4 * 32) + csub);
+                }
+            }
+            mbar_wait_a(tfull0 + buf * 8, acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int ci = 0; ci < 4; ++ci) {
+                const long pb = pb0 + ci * 32;
+                if (has_res && ci < 3) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const long q = pb + 32 + i * 8 + rsub;
+                        rnext[i] = make_uint4(0u, 0u, 0u, 0u);
+                        if (q < p.rows_total)
+                            rnext[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + q * (long)p.res_pitch + q4 * 32) + csub);
+                    }
+                }
+                const int drow = (int)decode_row(p, pb + lane, 0).row;       // destination row of pixel (pb + lane), -1 = halo
+                uint32_t r[32];
+                tmem_ld32(t_row + ci * 32, r);
+                float v[32];
+                if (has_res) {                                       // pixel-major residual -> this thread's channel column
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) stage[(i * 8 + rsub) * 4 + csub] = rcur[i];
+                    __syncwarp();
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        v[j] = __uint_as_float(r[j]) + bias + __uint_as_float((uint32_t)stage16[j * 32 + lane] << 16);
+                    __syncwarp();
+                } else {
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const uint32_t pk = p.relu ? pack_bf16_relu(v[j], v[j + 1]) : pack_bf16(v[j], v[j + 1]);
+                    stage16w[j * 32 + lane] = (uint16_t)(pk & 0xFFFFu);
+                    stage16w[(j + 1) * 32 + lane] = (uint16_t)(pk >> 16);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int R = i * 8 + rsub;
+                    const uint4 val = stage[R * 4 + csub];
+                    const int dr = __shfl_sync(0xffffffffu, drow, R);
+                    if (dr >= 0)
+                        reinterpret_cast<uint4*>(p.out + (long)dr * p.out_pitch + p.out_ch_off + q4 * 32)[csub] = val;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rcur[i] = rnext[i];
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+        }
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_gemm_tct_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
                      const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ ConvParams p, int m_tiles) {
@@ -602,85 +686,327 @@ conv_gemm_tct_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
             }
         }
     } else if (warp < 8) {
-        // epilogue: warp -> channels [32*q4, +32) (TMEM lane quarter), pixel columns [128*half, +128) in 4 chunks of 32
-        const int q4 = warp & 3, half = warp >> 2;
-        const int ch = q4 * 32 + lane;
-        const float bias = s_bias[ch];
-        uint4* stage = s_stage[warp];
-        const uint16_t* stage16 = reinterpret_cast<const uint16_t*>(stage);
-        uint16_t* stage16w = reinterpret_cast<uint16_t*>(stage);
-        const int rsub = lane >> 2, csub = lane & 3;                 // row-in-8 / 16-byte chunk for the pixel-major accesses
-        const bool has_res = p.residual != nullptr;
+        tct_epilogue(p, s_bias, s_stage[warp], tmem_base, tfull0, tmem_empty_bar, m_tiles, warp, lane);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == W_ALLOC) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// Halo variant for Cout = 64 layers (level 0).  The pixel-major kernel above is shared-memory-bandwidth bound at
+// N = 64 (profiles/r1_conv_analysis.md section 3: 24 KB of TMA writes + 24 KB of operand reads per 128-cycle K-step).
+// Two changes cut the TMA writes ~4x:
+//   * the three taps of one filter row (row shifts d-1, d, d+1 of the flattened PF pixel index) are served by ONE
+//     TMA box of 130 rows; the MMA descriptors of the three taps start 0 / 128 / 256 bytes into that box
+//     (SWIZZLE_128B is a function of the shared-memory address bits, so a row-shifted start stays consistent with
+//     what the TMA wrote);
+//   * the whole weight matrix (<= 10 K-steps x 8 KB) is loaded once per CTA and stays resident.
+// Work items = groups of K-steps sharing one A box, built by the host from the K-step table (HaloItems).
+// ----------------------------------------------------------------------------------------------------------
+constexpr int HALO_ROWS = BM + 2;
+constexpr int HALO_BYTES = HALO_ROWS * BK * 2;            // 16640 bytes per A box
+constexpr int HALO_STRIDE = 17 * 1024;                    // stage pitch: keeps every stage 1 KB aligned
+constexpr int HALO_MAX_ITEMS = 60;
+struct HaloItems {
+    int n;
+    uint8_t first[HALO_MAX_ITEMS];                        // index of the item's first K-step
+    uint8_t nsub[HALO_MAX_ITEMS];                         // 1..3 K-steps with consecutive row shifts
+};
+struct Halo64Cfg {
+    static constexpr int BN = 64;
+    static constexpr int W_BYTES = BN * BK * 2;           // 8 KB per K-step
+    static constexpr int MAX_KSTEPS = 10;
+    static constexpr int STAGES = 6;
+    static constexpr int SMEM_BYTES = 1024 + STAGES * HALO_STRIDE + MAX_KSTEPS * W_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_gemm_halo64_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
+                        const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out,
+                        const __grid_constant__ ConvParams p, const __grid_constant__ HaloItems items, int m_tiles,
+                        int bo_mode, int use_tma) {
+    using Cfg = Halo64Cfg;
+    constexpr int BN = Cfg::BN, STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ __align__(8) uint64_t w_bar;
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(16) float s_bias[256];
+    __shared__ __align__(1024) uint4 s_stage[2][1024];
+
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+    uint8_t* smem = smem_raw + pad;
+    for (int i = threadIdx.x; i < 256; i += TC_THREADS) s_bias[i] = i < p.cout_mod ? p.bias[i] : 0.f;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nk = p.n_ksteps;
+    const int n_items = items.n;
+
+    if (warp == W_PRODUCER && lane == 0) {
+        prefetch_tmap(&tmap_a0);
+        prefetch_tmap(&tmap_a1);
+        prefetch_tmap(&tmap_w);
+        prefetch_tmap(&tmap_out);
+    }
+    if (warp == W_MMA && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 8); }
+        mbar_init(&w_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == W_ALLOC) {
+        tmem_alloc(&tmem_base_smem, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    pdl_launch_dependents();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    const uint32_t smem_a0 = smem_u32(smem);
+    const uint32_t smem_w0 = smem_a0 + STAGES * HALO_STRIDE;
+    const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+    const uint32_t tfull0 = smem_u32(&tmem_full_bar[0]), tempty0 = smem_u32(&tmem_empty_bar[0]);
+    const uint32_t wbar = smem_u32(&w_bar);
+
+    if (warp == W_PRODUCER) {
+        // ------------------------------------------------------------------ TMA producer
+        if (elect_one()) {
+            // resident weights: independent of the predecessor kernel, so issued before the PDL wait
+            mbar_expect_tx_a(wbar, (uint32_t)nk * Cfg::W_BYTES);
+            for (int j = 0; j < nk; ++j)
+                tma_load_2d_a(smem_w0 + j * Cfg::W_BYTES, &tmap_w, wbar, p.ksteps[j].w_k, 0);
+            pdl_wait();
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+                const int m0 = tile * BM;
+                for (int ii = 0; ii < n_items; ++ii) {
+                    const cb_kstep st = p.ksteps[items.first[ii]];
+                    const uint32_t fb = full0 + stage * 8;
+                    mbar_wait_a(empty0 + stage * 8, phase ^ 1);
+                    mbar_expect_tx_a(fb, (uint32_t)HALO_BYTES);
+                    tma_load_2d_a(smem_a0 + stage * HALO_STRIDE, st.a_sel ? &tmap_a1 : &tmap_a0, fb, (int)st.col,
+                                  m0 + st.row_off);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == W_MMA) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+            const uint64_t adesc0 = make_sw128_desc(smem_a0);
+            const uint64_t wdesc0 = make_sw128_desc(smem_w0);
+            mbar_wait_a(wbar, 0);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait_a(tempty0 + buf * 8, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * BN;
+                for (int ii = 0; ii < n_items; ++ii) {
+                    const int first = items.first[ii], ns = items.nsub[ii];
+                    mbar_wait_a(full0 + stage * 8, phase);
+                    tc_fence_after();
+                    const uint64_t adesc = adesc0 + (uint64_t)(stage * (HALO_STRIDE >> 4));
+                    for (int s = 0; s < ns; ++s) {
+                        // tap s of the filter row: same box, start shifted by s rows (128 B); bo_mode 1 additionally
+                        // records the shift in the descriptor's matrix-base-offset field (bits 49..51)
+                        const uint64_t ad = adesc + (uint64_t)(s * 8) + (bo_mode ? ((uint64_t)s << 49) : 0ull);
+                        const uint64_t wd = wdesc0 + (uint64_t)((first + s) * (Cfg::W_BYTES >> 4));
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            umma_bf16(d_tmem, ad + (uint64_t)(2 * k), wd + (uint64_t)(2 * k), idesc,
+                                      (ii > 0 || s > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit_a(empty0 + stage * 8);
+                    if (ii + 1 == n_items) umma_commit_a(tfull0 + buf * 8);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp < 8) {
+        // ------------------------------------------------------------------ epilogue (8 warps)
+        pdl_wait();
+        const int q4 = warp & 3;
+        const int half = warp >> 2;
+        constexpr int CW = BN / 2;
+        const int c_lo = half * CW, c_hi = c_lo + CW;
+        bool store_pending = false;
         int it = 0;
         for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const long pb0 = (long)tile * TP + half * 128;
-            const uint32_t t_row = tmem_base + buf * TP + half * 128 + ((uint32_t)(q4 * 32) << 16);
-            uint4 rcur[4] = {}, rnext[4] = {};
-            if (has_res) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const long q = pb0 + i * 8 + rsub;
-                    if (q < p.rows_total)
-                        rcur[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + q * (long)p.res_pitch + q4 * 32) + csub);
-                }
-            }
-            mbar_wait_a(tfull0 + buf * 8, acc_phase);
-            tc_fence_after();
-#pragma unroll 1
-            for (int ci = 0; ci < 4; ++ci) {
-                const long pb = pb0 + ci * 32;
-                if (has_res && ci < 3) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const long q = pb + 32 + i * 8 + rsub;
-                        rnext[i] = make_uint4(0u, 0u, 0u, 0u);
-                        if (q < p.rows_total)
-                            rnext[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + q * (long)p.res_pitch + q4 * 32) + csub);
-                    }
-                }
-                const int drow = (int)decode_row(p, pb + lane, 0).row;       // destination row of pixel (pb + lane), -1 = halo
-                uint32_t r[32];
-                tmem_ld32(t_row + ci * 32, r);
-                float v[32];
-                if (has_res) {                                       // pixel-major residual -> this thread's channel column
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) stage[(i * 8 + rsub) * 4 + csub] = rcur[i];
-                    __syncwarp();
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        v[j] = __uint_as_float(r[j]) + bias + __uint_as_float((uint32_t)stage16[j * 32 + lane] << 16);
-                    __syncwarp();
-                } else {
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias;
-                }
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const uint32_t pk = p.relu ? pack_bf16_relu(v[j], v[j + 1]) : pack_bf16(v[j], v[j + 1]);
-                    stage16w[j * 32 + lane] = (uint16_t)(pk & 0xFFFFu);
-                    stage16w[(j + 1) * 32 + lane] = (uint16_t)(pk >> 16);
-                }
-                __syncwarp();
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int R = i * 8 + rsub;
-                    const uint4 val = stage[R * 4 + csub];
-                    const int dr = __shfl_sync(0xffffffffu, drow, R);
-                    if (dr >= 0)
-                        reinterpret_cast<uint4*>(p.out + (long)dr * p.out_pitch + p.out_ch_off + q4 * 32)[csub] = val;
-                }
-                __syncwarp();
-#pragma unroll
-                for (int i = 0; i < 4; ++i) rcur[i] = rnext[i];
-            }
+            const long q = (long)tile * BM + q4 * 32 + lane;
+            const uint32_t t_row = tmem_base + buf * BN + ((uint32_t)(q4 * 32) << 16);
+            if (use_tma)
+                epilogue_tile_tma<BN>(p, s_bias, s_stage[half], &tmap_out, t_row, q, tile * BM, 0, half, q4, lane,
+                                      tfull0 + buf * 8, acc_phase, store_pending);
+            else
+                epilogue_tile<BN>(p, s_bias, &s_stage[0][0] + warp * 128, t_row, q, 0, c_lo, c_hi, tfull0 + buf * 8,
+                                  acc_phase, 0);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
         }
+        if (store_pending && q4 == 0 && lane == 0) tma_store_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == W_ALLOC) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// Channel-major kernel with halo boxes (Cout = 128 layers): as conv_gemm_tct_kernel, but the 256-pixel activation tile
+// (UMMA B operand) of the three taps of one filter row is loaded once as a 258-row box (TMA boxes are limited to 256
+// rows: 256 + 2) and the tap shift goes into the B descriptor's start address.  Activation boxes and weight tiles run
+// through separate rings: 3 x 33 KB pixel boxes, 6 x 16 KB weight tiles.
+// ----------------------------------------------------------------------------------------------------------
+struct TctHaloCfg {
+    static constexpr int P_ROWS = TP + 2;
+    static constexpr int P_BYTES = P_ROWS * BK * 2;       // 33024
+    static constexpr int P_STRIDE = 33 * 1024;
+    static constexpr int W_BYTES = 128 * BK * 2;          // 16384
+    static constexpr int PST = 3, WST = 6;
+    static constexpr int SMEM_BYTES = 1024 + PST * P_STRIDE + WST * W_BYTES;
+    static constexpr int TMEM_COLS = 2 * TP;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_gemm_tct_halo_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
+                          const __grid_constant__ CUtensorMap tmap_a0t, const __grid_constant__ CUtensorMap tmap_a1t,
+                          const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ ConvParams p,
+                          const __grid_constant__ HaloItems items, int m_tiles, int bo_mode) {
+    using Cfg = TctHaloCfg;
+    constexpr int PST = Cfg::PST, WST = Cfg::WST;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t pfull_bar[PST];
+    __shared__ __align__(8) uint64_t pempty_bar[PST];
+    __shared__ __align__(8) uint64_t wfull_bar[WST];
+    __shared__ __align__(8) uint64_t wempty_bar[WST];
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(16) float s_bias[128];
+    __shared__ __align__(16) uint4 s_stage[8][128];
+
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+    uint8_t* smem = smem_raw + pad;
+    for (int i = threadIdx.x; i < 128; i += TC_THREADS) s_bias[i] = p.bias[i];
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_items = items.n;
+
+    if (warp == W_PRODUCER && lane == 0) {
+        prefetch_tmap(&tmap_a0);
+        prefetch_tmap(&tmap_a1);
+        prefetch_tmap(&tmap_a0t);
+        prefetch_tmap(&tmap_a1t);
+        prefetch_tmap(&tmap_w);
+    }
+    if (warp == W_MMA && lane == 0) {
+        for (int s = 0; s < PST; ++s) { mbar_init(&pfull_bar[s], 1); mbar_init(&pempty_bar[s], 1); }
+        for (int s = 0; s < WST; ++s) { mbar_init(&wfull_bar[s], 1); mbar_init(&wempty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 8); }
+        fence_barrier_init();
+    }
+    if (warp == W_ALLOC) {
+        tmem_alloc(&tmem_base_smem, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    pdl_launch_dependents();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    pdl_wait();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    const uint32_t smem_p0 = smem_u32(smem);
+    const uint32_t smem_w0 = smem_p0 + PST * Cfg::P_STRIDE;
+    const uint32_t pfull0 = smem_u32(&pfull_bar[0]), pempty0 = smem_u32(&pempty_bar[0]);
+    const uint32_t wfull0 = smem_u32(&wfull_bar[0]), wempty0 = smem_u32(&wempty_bar[0]);
+    const uint32_t tfull0 = smem_u32(&tmem_full_bar[0]), tempty0 = smem_u32(&tmem_empty_bar[0]);
+
+    if (warp == W_PRODUCER) {
+        if (elect_one()) {
+            int ps = 0, ws = 0; uint32_t pphase = 0, wphase = 0;
+            for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+                const int m0 = tile * TP;
+                for (int ii = 0; ii < n_items; ++ii) {
+                    const int first = items.first[ii], ns = items.nsub[ii];
+                    const cb_kstep st = p.ksteps[first];
+                    const uint32_t pb = pfull0 + ps * 8;
+                    const uint32_t sa = smem_p0 + ps * Cfg::P_STRIDE;
+                    mbar_wait_a(pempty0 + ps * 8, pphase ^ 1);
+                    mbar_expect_tx_a(pb, (uint32_t)Cfg::P_BYTES);
+                    tma_load_2d_a(sa, st.a_sel ? &tmap_a1 : &tmap_a0, pb, (int)st.col, m0 + st.row_off);
+                    tma_load_2d_a(sa + TP * BK * 2, st.a_sel ? &tmap_a1t : &tmap_a0t, pb, (int)st.col, m0 + st.row_off + TP);
+                    if (++ps == PST) { ps = 0; pphase ^= 1; }
+                    for (int s = 0; s < ns; ++s) {
+                        const uint32_t wb = wfull0 + ws * 8;
+                        mbar_wait_a(wempty0 + ws * 8, wphase ^ 1);
+                        mbar_expect_tx_a(wb, (uint32_t)Cfg::W_BYTES);
+                        tma_load_2d_a(smem_w0 + ws * Cfg::W_BYTES, &tmap_w, wb, p.ksteps[first + s].w_k, 0);
+                        if (++ws == WST) { ws = 0; wphase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == W_MMA) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, TP);          // M = channels, N = pixels
+            const uint64_t pdesc0 = make_sw128_desc(smem_p0);
+            const uint64_t wdesc0 = make_sw128_desc(smem_w0);
+            int ps = 0, ws = 0; uint32_t pphase = 0, wphase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait_a(tempty0 + buf * 8, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * TP;
+                for (int ii = 0; ii < n_items; ++ii) {
+                    const int ns = items.nsub[ii];
+                    mbar_wait_a(pfull0 + ps * 8, pphase);
+                    const uint64_t pdesc = pdesc0 + (uint64_t)(ps * (Cfg::P_STRIDE >> 4));
+                    for (int s = 0; s < ns; ++s) {
+                        mbar_wait_a(wfull0 + ws * 8, wphase);
+                        tc_fence_after();
+                        const uint64_t pd = pdesc + (uint64_t)(s * 8) + (bo_mode ? ((uint64_t)s << 49) : 0ull);
+                        const uint64_t wd = wdesc0 + (uint64_t)(ws * (Cfg::W_BYTES >> 4));
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            umma_bf16(d_tmem, wd + (uint64_t)(2 * k), pd + (uint64_t)(2 * k), idesc,
+                                      (ii > 0 || s > 0 || k > 0) ? 1u : 0u);
+                        umma_commit_a(wempty0 + ws * 8);
+                        if (++ws == WST) { ws = 0; wphase ^= 1; }
+                    }
+                    umma_commit_a(pempty0 + ps * 8);
+                    if (ii + 1 == n_items) umma_commit_a(tfull0 + buf * 8);
+                    if (++ps == PST) { ps = 0; pphase ^= 1; }
+                }
+            }
+        }
+    } else if (warp < 8) {
+        tct_epilogue(p, s_bias, s_stage[warp], tmem_base, tfull0, tmem_empty_bar, m_tiles, warp, lane);
     }
     tc_fence_before();
     __syncthreads();
@@ -815,6 +1141,25 @@ static int launch2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorM
 
 }  // namespace cb
 
+
+// Group K-steps that read the same channel block at consecutive row shifts (the taps of one 3x3 filter row in the
+// flattened PF row space): each group is served by one halo box.
+static int build_halo_items(const cb_conv_desc* d, cb::HaloItems& items) {
+    items.n = 0;
+    for (int i = 0; i < d->n_ksteps;) {
+        int ns = 1;
+        while (ns < 3 && i + ns < d->n_ksteps && d->ksteps[i + ns].a_sel == d->ksteps[i].a_sel &&
+               d->ksteps[i + ns].col == d->ksteps[i].col && d->ksteps[i + ns].row_off == d->ksteps[i].row_off + ns)
+            ++ns;
+        if (items.n >= cb::HALO_MAX_ITEMS || i > 255) return CB_ERR_ARG;
+        items.first[items.n] = (uint8_t)i;
+        items.nsub[items.n] = (uint8_t)ns;
+        ++items.n;
+        i += ns;
+    }
+    return CB_OK;
+}
+
 static int conv_gemm_impl(const cb_conv_desc* d, int max_ctas, void* stream, bool pair) {
     using namespace cb;
     if (!d) return CB_ERR_ARG;
@@ -922,5 +1267,119 @@ extern "C" int cb_conv_gemm_t(const cb_conv_desc* d, int max_ctas, void* stream)
     if (grid > cap) grid = cap;
     cudaError_t le = launch_pdl(conv_gemm_tct_kernel, dim3(grid), dim3(TC_THREADS), TctCfg::SMEM_BYTES, (cudaStream_t)stream,
                                 ta0, ta1, tw, p, m_tiles);
+    return le == cudaSuccess ? CB_OK : (int)le;
+}
+
+/* Halo / resident-weight tensor-core path for Cout = 64 layers (see conv_gemm_halo64_kernel). */
+extern "C" int cb_conv_gemm_halo(const cb_conv_desc* d, int max_ctas, void* stream) {
+    using namespace cb;
+    if (!d) return CB_ERR_ARG;
+    static thread_local ConvParams p;
+    int rc = fill_params(d, p);
+    if (rc) return rc;
+    if (d->n_total != 64 || d->cout_mod != 64 || d->w_rows < 64) return CB_ERR_ARG;
+    if (d->out_mode != CB_OUT_PF && d->out_mode != CB_OUT_PS) return CB_ERR_ARG;
+    if (d->out_lo_off != 0 || d->res_lo_off != 0) return CB_ERR_ARG;
+    if (d->n_ksteps > Halo64Cfg::MAX_KSTEPS) return CB_ERR_ARG;
+    for (int i = 0; i < d->n_ksteps; ++i) {
+        const cb_kstep& s = d->ksteps[i];
+        if (s.a_sel > 1 || d->a_ptr[s.a_sel] == nullptr) return CB_ERR_ARG;
+        if (s.col % 8 || s.col + 64 > d->a_pitch[s.a_sel]) return CB_ERR_ARG;
+        if (s.w_k % 8 || s.w_k < 0 || s.w_k + 64 > d->w_k_total) return CB_ERR_ARG;
+    }
+    HaloItems items;
+    if (build_halo_items(d, items)) return CB_ERR_ARG;
+    CUtensorMap ta0, ta1, tw;
+    rc = make_tmap(&ta0, d->a_ptr[0], d->a_rows[0], d->a_pitch[0], d->a_pitch[0], HALO_ROWS);
+    if (rc) return rc;
+    if (d->a_ptr[1]) {
+        rc = make_tmap(&ta1, d->a_ptr[1], d->a_rows[1], d->a_pitch[1], d->a_pitch[1], HALO_ROWS);
+        if (rc) return rc;
+    } else {
+        ta1 = ta0;
+    }
+    rc = make_tmap(&tw, d->w_ptr, d->w_rows, d->w_k_total, d->w_k_total, 64);
+    if (rc) return rc;
+    CUtensorMap tout = tw;
+    int use_tma = 0;
+    if (d->out_mode == CB_OUT_PF) {
+        rc = make_tmap(&tout, d->out, p.rows_total, d->out_pitch, d->out_pitch, BM, 32);
+        if (rc) return rc;
+        use_tma = 1;
+    }
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(conv_gemm_halo64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Halo64Cfg::SMEM_BYTES);
+    });
+    if (attr_err != cudaSuccess) return (int)attr_err;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int m_tiles = (int)((p.rows_total + BM - 1) / BM);
+    int grid = m_tiles;
+    const int cap = max_ctas > 0 ? max_ctas : sms;
+    if (grid > cap) grid = cap;
+    const char* e = getenv("CB_HALO_BO");
+    const int bo_mode = e ? atoi(e) : 0;
+    cudaError_t le = launch_pdl(conv_gemm_halo64_kernel, dim3(grid), dim3(TC_THREADS), Halo64Cfg::SMEM_BYTES,
+                                (cudaStream_t)stream, ta0, ta1, tw, tout, p, items, m_tiles, bo_mode, use_tma);
+    return le == cudaSuccess ? CB_OK : (int)le;
+}
+
+/* Channel-major path with halo boxes (see conv_gemm_tct_halo_kernel); same envelope as cb_conv_gemm_t. */
+extern "C" int cb_conv_gemm_t_halo(const cb_conv_desc* d, int max_ctas, void* stream) {
+    using namespace cb;
+    if (!d) return CB_ERR_ARG;
+    static thread_local ConvParams p;
+    int rc = fill_params(d, p);
+    if (rc) return rc;
+    if (d->n_total != 128 || d->cout_mod != 128 || d->w_rows < 128) return CB_ERR_ARG;
+    if (d->out_mode != CB_OUT_PF && d->out_mode != CB_OUT_PS) return CB_ERR_ARG;
+    if (d->out_lo_off != 0 || d->res_lo_off != 0) return CB_ERR_ARG;
+    if (p.rows_total >= (1L << 31) - 4 * TP) return CB_ERR_ARG;
+    for (int i = 0; i < d->n_ksteps; ++i) {
+        const cb_kstep& s = d->ksteps[i];
+        if (s.a_sel > 1 || d->a_ptr[s.a_sel] == nullptr) return CB_ERR_ARG;
+        if (s.col % 8 || s.col + 64 > d->a_pitch[s.a_sel]) return CB_ERR_ARG;
+        if (s.w_k % 8 || s.w_k < 0 || s.w_k + 64 > d->w_k_total) return CB_ERR_ARG;
+    }
+    HaloItems items;
+    if (build_halo_items(d, items)) return CB_ERR_ARG;
+    CUtensorMap ta0, ta1, ta0t, ta1t, tw;
+    rc = make_tmap(&ta0, d->a_ptr[0], d->a_rows[0], d->a_pitch[0], d->a_pitch[0], TP);
+    if (rc) return rc;
+    rc = make_tmap(&ta0t, d->a_ptr[0], d->a_rows[0], d->a_pitch[0], d->a_pitch[0], 2);
+    if (rc) return rc;
+    if (d->a_ptr[1]) {
+        rc = make_tmap(&ta1, d->a_ptr[1], d->a_rows[1], d->a_pitch[1], d->a_pitch[1], TP);
+        if (rc) return rc;
+        rc = make_tmap(&ta1t, d->a_ptr[1], d->a_rows[1], d->a_pitch[1], d->a_pitch[1], 2);
+        if (rc) return rc;
+    } else {
+        ta1 = ta0;
+        ta1t = ta0t;
+    }
+    rc = make_tmap(&tw, d->w_ptr, d->w_rows, d->w_k_total, d->w_k_total, 128);
+    if (rc) return rc;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(conv_gemm_tct_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        TctHaloCfg::SMEM_BYTES);
+    });
+    if (attr_err != cudaSuccess) return (int)attr_err;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int m_tiles = (int)((p.rows_total + TP - 1) / TP);
+    int grid = m_tiles;
+    const int cap = max_ctas > 0 ? max_ctas : sms;
+    if (grid > cap) grid = cap;
+    const char* e = getenv("CB_HALO_BO");
+    const int bo_mode = e ? atoi(e) : 0;
+    cudaError_t le = launch_pdl(conv_gemm_tct_halo_kernel, dim3(grid), dim3(TC_THREADS), TctHaloCfg::SMEM_BYTES,
+                                (cudaStream_t)stream, ta0, ta1, ta0t, ta1t, tw, p, items, m_tiles, bo_mode);
     return le == cudaSuccess ? CB_OK : (int)le;
 }

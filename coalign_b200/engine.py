@@ -112,6 +112,7 @@ class CoAlignEngine:
         self.pair = pair                      # CTA-pair (cta_group::2) conv kernel ...
         self.chan_major = os.environ.get('CB_CHAN_MAJOR', '1') != '0'      # Cout=128 layers: channel-major 128x256 tiles
         self.pair_min_bn = int(os.environ.get('CB_PAIR_MIN_BN', '256'))   # ... for tiles at least this wide (measured)
+        self.halo = os.environ.get('CB_HALO', '0') != '0'                 # halo-box kernels for the Cout=64/128 layers
         nx, ny, nz = [int(v) for v in args["point_pillar_scatter"]["grid_size"]]
         if nz != 1:
             raise ValueError("PointPillarScatter requires nz == 1")
@@ -317,8 +318,10 @@ class CoAlignEngine:
 
     @staticmethod
     def _steps_3x3_s1(cin: int, Wp: int, sel: int = 0, k0: int = 0):
+        # order (filter row, channel block, filter column): the three taps of a filter row are consecutive K-steps with
+        # row shifts d-1, d, d+1, which the halo kernels serve from one TMA box
         return [((r - 1) * Wp + (s - 1), cb * 64, k0 + (r * 3 + s) * cin + cb * 64, sel)
-                for r in range(3) for s in range(3) for cb in range(cin // 64)]
+                for r in range(3) for cb in range(cin // 64) for s in range(3)]
 
     @staticmethod
     def _steps_3x3_s2(cin: int, src: Act, sel: int = 0, k0: int = 0):
@@ -404,9 +407,15 @@ class CoAlignEngine:
             if kind == "conv":
                 if self.simt_conv:
                     _lib.check(lib.cb_conv_gemm_simt(C.byref(o), stream_ptr), "cb_conv_gemm_simt")
+                elif (self.halo and not self.precise and o.n_total == 64 and o.cout_mod == 64 and o.n_ksteps <= 10
+                      and o.out_mode in (CB_OUT_PF, CB_OUT_PS)):
+                    _lib.check(lib.cb_conv_gemm_halo(C.byref(o), 0, stream_ptr), "cb_conv_gemm_halo")
                 elif (self.chan_major and not self.precise and o.n_total == 128 and o.cout_mod == 128
                       and o.out_mode in (CB_OUT_PF, CB_OUT_PS)):
-                    _lib.check(lib.cb_conv_gemm_t(C.byref(o), 0, stream_ptr), "cb_conv_gemm_t")
+                    if self.halo:
+                        _lib.check(lib.cb_conv_gemm_t_halo(C.byref(o), 0, stream_ptr), "cb_conv_gemm_t_halo")
+                    else:
+                        _lib.check(lib.cb_conv_gemm_t(C.byref(o), 0, stream_ptr), "cb_conv_gemm_t")
                 elif self.pair and o.block_n >= self.pair_min_bn:
                     _lib.check(lib.cb_conv_gemm_pair(C.byref(o), 0, stream_ptr), "cb_conv_gemm_pair")
                 else:

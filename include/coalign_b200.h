@@ -169,6 +169,15 @@ int cb_conv_gemm_pair(const cb_conv_desc* desc, int max_clusters, void* stream);
  * rows are read from shared memory once per 256-wide tile.  Same descriptor; block_n is ignored.  Returns
  * CB_ERR_ARG for descriptors outside that envelope (callers fall back to cb_conv_gemm). */
 int cb_conv_gemm_t(const cb_conv_desc* desc, int max_ctas, void* stream);
+/* Halo / resident-weight variant for n_total == cout_mod == 64 layers with at most 10 K-steps, bf16 PF/PS outputs:
+ * K-steps whose row shifts are consecutive (the three taps of a 3x3 filter row in the flattened PF row space) share ONE
+ * 130-row TMA box - the tap shift is applied to the UMMA descriptor start address - and the weight matrix stays resident
+ * in shared memory for the whole launch.  Cuts the TMA shared-memory writes of the N = 64 layers ~4x (they are
+ * shared-memory-bandwidth bound).  Returns CB_ERR_ARG outside that envelope (callers use cb_conv_gemm). */
+int cb_conv_gemm_halo(const cb_conv_desc* desc, int max_ctas, void* stream);
+/* cb_conv_gemm_t with halo boxes: the 256-pixel activation tile of the three taps of a filter row is loaded once
+ * (258 rows) and the tap shift is applied to the UMMA B descriptor.  Same envelope as cb_conv_gemm_t. */
+int cb_conv_gemm_t_halo(const cb_conv_desc* desc, int max_ctas, void* stream);
 /* Plain SIMT fp32-accumulate evaluation of the same descriptor: a validation kernel for the
  * tensor-core path (tests only; never used by the model). */
 int cb_conv_gemm_simt(const cb_conv_desc* desc, void* stream);

@@ -163,6 +163,52 @@ def test_channel_major_conv_kernel_matches_pixel_major():
         assert rel_l2(big[True][0][k], big[False][0][k]) < 3e-3, k
 
 
+def _run_small_and_big(configure):
+    """Small config (every K-step kind: stride 2 + fused downsample, residual, PS output) and a full-size DAIR-V2X
+    shape scene (odd 50x126 level, many tiles per CTA, partial last tile) through an engine set up by `configure`."""
+    seed = 4
+    args = G.small_args("att")
+    sd = synth.random_state_dict(args, seed)
+    inp = G.small_case_inputs([3, 2], seed0=100 + seed)
+    eng = make_engine(args, sd, 5, 2, precise=False, use_graph=False)
+    configure(eng)
+    out = eng.forward_voxels(*cuda_batch(inp))
+    torch.cuda.synchronize()
+    small = ({k: v.cpu().numpy() for k, v in out.items()}, engine_stages(eng, 5, 2))
+    del eng
+    args = synth.dairv2x_args()
+    sd = synth.random_state_dict(args, 0)
+    sc = synth.make_scene(21, 3, 60000, args["lidar_range"], pose_noise=True)
+    pts = torch.from_numpy(np.concatenate(sc["points"])).cuda()
+    off = (np.arange(4) * 60000).astype(np.int32)
+    pw = torch.from_numpy(sc["pairwise_t_matrix"][None]).cuda()
+    eng = make_engine(args, sd, 3, 1, precise=False)
+    configure(eng)
+    out = eng.forward_points(pts, off, [3], pw)
+    big = ({k: v.cpu().numpy() for k, v in out.items()}, engine_stages(eng, 3, 1))
+    del eng
+    return small, big
+
+
+def test_halo_conv_kernels_match_plain_kernels():
+    """cb_conv_gemm_halo (Cout=64: one 130-row TMA box per filter row, resident weights) and cb_conv_gemm_t_halo
+    (Cout=128: 258-row pixel boxes) against the plain tcgen05 kernels on the same descriptors: identical bf16 operands
+    and fp32 accumulation in the same K order, so every stage agrees to a few flipped bf16 roundings."""
+    def plain(eng):
+        eng.halo = False
+
+    def halo(eng):
+        eng.halo = True
+
+    ref = _run_small_and_big(plain)
+    got = _run_small_and_big(halo)
+    for (r_out, r_st), (g_out, g_st) in zip(ref, got):
+        for k in r_st:
+            assert rel_l2(g_st[k], r_st[k]) < 3e-3, (k, rel_l2(g_st[k], r_st[k]))
+        for k in r_out:
+            assert rel_l2(g_out[k], r_out[k]) < 3e-3, (k, rel_l2(g_out[k], r_out[k]))
+
+
 def test_voxelize_bit_exact_and_fused_path():
     """Integer pillar indices bit-exact with the serial generator restatement (oracle/voxelize.c);
     fused points->canvas == voxels->canvas."""
