@@ -1191,7 +1191,9 @@ static int conv_gemm_impl(const cb_conv_desc* d, int max_ctas, void* stream, boo
     CUtensorMap tout = tw;
     int use_tma = 0;
     {
-        static const bool no_tma_store = [] { const char* e = getenv("CB_NO_TMA_STORE"); return e && e[0] == '1'; }();
+        // TMA-store epilogue: measured slower than the transposed 64-byte STG path on the residual layers (BN=64: 127 vs
+        // 107 us) and equal elsewhere (profiles/r1_exp_halo.txt), so it is opt-in (CB_TMA_STORE=1)
+        static const bool no_tma_store = [] { const char* e = getenv("CB_TMA_STORE"); return !(e && e[0] == '1'); }();
         if (!no_tma_store && d->out_mode == CB_OUT_PF && d->out_lo_off == 0 && d->res_lo_off == 0 && d->block_n >= 64 &&
             !(dbg_flags() & 7)) {
             rc = make_tmap(&tout, d->out, p.rows_total, d->out_pitch, d->out_pitch, BM, d->block_n >= 128 ? 64 : 32);
@@ -1302,7 +1304,8 @@ extern "C" int cb_conv_gemm_halo(const cb_conv_desc* d, int max_ctas, void* stre
     if (rc) return rc;
     CUtensorMap tout = tw;
     int use_tma = 0;
-    if (d->out_mode == CB_OUT_PF) {
+    static const bool no_tma_store = [] { const char* e = getenv("CB_TMA_STORE"); return !(e && e[0] == '1'); }();
+    if (d->out_mode == CB_OUT_PF && !no_tma_store) {
         rc = make_tmap(&tout, d->out, p.rows_total, d->out_pitch, d->out_pitch, BM, 32);
         if (rc) return rc;
         use_tma = 1;

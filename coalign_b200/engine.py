@@ -112,7 +112,7 @@ class CoAlignEngine:
         self.pair = pair                      # CTA-pair (cta_group::2) conv kernel ...
         self.chan_major = os.environ.get('CB_CHAN_MAJOR', '1') != '0'      # Cout=128 layers: channel-major 128x256 tiles
         self.pair_min_bn = int(os.environ.get('CB_PAIR_MIN_BN', '256'))   # ... for tiles at least this wide (measured)
-        self.halo = os.environ.get('CB_HALO', '0') != '0'                 # halo-box kernels for the Cout=64/128 layers
+        self.halo = os.environ.get('CB_HALO', '1') != '0'                 # halo-box kernels for the Cout=64/128 layers
         nx, ny, nz = [int(v) for v in args["point_pillar_scatter"]["grid_size"]]
         if nz != 1:
             raise ValueError("PointPillarScatter requires nz == 1")
@@ -399,6 +399,16 @@ class CoAlignEngine:
         return ops
 
     # ------------------------------------------------------------------ launches
+    @staticmethod
+    def _has_tap_triples(o) -> bool:
+        """True for 3x3/s1 K-step tables (first three K-steps = one filter row: same channels, row shifts d, d+1, d+2):
+        the halo kernels pay off there; stride-2 / 1x1 tables (no groups) are faster on the plain kernels (measured)."""
+        if o.n_ksteps < 3:
+            return False
+        k = o.ksteps
+        return all(k[i].a_sel == k[0].a_sel and k[i].col == k[0].col and k[i].row_off == k[0].row_off + i
+                   for i in (1, 2))
+
     def _launch_ops(self, ops, n_scenes: int, stream_ptr: int):
         if self.plan_only:
             raise RuntimeError("plan_only engine cannot launch (no CUDA library loaded)")
@@ -407,12 +417,12 @@ class CoAlignEngine:
             if kind == "conv":
                 if self.simt_conv:
                     _lib.check(lib.cb_conv_gemm_simt(C.byref(o), stream_ptr), "cb_conv_gemm_simt")
-                elif (self.halo and not self.precise and o.n_total == 64 and o.cout_mod == 64 and o.n_ksteps <= 10
-                      and o.out_mode in (CB_OUT_PF, CB_OUT_PS)):
+                elif (self.halo and not self.precise and self._has_tap_triples(o) and o.n_total == 64
+                      and o.cout_mod == 64 and o.n_ksteps <= 10 and o.out_mode in (CB_OUT_PF, CB_OUT_PS)):
                     _lib.check(lib.cb_conv_gemm_halo(C.byref(o), 0, stream_ptr), "cb_conv_gemm_halo")
                 elif (self.chan_major and not self.precise and o.n_total == 128 and o.cout_mod == 128
                       and o.out_mode in (CB_OUT_PF, CB_OUT_PS)):
-                    if self.halo:
+                    if self.halo and self._has_tap_triples(o):
                         _lib.check(lib.cb_conv_gemm_t_halo(C.byref(o), 0, stream_ptr), "cb_conv_gemm_t_halo")
                     else:
                         _lib.check(lib.cb_conv_gemm_t(C.byref(o), 0, stream_ptr), "cb_conv_gemm_t")

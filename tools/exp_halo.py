@@ -54,7 +54,8 @@ def child():
     for kind, o in ops:
         if kind != "conv":
             continue
-        key = (o.n_img * (o.Hp - 2) * (o.Wp - 2), o.n_total, o.n_ksteps * 64, o.block_n, o.out_mode, bool(o.residual))
+        key = (o.n_img * (o.Hp - 2) * (o.Wp - 2), o.n_total, o.n_ksteps * 64, o.block_n, o.out_mode, bool(o.residual),
+               CoAlignEngine._has_tap_triples(o))
         if key in seen:
             continue
         for _ in range(2):
@@ -91,8 +92,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         child()
     else:
-        for name, envs in (("plain", {"CB_HALO": "0", "CB_KEYS": "1"}), ("halo bo=0", {"CB_HALO": "1", "CB_HALO_BO": "0"}),
-                           ("halo bo=1", {"CB_HALO": "1", "CB_HALO_BO": "1"})):
+        for name, envs in (("plain, TMA store", {"CB_HALO": "0", "CB_TMA_STORE": "1", "CB_KEYS": "1"}),
+                           ("halo, TMA store", {"CB_HALO": "1", "CB_TMA_STORE": "1"}),
+                           ("halo, STG epilogue (default)", {"CB_HALO": "1"}), ("plain, STG epilogue", {"CB_HALO": "0"})):
             env = dict(os.environ)
             env.update(envs)
             try:
