@@ -206,6 +206,34 @@ int cb_warp_att_fuse(const void* feat, int in_ps, int64_t in_lo_off, int sum_age
                      void* out_pf, int64_t out_lo_off, void* stream);
 
 /* --------------------------------------------------------------------------------------------
+ * Detection post-processing (the step after the forward), intermediate fusion:
+ *   VoxelPostprocessor.post_process / delta_to_boxes3d
+ *       /root/reference/opencood/data_utils/post_processor/voxel_postprocessor.py:243-449
+ *   boxes_to_corners_3d, project_box3d, remove_large_pred_bbx, remove_bbx_abnormal_z, nms_rotated,
+ *   mask_boxes_outside_range_numpy   /root/reference/opencood/utils/box_utils.py:152-204,278-316,384-421,693-738,840-890
+ *   limit_period, rotate_points_along_z, compute_iou (shapely polygon IoU)
+ *       /root/reference/opencood/utils/common_utils.py:70-79,105-127,196-218
+ * Each of the n_scenes head-output sets is one independent problem (the reference asserts batch 1 per call).
+ *   cls/reg/dir_preds : DEVICE float32 NCHW (n, A, H, W), (n, 7A, H, W), (n, num_bins*A, H, W); dir_preds may be NULL
+ *   anchors           : DEVICE float32 [H][W][A][7] (generate_anchor_box, cast to float like delta_to_boxes3d does)
+ *   tfm               : DEVICE float32 [n][4][4] cav -> ego (`transformation_matrix`)
+ *   gt_range          : HOST float64 [6]
+ *   order_hwl         : 1 for params['order'] == 'hwl' (boxes [x,y,z,h,w,l,yaw]), 0 otherwise
+ *   top_k             : boxes kept for the NMS (reference: 1000), <= 1024
+ * outputs (device): out_boxes [n][top_k][8][3] corners, out_scores [n][top_k], both in pick order (score descending);
+ *   out_count [n][2] = {boxes returned, anchors above score_threshold (0 -> the reference returns (None, None))}.
+ * Ties between equal scores are broken by the lower anchor index (numpy's argsort order is unspecified there).
+ * ------------------------------------------------------------------------------------------ */
+size_t cb_postprocess_workspace_bytes(int n_scenes, int H, int W, int anchor_num);
+int cb_postprocess(const float* cls_preds, const float* reg_preds, const float* dir_preds,
+                   int n_scenes, int H, int W, int anchor_num, int num_bins,
+                   const float* anchors, const float* tfm,
+                   float score_threshold, float dir_offset, float nms_thresh, const double* gt_range,
+                   int order_hwl, int top_k,
+                   float* out_boxes, float* out_scores, int32_t* out_count,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* --------------------------------------------------------------------------------------------
  * layout helpers (tests, debugging, interop): dense NCHW float32 <-> PF / PS bf16
  * ------------------------------------------------------------------------------------------ */
 int cb_nchw_to_layout(const float* src, int n, int c, int h, int w, int to_ps,

@@ -46,3 +46,50 @@ def to_torch_batch(inp):
                                 "voxel_num_points": torch.from_numpy(inp["voxel_num_points"])},
             "record_len": torch.from_numpy(inp["record_len"]),
             "pairwise_t_matrix": torch.from_numpy(inp["pairwise_t_matrix"])}
+
+
+# ------------------------------------------------------------------------------------------
+# detection post-processing cases
+# ------------------------------------------------------------------------------------------
+def post_params(lidar_range=None, voxel_size=None, H_map=None, W_map=None):
+    """`postprocess` block of opv2v/lidar_only_with_noise/coalign/pointpillar_coalign.yaml:69-90 plus the
+    anchor_args fields that yaml_utils.load_point_pillar_params (yaml_utils.py:121-135) derives.  With H_map/W_map the
+    lidar range is chosen so that the head maps are H_map x W_map (feature_stride 2, 0.4 m voxels)."""
+    import math
+    vs = list(voxel_size or [0.4, 0.4, 4])
+    if lidar_range is None:
+        if H_map is None:
+            lidar_range = [-140.8, -40, -3, 140.8, 40, 1]
+        else:
+            lidar_range = [-W_map * vs[0], -H_map * vs[1], -3, W_map * vs[0], H_map * vs[1], 1]
+    r = list(lidar_range)
+    return {"core_method": "VoxelPostprocessor", "gt_range": r,
+            "anchor_args": {"cav_lidar_range": r, "l": 3.9, "w": 1.6, "h": 1.56, "r": [0, 90], "feature_stride": 2, "num": 2,
+                            "vw": vs[0], "vh": vs[1], "vd": vs[2],
+                            "W": math.ceil((r[3] - r[0]) / vs[0]), "H": math.ceil((r[4] - r[1]) / vs[1]),
+                            "D": math.ceil((r[5] - r[2]) / vs[2])},
+            "target_args": {"pos_threshold": 0.6, "neg_threshold": 0.45, "score_threshold": 0.20},
+            "order": "hwl", "max_num": 100, "nms_thresh": 0.15,
+            "dir_args": {"dir_offset": 0.7853, "num_bins": 2, "anchor_yaw": [0, 90]}}
+
+
+def post_case_inputs(params, anchors, seed, cls_bias=-3.0, n_objects=12, yaw_deg=0.0, shift=(0.0, 0.0, 0.0),
+                     n_scenes=1):
+    """Synthetic head outputs with detection-like structure: background logits N(cls_bias, 1.5), plus `n_objects` blobs of
+    high-score anchors (overlapping boxes for the NMS to suppress); regression deltas N(0, 0.3); direction logits N(0,1).
+    Returns float32 arrays cls (n,2,H,W), reg (n,14,H,W), dir (n,4,H,W) and the 4x4 cav->ego matrix tfm."""
+    H, W, A = anchors.shape[:3]
+    rng = np.random.default_rng(seed)
+    cls = rng.normal(cls_bias, 1.5, (n_scenes, A, H, W))
+    for b in range(n_scenes):
+        for _ in range(n_objects):
+            h0, w0 = int(rng.integers(1, H - 1)), int(rng.integers(1, W - 1))
+            cls[b, :, h0 - 1:h0 + 2, w0 - 1:w0 + 2] += rng.uniform(2.0, 6.0, (A, 3, 3))
+    reg = rng.normal(0.0, 0.3, (n_scenes, 7 * A, H, W))
+    dr = rng.normal(0.0, 1.0, (n_scenes, 2 * A, H, W))
+    c, s = np.cos(np.deg2rad(yaw_deg)), np.sin(np.deg2rad(yaw_deg))
+    tfm = np.eye(4)
+    tfm[:2, :2] = [[c, -s], [s, c]]
+    tfm[:3, 3] = shift
+    return {"cls": cls.astype(np.float32), "reg": reg.astype(np.float32), "dir": dr.astype(np.float32),
+            "tfm": tfm.astype(np.float32)}
