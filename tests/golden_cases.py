@@ -51,26 +51,7 @@ def to_torch_batch(inp):
 # ------------------------------------------------------------------------------------------
 # detection post-processing cases
 # ------------------------------------------------------------------------------------------
-def post_params(lidar_range=None, voxel_size=None, H_map=None, W_map=None):
-    """`postprocess` block of opv2v/lidar_only_with_noise/coalign/pointpillar_coalign.yaml:69-90 plus the
-    anchor_args fields that yaml_utils.load_point_pillar_params (yaml_utils.py:121-135) derives.  With H_map/W_map the
-    lidar range is chosen so that the head maps are H_map x W_map (feature_stride 2, 0.4 m voxels)."""
-    import math
-    vs = list(voxel_size or [0.4, 0.4, 4])
-    if lidar_range is None:
-        if H_map is None:
-            lidar_range = [-140.8, -40, -3, 140.8, 40, 1]
-        else:
-            lidar_range = [-W_map * vs[0], -H_map * vs[1], -3, W_map * vs[0], H_map * vs[1], 1]
-    r = list(lidar_range)
-    return {"core_method": "VoxelPostprocessor", "gt_range": r,
-            "anchor_args": {"cav_lidar_range": r, "l": 3.9, "w": 1.6, "h": 1.56, "r": [0, 90], "feature_stride": 2, "num": 2,
-                            "vw": vs[0], "vh": vs[1], "vd": vs[2],
-                            "W": math.ceil((r[3] - r[0]) / vs[0]), "H": math.ceil((r[4] - r[1]) / vs[1]),
-                            "D": math.ceil((r[5] - r[2]) / vs[2])},
-            "target_args": {"pos_threshold": 0.6, "neg_threshold": 0.45, "score_threshold": 0.20},
-            "order": "hwl", "max_num": 100, "nms_thresh": 0.15,
-            "dir_args": {"dir_offset": 0.7853, "num_bins": 2, "anchor_yaw": [0, 90]}}
+post_params = synth.post_params
 
 
 def post_case_inputs(params, anchors, seed, cls_bias=-3.0, n_objects=12, yaw_deg=0.0, shift=(0.0, 0.0, 0.0),
