@@ -166,6 +166,22 @@ __device__ __forceinline__ void epilogue_chunk_fast(const ConvParams& p, int dro
             v[8 * t + 6] += bf16_lo(res[t].w); v[8 * t + 7] += bf16_hi(res[t].w);
         }
     }
+    if (dbg & 8) {
+        // direct mode: the thread's 32 columns (64 B of one output row) leave as two 256-bit stores - full 32-byte
+        // sectors without the shared-memory transposition (no smem traffic, no warp syncs)
+        if (drow >= 0) {
+            uint32_t w[16];
+#pragma unroll
+            for (int t = 0; t < 16; ++t)
+                w[t] = p.relu ? pack_bf16_relu(v[2 * t], v[2 * t + 1]) : pack_bf16(v[2 * t], v[2 * t + 1]);
+            __nv_bfloat16* o = p.out + (long)drow * p.out_pitch + p.out_ch_off + c_base;
+            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                         "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o + 16), "r"(w[8]), "r"(w[9]), "r"(w[10]),
+                         "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]) : "memory");
+        }
+        return;
+    }
     const int sw = (lane >> 1) & 3;                         // 16-byte chunk swizzle: conflict-free writes and reads
 #pragma unroll
     for (int t = 0; t < 4; ++t) {

@@ -297,12 +297,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_co
             const uint32_t acc_phase = (it >> 1) & 1;
             const long q = (long)mt * BM + q4 * 32 + lane;
             const uint32_t t_row = tmem_base + buf * BN + ((uint32_t)(q4 * 32) << 16);
-            if (BN >= 64 && use_tma)
+            if (BN >= 64 && use_tma == 1)
                 epilogue_tile_tma<(BN >= 64 ? BN : 64)>(p, s_bias, s_stage[half], &tmap_out, t_row, q, mt * BM, nt * BN, half,
                                                        q4, lane, tfull0 + buf * 8, acc_phase, store_pending);
             else
                 epilogue_tile<BN>(p, s_bias, &s_stage[0][0] + warp * 128, t_row, q, nt * BN, c_lo, c_hi, tfull0 + buf * 8,
-                                  acc_phase, dbg);
+                                  acc_phase, dbg | (use_tma == 2 ? 8 : 0));
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
@@ -470,12 +470,12 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
             const uint32_t acc_phase = (it >> 1) & 1;
             const long q = (long)(mp * 2 + (int)rank) * BM + q4 * 32 + lane;
             const uint32_t t_row = tmem_base + buf * BN + ((uint32_t)(q4 * 32) << 16);
-            if (use_tma)
+            if (use_tma == 1)
                 epilogue_tile_tma<BN>(p, s_bias, s_stage[half], &tmap_out, t_row, q, (mp * 2 + (int)rank) * BM, nt * BN, half,
                                       q4, lane, tfull0 + buf * 8, acc_phase, store_pending);
             else
                 epilogue_tile<BN>(p, s_bias, &s_stage[0][0] + warp * 128, t_row, q, nt * BN, c_lo, c_hi, tfull0 + buf * 8,
-                                  acc_phase, dbg & 7);
+                                  acc_phase, (dbg & 7) | (use_tma == 2 ? 8 : 0));
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[buf], 0);      // leader's barrier
@@ -852,12 +852,12 @@ conv_gemm_halo64_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __gri
             const uint32_t acc_phase = (it >> 1) & 1;
             const long q = (long)tile * BM + q4 * 32 + lane;
             const uint32_t t_row = tmem_base + buf * BN + ((uint32_t)(q4 * 32) << 16);
-            if (use_tma)
+            if (use_tma == 1)
                 epilogue_tile_tma<BN>(p, s_bias, s_stage[half], &tmap_out, t_row, q, tile * BM, 0, half, q4, lane,
                                       tfull0 + buf * 8, acc_phase, store_pending);
             else
                 epilogue_tile<BN>(p, s_bias, &s_stage[0][0] + warp * 128, t_row, q, 0, c_lo, c_hi, tfull0 + buf * 8,
-                                  acc_phase, 0);
+                                  acc_phase, use_tma == 2 ? 8 : 0);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
@@ -1160,6 +1160,14 @@ static int build_halo_items(const cb_conv_desc* d, cb::HaloItems& items) {
     return CB_OK;
 }
 
+// Direct epilogue (two 256-bit stores per thread and 32-column chunk instead of the shared-memory transposition):
+// bf16 outputs whose rows and channel offsets keep every 64-byte chunk 32-byte aligned.  CB_EPI_DIRECT=0 disables it.
+static bool epi_direct_ok(const cb_conv_desc* d) {
+    static const bool enabled = [] { const char* e = getenv("CB_EPI_DIRECT"); return !(e && e[0] == '0'); }();
+    return enabled && d->out_mode != CB_OUT_HEADS && d->out_lo_off == 0 && d->res_lo_off == 0 && d->out_pitch % 16 == 0 &&
+           d->out_ch_off % 16 == 0 && ((uintptr_t)d->out % 32) == 0 && d->block_n >= 64;
+}
+
 static int conv_gemm_impl(const cb_conv_desc* d, int max_ctas, void* stream, bool pair) {
     using namespace cb;
     if (!d) return CB_ERR_ARG;
@@ -1201,6 +1209,7 @@ static int conv_gemm_impl(const cb_conv_desc* d, int max_ctas, void* stream, boo
             use_tma = 1;
         }
     }
+    if (!use_tma && epi_direct_ok(d)) use_tma = 2;
     if (pair) {
         switch (d->block_n) {
             case 64: return launch2<64>(ta0, ta1, tw, tout, use_tma, p, m_tiles, n_tiles, max_ctas, st);
@@ -1324,6 +1333,7 @@ extern "C" int cb_conv_gemm_halo(const cb_conv_desc* d, int max_ctas, void* stre
     int grid = m_tiles;
     const int cap = max_ctas > 0 ? max_ctas : sms;
     if (grid > cap) grid = cap;
+    if (!use_tma && epi_direct_ok(d)) use_tma = 2;
     const char* e = getenv("CB_HALO_BO");
     const int bo_mode = e ? atoi(e) : 0;
     cudaError_t le = launch_pdl(conv_gemm_halo64_kernel, dim3(grid), dim3(TC_THREADS), Halo64Cfg::SMEM_BYTES,

@@ -313,6 +313,189 @@ __global__ void __launch_bounds__(256, (MAXN <= 5 ? 3 : 2)) warp_att_fuse_v8_ker
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// v9: 16 channels (one 256-bit load) per lane and tap, LPP = C/16 lanes per pixel, so the per-pixel scalar work
+// (tap records, soft-max, shuffles) is replicated over half as many lanes as in v8; agents are folded in one by one
+// with an online soft-max (running max / denominator / weighted sum), so only the ego vector, the current agent's
+// vector and the accumulator are live (3 x 16 registers instead of MAXN x 8 + 8); bilinear blending and the
+// accumulator updates use packed FFMA2 (fma.rn.f32x2).  A CTA covers 8 rows x PPW columns and walks a contiguous
+// range of such tiles along the row, so the four bilinear taps of neighbouring pixels hit L1.
+// ---------------------------------------------------------------------------------------------------------
+struct f2 { float x, y; };
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+    unsigned long long ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    f2 d;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+struct u8x { uint32_t w[8]; };
+__device__ __forceinline__ u8x ldg256(const void* p) {
+    u8x r;
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&w)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                 "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+
+template <int LPP, int MAXN, bool HAS_LO>
+__global__ void __launch_bounds__(256, 3) warp_att_fuse_v9_kernel(const __nv_bfloat16* __restrict__ feat, long in_lo_off,
+                                                                  const double* __restrict__ affine,
+                                                                  const int* __restrict__ agent_off, int n_scenes, int L,
+                                                                  const FuseGeom g, int method,
+                                                                  __nv_bfloat16* __restrict__ out, long out_lo_off,
+                                                                  int tiles_x, int tiles_per_cta) {
+    constexpr int PPW = 32 / LPP;                          // pixels per warp (consecutive columns of one row)
+    __shared__ __align__(16) uint4 s_tap[8][PPW][MAXN][2];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31, sub = lane % LPP, pin = lane / LPP, wid = threadIdx.x >> 5;
+    const int bands = (g.H + 7) >> 3;
+    const int total_tiles = n_scenes * bands * tiles_x;
+    const int plane_rows = (int)g.plane_rows;
+    const float inv_sqrt_c = g.inv_sqrt_c;
+    const char* featb = reinterpret_cast<const char*>(feat);
+    const int t_begin = blockIdx.x * tiles_per_cta;
+    const int t_end = min(total_tiles, t_begin + tiles_per_cta);
+    for (int tile = t_begin; tile < t_end; ++tile) {
+        const int tx = tile % tiles_x;
+        const int bb = tile / tiles_x;
+        const int band = bb % bands, b = bb / bands;
+        const int h = band * 8 + wid;
+        const int w = tx * PPW + pin;
+        const bool row_ok = h < g.H;                         // warp-uniform
+        const bool live = row_ok && w < g.W;
+        const int hc = row_ok ? h : g.H - 1, wc = w < g.W ? w : g.W - 1;
+        const int a0 = agent_off[b];
+        int n = agent_off[b + 1] - a0;
+        n = n < MAXN ? n : MAXN;
+        if (row_ok) {
+            for (int j = sub; j < n; j += LPP) {
+                const double xs = fma((double)(2 * wc + 1), g.inv_W, -1.0);   // affine_grid base grid, align_corners=False
+                const double ys = fma((double)(2 * hc + 1), g.inv_H, -1.0);
+                const double* A = affine + (b * L + j) * 6;
+                const float gx = (float)(A[0] * xs + A[1] * ys + A[2]);   // grid in f64, cast to f32 (reference `.to(src)`)
+                const float gy = (float)(A[3] * xs + A[4] * ys + A[5]);
+                const float ix = ((gx + 1.f) * g.W - 1.f) * 0.5f;         // grid_sample unnormalise
+                const float iy = ((gy + 1.f) * g.H - 1.f) * 0.5f;
+                const float fx0 = floorf(ix), fy0 = floorf(iy);
+                const float wx1 = ix - fx0, wy1 = iy - fy0;
+                const int x0 = (int)fminf(fmaxf(fx0, -2.f), (float)g.W + 1.f);
+                const int y0 = (int)fminf(fmaxf(fy0, -2.f), (float)g.H + 1.f);
+                const float wxa = (x0 >= 0 && x0 < g.W) ? 1.f - wx1 : 0.f, wxb = (x0 + 1 >= 0 && x0 + 1 < g.W) ? wx1 : 0.f;
+                const float wya = (y0 >= 0 && y0 < g.H) ? 1.f - wy1 : 0.f, wyb = (y0 + 1 >= 0 && y0 + 1 < g.H) ? wy1 : 0.f;
+                const int xa = min(max(x0, 0), g.W - 1), xb = min(max(x0 + 1, 0), g.W - 1);
+                const int ya = min(max(y0, 0), g.H - 1), yb = min(max(y0 + 1, 0), g.H - 1);
+                const int ag = a0 + j;
+                uint4 rr, ww;                                             // byte offsets of the 4 tap rows (row pitch 2*C)
+                rr.x = (unsigned)in_row_i(g, plane_rows, ag, ya, xa) * (unsigned)(LPP * 32);
+                rr.y = (unsigned)in_row_i(g, plane_rows, ag, ya, xb) * (unsigned)(LPP * 32);
+                rr.z = (unsigned)in_row_i(g, plane_rows, ag, yb, xa) * (unsigned)(LPP * 32);
+                rr.w = (unsigned)in_row_i(g, plane_rows, ag, yb, xb) * (unsigned)(LPP * 32);
+                ww.x = __float_as_uint(wya * wxa); ww.y = __float_as_uint(wya * wxb);
+                ww.z = __float_as_uint(wyb * wxa); ww.w = __float_as_uint(wyb * wxb);
+                s_tap[wid][pin][j][0] = rr;
+                s_tap[wid][pin][j][1] = ww;
+            }
+        }
+        __syncwarp();
+        if (row_ok) {
+            f2 x0[8], o[8];
+            float m_run = -INFINITY, l_run = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { o[c].x = 0.f; o[c].y = 0.f; x0[c].x = 0.f; x0[c].y = 0.f; }
+            for (int j = 0; j < n; ++j) {
+                const uint4 rq = s_tap[wid][pin][j][0];
+                const uint4 wq = s_tap[wid][pin][j][1];
+                const float wt[4] = {__uint_as_float(wq.x), __uint_as_float(wq.y), __uint_as_float(wq.z), __uint_as_float(wq.w)};
+                const unsigned rr[4] = {rq.x, rq.y, rq.z, rq.w};
+                u8x u[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) u[t] = ldg256(featb + (size_t)rr[t] + sub * 32);
+                f2 x[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) { x[c].x = 0.f; x[c].y = 0.f; }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const f2 w2 = {wt[t], wt[t]};
+                    if (HAS_LO) {
+                        const u8x ul = ldg256(featb + 2 * in_lo_off + (size_t)rr[t] + sub * 32);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const f2 v = {bf16_lo(u[t].w[c]) + bf16_lo(ul.w[c]), bf16_hi(u[t].w[c]) + bf16_hi(ul.w[c])};
+                            x[c] = fma2(w2, v, x[c]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const f2 v = {bf16_lo(u[t].w[c]), bf16_hi(u[t].w[c])};
+                            x[c] = fma2(w2, v, x[c]);
+                        }
+                    }
+                }
+                if (j == 0) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) x0[c] = x[c];
+                }
+                if (method == 1) {                           // MaxFusion
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        o[c].x = j == 0 ? x[c].x : fmaxf(o[c].x, x[c].x);
+                        o[c].y = j == 0 ? x[c].y : fmaxf(o[c].y, x[c].y);
+                    }
+                } else {
+                    f2 d2 = {0.f, 0.f};
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) d2 = fma2(x0[c], x[c], d2);
+                    float d = d2.x + d2.y;
+#pragma unroll
+                    for (int sft = LPP / 2; sft > 0; sft >>= 1) d += __shfl_xor_sync(0xffffffffu, d, sft);
+                    const float sc = d * inv_sqrt_c;                       // att_fuse.py:44
+                    const float m_new = fmaxf(m_run, sc);
+                    const float alpha = HAS_LO ? expf(m_run - m_new) : __expf(m_run - m_new);   // 0 on the first agent
+                    const float pj = HAS_LO ? expf(sc - m_new) : __expf(sc - m_new);
+                    l_run = fmaf(l_run, alpha, pj);
+                    const f2 a2 = {alpha, alpha}, p2 = {pj, pj};
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const f2 t2 = {o[c].x * alpha, o[c].y * alpha};
+                        (void)a2;
+                        o[c] = fma2(p2, x[c], t2);
+                    }
+                    m_run = m_new;
+                }
+            }
+            if (method != 1) {
+                const float inv = 1.f / l_run;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) { o[c].x *= inv; o[c].y *= inv; }
+            }
+            if (live) {
+                const int orow = (b * (g.H + 2) + h + 1) * (g.W + 2) + w + 1;   // PF output
+                uint32_t hi[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) hi[c] = pack_bf16(o[c].x, o[c].y);
+                stg256(reinterpret_cast<char*>(out) + ((size_t)orow * LPP + sub) * 32, hi);
+                if (HAS_LO) {
+                    uint32_t lo[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) lo[c] = pack_bf16(o[c].x - bf16_lo(hi[c]), o[c].y - bf16_hi(hi[c]));
+                    stg256(reinterpret_cast<char*>(out + out_lo_off) + ((size_t)orow * LPP + sub) * 32, lo);
+                }
+            }
+        }
+        __syncwarp();                                        // tap records consumed; next tile may overwrite
+    }
+}
+
 }  // namespace cb
 
 extern "C" int cb_normalize_affine(const double* pairwise_t_matrix, int n_scenes, int max_cav, int H, int W,
@@ -357,7 +540,34 @@ extern "C" int cb_warp_att_fuse(const void* feat, int in_ps, int64_t in_lo_off, 
                        f, (long)in_lo_off, affine, agent_off, n_scenes, max_cav, g, method, o, (long)out_lo_off); \
         else launch_pdl(warp_att_fuse_v8_kernel<LPP_, MAXN_, false>, dim3((unsigned)nb), dim3(256), 0, st, \
                        f, (long)in_lo_off, affine, agent_off, n_scenes, max_cav, g, method, o, (long)out_lo_off); } while (0)
+        static const int fuse_ver = [] { const char* e = getenv("CB_FUSE_V"); return e ? atoi(e) : 9; }();
         const bool small = max_cav <= 5;
+        // v9 indexes tap rows by 32-bit BYTE offsets and needs 32-byte aligned buffers
+        const bool v9_ok = fuse_ver >= 9 && (long)sum_agents * g.Hp * g.Wp * (in_ps ? 4 : 1) * (long)(2 * C) < (1L << 32) &&
+                           ((uintptr_t)feat % 32) == 0 && ((uintptr_t)out_pf % 32) == 0 && (in_lo_off % 16) == 0 &&
+                           (out_lo_off % 16) == 0;
+        if (v9_ok) {
+            const int lpp = C / 16, ppw9 = 32 / lpp;
+            const int tiles_x = (W + ppw9 - 1) / ppw9;
+            const int total_tiles = n_scenes * ((H + 7) / 8) * tiles_x;
+            int grid = 148 * 3 * 4;                                   // ~4 contiguous tile ranges per resident CTA slot
+            if (grid > total_tiles) grid = total_tiles;
+            const int tiles_per_cta = (total_tiles + grid - 1) / grid;
+            grid = (total_tiles + tiles_per_cta - 1) / tiles_per_cta;
+#define CB_FUSE9_LAUNCH(LPP_, MAXN_) do { if (in_lo_off != 0) \
+            launch_pdl(warp_att_fuse_v9_kernel<LPP_, MAXN_, true>, dim3((unsigned)grid), dim3(256), 0, st, \
+                       f, (long)in_lo_off, affine, agent_off, n_scenes, max_cav, g, method, o, (long)out_lo_off, tiles_x, tiles_per_cta); \
+        else launch_pdl(warp_att_fuse_v9_kernel<LPP_, MAXN_, false>, dim3((unsigned)grid), dim3(256), 0, st, \
+                       f, (long)in_lo_off, affine, agent_off, n_scenes, max_cav, g, method, o, (long)out_lo_off, tiles_x, tiles_per_cta); } while (0)
+            switch (C) {
+                case 64: if (small) CB_FUSE9_LAUNCH(4, 5); else CB_FUSE9_LAUNCH(4, FUSE_MAX_AGENTS); break;
+                case 128: if (small) CB_FUSE9_LAUNCH(8, 5); else CB_FUSE9_LAUNCH(8, FUSE_MAX_AGENTS); break;
+                default: if (small) CB_FUSE9_LAUNCH(16, 5); else CB_FUSE9_LAUNCH(16, FUSE_MAX_AGENTS); break;
+            }
+#undef CB_FUSE9_LAUNCH
+            CB_CHECK_LAUNCH();
+            return CB_OK;
+        }
         switch (C) {
             case 64: if (small) CB_FUSE_LAUNCH(8, 5); else CB_FUSE_LAUNCH(8, FUSE_MAX_AGENTS); break;
             case 128: if (small) CB_FUSE_LAUNCH(16, 5); else CB_FUSE_LAUNCH(16, FUSE_MAX_AGENTS); break;

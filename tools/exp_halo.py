@@ -19,7 +19,7 @@ def child():
     from tests import golden_cases as G
     from tests.test_parity_gpu import cuda_batch, engine_stages, rel_l2
 
-    halo = os.environ.get("CB_HALO", "0") != "0"
+    halo = os.environ.get("CB_HALO", "1") != "0"
     # 1. parity vs SIMT on the small config
     args = G.small_args("att")
     sd = synth.random_state_dict(args, 4)
@@ -92,9 +92,8 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         child()
     else:
-        for name, envs in (("plain, TMA store", {"CB_HALO": "0", "CB_TMA_STORE": "1", "CB_KEYS": "1"}),
-                           ("halo, TMA store", {"CB_HALO": "1", "CB_TMA_STORE": "1"}),
-                           ("halo, STG epilogue (default)", {"CB_HALO": "1"}), ("plain, STG epilogue", {"CB_HALO": "0"})):
+        for name, envs in (("staged STG epilogue", {"CB_EPI_DIRECT": "0", "CB_KEYS": "1"}),
+                           ("direct 256-bit store epilogue (default)", {})):
             env = dict(os.environ)
             env.update(envs)
             try:
