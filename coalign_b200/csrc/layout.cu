@@ -44,7 +44,39 @@ __global__ void layout_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, lon
     dst[i] = v;
 }
 
+// PS -> PF copy of (n, H, W, C) bf16 maps, 16 bytes per thread (exact; used where a stride-2 consumer wants the phase-
+// split layout and a second consumer wants the padded-flat one, e.g. the per-level outputs of the single-agent model).
+__global__ void ps_to_pf_kernel(const uint4* __restrict__ src, int n_cap, int n, int H, int W, int c8,
+                                uint4* __restrict__ dst) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;      // over (n, h, w, c8)
+    const long total = (long)n * H * W * c8;
+    if (i >= total) return;
+    const int c = (int)(i % c8);
+    long t = i / c8;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H);
+    const int a = (int)(t / H);
+    dst[layout_row(0, n, H, W, a, h, w) * c8 + c] = __ldg(src + layout_row(1, n_cap, H, W, a, h, w) * c8 + c);
+}
+
 }  // namespace cb
+
+extern "C" int cb_ps_to_pf(const void* src_ps, int64_t src_lo_off, int n_cap, int n, int h, int w, int c, void* dst_pf,
+                           int64_t dst_lo_off, void* stream) {
+    if (!src_ps || !dst_pf || n < 1 || n > n_cap || h < 1 || w < 1 || c < 8 || c % 8) return CB_ERR_ARG;
+    if ((src_lo_off != 0) != (dst_lo_off != 0) || src_lo_off % 8 || dst_lo_off % 8) return CB_ERR_ARG;
+    const long total = (long)n * h * w * (c / 8);
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    cb::ps_to_pf_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)src_ps, n_cap, n, h, w, c / 8, (uint4*)dst_pf);
+    CB_CHECK_LAUNCH();
+    if (src_lo_off != 0) {
+        cb::ps_to_pf_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+            (const uint4*)((const __nv_bfloat16*)src_ps + src_lo_off), n_cap, n, h, w, c / 8,
+            (uint4*)((__nv_bfloat16*)dst_pf + dst_lo_off));
+        CB_CHECK_LAUNCH();
+    }
+    return CB_OK;
+}
 
 extern "C" int cb_version(void) { return 100; }
 

@@ -97,7 +97,11 @@ def pack_conv_weight(w: torch.Tensor, scale: Optional[torch.Tensor]) -> torch.Te
 class CoAlignEngine:
     def __init__(self, args: dict, state_dict: Dict[str, torch.Tensor], max_agents: int, max_scenes: int,
                  device="cuda", precise: bool = False, max_cav: int = 5, block_n_cap: int = 128,
-                 use_graph: bool = True, simt_conv: bool = False, pair: bool = True, plan_only: bool = False):
+                 use_graph: bool = True, simt_conv: bool = False, pair: bool = True, plan_only: bool = False,
+                 backbone: str = "resnet", fusion: bool = True):
+        # backbone "resnet": ResNetBEVBackbone (CoAlign); "plain": BaseBEVBackbone conv stacks (single-agent point_pillar,
+        # /root/reference/opencood/models/sub_modules/base_bev_backbone.py).  fusion=False: every agent is its own
+        # scene and the per-level maps go straight to the deblocks (point_pillar.py:52-84).
         # plan_only: build weights, buffers and launch descriptors on any torch device WITHOUT loading the CUDA library;
         # nothing can be launched.  Used by the CPU test that interprets the launch plan (tests/plan_interpreter.py).
         self.plan_only = bool(plan_only)
@@ -118,8 +122,10 @@ class CoAlignEngine:
             raise ValueError("PointPillarScatter requires nz == 1")
         self.nx, self.ny = nx, ny
         bb = args["base_bev_backbone"]
-        if not bb.get("resnet", True):
-            raise NotImplementedError("only the ResNet BEV backbone (CoAlign) is on the B200 path")
+        if backbone not in ("resnet", "plain"):
+            raise ValueError("backbone must be 'resnet' or 'plain'")
+        self.backbone_kind = backbone
+        self.fusion = bool(fusion)
         self.layer_nums = list(bb["layer_nums"])
         self.layer_strides = list(bb["layer_strides"])
         self.num_filters = list(bb["num_filters"])
@@ -133,7 +139,7 @@ class CoAlignEngine:
             raise NotImplementedError("layer strides must be 1 or 2")
         if "compression" in args and args["compression"]:
             raise NotImplementedError("naive compressor is not on the CoAlign path")
-        self.method = {"att": 0, "max": 1}[args.get("fusion_method", "att")]
+        self.method = {"att": 0, "max": 1}[args.get("fusion_method", "att")] if self.fusion else 0
         self.voxel_size = [float(v) for v in args["voxel_size"]]
         self.lidar_range = [float(v) for v in args["lidar_range"]]
         # level geometry
@@ -168,6 +174,15 @@ class CoAlignEngine:
         self.blocks = []
         inpl = self.inplanes
         for li, (nb, st, pl) in enumerate(zip(self.layer_nums, self.layer_strides, self.num_filters)):
+            if self.backbone_kind == "plain":
+                # BaseBEVBackbone.blocks[li]: [ZeroPad2d(1), Conv3x3(s, pad 0), BN(eps 1e-3), ReLU] + nb x [Conv3x3, BN, ReLU]
+                for j in range(nb + 1):
+                    sc, sh = bn_fold(sd, f"backbone.blocks.{li}.{2 + 3 * j}", 1e-3)
+                    w = pack_conv_weight(sd[f"backbone.blocks.{li}.{1 + 3 * j}.weight"], sc)
+                    self.blocks.append({"layer": li, "k": j, "stride": st if j == 0 else 1, "cin": inpl if j == 0 else pl,
+                                        "cout": pl, "pc": PackedConv(w, sh, pr, dev)})
+                inpl = pl
+                continue
             for k in range(nb):
                 p = f"backbone.resnet.layer{li}.{k}"
                 s1, t1 = bn_fold(sd, p + ".bn1", 1e-5)
@@ -352,6 +367,19 @@ class CoAlignEngine:
         for li, nb in enumerate(self.layer_nums):
             L = self.lvl[li]
             h, w, c = self.levels[li]
+            if self.backbone_kind == "plain":
+                for j in range(nb + 1):
+                    blk = self.blocks[bi]
+                    bi += 1
+                    cin, cout, st = blk["cin"], blk["cout"], blk["stride"]
+                    dst = L["out"] if j == nb else (L["tmp"] if j % 2 == 0 else L["ping"])
+                    steps = self._steps_3x3_s2(cin, x) if st == 2 else self._steps_3x3_s1(cin, x.Wp)
+                    mode = CB_OUT_PS if dst.layout == "ps" else CB_OUT_PF
+                    ops.append(("conv", self._desc([x, None], blk["pc"], steps, n_img, L["tmp"].Hp, L["tmp"].Wp, cout,
+                                                   self._bn_for(cout), cout, True, dst, mode)))
+                    x = dst
+                ops.append(("fuse" if self.fusion else "copy", li))
+                continue
             for k in range(nb):
                 blk = self.blocks[bi]
                 bi += 1
@@ -376,11 +404,13 @@ class CoAlignEngine:
                 ops.append(("conv", self._desc([tmp, a1], blk["c2"], steps2, n_img, tmp.Hp, tmp.Wp, cout, bn, cout, True,
                                                dst, mode, residual=res)))
                 x = dst
-            ops.append(("fuse", li))
+            ops.append(("fuse" if self.fusion else "copy", li))
         # decoder: ConvTranspose(k==s)+BN+ReLU as GEMM with pixel-shuffle store into the concat buffer
         ch = 0
         for li, dc in enumerate(self.deconvs):
             f = self.lvl[li]["fused"]
+            if not self.fusion and self.lvl[li]["out"].layout == "pf":
+                f = self.lvl[li]["out"]                      # no fusion stage: a PF level output feeds the deblock directly
             k, cu = dc["k"], dc["cout"]
             bn = self._bn_for(cu)
             ops.append(("conv", self._desc([f, None], dc["pc"], self._steps_1x1(dc["cin"]), n_scenes, f.Hp, f.Wp,
@@ -430,6 +460,12 @@ class CoAlignEngine:
                     _lib.check(lib.cb_conv_gemm_pair(C.byref(o), 0, stream_ptr), "cb_conv_gemm_pair")
                 else:
                     _lib.check(lib.cb_conv_gemm(C.byref(o), 0, stream_ptr), "cb_conv_gemm")
+            elif kind == "copy":
+                src, dst = self.lvl[o]["out"], self.lvl[o]["fused"]
+                if src.layout == "ps":                       # PF outputs are consumed in place (build_descs)
+                    h, w, c = self.levels[o]
+                    _lib.check(lib.cb_ps_to_pf(src.ptr, src.lo_off, src.n_cap, n_scenes, h, w, c, dst.ptr, dst.lo_off,
+                                               stream_ptr), "cb_ps_to_pf")
             else:
                 li = o
                 src, dst = self.lvl[li]["out"], self.lvl[li]["fused"]
@@ -440,6 +476,9 @@ class CoAlignEngine:
                            "cb_warp_att_fuse")
 
     def _run_backbone(self, ent, n_scenes: int, stream_ptr: int):
+        if not self.fusion:
+            self._launch_ops(ent["ops"], n_scenes, stream_ptr)
+            return
         _lib.check(self.lib.cb_normalize_affine(self.pairwise.data_ptr(), n_scenes, self.max_cav, self.ny, self.nx,
                                                 float(self.voxel_size[0]), self.affine.data_ptr(), stream_ptr),
                    "cb_normalize_affine")
@@ -475,6 +514,10 @@ class CoAlignEngine:
         n_scenes = len(record_len)
         if n_scenes > self.max_scenes or sum(record_len) > self.max_agents:
             raise ValueError("batch exceeds the engine capacity (max_scenes / max_agents)")
+        if not self.fusion:
+            if any(v != 1 for v in record_len):
+                raise ValueError("a no-fusion engine takes one agent per scene")
+            return
         if max(record_len) > min(self.max_cav, 8) or min(record_len) < 1:
             raise ValueError("record_len entries must be in [1, max_cav]")
         if tuple(pairwise.shape[1:]) != (self.max_cav, self.max_cav, 4, 4) or pairwise.shape[0] != n_scenes:

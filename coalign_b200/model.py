@@ -173,3 +173,96 @@ class PointPillarCoalignB200(nn.Module):
             self.invalidate()
         eng = self.engine(sum(record_len), len(record_len))
         return eng.forward_points(points, pt_offset, record_len, pairwise_t_matrix, max_pts, max_voxels)
+
+
+class _PlainBackbone(nn.Module):               # base_bev_backbone.py:5-94 parameter container (BaseBEVBackbone)
+    def __init__(self, cfg, cin=64):
+        super().__init__()
+        self.blocks = nn.ModuleList()
+        self.deblocks = nn.ModuleList()
+        c_in = [cin, *cfg["num_filters"][:-1]]
+        for i, (n, s, f) in enumerate(zip(cfg["layer_nums"], cfg["layer_strides"], cfg["num_filters"])):
+            layers = [nn.ZeroPad2d(1), nn.Conv2d(c_in[i], f, 3, stride=s, padding=0, bias=False),
+                      nn.BatchNorm2d(f, eps=1e-3, momentum=0.01), nn.ReLU()]
+            for _ in range(n):
+                layers += [nn.Conv2d(f, f, 3, padding=1, bias=False), nn.BatchNorm2d(f, eps=1e-3, momentum=0.01), nn.ReLU()]
+            self.blocks.append(nn.Sequential(*layers))
+        for cin_, cout, s in zip(cfg["num_filters"], cfg["num_upsample_filter"], cfg["upsample_strides"]):
+            if s < 1:
+                raise NotImplementedError("fractional upsample strides are not on the B200 path")
+            self.deblocks.append(nn.Sequential(nn.ConvTranspose2d(cin_, cout, s, stride=s, bias=False),
+                                               nn.BatchNorm2d(cout, eps=1e-3, momentum=0.01), nn.ReLU()))
+        if len(cfg["upsample_strides"]) > len(cfg["layer_nums"]):
+            raise NotImplementedError("extra final deblock is not on the B200 path")
+
+
+class PointPillarB200(nn.Module):
+    """core_method: point_pillar_b200 - state_dict-compatible twin of the single-agent detector
+    /root/reference/opencood/models/point_pillar.py:17-84 (BASELINE configs[0]; yaml
+    opv2v/lidar_only_with_noise/pointpillar_single.yaml): PillarVFE -> scatter -> BaseBEVBackbone (or the ResNet
+    backbone with `base_bev_backbone.resnet: true`) -> shrink header -> cls/reg/dir heads, no fusion: every sample of the
+    batch is an independent frame.  Same kernels and engine as the CoAlign model; inference only."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.pillar_vfe = _PillarVFE(args["pillar_vfe"])
+        self.resnet = bool(args["base_bev_backbone"].get("resnet", False))         # point_pillar.py:27-31
+        self.backbone = _Backbone(args["base_bev_backbone"]) if self.resnet else _PlainBackbone(args["base_bev_backbone"])
+        out_c = sum(args["base_bev_backbone"]["num_upsample_filter"])
+        if "shrink_header" in args:
+            self.shrink_conv = _Shrink(args["shrink_header"])
+            out_c = args["shrink_header"]["dim"][-1]
+        an = args["anchor_number"]
+        self.cls_head = nn.Conv2d(out_c, an, 1)
+        self.reg_head = nn.Conv2d(out_c, 7 * an, 1)
+        if "dir_args" in args:
+            self.dir_head = nn.Conv2d(out_c, args["dir_args"]["num_bins"] * an, 1)
+        self.precise = bool(args.get("b200_precise", False))
+        self.block_n_cap = int(args.get("b200_block_n", 128))
+        self._engine = None
+        self._engine_key = None
+
+    def _weights_version(self):
+        return tuple(int(p._version) for p in self.parameters()) + tuple(int(b._version) for b in self.buffers())
+
+    def invalidate(self):
+        self._engine = None
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self.invalidate()
+        return r
+
+    def engine(self, n_frames: int):
+        from .engine import CoAlignEngine
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("PointPillarB200 runs on a B200 only: call .to('cuda') (no CPU fallback)")
+        key = (dev, self._weights_version())
+        e = self._engine
+        if e is None or self._engine_key != key or e.max_agents < n_frames:
+            cap = max(n_frames, e.max_agents if e is not None else 1)
+            self._engine = None
+            self._engine = CoAlignEngine(self.args, self.state_dict(), cap, cap, device=dev, precise=self.precise,
+                                         block_n_cap=self.block_n_cap, backbone="resnet" if self.resnet else "plain",
+                                         fusion=False)
+            self._engine_key = key
+        return self._engine
+
+    def forward(self, data_dict: Dict):
+        if self.training:
+            raise NotImplementedError("coalign_b200: training-mode forward/backward is not implemented yet "
+                                      "(inference path only; see DESIGN.md)")
+        pl = data_dict["processed_lidar"]
+        vc, vn = pl["voxel_coords"], pl["voxel_num_points"]
+        n = int(vc[:, 0].max().item()) + 1 if vc.shape[0] else 1        # point_pillar_scatter.py:41 (same host sync)
+        eng = self.engine(n)
+        return eng.forward_voxels(pl["voxel_features"].float(), vc.int() if vc.dtype != torch.int32 else vc,
+                                  vn.int() if vn.dtype != torch.int32 else vn, [1] * n, None)
+
+    @torch.no_grad()
+    def forward_points(self, points, pt_offset, max_pts=32, max_voxels=70000):
+        """Extension of the boundary: raw clouds of n independent frames in, voxelisation fused on the GPU."""
+        n = len(pt_offset) - 1
+        return self.engine(n).forward_points(points, pt_offset, [1] * n, None, max_pts, max_voxels)

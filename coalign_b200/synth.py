@@ -48,6 +48,15 @@ def opv2v_args():
     return make_args()
 
 
+def single_args(lidar_range=None, voxel_size=None):
+    """model.args of opv2v/lidar_only_with_noise/pointpillar_single.yaml:69-95 (core_method point_pillar: BaseBEVBackbone,
+    no fusion keys)."""
+    a = make_args(lidar_range, voxel_size)
+    a.pop("fusion_method", None)
+    a.pop("att", None)
+    return a
+
+
 def dairv2x_args():
     """dairv2x/lidar_only_with_noise/coalign/pointpillar_coalign.yaml:52,57."""
     return make_args([-100.8, -40, -3.5, 100.8, 40, 1.5], [0.4, 0.4, 5])
@@ -68,9 +77,10 @@ def _conv(shape, g, fan):
     return torch.empty(*shape).normal_(0.0, math.sqrt(2.0 / fan), generator=g)
 
 
-def random_state_dict(args, seed=0) -> Dict[str, torch.Tensor]:
+def random_state_dict(args, seed=0, backbone="resnet") -> Dict[str, torch.Tensor]:
     """Random weights with the reference's state_dict key names and shapes, with
-    non-trivial BatchNorm statistics so that BN-folding mistakes show up."""
+    non-trivial BatchNorm statistics so that BN-folding mistakes show up.  backbone="plain": the key layout of
+    BaseBEVBackbone (opencood/models/sub_modules/base_bev_backbone.py:37-56) used by the single-agent `point_pillar`."""
     g = torch.Generator().manual_seed(seed)
     sd: Dict[str, torch.Tensor] = {}
     nf = args["pillar_vfe"]["num_filters"][0]
@@ -78,7 +88,15 @@ def random_state_dict(args, seed=0) -> Dict[str, torch.Tensor]:
     _bn(sd, "pillar_vfe.pfn_layers.0.norm", nf, g)
     bb = args["base_bev_backbone"]
     inpl = bb.get("inplanes", 64)
+    plain = backbone == "plain"
     for li, (nb, st, pl) in enumerate(zip(bb["layer_nums"], bb["layer_strides"], bb["num_filters"])):
+        if plain:           # BaseBEVBackbone.blocks[li] = [ZeroPad2d, Conv, BN, ReLU] + nb * [Conv, BN, ReLU]
+            for j in range(nb + 1):
+                cin = inpl if j == 0 else pl
+                sd[f"backbone.blocks.{li}.{1 + 3 * j}.weight"] = _conv((pl, cin, 3, 3), g, 9 * cin)
+                _bn(sd, f"backbone.blocks.{li}.{2 + 3 * j}", pl, g)
+            inpl = pl
+            continue
         for k in range(nb):
             p = f"backbone.resnet.layer{li}.{k}"
             cin = inpl if k == 0 else pl

@@ -238,6 +238,11 @@ int cb_postprocess(const float* cls_preds, const float* reg_preds, const float* 
  * ------------------------------------------------------------------------------------------ */
 int cb_nchw_to_layout(const float* src, int n, int c, int h, int w, int to_ps,
                       void* dst, int64_t lo_off, void* stream);
+/* Exact PS -> PF copy of (n, H, W, C) bf16 maps (hi and, when the offsets are non-zero, lo planes).  n_cap = agent
+ * capacity of the PS buffer (plane stride).  Used by the single-agent PointPillar path
+ * (/root/reference/opencood/models/point_pillar.py:52-84: no fusion stage between encoder level and deblock). */
+int cb_ps_to_pf(const void* src_ps, int64_t src_lo_off, int n_cap, int n, int h, int w, int c,
+                void* dst_pf, int64_t dst_lo_off, void* stream);
 int cb_layout_to_nchw(const void* src, int64_t lo_off, int from_ps, int n, int c, int h, int w,
                       int pitch, int ch_off, float* dst, void* stream);
 

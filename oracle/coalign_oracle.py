@@ -249,6 +249,45 @@ def forward(sd, args, data_dict, stages: Optional[dict] = None):
 
 
 # --------------------------------------------------------------------------------------
+# single-agent PointPillar (BASELINE configs[0]): opencood/models/point_pillar.py:52-84 with
+# BaseBEVBackbone                          opencood/models/sub_modules/base_bev_backbone.py:37-56,96-125
+# --------------------------------------------------------------------------------------
+def plain_encoder(sd, args, x) -> List[torch.Tensor]:
+    """BaseBEVBackbone.blocks: [ZeroPad2d(1), Conv3x3(stride s, pad 0), BN(eps 1e-3), ReLU] + n x [Conv3x3(pad 1), BN, ReLU]."""
+    bb = args["base_bev_backbone"]
+    feats = []
+    for li, (nb, stride) in enumerate(zip(bb["layer_nums"], bb["layer_strides"])):
+        for j in range(nb + 1):
+            pre = f"backbone.blocks.{li}."
+            if j == 0:
+                x = F.conv2d(F.pad(x, (1, 1, 1, 1)), sd[pre + "1.weight"], None, stride, 0)
+            else:
+                x = F.conv2d(x, sd[pre + f"{1 + 3 * j}.weight"], None, 1, 1)
+            x = F.relu(_bn2d(x, sd, pre + f"{2 + 3 * j}", 1e-3))
+        feats.append(x)
+    return feats
+
+
+@torch.no_grad()
+def forward_single(sd, args, data_dict, stages: Optional[dict] = None):
+    """PointPillar.forward (point_pillar.py:52-84): every sample of the batch is an independent single-agent frame."""
+    pl = data_dict["processed_lidar"]
+    vf, vc, vn = pl["voxel_features"], pl["voxel_coords"], pl["voxel_num_points"]
+    nx, ny, nz = [int(v) for v in args["point_pillar_scatter"]["grid_size"]]
+    n = int(vc[:, 0].max()) + 1                                                  # point_pillar_scatter.py:41
+    pf = pillar_vfe(sd, args, vf, vc, vn)
+    canvas = scatter(pf, vc, n, ny, nx)
+    resnet = args["base_bev_backbone"].get("resnet", False)                      # point_pillar.py:27-31
+    feats = encoder(sd, args, canvas) if resnet else plain_encoder(sd, args, canvas)
+    dec = decoder(sd, args, feats)                                               # base_bev_backbone.py:107-119
+    sh = shrink(sd, args, dec) if "shrink_header" in args else dec
+    out = heads(sd, sh)
+    if stages is not None:
+        stages.update(pillar_features=pf, canvas=canvas, feats=feats, decoded=dec, shrunk=sh)
+    return out
+
+
+# --------------------------------------------------------------------------------------
 # synthetic inputs shared by tests / bench / golden generation (SURVEY 8d)
 # --------------------------------------------------------------------------------------
 def pose_to_tfm(pose):

@@ -74,3 +74,12 @@ def post_case_inputs(params, anchors, seed, cls_bias=-3.0, n_objects=12, yaw_deg
     tfm[:3, 3] = shift
     return {"cls": cls.astype(np.float32), "reg": reg.astype(np.float32), "dir": dr.astype(np.float32),
             "tfm": tfm.astype(np.float32)}
+
+
+def single_case_inputs(n_frames, seed0, n_points=1800):
+    """A batch of `n_frames` independent single-agent frames (the single-agent `point_pillar` model): reference collate
+    format with the batch index in voxel_coords[:, 0]."""
+    scenes = [synth.make_scene(seed0 + b, 1, n_points, SMALL_RANGE, max_cav=5, spread=5.0, sigma=5.0) for b in range(n_frames)]
+    b = scenes_to_batch(scenes, SMALL_RANGE, SMALL_VOXEL)
+    b["points"] = [sc["points"][0] for sc in scenes]
+    return b

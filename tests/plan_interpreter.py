@@ -111,10 +111,17 @@ def run_plan(eng, sd, args, batch):
     full = torch.zeros(eng.canvas.n_cap, 64, eng.ny, eng.nx)
     full[:n_img] = canvas
     nchw_to_act(full, eng.canvas)
-    affine = O.normalize_pairwise_tfm(batch["pairwise_t_matrix"], eng.ny, eng.nx, float(args["voxel_size"][0]))
+    affine = (O.normalize_pairwise_tfm(batch["pairwise_t_matrix"], eng.ny, eng.nx, float(args["voxel_size"][0]))
+              if eng.fusion else None)
     for kind, o in eng.build_descs(n_img, n_sc):
         if kind == "conv":
             run_conv(eng, o)
+        elif kind == "copy":                                  # no-fusion engines: PS level output -> PF (cb_ps_to_pf)
+            src, dst = eng.lvl[o]["out"], eng.lvl[o]["fused"]
+            if src.layout == "ps":
+                full = torch.zeros(dst.n_cap, dst.C, dst.H, dst.W)
+                full[:n_img] = act_to_nchw(src, src.n_cap)[:n_img]
+                nchw_to_act(full, dst)
         else:
             src, dst = eng.lvl[o]["out"], eng.lvl[o]["fused"]
             x = act_to_nchw(src, src.n_cap)[:n_img]

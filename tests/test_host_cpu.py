@@ -69,6 +69,23 @@ def test_state_dict_contract():
     m.load_state_dict(sd, strict=True)
 
 
+def test_single_agent_state_dict_contract():
+    """PointPillarB200 (reference core_method `point_pillar`, BaseBEVBackbone): same keys / shapes as the reference
+    model (the synthetic state_dict was checked key-by-key against the reference in tests/golden/gen_golden_single.py)."""
+    from coalign_b200 import synth
+    from coalign_b200.model import PointPillarB200
+    args = synth.single_args()
+    m = PointPillarB200(args)
+    sd = synth.random_state_dict(args, 0, backbone="plain")
+    assert set(m.state_dict()) == set(sd)
+    for k, v in m.state_dict().items():
+        assert tuple(v.shape) == tuple(sd[k].shape), k
+    m.load_state_dict(sd, strict=True)
+    with pytest.raises(RuntimeError):                  # CPU module: no fallback
+        m.eval()({"processed_lidar": {"voxel_features": torch.zeros(1, 32, 4), "voxel_coords": torch.zeros(1, 4, dtype=torch.int32),
+                                      "voxel_num_points": torch.ones(1, dtype=torch.int32)}})
+
+
 def test_weight_packing_is_a_gemm_restatement_of_conv():
     """pack_conv_weight + tap shifts reproduce F.conv2d (the host logic behind the K-step tables)."""
     from coalign_b200.engine import CoAlignEngine, pack_conv_weight

@@ -85,3 +85,23 @@ def test_voxelizer_c_vs_python_loop():
         assert a[0].shape[0] <= max_vox and a[2].max() <= max_pts
     empty = V.voxelize_c(np.zeros((0, 4), np.float32), G.SMALL_RANGE, G.SMALL_VOXEL, 32, 10)
     assert empty[0].shape == (0, 32, 4)
+
+
+def test_single_agent_pointpillar_golden():
+    """BASELINE configs[0]: the single-agent `point_pillar` model (BaseBEVBackbone, no fusion) - oracle restatement
+    against the unmodified reference created through its yaml + registry (tests/golden/gen_golden_single.py)."""
+    g = np.load(os.path.join(GOLD, "model_single_plain.npz"))
+    seed, n = int(g["seed"]), int(g["n_frames"])
+    args = synth.single_args(G.SMALL_RANGE, G.SMALL_VOXEL)
+    sd = synth.random_state_dict(args, seed, backbone="plain")
+    inp = G.single_case_inputs(n, seed0=100 + seed)
+    assert np.array_equal(inp["voxel_coords"], g["voxel_coords"])
+    assert np.array_equal(inp["voxel_num_points"], g["voxel_num_points"])
+    st = {}
+    out = O.forward_single(sd, args, G.to_torch_batch(inp), st)
+    for i in range(3):
+        _close(st["feats"][i].numpy(), g[f"feat{i}"])
+    _close(st["decoded"].numpy(), g["decoded"])
+    _close(st["shrunk"].numpy(), g["shrunk"])
+    for k in ("cls_preds", "reg_preds", "dir_preds"):
+        _close(out[k].numpy(), g[k])

@@ -434,3 +434,40 @@ def test_full_size_opv2v_two_agents_vs_oracle():
 def test_full_size_dairv2x_two_agents_pose_noise_vs_oracle():
     """BASELINE configs[3]: DAIR-V2X shape (200x504 canvas, voxel z 5 m, odd 25x63 top level), 2 agents, pose noise."""
     _full_size_case(synth.dairv2x_args(), 2, seed=12, pose_noise=True)
+
+
+def test_single_agent_pointpillar_matches_reference_golden():
+    """BASELINE configs[0]: single-agent `point_pillar` (BaseBEVBackbone, no fusion) through the nn.Module twin:
+    precise mode within rtol 1e-3 of the unmodified reference's outputs; bf16 mode at bf16-level drift; raw-point entry
+    == voxel entry."""
+    from coalign_b200.model import PointPillarB200
+    g = np.load(os.path.join(GOLD, "model_single_plain.npz"))
+    seed, n = int(g["seed"]), int(g["n_frames"])
+    inp = G.single_case_inputs(n, seed0=100 + seed)
+    batch = G.to_torch_batch(inp)
+    dev = {"processed_lidar": {k: v.cuda() for k, v in batch["processed_lidar"].items()}}
+    outs = {}
+    for precise in (True, False):
+        args = synth.single_args(G.SMALL_RANGE, G.SMALL_VOXEL)
+        args["b200_precise"] = precise
+        sd = synth.random_state_dict(args, seed, backbone="plain")
+        m = PointPillarB200(args)
+        m.load_state_dict(sd, strict=True)
+        m = m.cuda().eval()
+        with torch.no_grad():
+            out = m(dev)
+        torch.cuda.synchronize()
+        outs[precise] = {k: v.cpu().numpy() for k, v in out.items()}
+        if precise:
+            eng = m.engine(n)
+            for i in range(3):
+                assert_close(eng.read_act(eng.lvl[i]["out"], n).cpu().numpy(), g[f"feat{i}"], 1e-3, 1e-3, f"feat{i}")
+            assert_close(eng.read_act(eng.cat, n).cpu().numpy(), g["decoded"], 1e-3, 1e-3, "decoded")
+            pts = torch.from_numpy(np.concatenate(inp["points"]).astype(np.float32)).cuda()
+            off = np.concatenate([[0], np.cumsum([p.shape[0] for p in inp["points"]])]).astype(np.int32)
+            out_p = m.forward_points(pts, off)
+            for k in out:
+                assert_close(out_p[k].cpu().numpy(), outs[True][k], 1e-5, 1e-5, f"points vs voxels {k}")
+    for k in ("cls_preds", "reg_preds", "dir_preds"):
+        assert_close(outs[True][k], g[k], 1e-3, 1e-3, k)
+        assert rel_l2(outs[False][k], g[k]) < 5e-2, (k, rel_l2(outs[False][k], g[k]))

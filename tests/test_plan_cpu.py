@@ -35,3 +35,25 @@ def test_launch_plan_reproduces_reference_golden(name, fusion):
         assert (err <= 1e-3 * np.abs(b) + 1e-3 * np.sqrt((b * b).mean())).all(), (k, err.max())
     with pytest.raises(RuntimeError):
         eng._launch_ops([], 1, 0)
+
+
+def test_single_agent_plan_reproduces_reference_golden():
+    """BASELINE configs[0] (single-agent `point_pillar`, BaseBEVBackbone, no fusion): the plain-backbone launch plan
+    (BN eps 1e-3 folding, conv stacks without residuals, PS->PF copies instead of fusion) against the golden vectors
+    of the unmodified reference model."""
+    from coalign_b200.engine import CoAlignEngine
+    g = np.load(os.path.join(GOLD, "model_single_plain.npz"))
+    seed, n = int(g["seed"]), int(g["n_frames"])
+    args = synth.single_args(G.SMALL_RANGE, G.SMALL_VOXEL)
+    sd = synth.random_state_dict(args, seed, backbone="plain")
+    inp = G.single_case_inputs(n, seed0=100 + seed)
+    eng = CoAlignEngine(args, sd, n, n, device="cpu", precise=True, plan_only=True, backbone="plain", fusion=False)
+    out = PI.run_plan(eng, sd, args, G.to_torch_batch(inp))
+    for i in range(3):
+        got = PI.act_to_nchw(eng.lvl[i]["out"], eng.lvl[i]["out"].n_cap)[:n].numpy()
+        ref = g[f"feat{i}"]
+        assert np.abs(got - ref).max() <= 1e-3 * np.sqrt((ref * ref).mean()) + 1e-3 * np.abs(ref).max(), f"feat{i}"
+    for k in ("cls_preds", "reg_preds", "dir_preds"):
+        a, b = out[k].numpy().astype(np.float64), g[k].astype(np.float64)
+        err = np.abs(a - b)
+        assert (err <= 1e-3 * np.abs(b) + 1e-3 * np.sqrt((b * b).mean())).all(), (k, err.max())
