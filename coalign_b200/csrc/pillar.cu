@@ -37,6 +37,7 @@ struct VoxWs {            // workspace carve-up (device pointers)
     float4* vp;           // [sum_P]  points regrouped per voxel in slot order (first max_pts of each voxel)
     int* perm;            // [n_agents][NCLS][vcap]  voxel ids bucketed by point-count class
     int* bucket;          // [n_agents][NCLS]        bucket fill counters
+    float* coef;          // [PFN_NCOEF][64]         derived PFN coefficients (staging for the constant bank)
     int ncell, vcap, max_chunks;
 };
 
@@ -245,132 +246,182 @@ __global__ void vox_rank_gather_kernel(const float4* __restrict__ pts, const __g
 }
 
 // K4 helpers ----------------------------------------------------------------------------------
-// 8 lanes ("group") cooperate on one voxel.  sub = lane & 7.
+// PFN in "centred" form.  With q = p - centre (the reference's f_center, pillar_vfe.py:127-131) and m' = mean(q) =
+// mean(p) - centre, the 10 input features of pillar_vfe.py:118-135 are  [q + centre, i, q - m', q], so
+//   bn(linear(f))_c = A0_c qx + A1_c qy + A2_c qz + A3_c i  +  [ sh_c + C_c . centre + M_c . m' ]
+// with A0 = sc (w0 + w4 + w7), A1 = sc (w1 + w5 + w8), A2 = sc (w2 + w6 + w9), A3 = sc w3, C = sc (w0, w1, w2),
+// M = -sc (w4, w5, w6).  The bracket is a per-pillar constant, so a point costs 4 FMAs per channel instead of 11 (and
+// they are issued two channels at a time as FFMA2).  All large-magnitude terms (centre up to 140 m) are separated from
+// the small ones (|q| <= voxel/2), so the result carries the same ~1e-7 relative rounding as the reference's fp32.
 struct PfnParams {
     const float* w; const float* scale; const float* shift;     // [64][10], [64], [64]
     float vx, vy, vz, offx, offy, offz;                         // voxel size, voxel/2 + range_min
 };
-
-struct PfnRegs { float w[8][10], sc[8], sh[8]; };               // channels 8*sub .. 8*sub+7
-__device__ __forceinline__ void load_pfn(PfnRegs& r, const PfnParams& pp, int sub) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-#pragma unroll
-        for (int j = 0; j < 10; ++j) r.w[c][j] = __ldg(pp.w + (8 * sub + c) * 10 + j);
-        r.sc[c] = __ldg(pp.scale + 8 * sub + c);
-        r.sh[c] = __ldg(pp.shift + 8 * sub + c);
+constexpr int PFN_NCOEF = 11;                                   // A0..A3, C0..C2, M0..M2, shift
+__device__ __forceinline__ float pfn_coef(int j, const float* wc, float sc, float sh) {
+    const double s = (double)sc;
+    switch (j) {
+        case 0: return (float)(s * ((double)wc[0] + (double)wc[4] + (double)wc[7]));
+        case 1: return (float)(s * ((double)wc[1] + (double)wc[5] + (double)wc[8]));
+        case 2: return (float)(s * ((double)wc[2] + (double)wc[6] + (double)wc[9]));
+        case 3: return (float)(s * (double)wc[3]);
+        case 4: return (float)(s * (double)wc[0]);
+        case 5: return (float)(s * (double)wc[1]);
+        case 6: return (float)(s * (double)wc[2]);
+        case 7: return (float)(-s * (double)wc[4]);
+        case 8: return (float)(-s * (double)wc[5]);
+        case 9: return (float)(-s * (double)wc[6]);
+        default: return sh;
     }
 }
-
-// Per-pillar geometry terms shared by both PFN mappings (pillar_vfe.py:118-132): mean over the valid slots
-// (slot order) and the pillar centre = coord*voxel + (voxel/2 + range_min), fp32, unfused like the reference.
-struct PillarTerms { float mx, my, mz, ctrx, ctry, ctrz; };
-template <class PointFn>
-__device__ __forceinline__ PillarTerms pillar_terms(PointFn pt, const float4& p0, int n, int cz, int cy, int cx,
-                                                    const PfnParams& pp) {
-    float sx = p0.x, sy = p0.y, sz = p0.z;
-    for (int k = 1; k < n; ++k) { const float4 p = pt(k); sx += p.x; sy += p.y; sz += p.z; }
-    const float fn = (float)n;
-    PillarTerms t;
-    t.mx = __fdiv_rn(sx, fn); t.my = __fdiv_rn(sy, fn); t.mz = __fdiv_rn(sz, fn);
-    t.ctrx = __fadd_rn(__fmul_rn((float)cx, pp.vx), pp.offx);
-    t.ctry = __fadd_rn(__fmul_rn((float)cy, pp.vy), pp.offy);
-    t.ctrz = __fadd_rn(__fmul_rn((float)cz, pp.vz), pp.offz);
-    return t;
-}
-__device__ __forceinline__ void point_features(const float4& p, const PillarTerms& t, float (&f)[10]) {
-    f[0] = p.x; f[1] = p.y; f[2] = p.z; f[3] = p.w;
-    f[4] = p.x - t.mx; f[5] = p.y - t.my; f[6] = p.z - t.mz;
-    f[7] = p.x - t.ctrx; f[8] = p.y - t.ctry; f[9] = p.z - t.ctrz;
-}
-
-// PFN of one pillar by one 8-lane group (staged path): PointFn(k) returns slot k (k < n, n >= 1).  Every lane walks
-// all n points (broadcast loads) and produces 8 of the 64 channels; one 16-byte store per lane.
-template <class PointFn>
-__device__ __forceinline__ void pfn_group_store(PointFn pt, int n, int max_pts, int a, int cz, int cy, int cx,
-                                                const PfnParams& pp, const PfnRegs& r, const CanvasGeom& cg,
-                                                __nv_bfloat16* canvas, long lo_off, int sub, long* dirty_slot) {
-    const float4 p0 = pt(0);
-    const PillarTerms t = pillar_terms(pt, p0, n, cz, cy, cx, pp);
-    float best[8];
+// coefficient table [11][64] (pair-interleaved when read as float2) for the constant bank
+__global__ void pfn_coef_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                const float* __restrict__ shift, float* __restrict__ out) {
+    const int c = threadIdx.x;
+    if (c >= 64) return;
+    float wc[10];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) best[c] = (n < max_pts) ? fmaxf(r.sh[c], 0.f) : 0.f;   // zero-padded slots join the max
+    for (int j = 0; j < 10; ++j) wc[j] = w[c * 10 + j];
+#pragma unroll
+    for (int j = 0; j < PFN_NCOEF; ++j) out[j * 64 + c] = pfn_coef(j, wc, scale[c], shift[c]);
+}
+__constant__ float2 c_pfn_k[PFN_NCOEF][32];
+
+__device__ __forceinline__ void pillar_centre(const PfnParams& pp, int cz, int cy, int cx, float& ctrx, float& ctry,
+                                              float& ctrz) {
+    ctrx = __fadd_rn(__fmul_rn((float)cx, pp.vx), pp.offx);     // pillar_vfe.py:127-131, fp32, unfused
+    ctry = __fadd_rn(__fmul_rn((float)cy, pp.vy), pp.offy);
+    ctrz = __fadd_rn(__fmul_rn((float)cz, pp.vz), pp.offz);
+}
+
+// PFN of one pillar for NP channel pairs.  K(j, c) = coefficient j of local pair c (f2); pt(k) = slot k (1 <= k < n).
+// Zero-padded slots (n < max_pts) contribute relu(shift) to the max (their 10 features are all zero).
+template <int NP, class CoefFn, class PointFn>
+__device__ __forceinline__ void pfn_eval(CoefFn K, PointFn pt, const float4 p0, int n, int max_pts, float ctrx,
+                                         float ctry, float ctrz, f2 (&best)[NP]) {
+    // mean of the centred coordinates, accumulated in fp64 (order-independent to 2^-53: the slot order of the fused
+    // path is the arrival order) and rounded to fp32 once
+    double sx = (double)__fsub_rn(p0.x, ctrx), sy = (double)__fsub_rn(p0.y, ctry), sz = (double)__fsub_rn(p0.z, ctrz);
+    for (int k = 1; k < n; ++k) {
+        const float4 p = pt(k);
+        sx += (double)__fsub_rn(p.x, ctrx); sy += (double)__fsub_rn(p.y, ctry); sz += (double)__fsub_rn(p.z, ctrz);
+    }
+    const double inv_n = 1.0 / (double)n;
+    const float mx = (float)(sx * inv_n), my = (float)(sy * inv_n), mz = (float)(sz * inv_n);
+    f2 B[NP];
+#pragma unroll
+    for (int c = 0; c < NP; ++c) {
+        const f2 sh = K(10, c);
+        f2 b = fma2(K(4, c), f2{ctrx, ctrx}, sh);
+        b = fma2(K(5, c), f2{ctry, ctry}, b);
+        b = fma2(K(6, c), f2{ctrz, ctrz}, b);
+        b = fma2(K(7, c), f2{mx, mx}, b);
+        b = fma2(K(8, c), f2{my, my}, b);
+        B[c] = fma2(K(9, c), f2{mz, mz}, b);
+        best[c].x = n < max_pts ? fmaxf(sh.x, 0.f) : 0.f;
+        best[c].y = n < max_pts ? fmaxf(sh.y, 0.f) : 0.f;
+    }
     for (int k = 0; k < n; ++k) {
         const float4 p = k == 0 ? p0 : pt(k);
-        float f[10];
-        point_features(p, t, f);
+        const float qx = __fsub_rn(p.x, ctrx), qy = __fsub_rn(p.y, ctry), qz = __fsub_rn(p.z, ctrz);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float y = 0.f;
-#pragma unroll
-            for (int j = 0; j < 10; ++j) y = fmaf(r.w[c][j], f[j], y);
-            best[c] = fmaxf(best[c], fmaf(y, r.sc[c], r.sh[c]));       // ReLU folded into the max (best >= 0)
+        for (int c = 0; c < NP; ++c) {
+            f2 y = fma2(K(0, c), f2{qx, qx}, B[c]);
+            y = fma2(K(1, c), f2{qy, qy}, y);
+            y = fma2(K(2, c), f2{qz, qz}, y);
+            y = fma2(K(3, c), f2{p.w, p.w}, y);
+            best[c].x = fmaxf(best[c].x, y.x);                  // ReLU folded into the max (best >= 0)
+            best[c].y = fmaxf(best[c].y, y.y);
         }
     }
-    const long row = canvas_row(cg, a, cy, cx);
-    uint4 hi;
-    hi.x = pack_bf16(best[0], best[1]); hi.y = pack_bf16(best[2], best[3]);
-    hi.z = pack_bf16(best[4], best[5]); hi.w = pack_bf16(best[6], best[7]);
-    reinterpret_cast<uint4*>(canvas + row * 64)[sub] = hi;
-    if (lo_off != 0) {
-        uint4 lo;
-        lo.x = pack_bf16(best[0] - bf16_lo(hi.x), best[1] - bf16_hi(hi.x));
-        lo.y = pack_bf16(best[2] - bf16_lo(hi.y), best[3] - bf16_hi(hi.y));
-        lo.z = pack_bf16(best[4] - bf16_lo(hi.z), best[5] - bf16_hi(hi.z));
-        lo.w = pack_bf16(best[6] - bf16_lo(hi.w), best[7] - bf16_hi(hi.w));
-        reinterpret_cast<uint4*>(canvas + lo_off + row * 64)[sub] = lo;
-    }
-    if (dirty_slot && sub == 0) *dirty_slot = row;
 }
 
-// Fused path: ONE THREAD per pillar and channel half; the PFN parameters live in constant memory, so every FFMA
-// takes its weight as a constant-bank operand (no weight registers, no shared-memory traffic).  Pillars are visited
-// class by class (same point count inside a warp, see vox_chunk_assign_kernel) so warps do not diverge on n.
-__constant__ float c_pfn_w[64 * 10];
-__constant__ float c_pfn_sc[64];
-__constant__ float c_pfn_sh[64];
-
-template <int HALF, class PointFn>
-__device__ __forceinline__ void pfn_thread_store(PointFn pt, const float4 p0, int n, int max_pts, int a, int cz, int cy,
-                                                 int cx, const PfnParams& pp, const CanvasGeom& cg, __nv_bfloat16* canvas,
-                                                 long lo_off, long* dirty_slot) {
-    const PillarTerms t = pillar_terms(pt, p0, n, cz, cy, cx, pp);
-    float best[32];
+// bf16 (hi [+ lo]) store of NP channel pairs = NP/4 16-byte vectors at dst (channel offset already applied)
+template <int NP>
+__device__ __forceinline__ void pfn_store(const f2 (&best)[NP], __nv_bfloat16* dst, long lo_off) {
+    uint32_t hi[NP];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) best[c] = (n < max_pts) ? fmaxf(c_pfn_sh[HALF * 32 + c], 0.f) : 0.f;
-    for (int k = 0; k < n; ++k) {
-        const float4 p = k == 0 ? p0 : pt(k);
-        float f[10];
-        point_features(p, t, f);
+    for (int c = 0; c < NP; ++c) hi[c] = pack_bf16(best[c].x, best[c].y);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            float y = 0.f;
-#pragma unroll
-            for (int j = 0; j < 10; ++j) y = fmaf(c_pfn_w[(HALF * 32 + c) * 10 + j], f[j], y);
-            best[c] = fmaxf(best[c], fmaf(y, c_pfn_sc[HALF * 32 + c], c_pfn_sh[HALF * 32 + c]));
-        }
-    }
-    const long row = canvas_row(cg, a, cy, cx);
-    uint4* dst = reinterpret_cast<uint4*>(canvas + row * 64 + HALF * 32);
-    uint32_t hi[16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) hi[c] = pack_bf16(best[2 * c], best[2 * c + 1]);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) dst[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+    for (int q = 0; q < NP / 4; ++q)
+        reinterpret_cast<uint4*>(dst)[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
     if (lo_off != 0) {
-        uint4* dl = reinterpret_cast<uint4*>(canvas + lo_off + row * 64 + HALF * 32);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < NP / 4; ++q) {
             uint32_t lo[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int c = 4 * q + e;
-                lo[e] = pack_bf16(best[2 * c] - bf16_lo(hi[c]), best[2 * c + 1] - bf16_hi(hi[c]));
+                lo[e] = pack_bf16(best[c].x - bf16_lo(hi[c]), best[c].y - bf16_hi(hi[c]));
             }
-            dl[q] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            reinterpret_cast<uint4*>(dst + lo_off)[q] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
     }
-    if (dirty_slot && HALF == 0) *dirty_slot = row;
+}
+
+// Staged path: 8 lanes ("group") cooperate on one voxel, lane sub = lane & 7 owns channels 8*sub .. 8*sub+7 with its
+// coefficients in registers.
+struct PfnRegs { f2 k[PFN_NCOEF][4]; };
+__device__ __forceinline__ void load_pfn(PfnRegs& r, const PfnParams& pp, int sub) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float wc[10];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) wc[j] = __ldg(pp.w + (8 * sub + c) * 10 + j);
+        const float sc = __ldg(pp.scale + 8 * sub + c), sh = __ldg(pp.shift + 8 * sub + c);
+#pragma unroll
+        for (int j = 0; j < PFN_NCOEF; ++j) {
+            const float v = pfn_coef(j, wc, sc, sh);
+            if (c & 1) r.k[j][c >> 1].y = v; else r.k[j][c >> 1].x = v;
+        }
+    }
+}
+template <class PointFn>
+__device__ __forceinline__ void pfn_group_store(PointFn pt, int n, int max_pts, int a, int cz, int cy, int cx,
+                                                const PfnParams& pp, const PfnRegs& r, const CanvasGeom& cg,
+                                                __nv_bfloat16* canvas, long lo_off, int sub, long* dirty_slot) {
+    float ctrx, ctry, ctrz;
+    pillar_centre(pp, cz, cy, cx, ctrx, ctry, ctrz);
+    f2 best[4];
+    pfn_eval<4>([&](int j, int c) { return r.k[j][c]; }, pt, pt(0), n, max_pts, ctrx, ctry, ctrz, best);
+    const long row = canvas_row(cg, a, cy, cx);
+    pfn_store<4>(best, canvas + row * 64 + sub * 8, lo_off);
+    if (dirty_slot && sub == 0) *dirty_slot = row;
+}
+
+// Fused path: ONE THREAD per pillar and channel group of 2*NP channels (group index GRP); the coefficients live in
+// constant memory, so every FFMA2 takes them as a uniform-register operand (no weight registers, no shared-memory
+// traffic).  Pillars are visited class by class (same point count inside a warp) so warps do not diverge on n.
+template <int NP, int GRP, class PointFn>
+__device__ __forceinline__ void pfn_thread_store(PointFn pt, const float4 p0, int n, int max_pts, int a, int cz,
+                                                 int cy, int cx, const PfnParams& pp, const CanvasGeom& cg,
+                                                 __nv_bfloat16* canvas, long lo_off, long* dirty_slot) {
+    float ctrx, ctry, ctrz;
+    pillar_centre(pp, cz, cy, cx, ctrx, ctry, ctrz);
+    f2 best[NP];
+    pfn_eval<NP>([&](int j, int c) { const float2 v = c_pfn_k[j][GRP * NP + c]; return f2{v.x, v.y}; }, pt, p0, n,
+                 max_pts, ctrx, ctry, ctrz, best);
+    const long row = canvas_row(cg, a, cy, cx);
+    pfn_store<NP>(best, canvas + row * 64 + GRP * 2 * NP, lo_off);
+    if (dirty_slot && GRP == 0) *dirty_slot = row;
+}
+// grp (warp-uniform) -> compile-time channel group, so the constant-bank addresses are immediates
+template <int NP, class PointFn>
+__device__ __forceinline__ void pfn_thread_dispatch(int grp, PointFn pt, const float4 p0, int n, int max_pts, int a,
+                                                    int cz, int cy, int cx, const PfnParams& pp, const CanvasGeom& cg,
+                                                    __nv_bfloat16* canvas, long lo_off, long* dirty_slot) {
+    static_assert(NP == 16 || NP == 8, "2 or 4 channel groups");
+    if (NP == 16) {
+        if (grp == 0) pfn_thread_store<NP, 0>(pt, p0, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dirty_slot);
+        else          pfn_thread_store<NP, (NP == 16 ? 1 : 0)>(pt, p0, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dirty_slot);
+    } else {
+        switch (grp) {
+            case 0: pfn_thread_store<NP, 0>(pt, p0, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dirty_slot); break;
+            case 1: pfn_thread_store<NP, 1>(pt, p0, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dirty_slot); break;
+            case 2: pfn_thread_store<NP, (NP == 8 ? 2 : 0)>(pt, p0, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dirty_slot); break;
+            default: pfn_thread_store<NP, (NP == 8 ? 3 : 0)>(pt, p0, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dirty_slot); break;
+        }
+    }
 }
 
 // K4a: emit reference-format voxel tensors (8 lanes per voxel, voxels of all agents flattened) ---------
@@ -406,7 +457,7 @@ __global__ void __launch_bounds__(256) vox_emit_kernel(const __grid_constant__ A
 // K4b: fused PFN + scatter from the regrouped points: thread per (pillar, channel half) -------------------
 // Work items are the pillars of all agents flattened class-major (class, agent, index): every thread of the grid has
 // work and the pillars of a warp share a point-count class.
-__global__ void __launch_bounds__(256, 3) vox_pfn_kernel(const __grid_constant__ AgentOffsets ao, const VoxWs ws,
+__global__ void __launch_bounds__(256, 2) vox_pfn_kernel(const __grid_constant__ AgentOffsets ao, const VoxWs ws,
                                                          int max_pts, const PfnParams pp, const CanvasGeom cg,
                                                          __nv_bfloat16* canvas, long lo_off, long* dirty_rows) {
     __shared__ int s_base[CB_MAX_AGENTS + 1];                      // first output voxel row of each agent
@@ -453,8 +504,266 @@ __global__ void __launch_bounds__(256, 3) vox_pfn_kernel(const __grid_constant__
         const float4* vpp = ws.vp + ao.off[a] + m.x;
         const int cz = (m.z >> 24) & 0xFF, cy = (m.z >> 12) & 0xFFF, cx = m.z & 0xFFF;
         long* dslot = dirty_rows ? dirty_rows + s_base[a] + cur.v : nullptr;
-        if (half == 0) pfn_thread_store<0>([&](int k) { return vpp[k]; }, cur.p0, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dslot);
-        else           pfn_thread_store<1>([&](int k) { return vpp[k]; }, cur.p0, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dslot);
+        pfn_thread_dispatch<16>(half, [&](int k) { return vpp[k]; }, cur.p0, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dslot);
+        cur = nxt;
+    }
+}
+
+// =============================================================================================================
+// v2 front-end of the fused points -> canvas path.  The canvas result does not depend on the ORDER of the voxels, only
+// on which points each cell keeps (its first max_pts by index) and on which cells survive the max_voxels cap (the first
+// max_voxels by first appearance), so the ordered scan over the points is only run when a cap is actually hit:
+//   V1 (points)  cell id, count[cell]++ (arrival position), first[cell] = min index, the point goes straight into the
+//                cell's slot array slots[cell][pos]; non-empty cells per agent are counted on the way
+//   V2a/b        ONLY for agents with more than max_voxels non-empty cells (else the CTAs exit at once): ordered
+//                per-chunk leader counts -> leader ranks -> cells past the cap are marked refused
+//   V3 (cells)   non-empty cells -> work items {cell, n, x, y} bucketed by point-count class (CTA-aggregated atomics);
+//                cells with more than max_pts points get an index list and are re-filled by V4a/b in index order
+//   V4a/b        ONLY when such cells exist: index list fill, rank by index, first max_pts points re-written to the slots
+//   V5           PFN + canvas store, one thread per (pillar, channel group)
+// Slot order inside a pillar is the arrival order (run-dependent) for cells with <= max_pts points; the max is order-
+// independent and the mean is accumulated in fp64 from the centred fp32 coordinates (exact: <= 32 addends of 24-bit
+// mantissas within a 2^12 range), so the canvas is bit-reproducible from run to run.
+// =============================================================================================================
+constexpr int V2_BIG = 1 << 30;          // count[cell] >= V2_BIG: overflow cell being re-counted by V4a
+constexpr int V2_SCAL = 8;               // scal[0..4] class fill, [5] overflow list top, [6] any overflow cell
+
+struct Vox2Ws {
+    int* count;           // [n_agents*ncell]   points per cell; -1 = refused by the max_voxels cap
+    int* scal;            // [V2_SCAL + n_agents]  scalars above, then non-empty cells per agent
+    int* first;           // [n_agents*ncell]   min point index per cell; later the overflow-list base of big cells
+    int* cellid;          // [sum_P]
+    int* list;            // [sum_P]            index lists of the cells with more than max_pts points
+    int* chunk_tot;       // [n_agents][max_chunks]
+    int2* items;          // [NCLS][item_cap]   {global cell, n | x << 6 | y << 18}
+    float* coef;          // [PFN_NCOEF][64]
+    float4* slots;        // [n_agents*ncell][S]
+    int ncell, S, max_chunks, item_cap;
+};
+
+__device__ __forceinline__ int find_agent_bs(const AgentOffsets& ao, int i) {      // largest a with off[a] <= i
+    int lo = 0, hi = ao.n_agents;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ao.off[mid] <= i) lo = mid; else hi = mid; }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) vox2_assign_kernel(const float4* __restrict__ pts,
+                                                          const __grid_constant__ AgentOffsets ao, const Geom g,
+                                                          const Vox2Ws ws, int max_pts, int use_first,
+                                                          const PfnParams pp) {
+    const int total = ao.off[ao.n_agents];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int a_lo = find_agent_bs(ao, blockIdx.x * 256);          // CTA-uniform
+    const int a_hi = find_agent_bs(ao, min(blockIdx.x * 256 + 255, total - 1));
+    int a = a_lo, opened = 0;
+    if (i < total) {
+        if (a_lo != a_hi) a = find_agent_bs(ao, i);
+        const float4 p = __ldg(pts + i);
+        const float fx = floorf(__fdiv_rn(__fsub_rn(p.x, g.r0), g.v0));      // as vox_assign_kernel (serial generator)
+        const float fy = floorf(__fdiv_rn(__fsub_rn(p.y, g.r1), g.v1));
+        const float fz = floorf(__fdiv_rn(__fsub_rn(p.z, g.r2), g.v2));
+        int cell = -1;
+        if (fx >= 0.f && fx < (float)g.gx && fy >= 0.f && fy < (float)g.gy && fz >= 0.f && fz < (float)g.gz) {
+            cell = ((int)fz * g.gy + (int)fy) * g.gx + (int)fx;
+            const long gc = (long)a * ws.ncell + cell;
+            const int pos = atomicAdd(ws.count + gc, 1);
+            if (use_first) atomicMin(ws.first + gc, i - ao.off[a]);  // only the max_voxels cap needs it
+            if (pos < max_pts) ws.slots[gc * ws.S + pos] = p;
+            opened = pos == 0;
+        }
+        ws.cellid[i] = cell;
+    }
+    // non-empty cells per agent: one atomic per CTA when the CTA lies inside one agent (the usual case)
+    if (a_lo == a_hi) {
+        const int c = __syncthreads_count(opened);
+        if (threadIdx.x == 0 && c > 0) atomicAdd(ws.scal + V2_SCAL + a_lo, c);
+    } else if (opened) {
+        atomicAdd(ws.scal + V2_SCAL + a, 1);
+    }
+    // the last CTA also derives the PFN coefficient table (staging copy for the constant bank)
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x < 64) {
+        const int c = threadIdx.x;
+        float wc[10];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) wc[j] = pp.w[c * 10 + j];
+#pragma unroll
+        for (int j = 0; j < PFN_NCOEF; ++j) ws.coef[j * 64 + c] = pfn_coef(j, wc, pp.scale[c], pp.shift[c]);
+    }
+}
+
+// V2a/b: max_voxels cap.  "Leader" = the first point of its cell; voxel rank = number of leaders before it.
+__device__ __forceinline__ int cap_leaders(const AgentOffsets& ao, const Vox2Ws& ws, int a, int chunk, long (&gc)[4]) {
+    const int p0 = ao.off[a], np = ao.off[a + 1] - p0;
+    int mask = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = chunk * CHUNK + threadIdx.x * 4 + j;
+        gc[j] = -1;
+        if (i < np) {
+            const int cell = ws.cellid[p0 + i];
+            if (cell >= 0) {
+                gc[j] = (long)a * ws.ncell + cell;
+                if (ws.first[gc[j]] == i) mask |= 1 << j;
+            }
+        }
+    }
+    return mask;
+}
+__global__ void __launch_bounds__(256) vox2_cap_count_kernel(const __grid_constant__ AgentOffsets ao, const Vox2Ws ws,
+                                                             int max_voxels) {
+    const int a = blockIdx.y, chunk = blockIdx.x;
+    if (ws.scal[V2_SCAL + a] <= max_voxels) return;                 // uniform: this agent is under the cap
+    long gc[4];
+    const int mask = cap_leaders(ao, ws, a, chunk, gc);
+    int ev, ec, tv, tc;
+    block_scan2(__popc(mask), 0, ev, ec, tv, tc);
+    if (threadIdx.x == 0) ws.chunk_tot[(long)a * ws.max_chunks + chunk] = tv;
+}
+__global__ void __launch_bounds__(256) vox2_cap_refuse_kernel(const __grid_constant__ AgentOffsets ao, const Vox2Ws ws,
+                                                              int max_voxels) {
+    const int a = blockIdx.y, chunk = blockIdx.x;
+    if (ws.scal[V2_SCAL + a] <= max_voxels) return;
+    int part = 0;
+    for (int c = threadIdx.x; c < chunk; c += 256) part += ws.chunk_tot[(long)a * ws.max_chunks + c];
+    int ev, ec, before, tc;
+    block_scan2(part, 0, ev, ec, before, tc);                       // leaders in the preceding chunks
+    long gc[4];
+    const int mask = cap_leaders(ao, ws, a, chunk, gc);
+    int tv;
+    block_scan2(__popc(mask), 0, ev, ec, tv, tc);
+    int rank = before + ev;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (mask & (1 << j)) {
+            if (rank >= max_voxels) ws.count[gc[j]] = -1;           // refused: max_voxels reached
+            ++rank;
+        }
+}
+
+// V3: one thread per 4 consecutive cells
+__global__ void __launch_bounds__(256) vox2_cells_kernel(const Vox2Ws ws, unsigned total_cells, int gx, int max_pts) {
+    __shared__ int s_cnt[NCLS], s_base[NCLS];
+    if (threadIdx.x < NCLS) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned g0 = (blockIdx.x * 256u + threadIdx.x) * 4u;
+    int cnt[4] = {0, 0, 0, 0};
+    if (g0 + 3 < total_cells) {
+        const int4 v = *reinterpret_cast<const int4*>(ws.count + g0);
+        cnt[0] = v.x; cnt[1] = v.y; cnt[2] = v.z; cnt[3] = v.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (g0 + j < total_cells) cnt[j] = ws.count[g0 + j];
+    }
+    int lpos[4], cls[4], word[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) lpos[j] = -1;
+    if (cnt[0] > 0 || cnt[1] > 0 || cnt[2] > 0 || cnt[3] > 0) {
+        unsigned cell = g0 % (unsigned)ws.ncell;                   // nz == 1 on this path: cell = y * gx + x
+        unsigned cy = cell / (unsigned)gx, cx = cell - cy * (unsigned)gx;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (cnt[j] > 0) {
+                const int n = cnt[j] < max_pts ? cnt[j] : max_pts;
+                word[j] = n | ((int)cx << 6) | ((int)cy << 18);
+                cls[j] = n <= 1 ? 0 : (n == 2 ? 1 : (n <= 4 ? 2 : (n <= 8 ? 3 : 4)));
+                lpos[j] = atomicAdd(&s_cnt[cls[j]], 1);
+                if (cnt[j] > max_pts) {                             // keep the first max_pts BY INDEX: V4a/b redo the slots
+                    ws.first[g0 + j] = atomicAdd(ws.scal + 5, cnt[j]);
+                    ws.count[g0 + j] = V2_BIG;
+                    ws.scal[6] = 1;
+                }
+            }
+            if (++cx == (unsigned)gx) { cx = 0; if (++cy * (unsigned)gx == (unsigned)ws.ncell) cy = 0; }   // next row / next agent
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < NCLS && s_cnt[threadIdx.x] > 0)
+        s_base[threadIdx.x] = atomicAdd(ws.scal + threadIdx.x, s_cnt[threadIdx.x]);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (lpos[j] >= 0)
+            ws.items[(long)cls[j] * ws.item_cap + s_base[cls[j]] + lpos[j]] = make_int2((int)(g0 + j), word[j]);
+}
+
+// V4a/b: cells with more than max_pts points (grid-stride; the whole grid exits at once when there are none)
+__global__ void __launch_bounds__(256) vox2_big_fill_kernel(const __grid_constant__ AgentOffsets ao, const Vox2Ws ws) {
+    if (ws.scal[6] == 0) return;
+    const int total = ao.off[ao.n_agents];
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+        const int cell = ws.cellid[i];
+        if (cell < 0) continue;
+        const int a = find_agent_bs(ao, i);
+        const long gc = (long)a * ws.ncell + cell;
+        if (ws.count[gc] < V2_BIG) continue;
+        const int pos = atomicAdd(ws.count + gc, 1) - V2_BIG;
+        ws.list[ws.first[gc] + pos] = i - ao.off[a];
+    }
+}
+__global__ void __launch_bounds__(256) vox2_big_rank_kernel(const float4* __restrict__ pts,
+                                                            const __grid_constant__ AgentOffsets ao, const Vox2Ws ws,
+                                                            int max_pts) {
+    if (ws.scal[6] == 0) return;
+    const int total = ao.off[ao.n_agents];
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+        const int cell = ws.cellid[i];
+        if (cell < 0) continue;
+        const int a = find_agent_bs(ao, i);
+        const long gc = (long)a * ws.ncell + cell;
+        const int c = ws.count[gc];
+        if (c < V2_BIG) continue;
+        const int cnt = c - V2_BIG, li = i - ao.off[a];
+        const int* lst = ws.list + ws.first[gc];
+        int rank = 0;
+        for (int k = 0; k < cnt; ++k) rank += (lst[k] < li) ? 1 : 0;
+        if (rank < max_pts) ws.slots[gc * ws.S + rank] = __ldg(pts + i);
+    }
+}
+
+// V5: PFN + scatter, thread per (pillar, channel group of 2*NP channels); the 64/(2*NP) groups of a pillar are
+// consecutive warps of one CTA.  Work items are taken class-major so the pillars of a warp share a point-count class.
+template <int NP>
+__global__ void __launch_bounds__(256, (NP == 16 ? 2 : 3)) vox2_pfn_kernel(const Vox2Ws ws, int max_pts,
+                                                                          const PfnParams pp, const CanvasGeom cg,
+                                                                          __nv_bfloat16* canvas, long lo_off,
+                                                                          long* dirty_rows, int* dirty_count) {
+    constexpr int NG = 32 / NP;                                    // channel groups per pillar (2 or 4)
+    constexpr int PW = 8 / NG;                                     // pillar-warps per CTA (4 or 2)
+    __shared__ int s_seg[NCLS + 1];
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int c = 0; c < NCLS; ++c) { s_seg[c] = t; t += ws.scal[c]; }
+        s_seg[NCLS] = t;
+        if (blockIdx.x == 0 && dirty_count) *dirty_count = t;
+    }
+    __syncthreads();
+    const int total = s_seg[NCLS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = warp % NG;
+    const int slot = (blockIdx.x * PW + warp / NG) * 32 + lane;
+    const int nslot = gridDim.x * PW * 32;
+    struct Item { int2 it; float4 p0; };
+    auto fetch = [&](int gidx) {
+        Item r;
+        int c = 0;
+#pragma unroll
+        for (int k = 1; k < NCLS; ++k) c += (gidx >= s_seg[k]) ? 1 : 0;
+        r.it = ws.items[(long)c * ws.item_cap + (gidx - s_seg[c])];
+        r.p0 = ws.slots[(long)r.it.x * ws.S];
+        return r;
+    };
+    Item cur;
+    if (slot < total) cur = fetch(slot);
+    for (int gidx = slot; gidx < total; gidx += nslot) {
+        Item nxt = cur;
+        if (gidx + nslot < total) nxt = fetch(gidx + nslot);
+        const int gcell = cur.it.x, word = cur.it.y;
+        const int n = word & 63, cx = (word >> 6) & 0xFFF, cy = (word >> 18) & 0xFFF;
+        const int a = gcell / ws.ncell;
+        const float4* sp = ws.slots + (long)gcell * ws.S;
+        long* dslot = dirty_rows ? dirty_rows + gidx : nullptr;
+        pfn_thread_dispatch<NP>(grp, [&](int k) { return sp[k]; }, cur.p0, n, max_pts, a, 0, cy, cx, pp, cg, canvas, lo_off,
+                                dslot);
         cur = nxt;
     }
 }
@@ -494,11 +803,16 @@ __global__ void __launch_bounds__(256) canvas_clear_kernel(__nv_bfloat16* canvas
     int n = *dirty_count;
     n = n < capacity ? n : capacity;
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = gg; i < n; i += ng) {
-        const long row = dirty_rows[i];
-        if (row < 0) continue;
-        reinterpret_cast<uint4*>(canvas + row * 64)[sub] = z;
-        if (lo_off != 0) reinterpret_cast<uint4*>(canvas + lo_off + row * 64)[sub] = z;
+    for (int i = gg; i < n; i += 4 * ng) {                          // 4 independent row loads in flight per group
+        long row[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) row[u] = (i + u * ng < n) ? __ldg(dirty_rows + i + u * ng) : -1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (row[u] < 0) continue;
+            reinterpret_cast<uint4*>(canvas + row[u] * 64)[sub] = z;
+            if (lo_off != 0) reinterpret_cast<uint4*>(canvas + lo_off + row[u] * 64)[sub] = z;
+        }
     }
 }
 
@@ -529,6 +843,7 @@ static int carve(VoxWs& ws, void* base, size_t bytes, int n_agents, int sum_poin
     ws.chunk_tot = (int2*)take((size_t)n_agents * max_chunks * 8);
     ws.vp = (float4*)take((size_t)sp * 16);
     ws.perm = (int*)take((size_t)n_agents * NCLS * vcap * 4);
+    ws.coef = (float*)take((size_t)11 * 64 * 4);
     ws.ncell = (int)ncell;
     ws.vcap = vcap;
     ws.max_chunks = max_chunks;
@@ -587,6 +902,99 @@ static int run_front(const float* points, const int32_t* pt_offset, int n_agents
     return CB_OK;
 }
 
+static int carve2(Vox2Ws& ws, void* base, size_t bytes, int n_agents, int sum_points, const int32_t* grid, int max_pts,
+                  int max_voxels, size_t* clear_bytes, size_t* total_bytes) {
+    const long ncell = (long)grid[0] * grid[1] * grid[2];
+    const int sp = sum_points > 0 ? sum_points : 1;
+    const long per_agent = max_voxels < ncell ? max_voxels : ncell;
+    const long cap = (long)n_agents * per_agent < sp ? (long)n_agents * per_agent : sp;
+    const int max_chunks = (sp + CHUNK - 1) / CHUNK;
+    uint8_t* p = (uint8_t*)base;
+    size_t o = 0;
+    auto take = [&](size_t n_bytes) { void* r = p ? p + o : nullptr; o += align256(n_bytes); return r; };
+    ws.count = (int*)take((size_t)n_agents * ncell * 4);
+    ws.scal = (int*)take((size_t)(V2_SCAL + n_agents) * 4);
+    size_t o_zero_end = o;
+    ws.first = (int*)take((size_t)n_agents * ncell * 4);
+    size_t o_first_end = o;
+    ws.cellid = (int*)take((size_t)sp * 4);
+    ws.list = (int*)take((size_t)sp * 4);
+    ws.chunk_tot = (int*)take((size_t)n_agents * max_chunks * 4);
+    ws.items = (int2*)take((size_t)NCLS * cap * 8);
+    ws.coef = (float*)take((size_t)PFN_NCOEF * 64 * 4);
+    ws.S = (max_pts + 1) & ~1;                                   // 32-byte aligned cell records
+    ws.slots = (float4*)take((size_t)n_agents * ncell * ws.S * 16);
+    ws.ncell = (int)ncell;
+    ws.max_chunks = max_chunks;
+    ws.item_cap = (int)cap;
+    if (clear_bytes) { clear_bytes[0] = o_zero_end; clear_bytes[1] = o_first_end - o_zero_end; }
+    if (total_bytes) *total_bytes = o;
+    if (p && o > bytes) return CB_ERR_ARG;
+    return CB_OK;
+}
+
+// v2 front half (V1..V4) of the fused path.  pt_offset is a HOST array.
+static int run_front2(const float* points, const int32_t* pt_offset, int n_agents, const float* range,
+                      const float* vsize, const int32_t* grid, int max_pts, int max_voxels, void* workspace,
+                      size_t workspace_bytes, cudaStream_t st, Vox2Ws& ws, const PfnParams& pp) {
+    if (n_agents < 1 || n_agents > CB_MAX_AGENTS || max_pts < 1 || max_pts > 32 || max_voxels < 1) return CB_ERR_ARG;
+    if (!workspace || ((uintptr_t)points & 15)) return CB_ERR_ARG;
+    if (grid[0] > 4096 || grid[1] > 4096 || grid[2] != 1) return CB_ERR_ARG;          // packed work items; nz == 1
+    AgentOffsets ao; Geom g;
+    ao.n_agents = n_agents;
+    for (int i = 0; i <= n_agents; ++i) ao.off[i] = pt_offset[i];
+    if (ao.off[0] != 0) return CB_ERR_ARG;
+    int max_np = 0;
+    for (int i = 0; i < n_agents; ++i) {
+        if (ao.off[i + 1] < ao.off[i]) return CB_ERR_ARG;
+        if (ao.off[i + 1] - ao.off[i] > max_np) max_np = ao.off[i + 1] - ao.off[i];
+    }
+    const int total = ao.off[n_agents];
+    size_t clr[2];
+    int rc = carve2(ws, workspace, workspace_bytes, n_agents, total, grid, max_pts, max_voxels, clr, nullptr);
+    if (rc) return rc;
+    if ((long)n_agents * ws.ncell >= (1L << 31)) return CB_ERR_ARG;
+    g.r0 = range[0]; g.r1 = range[1]; g.r2 = range[2];
+    g.v0 = vsize[0]; g.v1 = vsize[1]; g.v2 = vsize[2];
+    g.gx = grid[0]; g.gy = grid[1]; g.gz = grid[2];
+    // an agent with no more points than max_voxels can never hit the voxel cap: then `first` and V2a/b are not needed
+    int may_cap = 0;
+    for (int i = 0; i < n_agents; ++i) may_cap |= (ao.off[i + 1] - ao.off[i]) > max_voxels;
+    cudaError_t e;
+    e = cudaMemsetAsync(ws.count, 0, clr[0], st);                 if (e) return (int)e;
+    if (may_cap) { e = cudaMemsetAsync(ws.first, 0x7f, clr[1], st); if (e) return (int)e; }
+    if (total > 0) {
+        const unsigned pblocks = (unsigned)((total + 255) / 256);
+        const unsigned sblocks = pblocks < 148u * 4u ? pblocks : 148u * 4u;
+        // development experiment (timing only, wrong results): CB_V1_EXP=1 no slot stores, =2 two slots per cell at stride 2
+        static const int v1_exp = [] { const char* e = getenv("CB_V1_EXP"); return e ? atoi(e) : 0; }();
+        Vox2Ws ws1 = ws;
+        int max_pts1 = max_pts;
+        if (v1_exp == 1) max_pts1 = 0;
+        if (v1_exp == 2) { ws1.S = 2; max_pts1 = 2; }
+        vox2_assign_kernel<<<pblocks, 256, 0, st>>>((const float4*)points, ao, g, ws1, max_pts1, may_cap, pp);
+        CB_CHECK_LAUNCH();
+        if (may_cap) {
+            const dim3 cgrid((unsigned)((max_np + CHUNK - 1) / CHUNK), (unsigned)n_agents);
+            vox2_cap_count_kernel<<<cgrid, 256, 0, st>>>(ao, ws, max_voxels);
+            CB_CHECK_LAUNCH();
+            vox2_cap_refuse_kernel<<<cgrid, 256, 0, st>>>(ao, ws, max_voxels);
+            CB_CHECK_LAUNCH();
+        }
+        const unsigned total_cells = (unsigned)n_agents * (unsigned)ws.ncell;
+        vox2_cells_kernel<<<(total_cells + 1023u) / 1024u, 256, 0, st>>>(ws, total_cells, grid[0], max_pts);
+        CB_CHECK_LAUNCH();
+        vox2_big_fill_kernel<<<sblocks, 256, 0, st>>>(ao, ws);
+        CB_CHECK_LAUNCH();
+        vox2_big_rank_kernel<<<sblocks, 256, 0, st>>>((const float4*)points, ao, ws, max_pts);
+        CB_CHECK_LAUNCH();
+    } else {
+        pfn_coef_kernel<<<1, 64, 0, st>>>(pp.w, pp.scale, pp.shift, ws.coef);
+        CB_CHECK_LAUNCH();
+    }
+    return CB_OK;
+}
+
 static CanvasGeom make_canvas_geom(int canvas_agents, int ny, int nx) {
     CanvasGeom cg;
     cg.ny = ny; cg.nx = nx;
@@ -609,9 +1017,13 @@ static PfnParams make_pfn(const float* w, const float* scale, const float* shift
 
 extern "C" size_t cb_voxelize_workspace_bytes(int n_agents, int sum_points, const int32_t* grid, int max_voxels) {
     cb::VoxWs ws;
-    size_t total = 0;
+    size_t total = 0, total2 = 0;
     cb::carve(ws, nullptr, 0, n_agents, sum_points, grid, max_voxels, nullptr, &total);
-    return total;
+    if (grid[2] == 1) {                                            // the fused canvas path (v2 front-end, 32 slots per cell)
+        cb::Vox2Ws ws2;
+        cb::carve2(ws2, nullptr, 0, n_agents, sum_points, grid, 32, max_voxels, nullptr, &total2);
+    }
+    return total > total2 ? total : total2;
 }
 
 extern "C" int cb_voxelize(const float* points, const int32_t* pt_offset, int n_agents, const float* range,
@@ -638,18 +1050,37 @@ extern "C" int cb_points_to_canvas(const float* points, const int32_t* pt_offset
     using namespace cb;
     if (grid[2] != 1 || !canvas_ps || canvas_agents < n_agents) return CB_ERR_ARG;   // nz == 1 (point_pillar_scatter.py:13)
     cudaStream_t st = (cudaStream_t)stream;
-    AgentOffsets ao; VoxWs ws; Geom g;
-    int rc = run_front(points, pt_offset, n_agents, range, vsize, grid, max_pts, max_voxels, workspace,
-                       workspace_bytes, st, ao, ws, g, nullptr, dirty_count);
-    if (rc) return rc;
     const CanvasGeom cg = make_canvas_geom(canvas_agents, grid[1], grid[0]);
     if (cg.plane_rows * 4 >= (1L << 31)) return CB_ERR_ARG;
     const PfnParams pp = make_pfn(w, scale, shift, vsize, center_off);
     cudaError_t ce;
-    ce = cudaMemcpyToSymbolAsync(c_pfn_w, w, sizeof(float) * 640, 0, cudaMemcpyDeviceToDevice, st);     if (ce) return (int)ce;
-    ce = cudaMemcpyToSymbolAsync(c_pfn_sc, scale, sizeof(float) * 64, 0, cudaMemcpyDeviceToDevice, st);  if (ce) return (int)ce;
-    ce = cudaMemcpyToSymbolAsync(c_pfn_sh, shift, sizeof(float) * 64, 0, cudaMemcpyDeviceToDevice, st);  if (ce) return (int)ce;
-    vox_pfn_kernel<<<148 * 3, 256, 0, st>>>(ao, ws, max_pts, pp, cg, (__nv_bfloat16*)canvas_ps, (long)lo_off,
+    static const int front_ver = [] { const char* e = getenv("CB_FRONT_V"); return e ? atoi(e) : 2; }();
+    static const int pfn_np = [] { const char* e = getenv("CB_PFN_NP"); return e ? atoi(e) : 16; }();
+    if (front_ver >= 2) {
+        Vox2Ws ws2;
+        int rc2 = run_front2(points, pt_offset, n_agents, range, vsize, grid, max_pts, max_voxels, workspace,
+                             workspace_bytes, st, ws2, pp);
+        if (rc2) return rc2;
+        ce = cudaMemcpyToSymbolAsync(c_pfn_k, ws2.coef, sizeof(float) * PFN_NCOEF * 64, 0, cudaMemcpyDeviceToDevice, st);
+        if (ce) return (int)ce;
+        if (pfn_np == 8)
+            vox2_pfn_kernel<8><<<148 * 4, 256, 0, st>>>(ws2, max_pts, pp, cg, (__nv_bfloat16*)canvas_ps, (long)lo_off,
+                                                        (long*)dirty_rows, dirty_count);
+        else
+            vox2_pfn_kernel<16><<<148 * 2, 256, 0, st>>>(ws2, max_pts, pp, cg, (__nv_bfloat16*)canvas_ps, (long)lo_off,
+                                                         (long*)dirty_rows, dirty_count);
+        CB_CHECK_LAUNCH();
+        return CB_OK;
+    }
+    AgentOffsets ao; VoxWs ws; Geom g;
+    int rc = run_front(points, pt_offset, n_agents, range, vsize, grid, max_pts, max_voxels, workspace,
+                       workspace_bytes, st, ao, ws, g, nullptr, dirty_count);
+    if (rc) return rc;
+    pfn_coef_kernel<<<1, 64, 0, st>>>(w, scale, shift, ws.coef);
+    CB_CHECK_LAUNCH();
+    ce = cudaMemcpyToSymbolAsync(c_pfn_k, ws.coef, sizeof(float) * PFN_NCOEF * 64, 0, cudaMemcpyDeviceToDevice, st);
+    if (ce) return (int)ce;
+    vox_pfn_kernel<<<148 * 2, 256, 0, st>>>(ao, ws, max_pts, pp, cg, (__nv_bfloat16*)canvas_ps, (long)lo_off,
                                             (long*)dirty_rows);
     CB_CHECK_LAUNCH();
     return CB_OK;
@@ -677,7 +1108,7 @@ extern "C" int cb_pfn_scatter(const float* voxels, const int32_t* coords, const 
 extern "C" int cb_canvas_clear(void* canvas_ps, int64_t lo_off, const int64_t* dirty_rows, const int32_t* dirty_count,
                                int capacity, void* stream) {
     if (!canvas_ps || !dirty_rows || !dirty_count || capacity < 1) return CB_ERR_ARG;
-    cb::canvas_clear_kernel<<<148 * 4, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)canvas_ps, (long)lo_off,
+    cb::canvas_clear_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)canvas_ps, (long)lo_off,
                                                                        (const long*)dirty_rows, dirty_count, capacity);
     CB_CHECK_LAUNCH();
     return CB_OK;

@@ -322,17 +322,6 @@ __global__ void __launch_bounds__(256, (MAXN <= 5 ? 3 : 2)) warp_att_fuse_v8_ker
 // accumulator updates use packed FFMA2 (fma.rn.f32x2).  A CTA covers 8 rows x PPW columns and walks a contiguous
 // range of such tiles along the row, so the four bilinear taps of neighbouring pixels hit L1.
 // ---------------------------------------------------------------------------------------------------------
-struct f2 { float x, y; };
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
-    unsigned long long ra, rb, rc, rd;
-    asm("mov.b64 %0, {%1,%2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
-    asm("mov.b64 %0, {%1,%2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
-    asm("mov.b64 %0, {%1,%2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-    f2 d;
-    asm("mov.b64 {%0,%1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
-    return d;
-}
 struct u8x { uint32_t w[8]; };
 __device__ __forceinline__ u8x ldg256(const void* p) {
     u8x r;
@@ -417,29 +406,41 @@ __global__ void __launch_bounds__(256, 3) warp_att_fuse_v9_kernel(const __nv_bfl
                 const uint4 wq = s_tap[wid][pin][j][1];
                 const float wt[4] = {__uint_as_float(wq.x), __uint_as_float(wq.y), __uint_as_float(wq.z), __uint_as_float(wq.w)};
                 const unsigned rr[4] = {rq.x, rq.y, rq.z, rq.w};
-                u8x u[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) u[t] = ldg256(featb + (size_t)rr[t] + sub * 32);
+                // Taps whose weight is zero for every pixel of the warp are neither loaded nor blended (0 * v adds
+                // nothing): the agent does not see this part of the map (all four zero), or its transform is a pure
+                // pixel-aligned shift such as the ego's identity (only tap 0 non-zero).  Mixed cases take all four.
+                const bool only0 = !__any_sync(0xffffffffu, (wq.y | wq.z | wq.w) != 0u);
+                const bool none = only0 && !__any_sync(0xffffffffu, wq.x != 0u);
                 f2 x[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) { x[c].x = 0.f; x[c].y = 0.f; }
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const f2 w2 = {wt[t], wt[t]};
+                auto blend = [&](const u8x& ut, float wgt, unsigned row_off) {
+                    const f2 w2 = {wgt, wgt};
                     if (HAS_LO) {
-                        const u8x ul = ldg256(featb + 2 * in_lo_off + (size_t)rr[t] + sub * 32);
+                        const u8x ul = ldg256(featb + 2 * in_lo_off + (size_t)row_off + sub * 32);
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
-                            const f2 v = {bf16_lo(u[t].w[c]) + bf16_lo(ul.w[c]), bf16_hi(u[t].w[c]) + bf16_hi(ul.w[c])};
+                            const f2 v = {bf16_lo(ut.w[c]) + bf16_lo(ul.w[c]), bf16_hi(ut.w[c]) + bf16_hi(ul.w[c])};
                             x[c] = fma2(w2, v, x[c]);
                         }
                     } else {
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
-                            const f2 v = {bf16_lo(u[t].w[c]), bf16_hi(u[t].w[c])};
+                            const f2 v = {bf16_lo(ut.w[c]), bf16_hi(ut.w[c])};
                             x[c] = fma2(w2, v, x[c]);
                         }
                     }
+                };
+                if (none) {
+                } else if (only0) {
+                    const u8x u0 = ldg256(featb + (size_t)rr[0] + sub * 32);
+                    blend(u0, wt[0], rr[0]);
+                } else {
+                    u8x u[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) u[t] = ldg256(featb + (size_t)rr[t] + sub * 32);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) blend(u[t], wt[t], rr[t]);
                 }
                 if (j == 0) {
 #pragma unroll

@@ -229,14 +229,19 @@ def test_voxelize_bit_exact_and_fused_path():
         assert np.array_equal(crd.cpu().numpy(), ref[1]), (max_pts, max_vox)
         assert np.array_equal(npt.cpu().numpy(), ref[2])
         assert np.array_equal(vox.cpu().numpy(), ref[0])          # bit-exact incl. slot order and zero padding
-    # fused path: same canvas as the staged path
+    # fused path (v2 front-end: arrival-order slots, caps handled by the rare-path kernels): same canvas as the staged
+    # path, bit for bit (max is order-independent, the pillar mean is accumulated in fp64), incl. the 32-point cap on the
+    # dense cloud (sigma 1.5 m: hundreds of points per cell), a 5-point cap and a 150-voxel cap
     pw = torch.from_numpy(np.tile(np.eye(4), (1, 5, 5, 1, 1))).cuda()
-    vox, crd, npt, nv = eng.voxelize(pts, off, 32, 70000)
-    eng.forward_voxels(vox, crd, npt, [4], pw)
-    c1 = eng.read_act(eng.canvas, 4).cpu().numpy()
-    eng.forward_points(pts, off, [4], pw, 32, 70000)
-    c2 = eng.read_act(eng.canvas, 4).cpu().numpy()
-    assert np.array_equal(c1, c2)
+    for max_pts, max_vox in ((32, 70000), (5, 70000), (32, 150), (7, 40)):
+        vox, crd, npt, nv = eng.voxelize(pts, off, max_pts, max_vox)
+        assert max_vox < 70000 or int(npt.max()) == max_pts               # the point cap is exercised
+        eng.forward_voxels(vox, crd, npt, [4], pw)
+        c1 = eng.read_act(eng.canvas, 4).cpu().numpy()
+        for rep in range(2):                                              # twice: sparse canvas clear between frames
+            eng.forward_points(pts, off, [4], pw, max_pts, max_vox)
+            c2 = eng.read_act(eng.canvas, 4).cpu().numpy()
+            assert np.array_equal(c1, c2), (max_pts, max_vox, rep, np.abs(c1 - c2).max(), (c1 != c2).sum())
 
 
 def test_warp_fuse_op_golden():
