@@ -316,5 +316,16 @@ __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
     asm("mov.b64 {%0,%1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
     return d;
 }
+__device__ __forceinline__ f2 fmul2(f2 a, f2 b) {
+    unsigned long long ra, rb, rd;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    f2 d;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+__device__ __forceinline__ __nv_bfloat162 u32_bf2(uint32_t v) { return *reinterpret_cast<__nv_bfloat162*>(&v); }
+__device__ __forceinline__ uint32_t bf2_u32(__nv_bfloat162 v) { return *reinterpret_cast<uint32_t*>(&v); }
 
 }  // namespace cb

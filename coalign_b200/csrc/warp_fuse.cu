@@ -335,7 +335,7 @@ __device__ __forceinline__ void stg256(void* p, const uint32_t (&w)[8]) {
                  "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
 }
 
-template <int LPP, int MAXN, bool HAS_LO>
+template <int LPP, int MAXN, bool HAS_LO, bool BF16_BLEND>
 __global__ void __launch_bounds__(256, 3) warp_att_fuse_v9_kernel(const __nv_bfloat16* __restrict__ feat, long in_lo_off,
                                                                   const double* __restrict__ affine,
                                                                   const int* __restrict__ agent_off, int n_scenes, int L,
@@ -397,11 +397,8 @@ __global__ void __launch_bounds__(256, 3) warp_att_fuse_v9_kernel(const __nv_bfl
         }
         __syncwarp();
         if (row_ok) {
-            f2 x0[8], o[8];
-            float m_run = -INFINITY, l_run = 0.f;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) { o[c].x = 0.f; o[c].y = 0.f; x0[c].x = 0.f; x0[c].y = 0.f; }
-            for (int j = 0; j < n; ++j) {
+            // x <- this lane's 16 channels of agent j's map, bilinearly sampled at this pixel
+            auto gather = [&](int j, f2 (&x)[8]) {
                 const uint4 rq = s_tap[wid][pin][j][0];
                 const uint4 wq = s_tap[wid][pin][j][1];
                 const float wt[4] = {__uint_as_float(wq.x), __uint_as_float(wq.y), __uint_as_float(wq.z), __uint_as_float(wq.w)};
@@ -411,73 +408,120 @@ __global__ void __launch_bounds__(256, 3) warp_att_fuse_v9_kernel(const __nv_bfl
                 // pixel-aligned shift such as the ego's identity (only tap 0 non-zero).  Mixed cases take all four.
                 const bool only0 = !__any_sync(0xffffffffu, (wq.y | wq.z | wq.w) != 0u);
                 const bool none = only0 && !__any_sync(0xffffffffu, wq.x != 0u);
-                f2 x[8];
+                if (none) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) { x[c].x = 0.f; x[c].y = 0.f; }
-                auto blend = [&](const u8x& ut, float wgt, unsigned row_off) {
-                    const f2 w2 = {wgt, wgt};
-                    if (HAS_LO) {
-                        const u8x ul = ldg256(featb + 2 * in_lo_off + (size_t)row_off + sub * 32);
+                    for (int c = 0; c < 8; ++c) { x[c].x = 0.f; x[c].y = 0.f; }
+                } else if (BF16_BLEND) {
+                    // bf16 production mode: the four taps are blended with packed bf16 FMAs (HFMA2.BF16, 16 channels in
+                    // 8 instructions per tap instead of 24); the blended vector carries one more bf16 rounding than the
+                    // fp32 blend, the same size as the rounding of any activation store of this mode.  Scores, soft-max
+                    // and the weighted sum stay fp32.
+                    uint32_t xb[8];
+                    if (only0) {
+                        const u8x u0 = ldg256(featb + (size_t)rr[0] + sub * 32);
+                            const __nv_bfloat162 w0 = __float2bfloat162_rn(wt[0]);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) xb[c] = bf2_u32(__hmul2(u32_bf2(u0.w[c]), w0));
+                    } else {
+                        __nv_bfloat162 wb[4];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) wb[t] = __float2bfloat162_rn(wt[t]);
+                        {
+                            u8x u[4];
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) u[t] = ldg256(featb + (size_t)rr[t] + sub * 32);
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                __nv_bfloat162 acc = __hmul2(u32_bf2(u[0].w[c]), wb[0]);
+                                acc = __hfma2(u32_bf2(u[1].w[c]), wb[1], acc);
+                                acc = __hfma2(u32_bf2(u[2].w[c]), wb[2], acc);
+                                acc = __hfma2(u32_bf2(u[3].w[c]), wb[3], acc);
+                                xb[c] = bf2_u32(acc);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) { x[c].x = bf16_lo(xb[c]); x[c].y = bf16_hi(xb[c]); }
+                } else {
+                    auto tap = [&](const u8x& ut, unsigned row_off, int c) {
+                        f2 v = {bf16_lo(ut.w[c]), bf16_hi(ut.w[c])};
+                        (void)row_off;
+                        return v;
+                    };
+                    if (only0) {
+                        const u8x u0 = ldg256(featb + (size_t)rr[0] + sub * 32);
+                            u8x l0 = u0;
+                        if (HAS_LO) l0 = ldg256(featb + 2 * in_lo_off + (size_t)rr[0] + sub * 32);
+                        const f2 w2 = {wt[0], wt[0]};
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
-                            const f2 v = {bf16_lo(ut.w[c]) + bf16_lo(ul.w[c]), bf16_hi(ut.w[c]) + bf16_hi(ul.w[c])};
-                            x[c] = fma2(w2, v, x[c]);
+                            f2 v = tap(u0, rr[0], c);
+                            if (HAS_LO) { v.x += bf16_lo(l0.w[c]); v.y += bf16_hi(l0.w[c]); }
+                            x[c] = fmul2(w2, v);
                         }
                     } else {
+                        u8x u[4];
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const f2 v = {bf16_lo(ut.w[c]), bf16_hi(ut.w[c])};
-                            x[c] = fma2(w2, v, x[c]);
+                        for (int t = 0; t < 4; ++t) u[t] = ldg256(featb + (size_t)rr[t] + sub * 32);
+    #pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            u8x lt = u[t];
+                            if (HAS_LO) lt = ldg256(featb + 2 * in_lo_off + (size_t)rr[t] + sub * 32);
+                            const f2 w2 = {wt[t], wt[t]};
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                f2 v = tap(u[t], rr[t], c);
+                                if (HAS_LO) { v.x += bf16_lo(lt.w[c]); v.y += bf16_hi(lt.w[c]); }
+                                x[c] = t == 0 ? fmul2(w2, v) : fma2(w2, v, x[c]);
+                            }
                         }
                     }
-                };
-                if (none) {
-                } else if (only0) {
-                    const u8x u0 = ldg256(featb + (size_t)rr[0] + sub * 32);
-                    blend(u0, wt[0], rr[0]);
-                } else {
-                    u8x u[4];
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) u[t] = ldg256(featb + (size_t)rr[t] + sub * 32);
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) blend(u[t], wt[t], rr[t]);
                 }
-                if (j == 0) {
+            };
+            // agents are folded in one by one, the ego first: online soft-max over the ego-row scores <x0, xj>/sqrt(C)
+            f2 x0[8], o[8];
+            gather(0, x0);
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) x0[c] = x[c];
-                }
+            for (int c = 0; c < 8; ++c) o[c] = x0[c];
+            float m_run = 0.f, l_run = 1.f;
+            if (method != 1) {
+                f2 d2 = fmul2(x0[0], x0[0]);
+#pragma unroll
+                for (int c = 1; c < 8; ++c) d2 = fma2(x0[c], x0[c], d2);
+                float d = d2.x + d2.y;
+#pragma unroll
+                for (int sft = LPP / 2; sft > 0; sft >>= 1) d += __shfl_xor_sync(0xffffffffu, d, sft);
+                m_run = d * inv_sqrt_c;                                    // att_fuse.py:44
+            }
+            for (int j = 1; j < n; ++j) {
+                f2 x[8];
+                gather(j, x);
                 if (method == 1) {                           // MaxFusion
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        o[c].x = j == 0 ? x[c].x : fmaxf(o[c].x, x[c].x);
-                        o[c].y = j == 0 ? x[c].y : fmaxf(o[c].y, x[c].y);
-                    }
+                    for (int c = 0; c < 8; ++c) { o[c].x = fmaxf(o[c].x, x[c].x); o[c].y = fmaxf(o[c].y, x[c].y); }
                 } else {
-                    f2 d2 = {0.f, 0.f};
+                    f2 d2 = fmul2(x0[0], x[0]);
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) d2 = fma2(x0[c], x[c], d2);
+                    for (int c = 1; c < 8; ++c) d2 = fma2(x0[c], x[c], d2);
                     float d = d2.x + d2.y;
 #pragma unroll
                     for (int sft = LPP / 2; sft > 0; sft >>= 1) d += __shfl_xor_sync(0xffffffffu, d, sft);
-                    const float sc = d * inv_sqrt_c;                       // att_fuse.py:44
+                    const float sc = d * inv_sqrt_c;
                     const float m_new = fmaxf(m_run, sc);
-                    const float alpha = HAS_LO ? expf(m_run - m_new) : __expf(m_run - m_new);   // 0 on the first agent
+                    const float alpha = HAS_LO ? expf(m_run - m_new) : __expf(m_run - m_new);
                     const float pj = HAS_LO ? expf(sc - m_new) : __expf(sc - m_new);
                     l_run = fmaf(l_run, alpha, pj);
                     const f2 a2 = {alpha, alpha}, p2 = {pj, pj};
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const f2 t2 = {o[c].x * alpha, o[c].y * alpha};
-                        (void)a2;
-                        o[c] = fma2(p2, x[c], t2);
-                    }
+                    for (int c = 0; c < 8; ++c) o[c] = fma2(o[c], a2, fmul2(p2, x[c]));
                     m_run = m_new;
                 }
             }
             if (method != 1) {
                 const float inv = 1.f / l_run;
+                const f2 i2 = {inv, inv};
 #pragma unroll
-                for (int c = 0; c < 8; ++c) { o[c].x *= inv; o[c].y *= inv; }
+                for (int c = 0; c < 8; ++c) o[c] = fmul2(o[c], i2);
             }
             if (live) {
                 const int orow = (b * (g.H + 2) + h + 1) * (g.W + 2) + w + 1;   // PF output
@@ -542,6 +586,8 @@ extern "C" int cb_warp_att_fuse(const void* feat, int in_ps, int64_t in_lo_off, 
         else launch_pdl(warp_att_fuse_v8_kernel<LPP_, MAXN_, false>, dim3((unsigned)nb), dim3(256), 0, st, \
                        f, (long)in_lo_off, affine, agent_off, n_scenes, max_cav, g, method, o, (long)out_lo_off); } while (0)
         static const int fuse_ver = [] { const char* e = getenv("CB_FUSE_V"); return e ? atoi(e) : 9; }();
+        // bf16 maps (no lo plane): blend the bilinear taps with packed bf16 FMAs; CB_FUSE_BLEND=32 keeps the fp32 blend
+        static const bool bf16_blend = [] { const char* e = getenv("CB_FUSE_BLEND"); return !(e && atoi(e) == 32); }();
         const bool small = max_cav <= 5;
         // v9 indexes tap rows by 32-bit BYTE offsets and needs 32-byte aligned buffers
         const bool v9_ok = fuse_ver >= 9 && (long)sum_agents * g.Hp * g.Wp * (in_ps ? 4 : 1) * (long)(2 * C) < (1L << 32) &&
@@ -556,9 +602,11 @@ extern "C" int cb_warp_att_fuse(const void* feat, int in_ps, int64_t in_lo_off, 
             const int tiles_per_cta = (total_tiles + grid - 1) / grid;
             grid = (total_tiles + tiles_per_cta - 1) / tiles_per_cta;
 #define CB_FUSE9_LAUNCH(LPP_, MAXN_) do { if (in_lo_off != 0) \
-            launch_pdl(warp_att_fuse_v9_kernel<LPP_, MAXN_, true>, dim3((unsigned)grid), dim3(256), 0, st, \
+            launch_pdl(warp_att_fuse_v9_kernel<LPP_, MAXN_, true, false>, dim3((unsigned)grid), dim3(256), 0, st, \
                        f, (long)in_lo_off, affine, agent_off, n_scenes, max_cav, g, method, o, (long)out_lo_off, tiles_x, tiles_per_cta); \
-        else launch_pdl(warp_att_fuse_v9_kernel<LPP_, MAXN_, false>, dim3((unsigned)grid), dim3(256), 0, st, \
+        else if (bf16_blend) launch_pdl(warp_att_fuse_v9_kernel<LPP_, MAXN_, false, true>, dim3((unsigned)grid), dim3(256), 0, st, \
+                       f, (long)in_lo_off, affine, agent_off, n_scenes, max_cav, g, method, o, (long)out_lo_off, tiles_x, tiles_per_cta); \
+        else launch_pdl(warp_att_fuse_v9_kernel<LPP_, MAXN_, false, false>, dim3((unsigned)grid), dim3(256), 0, st, \
                        f, (long)in_lo_off, affine, agent_off, n_scenes, max_cav, g, method, o, (long)out_lo_off, tiles_x, tiles_per_cta); } while (0)
             switch (C) {
                 case 64: if (small) CB_FUSE9_LAUNCH(4, 5); else CB_FUSE9_LAUNCH(4, FUSE_MAX_AGENTS); break;
