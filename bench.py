@@ -257,7 +257,8 @@ def run_ours(opt):
         ops = eng.build_descs(B * N_AGENTS, B)
         sp = torch.cuda.current_stream().cuda_stream
         n_conv = sum(1 for k, _ in ops if k == "conv")
-        launches_per_step = len(ops) + 1 + 10                  # + normalize_affine + pillar front-end kernels
+        launches_per_step = len(ops) + 1 + 6                   # + normalize_affine + pillar front-end kernels (clear, assign,
+                                                               #   cells, 2 x over-32-points path, PFN; max_voxels path not launched)
         reps = 5
         tot = {"conv": 0.0, "fuse": 0.0}
         by_bn = {}
@@ -293,7 +294,7 @@ def run_ours(opt):
                 "traffic_note": "avg dram read+write bytes per conv launch, ncu --set full, profiles/r1_ncu_full_conv_current.csv (4 scenes/step)",
                 "by_tile_width": {str(bn): {"launches": v[2] // reps, "tflops": v[1] / v[0] / 1e12} for bn, v in sorted(by_bn.items())}}
         fuse_bytes = (N_AGENTS + 1) * 3942400 * 2 * B          # (N+1)*sum(C*H*W)*2 B, bf16
-        hbm_roofs.append({"kernel": "warp_att_fuse_v8_kernel (3 scales)", "bound": "hbm",
+        hbm_roofs.append({"kernel": "warp_att_fuse_v9_kernel (3 scales, bf16x2 tap blend)", "bound": "hbm",
                           "achieved": fuse_bytes / tot["fuse"] / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                           "frac": fuse_bytes / tot["fuse"] / 1e9 / peaks["hbm_gbs"], "traffic": None})
         # pillar front-end: canvas clear + voxelise + PFN + scatter, SURVEY 8(d): P*16 + ny*nx*64*2 B per agent
@@ -307,7 +308,7 @@ def run_ours(opt):
         torch.cuda.synchronize()
         t_front = e0.elapsed_time(e1) * 1e-3 / reps
         pillar_bytes = B * N_AGENTS * (N_POINTS * 16 + 200 * 704 * 64 * 2)
-        hbm_roofs.append({"kernel": "pillar front-end (canvas_clear + vox_* + vox_pfn, 10 launches)", "bound": "hbm",
+        hbm_roofs.append({"kernel": "pillar front-end (canvas_clear + vox2_assign + vox2_cells + vox2_big_* + vox2_pfn, 6 launches + 2 memsets)", "bound": "hbm",
                           "achieved": pillar_bytes / t_front / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                           "frac": pillar_bytes / t_front / 1e9 / peaks["hbm_gbs"], "us": t_front * 1e6, "traffic": None,
                           "note": "algorithmic bytes count the full canvas; the sparse clear makes the real traffic smaller"})
@@ -381,7 +382,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scenes-per-step", type=int, default=6,
+    ap.add_argument("--scenes-per-step", type=int, default=12,
                     help="scenes per GPU per step (6 fills the 148 SMs evenly at every pyramid level; the reference "
                          "trains with batch_size 4)")
     ap.add_argument("--precise", action="store_true", help="bf16x3 split (fp32-class accuracy) instead of bf16")

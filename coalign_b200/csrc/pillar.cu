@@ -274,7 +274,7 @@ __device__ __forceinline__ float pfn_coef(int j, const float* wc, float sc, floa
         default: return sh;
     }
 }
-// coefficient table [11][64] (pair-interleaved when read as float2) for the constant bank
+// coefficient table [PFN_NCOEF][64] (pair-interleaved when read as float2) for the constant bank
 __global__ void pfn_coef_kernel(const float* __restrict__ w, const float* __restrict__ scale,
                                 const float* __restrict__ shift, float* __restrict__ out) {
     const int c = threadIdx.x;
@@ -359,31 +359,28 @@ __device__ __forceinline__ void pfn_store(const f2 (&best)[NP], __nv_bfloat16* d
     }
 }
 
-// Staged path: 8 lanes ("group") cooperate on one voxel, lane sub = lane & 7 owns channels 8*sub .. 8*sub+7 with its
-// coefficients in registers.
-struct PfnRegs { f2 k[PFN_NCOEF][4]; };
-__device__ __forceinline__ void load_pfn(PfnRegs& r, const PfnParams& pp, int sub) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
+// Staged path: 8 lanes ("group") cooperate on one voxel, lane sub = lane & 7 owns channels 8*sub .. 8*sub+7; the
+// coefficient table sits in shared memory (s_k[j][channel], filled by fill_pfn_table at kernel start).
+__device__ __forceinline__ void fill_pfn_table(float (*s_k)[64], const PfnParams& pp) {
+    for (int c = threadIdx.x; c < 64; c += blockDim.x) {
         float wc[10];
 #pragma unroll
-        for (int j = 0; j < 10; ++j) wc[j] = __ldg(pp.w + (8 * sub + c) * 10 + j);
-        const float sc = __ldg(pp.scale + 8 * sub + c), sh = __ldg(pp.shift + 8 * sub + c);
+        for (int j = 0; j < 10; ++j) wc[j] = __ldg(pp.w + c * 10 + j);
+        const float sc = __ldg(pp.scale + c), sh = __ldg(pp.shift + c);
 #pragma unroll
-        for (int j = 0; j < PFN_NCOEF; ++j) {
-            const float v = pfn_coef(j, wc, sc, sh);
-            if (c & 1) r.k[j][c >> 1].y = v; else r.k[j][c >> 1].x = v;
-        }
+        for (int j = 0; j < PFN_NCOEF; ++j) s_k[j][c] = pfn_coef(j, wc, sc, sh);
     }
+    __syncthreads();
 }
 template <class PointFn>
 __device__ __forceinline__ void pfn_group_store(PointFn pt, int n, int max_pts, int a, int cz, int cy, int cx,
-                                                const PfnParams& pp, const PfnRegs& r, const CanvasGeom& cg,
+                                                const PfnParams& pp, const float (*s_k)[64], const CanvasGeom& cg,
                                                 __nv_bfloat16* canvas, long lo_off, int sub, long* dirty_slot) {
     float ctrx, ctry, ctrz;
     pillar_centre(pp, cz, cy, cx, ctrx, ctry, ctrz);
     f2 best[4];
-    pfn_eval<4>([&](int j, int c) { return r.k[j][c]; }, pt, pt(0), n, max_pts, ctrx, ctry, ctrz, best);
+    pfn_eval<4>([&](int j, int c) { const float2 v = *reinterpret_cast<const float2*>(&s_k[j][8 * sub + 2 * c]); return f2{v.x, v.y}; },
+                pt, pt(0), n, max_pts, ctrx, ctry, ctrz, best);
     const long row = canvas_row(cg, a, cy, cx);
     pfn_store<4>(best, canvas + row * 64 + sub * 8, lo_off);
     if (dirty_slot && sub == 0) *dirty_slot = row;
@@ -526,6 +523,7 @@ __global__ void __launch_bounds__(256, 2) vox_pfn_kernel(const __grid_constant__
 // mantissas within a 2^12 range), so the canvas is bit-reproducible from run to run.
 // =============================================================================================================
 constexpr int V2_BIG = 1 << 30;          // count[cell] >= V2_BIG: overflow cell being re-counted by V4a
+constexpr int V2_S0 = 4;                // points per cell in the compact first-tier slot array
 constexpr int V2_SCAL = 8;               // scal[0..4] class fill, [5] overflow list top, [6] any overflow cell
 
 struct Vox2Ws {
@@ -537,9 +535,15 @@ struct Vox2Ws {
     int* chunk_tot;       // [n_agents][max_chunks]
     int2* items;          // [NCLS][item_cap]   {global cell, n | x << 6 | y << 18}
     float* coef;          // [PFN_NCOEF][64]
-    float4* slots;        // [n_agents*ncell][S]
-    int ncell, S, max_chunks, item_cap;
+    float4* slots;        // [n_agents*ncell][V2_S0]    the first V2_S0 points of every cell (64-byte records: the bulk of
+                          //                            the scattered traffic stays inside a compact region)
+    float4* slots2;       // [n_agents*ncell][S2]       points V2_S0 .. max_pts-1 of the few cells that have them
+    int ncell, S0, S2, max_chunks, item_cap;
 };
+
+__device__ __forceinline__ float4* slot_ptr(const Vox2Ws& ws, long gc, int k) {
+    return k < ws.S0 ? ws.slots + gc * ws.S0 + k : ws.slots2 + gc * ws.S2 + (k - ws.S0);
+}
 
 __device__ __forceinline__ int find_agent_bs(const AgentOffsets& ao, int i) {      // largest a with off[a] <= i
     int lo = 0, hi = ao.n_agents;
@@ -568,7 +572,7 @@ __global__ void __launch_bounds__(256) vox2_assign_kernel(const float4* __restri
             const long gc = (long)a * ws.ncell + cell;
             const int pos = atomicAdd(ws.count + gc, 1);
             if (use_first) atomicMin(ws.first + gc, i - ao.off[a]);  // only the max_voxels cap needs it
-            if (pos < max_pts) ws.slots[gc * ws.S + pos] = p;
+            if (pos < max_pts) *slot_ptr(ws, gc, pos) = p;
             opened = pos == 0;
         }
         ws.cellid[i] = cell;
@@ -716,7 +720,7 @@ __global__ void __launch_bounds__(256) vox2_big_rank_kernel(const float4* __rest
         const int* lst = ws.list + ws.first[gc];
         int rank = 0;
         for (int k = 0; k < cnt; ++k) rank += (lst[k] < li) ? 1 : 0;
-        if (rank < max_pts) ws.slots[gc * ws.S + rank] = __ldg(pts + i);
+        if (rank < max_pts) *slot_ptr(ws, gc, rank) = __ldg(pts + i);
     }
 }
 
@@ -742,29 +746,32 @@ __global__ void __launch_bounds__(256, (NP == 16 ? 2 : 3)) vox2_pfn_kernel(const
     const int grp = warp % NG;
     const int slot = (blockIdx.x * PW + warp / NG) * 32 + lane;
     const int nslot = gridDim.x * PW * 32;
-    struct Item { int2 it; float4 p0; };
-    auto fetch = [&](int gidx) {
-        Item r;
+    // Two-stage software pipeline over this thread's pillars: the work item of pillar i+2 and the first point of pillar
+    // i+1 (whose item arrived an iteration ago) are in flight while pillar i is computed, so neither the item -> slot
+    // address dependency nor the slot load latency sits on the critical path.
+    auto load_item = [&](int gidx) {
         int c = 0;
 #pragma unroll
         for (int k = 1; k < NCLS; ++k) c += (gidx >= s_seg[k]) ? 1 : 0;
-        r.it = ws.items[(long)c * ws.item_cap + (gidx - s_seg[c])];
-        r.p0 = ws.slots[(long)r.it.x * ws.S];
-        return r;
+        return ws.items[(long)c * ws.item_cap + (gidx - s_seg[c])];
     };
-    Item cur;
-    if (slot < total) cur = fetch(slot);
+    int2 it_cur = make_int2(0, 1), it_nxt = make_int2(0, 1);
+    float4 p_cur = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (slot < total) it_cur = load_item(slot);
+    if (slot + nslot < total) it_nxt = load_item(slot + nslot);
+    if (slot < total) p_cur = ws.slots[(long)it_cur.x * ws.S0];
     for (int gidx = slot; gidx < total; gidx += nslot) {
-        Item nxt = cur;
-        if (gidx + nslot < total) nxt = fetch(gidx + nslot);
-        const int gcell = cur.it.x, word = cur.it.y;
+        int2 it_nn = it_nxt;
+        if (gidx + 2 * nslot < total) it_nn = load_item(gidx + 2 * nslot);
+        float4 p_nxt = p_cur;
+        if (gidx + nslot < total) p_nxt = ws.slots[(long)it_nxt.x * ws.S0];
+        const int gcell = it_cur.x, word = it_cur.y;
         const int n = word & 63, cx = (word >> 6) & 0xFFF, cy = (word >> 18) & 0xFFF;
         const int a = gcell / ws.ncell;
-        const float4* sp = ws.slots + (long)gcell * ws.S;
         long* dslot = dirty_rows ? dirty_rows + gidx : nullptr;
-        pfn_thread_dispatch<NP>(grp, [&](int k) { return sp[k]; }, cur.p0, n, max_pts, a, 0, cy, cx, pp, cg, canvas, lo_off,
-                                dslot);
-        cur = nxt;
+        pfn_thread_dispatch<NP>(grp, [&](int k) { return *slot_ptr(ws, gcell, k); }, p_cur, n, max_pts, a, 0, cy, cx, pp, cg,
+                                    canvas, lo_off, dslot);
+        it_cur = it_nxt; it_nxt = it_nn; p_cur = p_nxt;
     }
 }
 
@@ -778,8 +785,8 @@ __global__ void __launch_bounds__(256, 2) pfn_scatter_kernel(const float4* __res
                                                           int* dirty_count) {
     const int lane = threadIdx.x & 31, sub = lane & 7, grp = threadIdx.x >> 3;
     const int gg = blockIdx.x * 32 + grp, ng = gridDim.x * 32;
-    PfnRegs r;
-    load_pfn(r, pp, sub);
+    __shared__ __align__(16) float s_k[PFN_NCOEF][64];
+    fill_pfn_table(s_k, pp);
     const int rows = n_rows_dev ? min(n_rows, *n_rows_dev) : n_rows;
     if (dirty_count && blockIdx.x == 0 && threadIdx.x == 0) *dirty_count = rows;
     for (int v = gg; v < rows; v += ng) {
@@ -789,7 +796,7 @@ __global__ void __launch_bounds__(256, 2) pfn_scatter_kernel(const float4* __res
         const bool ok = !(n < 1 || c.x < 0 || c.x >= n_agents || c.z < 0 || c.z >= cg.ny || c.w < 0 || c.w >= cg.nx);
         if (!ok) { if (dirty_rows && sub == 0) dirty_rows[v] = -1; continue; }
         const float4* vp = voxels + (long)v * max_pts;
-        pfn_group_store([&](int k) { return __ldg(vp + k); }, n, max_pts, c.x, c.y, c.z, c.w, pp, r, cg, canvas, lo_off,
+        pfn_group_store([&](int k) { return __ldg(vp + k); }, n, max_pts, c.x, c.y, c.z, c.w, pp, s_k, cg, canvas, lo_off,
                         sub, dirty_rows ? dirty_rows + v : nullptr);
     }
 }
@@ -843,7 +850,7 @@ static int carve(VoxWs& ws, void* base, size_t bytes, int n_agents, int sum_poin
     ws.chunk_tot = (int2*)take((size_t)n_agents * max_chunks * 8);
     ws.vp = (float4*)take((size_t)sp * 16);
     ws.perm = (int*)take((size_t)n_agents * NCLS * vcap * 4);
-    ws.coef = (float*)take((size_t)11 * 64 * 4);
+    ws.coef = (float*)take((size_t)PFN_NCOEF * 64 * 4);
     ws.ncell = (int)ncell;
     ws.vcap = vcap;
     ws.max_chunks = max_chunks;
@@ -922,8 +929,11 @@ static int carve2(Vox2Ws& ws, void* base, size_t bytes, int n_agents, int sum_po
     ws.chunk_tot = (int*)take((size_t)n_agents * max_chunks * 4);
     ws.items = (int2*)take((size_t)NCLS * cap * 8);
     ws.coef = (float*)take((size_t)PFN_NCOEF * 64 * 4);
-    ws.S = (max_pts + 1) & ~1;                                   // 32-byte aligned cell records
-    ws.slots = (float4*)take((size_t)n_agents * ncell * ws.S * 16);
+    static const int s0_env = [] { const char* e = getenv("CB_SLOT_S0"); return e ? atoi(e) : V2_S0; }();
+    ws.S0 = s0_env >= 2 && s0_env <= 32 ? (s0_env & ~1) : V2_S0;
+    ws.slots = (float4*)take((size_t)n_agents * ncell * ws.S0 * 16);
+    ws.S2 = max_pts > ws.S0 ? ((max_pts - ws.S0 + 1) & ~1) : 0;   // 32-byte aligned second-tier records
+    ws.slots2 = (float4*)take((size_t)n_agents * ncell * ws.S2 * 16);
     ws.ncell = (int)ncell;
     ws.max_chunks = max_chunks;
     ws.item_cap = (int)cap;
@@ -966,13 +976,7 @@ static int run_front2(const float* points, const int32_t* pt_offset, int n_agent
     if (total > 0) {
         const unsigned pblocks = (unsigned)((total + 255) / 256);
         const unsigned sblocks = pblocks < 148u * 4u ? pblocks : 148u * 4u;
-        // development experiment (timing only, wrong results): CB_V1_EXP=1 no slot stores, =2 two slots per cell at stride 2
-        static const int v1_exp = [] { const char* e = getenv("CB_V1_EXP"); return e ? atoi(e) : 0; }();
-        Vox2Ws ws1 = ws;
-        int max_pts1 = max_pts;
-        if (v1_exp == 1) max_pts1 = 0;
-        if (v1_exp == 2) { ws1.S = 2; max_pts1 = 2; }
-        vox2_assign_kernel<<<pblocks, 256, 0, st>>>((const float4*)points, ao, g, ws1, max_pts1, may_cap, pp);
+        vox2_assign_kernel<<<pblocks, 256, 0, st>>>((const float4*)points, ao, g, ws, max_pts, may_cap, pp);
         CB_CHECK_LAUNCH();
         if (may_cap) {
             const dim3 cgrid((unsigned)((max_np + CHUNK - 1) / CHUNK), (unsigned)n_agents);
