@@ -6,7 +6,7 @@ See DESIGN.md / INTEGRATION.md.  The CUDA library is mandatory; nothing here fal
 """
 import os
 
-__all__ = ["register", "PointPillarCoalignB200", "PointPillarB200"]
+__all__ = ["register", "PointPillarCoalignB200", "PointPillarB200", "PointPillarUncertaintyB200"]
 PLUGIN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "opencood_plugin")
 
 
@@ -19,7 +19,7 @@ def register():
 
 
 def __getattr__(name):
-    if name in ("PointPillarCoalignB200", "PointPillarB200"):
+    if name in ("PointPillarCoalignB200", "PointPillarB200", "PointPillarUncertaintyB200"):
         from . import model
         return getattr(model, name)
     raise AttributeError(name)

@@ -28,7 +28,7 @@ class ConvDesc(C.Structure):
         ("out", C.c_void_p), ("out_pitch", C.c_int32), ("out_ch_off", C.c_int32), ("out_lo_off", C.c_int64),
         ("out_mode", C.c_int32), ("up_k", C.c_int32), ("out_Hp", C.c_int32), ("out_Wp", C.c_int32),
         ("out_plane_rows", C.c_int64),
-        ("head_out", C.c_void_p * 3), ("head_c0", C.c_int32 * 3), ("head_cn", C.c_int32 * 3), ("n_heads", C.c_int32),
+        ("head_out", C.c_void_p * 4), ("head_c0", C.c_int32 * 4), ("head_cn", C.c_int32 * 4), ("n_heads", C.c_int32),
         ("n_ksteps", C.c_int32), ("ksteps", KStep * CB_MAX_KSTEPS),
     ]
 

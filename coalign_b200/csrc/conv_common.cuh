@@ -21,8 +21,8 @@ struct ConvParams {
     long out_lo_off;
     int out_mode, up_k, out_Hp, out_Wp;
     long out_plane_rows;
-    float* head_out[3];
-    int head_c0[3], head_cn[3], n_heads;
+    float* head_out[CB_MAX_HEADS];
+    int head_c0[CB_MAX_HEADS], head_cn[CB_MAX_HEADS], n_heads;
     int n_ksteps;
     cb_kstep ksteps[CB_MAX_KSTEPS];
 };
@@ -99,7 +99,7 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const RowDes
         for (int j = 0; j < 32; ++j) {
             const int c = col0 + j;
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
+            for (int s = 0; s < CB_MAX_HEADS; ++s) {
                 if (s < p.n_heads && c >= p.head_c0[s] && c < p.head_c0[s] + p.head_cn[s]) {
                     p.head_out[s][(((long)d.n * p.head_cn[s] + (c - p.head_c0[s])) * H + d.h) * W + d.w] = v[j];
                 }
@@ -214,7 +214,7 @@ __device__ __forceinline__ void epilogue_heads_fast(const ConvParams& p, const R
     const long HW = (long)(p.Hp - 2) * W;
     const long pix = (long)d.h * W + d.w;
 #pragma unroll
-    for (int s = 0; s < 3; ++s) {
+    for (int s = 0; s < CB_MAX_HEADS; ++s) {
         if (s < p.n_heads) {
             const int c0 = p.head_c0[s], cn = p.head_cn[s];
             float* base = p.head_out[s] + (long)d.n * cn * HW + pix - (long)c0 * HW;
@@ -242,7 +242,7 @@ inline int fill_params(const cb_conv_desc* d, ConvParams& p) {
     p.out_lo_off = d->out_lo_off;
     p.out_mode = d->out_mode; p.up_k = d->up_k; p.out_Hp = d->out_Hp; p.out_Wp = d->out_Wp;
     p.out_plane_rows = d->out_plane_rows;
-    for (int i = 0; i < 3; ++i) { p.head_out[i] = d->head_out[i]; p.head_c0[i] = d->head_c0[i]; p.head_cn[i] = d->head_cn[i]; }
+    for (int i = 0; i < CB_MAX_HEADS; ++i) { p.head_out[i] = d->head_out[i]; p.head_c0[i] = d->head_c0[i]; p.head_cn[i] = d->head_cn[i]; }
     p.n_heads = d->n_heads;
     p.n_ksteps = d->n_ksteps;
     for (int i = 0; i < d->n_ksteps; ++i) p.ksteps[i] = d->ksteps[i];

@@ -222,7 +222,8 @@ class CoAlignEngine:
                                         "pc": PackedConv(pack_conv_weight(w, None), sd[p + idx + ".bias"].double(), pr, dev)})
                 c_last = dim
         self.c_last = c_last
-        names = ["cls_head", "reg_head"] + (["dir_head"] if "dir_head.weight" in sd else [])
+        names = (["cls_head", "reg_head"] + (["unc_head"] if "unc_head.weight" in sd else []) +
+                 (["dir_head"] if "dir_head.weight" in sd else []))
         hw = torch.cat([sd[n + ".weight"].double().reshape(sd[n + ".weight"].shape[0], -1) for n in names], 0)
         hb = torch.cat([sd[n + ".bias"].double() for n in names], 0)
         self.head_names = [n.replace("_head", "_preds") for n in names]

@@ -216,6 +216,8 @@ class PointPillarB200(nn.Module):
         an = args["anchor_number"]
         self.cls_head = nn.Conv2d(out_c, an, 1)
         self.reg_head = nn.Conv2d(out_c, 7 * an, 1)
+        if "uncertainty_dim" in args:                                  # point_pillar_uncertainty.py:34-35
+            self.unc_head = nn.Conv2d(out_c, int(args["uncertainty_dim"]) * an, 1)
         if "dir_args" in args:
             self.dir_head = nn.Conv2d(out_c, args["dir_args"]["num_bins"] * an, 1)
         self.precise = bool(args.get("b200_precise", False))
@@ -266,3 +268,19 @@ class PointPillarB200(nn.Module):
         """Extension of the boundary: raw clouds of n independent frames in, voxelisation fused on the GPU."""
         n = len(pt_offset) - 1
         return self.engine(n).forward_points(points, pt_offset, [1] * n, None, max_pts, max_voxels)
+
+
+class PointPillarUncertaintyB200(PointPillarB200):
+    """core_method: point_pillar_uncertainty_b200 - state_dict-compatible twin of the stage-1 detector
+    /root/reference/opencood/models/point_pillar_uncertainty.py:15-76 (yaml
+    opv2v/lidar_only_with_noise/coalign/pointpillar_uncertainty.yaml): PillarVFE -> scatter -> BaseBEVBackbone ->
+    cls/reg/unc/dir 1x1 heads on the 384-channel decoded map (no shrink header).  Its boxes and `unc_preds`
+    (log-variances of x, y, yaw per anchor) are what `pose_graph_pre_calc.py` turns into `stage1_boxes.json` for the
+    box-alignment pose graph.  One N=32 head GEMM covers the 2+14+6+4 = 26 output channels."""
+
+    def __init__(self, args):
+        if "uncertainty_dim" not in args:
+            raise KeyError("point_pillar_uncertainty needs model.args.uncertainty_dim")
+        if "shrink_header" in args or args["base_bev_backbone"].get("resnet", False):
+            raise NotImplementedError("point_pillar_uncertainty has no shrink header and uses BaseBEVBackbone")
+        super().__init__(args)

@@ -57,6 +57,16 @@ def single_args(lidar_range=None, voxel_size=None):
     return a
 
 
+def uncertainty_args(lidar_range=None, voxel_size=None, uncertainty_dim=3):
+    """model.args of opv2v/lidar_only_with_noise/coalign/pointpillar_uncertainty.yaml:73-93 (core_method
+    point_pillar_uncertainty: the stage-1 detector whose boxes + uncertainties feed the pose-graph alignment): no shrink
+    header, heads on the 384-channel decoded map, extra `unc_head`."""
+    a = single_args(lidar_range, voxel_size)
+    a.pop("shrink_header", None)
+    a["uncertainty_dim"] = int(uncertainty_dim)
+    return a
+
+
 def dairv2x_args():
     """dairv2x/lidar_only_with_noise/coalign/pointpillar_coalign.yaml:52,57."""
     return make_args([-100.8, -40, -3.5, 100.8, 40, 1.5], [0.4, 0.4, 5])
@@ -126,6 +136,8 @@ def random_state_dict(args, seed=0, backbone="resnet") -> Dict[str, torch.Tensor
         out_c = sh["dim"][-1]
     an = args["anchor_number"]
     heads = [("cls_head", an), ("reg_head", 7 * an)]
+    if "uncertainty_dim" in args:                                   # point_pillar_uncertainty.py:34-35
+        heads.append(("unc_head", args["uncertainty_dim"] * an))
     if "dir_args" in args:
         heads.append(("dir_head", args["dir_args"]["num_bins"] * an))
     for name, co in heads:

@@ -31,6 +31,7 @@ extern "C" {
 
 #define CB_MAX_KSTEPS 168
 #define CB_MAX_AGENTS 64
+#define CB_MAX_HEADS 4    /* cls, reg, dir and the stage-1 detector's uncertainty head (point_pillar_uncertainty.py:34) */
 
 /* --------------------------------------------------------------------------------------------
  * cb_version / cb_device_check
@@ -150,9 +151,9 @@ typedef struct cb_conv_desc {
     int32_t out_Hp, out_Wp;    /* padded dims of the destination (PS plane dims / upsample target) */
     int64_t out_plane_rows;    /* CB_OUT_PS: rows per parity plane */
     /* CB_OUT_HEADS: fp32 NCHW outputs, channel segments [c0, c0+cn) */
-    float* head_out[3];
-    int32_t head_c0[3];
-    int32_t head_cn[3];
+    float* head_out[CB_MAX_HEADS];
+    int32_t head_c0[CB_MAX_HEADS];
+    int32_t head_cn[CB_MAX_HEADS];
     int32_t n_heads;
     /* K loop */
     int32_t n_ksteps;

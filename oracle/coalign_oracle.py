@@ -218,6 +218,8 @@ def shrink(sd, args, x):
 def heads(sd, x):
     out = {"cls_preds": F.conv2d(x, sd["cls_head.weight"], sd["cls_head.bias"]),
            "reg_preds": F.conv2d(x, sd["reg_head.weight"], sd["reg_head.bias"])}
+    if "unc_head.weight" in sd:                                                  # point_pillar_uncertainty.py:66,70
+        out["unc_preds"] = F.conv2d(x, sd["unc_head.weight"], sd["unc_head.bias"])
     if "dir_head.weight" in sd:
         out["dir_preds"] = F.conv2d(x, sd["dir_head.weight"], sd["dir_head.bias"])
     return out

@@ -152,3 +152,31 @@ def test_stride2_phase_split_ksteps(H, W):
     Ho, Wo = (H + 1) // 2, (W + 1) // 2
     got = out.view(N, Hq, Wq, cout)[:, 1:Ho + 1, 1:Wo + 1].permute(0, 3, 1, 2)
     assert torch.allclose(got, ref, atol=1e-3), (got - ref).abs().max()
+
+
+def test_stage1_uncertainty_state_dict_contract_and_registry():
+    """PointPillarUncertaintyB200 (reference core_method `point_pillar_uncertainty`): same keys / shapes as the reference
+    model (checked key-by-key against the reference in tests/golden/gen_golden_single.py::main_uncertainty); the plugin
+    module name resolves to the class the way train_utils.create_model does (train_utils.py:127-146)."""
+    import importlib
+    from coalign_b200 import synth, PLUGIN_DIR
+    from coalign_b200.model import PointPillarUncertaintyB200
+    args = synth.uncertainty_args()
+    m = PointPillarUncertaintyB200(args)
+    sd = synth.random_state_dict(args, 0, backbone="plain")
+    assert set(m.state_dict()) == set(sd)
+    for k, v in m.state_dict().items():
+        assert tuple(v.shape) == tuple(sd[k].shape), k
+    m.load_state_dict(sd, strict=True)
+    assert m.unc_head.weight.shape == (6, 384, 1, 1)
+    import sys
+    sys.path.insert(0, PLUGIN_DIR)
+    try:
+        mod = importlib.import_module("point_pillar_uncertainty_b200")
+    finally:
+        sys.path.remove(PLUGIN_DIR)
+    target = "point_pillar_uncertainty_b200".replace("_", "").lower()
+    found = [c for name, c in mod.__dict__.items() if name.lower() == target]
+    assert found == [PointPillarUncertaintyB200]
+    with pytest.raises(KeyError):
+        PointPillarUncertaintyB200(synth.single_args())

@@ -105,3 +105,21 @@ def test_single_agent_pointpillar_golden():
     _close(st["shrunk"].numpy(), g["shrunk"])
     for k in ("cls_preds", "reg_preds", "dir_preds"):
         _close(out[k].numpy(), g[k])
+
+
+def test_stage1_uncertainty_detector_golden():
+    """the stage-1 `point_pillar_uncertainty` detector (BaseBEVBackbone, no shrink header, extra
+    unc_head) - oracle restatement against the unmodified reference created through its yaml + registry
+    (tests/golden/gen_golden_single.py::main_uncertainty)."""
+    g = np.load(os.path.join(GOLD, "model_single_uncertainty.npz"))
+    seed, n = int(g["seed"]), int(g["n_frames"])
+    args = synth.uncertainty_args(G.SMALL_RANGE, G.SMALL_VOXEL)
+    sd = synth.random_state_dict(args, seed, backbone="plain")
+    assert sd["unc_head.weight"].shape == (6, 384, 1, 1) and "shrink_conv.layers.0.double_conv.0.weight" not in sd
+    inp = G.single_case_inputs(n, seed0=100 + seed)
+    st = {}
+    out = O.forward_single(sd, args, G.to_torch_batch(inp), st)
+    _close(st["decoded"].numpy(), g["decoded"])
+    assert list(out) == ["cls_preds", "reg_preds", "unc_preds", "dir_preds"]      # point_pillar_uncertainty.py:68-76
+    for k in out:
+        _close(out[k].numpy(), g[k])

@@ -476,3 +476,39 @@ def test_single_agent_pointpillar_matches_reference_golden():
     for k in ("cls_preds", "reg_preds", "dir_preds"):
         assert_close(outs[True][k], g[k], 1e-3, 1e-3, k)
         assert rel_l2(outs[False][k], g[k]) < 5e-2, (k, rel_l2(outs[False][k], g[k]))
+
+
+def test_stage1_uncertainty_detector_matches_reference_golden():
+    """the stage-1 `point_pillar_uncertainty` detector through the nn.Module twin - precise mode within
+    rtol 1e-3 of the unmodified reference's cls/reg/unc/dir outputs, bf16 mode at bf16-level drift, raw-point entry ==
+    voxel entry."""
+    from coalign_b200.model import PointPillarUncertaintyB200
+    g = np.load(os.path.join(GOLD, "model_single_uncertainty.npz"))
+    seed, n = int(g["seed"]), int(g["n_frames"])
+    inp = G.single_case_inputs(n, seed0=100 + seed)
+    batch = G.to_torch_batch(inp)
+    dev = {"processed_lidar": {k: v.cuda() for k, v in batch["processed_lidar"].items()}}
+    outs = {}
+    for precise in (True, False):
+        args = synth.uncertainty_args(G.SMALL_RANGE, G.SMALL_VOXEL)
+        args["b200_precise"] = precise
+        sd = synth.random_state_dict(args, seed, backbone="plain")
+        m = PointPillarUncertaintyB200(args)
+        m.load_state_dict(sd, strict=True)
+        m = m.cuda().eval()
+        with torch.no_grad():
+            out = m(dev)
+        torch.cuda.synchronize()
+        assert list(out) == ["cls_preds", "reg_preds", "unc_preds", "dir_preds"]
+        outs[precise] = {k: v.cpu().numpy() for k, v in out.items()}
+        if precise:
+            eng = m.engine(n)
+            assert_close(eng.read_act(eng.cat, n).cpu().numpy(), g["decoded"], 1e-3, 1e-3, "decoded")
+            pts = torch.from_numpy(np.concatenate(inp["points"]).astype(np.float32)).cuda()
+            off = np.concatenate([[0], np.cumsum([p.shape[0] for p in inp["points"]])]).astype(np.int32)
+            out_p = m.forward_points(pts, off)
+            for k in out:
+                assert_close(out_p[k].cpu().numpy(), outs[True][k], 1e-5, 1e-5, f"points vs voxels {k}")
+    for k in ("cls_preds", "reg_preds", "unc_preds", "dir_preds"):
+        assert_close(outs[True][k], g[k], 1e-3, 1e-3, k)
+        assert rel_l2(outs[False][k], g[k]) < 5e-2, (k, rel_l2(outs[False][k], g[k]))

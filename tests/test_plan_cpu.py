@@ -57,3 +57,21 @@ def test_single_agent_plan_reproduces_reference_golden():
         a, b = out[k].numpy().astype(np.float64), g[k].astype(np.float64)
         err = np.abs(a - b)
         assert (err <= 1e-3 * np.abs(b) + 1e-3 * np.sqrt((b * b).mean())).all(), (k, err.max())
+
+
+def test_stage1_uncertainty_plan_reproduces_reference_golden():
+    """SURVEY 8f row 4 (`point_pillar_uncertainty`): heads straight on the 384-channel decoded map, four head segments
+    (cls, reg, unc, dir) in one 32-column GEMM - launch plan against the golden vectors of the unmodified reference."""
+    from coalign_b200.engine import CoAlignEngine
+    g = np.load(os.path.join(GOLD, "model_single_uncertainty.npz"))
+    seed, n = int(g["seed"]), int(g["n_frames"])
+    args = synth.uncertainty_args(G.SMALL_RANGE, G.SMALL_VOXEL)
+    sd = synth.random_state_dict(args, seed, backbone="plain")
+    inp = G.single_case_inputs(n, seed0=100 + seed)
+    eng = CoAlignEngine(args, sd, n, n, device="cpu", precise=True, plan_only=True, backbone="plain", fusion=False)
+    assert eng.head_names == ["cls_preds", "reg_preds", "unc_preds", "dir_preds"] and eng.head_cn == [2, 14, 6, 4]
+    out = PI.run_plan(eng, sd, args, G.to_torch_batch(inp))
+    for k in ("cls_preds", "reg_preds", "unc_preds", "dir_preds"):
+        a, b = out[k].numpy().astype(np.float64), g[k].astype(np.float64)
+        err = np.abs(a - b)
+        assert (err <= 1e-3 * np.abs(b) + 1e-3 * np.sqrt((b * b).mean())).all(), (k, err.max())
