@@ -553,8 +553,9 @@ __device__ __forceinline__ int find_agent_bs(const AgentOffsets& ao, int i) {   
 
 __global__ void __launch_bounds__(256) vox2_assign_kernel(const float4* __restrict__ pts,
                                                           const __grid_constant__ AgentOffsets ao, const Geom g,
-                                                          const Vox2Ws ws, int max_pts, int use_first,
-                                                          const PfnParams pp) {
+                                                          const Vox2Ws ws, int max_pts, int use_first) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int total = ao.off[ao.n_agents];
     const int i = blockIdx.x * 256 + threadIdx.x;
     const int a_lo = find_agent_bs(ao, blockIdx.x * 256);          // CTA-uniform
@@ -584,15 +585,6 @@ __global__ void __launch_bounds__(256) vox2_assign_kernel(const float4* __restri
     } else if (opened) {
         atomicAdd(ws.scal + V2_SCAL + a, 1);
     }
-    // the last CTA also derives the PFN coefficient table (staging copy for the constant bank)
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x < 64) {
-        const int c = threadIdx.x;
-        float wc[10];
-#pragma unroll
-        for (int j = 0; j < 10; ++j) wc[j] = pp.w[c * 10 + j];
-#pragma unroll
-        for (int j = 0; j < PFN_NCOEF; ++j) ws.coef[j * 64 + c] = pfn_coef(j, wc, pp.scale[c], pp.shift[c]);
-    }
 }
 
 // V2a/b: max_voxels cap.  "Leader" = the first point of its cell; voxel rank = number of leaders before it.
@@ -615,6 +607,8 @@ __device__ __forceinline__ int cap_leaders(const AgentOffsets& ao, const Vox2Ws&
 }
 __global__ void __launch_bounds__(256) vox2_cap_count_kernel(const __grid_constant__ AgentOffsets ao, const Vox2Ws ws,
                                                              int max_voxels) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int a = blockIdx.y, chunk = blockIdx.x;
     if (ws.scal[V2_SCAL + a] <= max_voxels) return;                 // uniform: this agent is under the cap
     long gc[4];
@@ -625,6 +619,8 @@ __global__ void __launch_bounds__(256) vox2_cap_count_kernel(const __grid_consta
 }
 __global__ void __launch_bounds__(256) vox2_cap_refuse_kernel(const __grid_constant__ AgentOffsets ao, const Vox2Ws ws,
                                                               int max_voxels) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int a = blockIdx.y, chunk = blockIdx.x;
     if (ws.scal[V2_SCAL + a] <= max_voxels) return;
     int part = 0;
@@ -646,6 +642,8 @@ __global__ void __launch_bounds__(256) vox2_cap_refuse_kernel(const __grid_const
 
 // V3: one thread per 4 consecutive cells
 __global__ void __launch_bounds__(256) vox2_cells_kernel(const Vox2Ws ws, unsigned total_cells, int gx, int max_pts) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ int s_cnt[NCLS], s_base[NCLS];
     if (threadIdx.x < NCLS) s_cnt[threadIdx.x] = 0;
     __syncthreads();
@@ -692,6 +690,8 @@ __global__ void __launch_bounds__(256) vox2_cells_kernel(const Vox2Ws ws, unsign
 
 // V4a/b: cells with more than max_pts points (grid-stride; the whole grid exits at once when there are none)
 __global__ void __launch_bounds__(256) vox2_big_fill_kernel(const __grid_constant__ AgentOffsets ao, const Vox2Ws ws) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (ws.scal[6] == 0) return;
     const int total = ao.off[ao.n_agents];
     for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
@@ -707,6 +707,8 @@ __global__ void __launch_bounds__(256) vox2_big_fill_kernel(const __grid_constan
 __global__ void __launch_bounds__(256) vox2_big_rank_kernel(const float4* __restrict__ pts,
                                                             const __grid_constant__ AgentOffsets ao, const Vox2Ws ws,
                                                             int max_pts) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (ws.scal[6] == 0) return;
     const int total = ao.off[ao.n_agents];
     for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
@@ -733,6 +735,8 @@ __global__ void __launch_bounds__(256, (NP == 16 ? 2 : 3)) vox2_pfn_kernel(const
                                                                           long* dirty_rows, int* dirty_count) {
     constexpr int NG = 32 / NP;                                    // channel groups per pillar (2 or 4)
     constexpr int PW = 8 / NG;                                     // pillar-warps per CTA (4 or 2)
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ int s_seg[NCLS + 1];
     if (threadIdx.x == 0) {
         int t = 0;
@@ -970,31 +974,31 @@ static int run_front2(const float* points, const int32_t* pt_offset, int n_agent
     // an agent with no more points than max_voxels can never hit the voxel cap: then `first` and V2a/b are not needed
     int may_cap = 0;
     for (int i = 0; i < n_agents; ++i) may_cap |= (ao.off[i + 1] - ao.off[i]) > max_voxels;
+    // PFN coefficient table -> constant bank first, so that the kernel chain below is kernel -> kernel only (programmatic
+    // dependent launches: the launch latency of kernel n+1 overlaps the tail of kernel n)
     cudaError_t e;
+    pfn_coef_kernel<<<1, 64, 0, st>>>(pp.w, pp.scale, pp.shift, ws.coef);
+    CB_CHECK_LAUNCH();
+    e = cudaMemcpyToSymbolAsync(c_pfn_k, ws.coef, sizeof(float) * PFN_NCOEF * 64, 0, cudaMemcpyDeviceToDevice, st);
+    if (e) return (int)e;
     e = cudaMemsetAsync(ws.count, 0, clr[0], st);                 if (e) return (int)e;
     if (may_cap) { e = cudaMemsetAsync(ws.first, 0x7f, clr[1], st); if (e) return (int)e; }
     if (total > 0) {
         const unsigned pblocks = (unsigned)((total + 255) / 256);
         const unsigned sblocks = pblocks < 148u * 4u ? pblocks : 148u * 4u;
-        vox2_assign_kernel<<<pblocks, 256, 0, st>>>((const float4*)points, ao, g, ws, max_pts, may_cap, pp);
+        vox2_assign_kernel<<<pblocks, 256, 0, st>>>((const float4*)points, ao, g, ws, max_pts, may_cap);
         CB_CHECK_LAUNCH();
         if (may_cap) {
             const dim3 cgrid((unsigned)((max_np + CHUNK - 1) / CHUNK), (unsigned)n_agents);
-            vox2_cap_count_kernel<<<cgrid, 256, 0, st>>>(ao, ws, max_voxels);
-            CB_CHECK_LAUNCH();
-            vox2_cap_refuse_kernel<<<cgrid, 256, 0, st>>>(ao, ws, max_voxels);
-            CB_CHECK_LAUNCH();
+            e = launch_pdl(vox2_cap_count_kernel, cgrid, dim3(256), 0, st, ao, ws, max_voxels);       if (e) return (int)e;
+            e = launch_pdl(vox2_cap_refuse_kernel, cgrid, dim3(256), 0, st, ao, ws, max_voxels);      if (e) return (int)e;
         }
         const unsigned total_cells = (unsigned)n_agents * (unsigned)ws.ncell;
-        vox2_cells_kernel<<<(total_cells + 1023u) / 1024u, 256, 0, st>>>(ws, total_cells, grid[0], max_pts);
-        CB_CHECK_LAUNCH();
-        vox2_big_fill_kernel<<<sblocks, 256, 0, st>>>(ao, ws);
-        CB_CHECK_LAUNCH();
-        vox2_big_rank_kernel<<<sblocks, 256, 0, st>>>((const float4*)points, ao, ws, max_pts);
-        CB_CHECK_LAUNCH();
-    } else {
-        pfn_coef_kernel<<<1, 64, 0, st>>>(pp.w, pp.scale, pp.shift, ws.coef);
-        CB_CHECK_LAUNCH();
+        e = launch_pdl(vox2_cells_kernel, dim3((total_cells + 1023u) / 1024u), dim3(256), 0, st, ws, total_cells, (int)grid[0],
+                       max_pts);                                                                       if (e) return (int)e;
+        e = launch_pdl(vox2_big_fill_kernel, dim3(sblocks), dim3(256), 0, st, ao, ws);                if (e) return (int)e;
+        e = launch_pdl(vox2_big_rank_kernel, dim3(sblocks), dim3(256), 0, st, (const float4*)points, ao, ws, max_pts);
+        if (e) return (int)e;
     }
     return CB_OK;
 }
@@ -1065,14 +1069,13 @@ extern "C" int cb_points_to_canvas(const float* points, const int32_t* pt_offset
         int rc2 = run_front2(points, pt_offset, n_agents, range, vsize, grid, max_pts, max_voxels, workspace,
                              workspace_bytes, st, ws2, pp);
         if (rc2) return rc2;
-        ce = cudaMemcpyToSymbolAsync(c_pfn_k, ws2.coef, sizeof(float) * PFN_NCOEF * 64, 0, cudaMemcpyDeviceToDevice, st);
-        if (ce) return (int)ce;
         if (pfn_np == 8)
-            vox2_pfn_kernel<8><<<148 * 4, 256, 0, st>>>(ws2, max_pts, pp, cg, (__nv_bfloat16*)canvas_ps, (long)lo_off,
-                                                        (long*)dirty_rows, dirty_count);
+            ce = launch_pdl(vox2_pfn_kernel<8>, dim3(148 * 4), dim3(256), 0, st, ws2, max_pts, pp, cg, (__nv_bfloat16*)canvas_ps,
+                            (long)lo_off, (long*)dirty_rows, (int*)dirty_count);
         else
-            vox2_pfn_kernel<16><<<148 * 2, 256, 0, st>>>(ws2, max_pts, pp, cg, (__nv_bfloat16*)canvas_ps, (long)lo_off,
-                                                         (long*)dirty_rows, dirty_count);
+            ce = launch_pdl(vox2_pfn_kernel<16>, dim3(148 * 2), dim3(256), 0, st, ws2, max_pts, pp, cg, (__nv_bfloat16*)canvas_ps,
+                            (long)lo_off, (long*)dirty_rows, (int*)dirty_count);
+        if (ce) return (int)ce;
         CB_CHECK_LAUNCH();
         return CB_OK;
     }
