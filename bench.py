@@ -294,10 +294,17 @@ def run_ours(opt):
                 "avg_launch_us": tot["conv"] / n_conv * 1e6, "flop_per_step": conv_flop, "traffic": traffic,
                 "traffic_note": "avg dram read+write bytes per conv launch, ncu --set full, profiles/r1_ncu_full_conv_current.csv (4 scenes/step)",
                 "by_tile_width": {str(bn): {"launches": v[2] // reps, "tflops": v[1] / v[0] / 1e12} for bn, v in sorted(by_bn.items())}}
+        tj = json.load(open(tp)) if os.path.exists(tp) else {}
+        fuse_traffic = tj.get("fuse_dram_bytes_per_6_scene_step")
+        front_traffic = tj.get("front_dram_bytes_per_6_scene_step")
         fuse_bytes = (N_AGENTS + 1) * 3942400 * 2 * B          # (N+1)*sum(C*H*W)*2 B, bf16
         hbm_roofs.append({"kernel": "warp_att_fuse_v9_kernel (3 scales, bf16x2 tap blend)", "bound": "hbm",
                           "achieved": fuse_bytes / tot["fuse"] / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                          "frac": fuse_bytes / tot["fuse"] / 1e9 / peaks["hbm_gbs"], "traffic": None})
+                          "frac": fuse_bytes / tot["fuse"] / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": fuse_bytes,
+                          "us": tot["fuse"] * 1e6,
+                          "traffic": None if fuse_traffic is None else int(fuse_traffic * B / 6),
+                          "traffic_note": "dram read+write bytes of the 3 launches, ncu --set full at 6 scenes/step scaled to this "
+                                          "step (profiles/r1_ncu_traffic.json)"})
         # pillar front-end: canvas clear + voxelise + PFN + scatter, SURVEY 8(d): P*16 + ny*nx*64*2 B per agent
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for _ in range(2):
@@ -311,7 +318,9 @@ def run_ours(opt):
         pillar_bytes = B * N_AGENTS * (N_POINTS * 16 + 200 * 704 * 64 * 2)
         hbm_roofs.append({"kernel": "pillar front-end (canvas_clear + pfn_coef + vox2_assign + vox2_cells + vox2_big_fill/rank + vox2_pfn: 7 launches, 1 memset, 1 constant copy)", "bound": "hbm",
                           "achieved": pillar_bytes / t_front / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                          "frac": pillar_bytes / t_front / 1e9 / peaks["hbm_gbs"], "us": t_front * 1e6, "traffic": None,
+                          "frac": pillar_bytes / t_front / 1e9 / peaks["hbm_gbs"], "us": t_front * 1e6,
+                          "algorithmic_bytes": pillar_bytes,
+                          "traffic": None if front_traffic is None else int(front_traffic * B / 6),
                           "note": "algorithmic bytes count the full canvas; the sparse clear makes the real traffic smaller"})
 
     # ---- detection post-processing on the heads of the last step: decode + filters + top-1000 + rotated
