@@ -22,6 +22,7 @@ constexpr int PP_WORDS = PP_MAX_TOPK / 64;
 
 struct PostGeom {
     int H, W, A, num_bins, has_dir, order_hwl, top_k, cap;
+    int stage1;                    // UncertaintyVoxelPostprocessor.post_process_stage1: no projection, no filters, no range mask
     float score_thr, dir_offset, period, two_pi, nms_thr;
     double range[6];
 };
@@ -33,6 +34,7 @@ struct PostWs {
     float* sorted_score;           // [n_scenes][PP_MAX_TOPK]
     float* boxes;                  // [n_scenes][PP_MAX_TOPK][24]
     unsigned char* in_range;       // [n_scenes][PP_MAX_TOPK]
+    float* box7;                   // [n_scenes][PP_MAX_TOPK][7]  decoded boxes of the selected anchors (stage-1 output)
     unsigned long long* mask;      // [n_scenes][PP_MAX_TOPK][PP_WORDS]
 };
 
@@ -41,7 +43,7 @@ struct PostWs {
 __device__ __forceinline__ bool decode_box(const PostGeom& g, const float* __restrict__ cls, const float* __restrict__ reg,
                                            const float* __restrict__ dir, const float* __restrict__ anchors,
                                            const float* __restrict__ T, int idx, float& score, float (&c)[8][3],
-                                           bool& keep, bool& in_range) {
+                                           bool& keep, bool& in_range, float* __restrict__ box7 = nullptr) {
     const int a = idx % g.A;
     const int hw = idx / g.A;
     const int HW = g.H * g.W;
@@ -76,6 +78,10 @@ __device__ __forceinline__ bool decode_box(const PostGeom& g, const float* __res
         const float y2 = __fadd_rn(__fadd_rn(rot, g.dir_offset), __fmul_rn(g.period, (float)label));
         b[6] = __fsub_rn(y2, __fmul_rn(floorf(__fadd_rn(__fdiv_rn(y2, g.two_pi), 0.5f)), g.two_pi));
     }
+    if (box7) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) box7[k] = b[k];
+    }
     // boxes_to_corners_3d (box_utils.py:186-204): 'hwl' boxes are [x,y,z,h,w,l,yaw]
     const float L = g.order_hwl ? b[5] : b[3], Wd = b[4], Hh = g.order_hwl ? b[3] : b[5];
     const float cs = cosf(b[6]), sn = sinf(b[6]);
@@ -91,10 +97,14 @@ __device__ __forceinline__ bool decode_box(const PostGeom& g, const float* __res
         const float rx = __fadd_rn(fmaf(ly, -sn, __fmul_rn(lx, cs)), 0.0f);
         const float ry = __fadd_rn(fmaf(ly, cs, __fmul_rn(lx, sn)), 0.0f);
         const float px = __fadd_rn(rx, b[0]), py = __fadd_rn(ry, b[1]), pz = __fadd_rn(lz, b[2]);
-        // project_box3d: T @ [x y z 1]^T
-        const float X = fmaf(T[3], 1.0f, fmaf(T[2], pz, fmaf(T[1], py, __fmul_rn(T[0], px))));
-        const float Y = fmaf(T[7], 1.0f, fmaf(T[6], pz, fmaf(T[5], py, __fmul_rn(T[4], px))));
-        const float Z = fmaf(T[11], 1.0f, fmaf(T[10], pz, fmaf(T[9], py, __fmul_rn(T[8], px))));
+        // project_box3d: T @ [x y z 1]^T  (stage 1 keeps the corners in the agent's own frame,
+        // uncertainty_voxel_postprocessor.py:80-82)
+        float X = px, Y = py, Z = pz;
+        if (!g.stage1) {
+            X = fmaf(T[3], 1.0f, fmaf(T[2], pz, fmaf(T[1], py, __fmul_rn(T[0], px))));
+            Y = fmaf(T[7], 1.0f, fmaf(T[6], pz, fmaf(T[5], py, __fmul_rn(T[4], px))));
+            Z = fmaf(T[11], 1.0f, fmaf(T[10], pz, fmaf(T[9], py, __fmul_rn(T[8], px))));
+        }
         c[k][0] = X; c[k][1] = Y; c[k][2] = Z;
         xmin = fminf(xmin, X); xmax = fmaxf(xmax, X);
         ymin = fminf(ymin, Y); ymax = fmaxf(ymax, Y);
@@ -106,6 +116,7 @@ __device__ __forceinline__ bool decode_box(const PostGeom& g, const float* __res
     // remove_bbx_abnormal_z (:886-888)
     const float x_len = __fsub_rn(xmax, xmin), y_len = __fsub_rn(ymax, ymin);
     keep = (x_len <= 6.0f) && (y_len <= 6.0f) && (y_len != 0.0f) && (zmin >= -3.0f) && (zmax <= 1.0f);
+    if (g.stage1) { keep = true; in_range = true; }                       // stage 1 applies neither filter nor range mask
     return true;
 }
 
@@ -120,8 +131,8 @@ __global__ void __launch_bounds__(256) pp_decode_kernel(const float* __restrict_
     if (idx < g.cap) {
         float c[8][3];
         above = decode_box(g, cls + (size_t)b * g.A * HW, reg + (size_t)b * g.A * 7 * HW,
-                           g.has_dir ? dir + (size_t)b * g.A * g.num_bins * HW : nullptr, anchors, tfm + b * 16, idx, score,
-                           c, keep, inr);
+                           g.has_dir ? dir + (size_t)b * g.A * g.num_bins * HW : nullptr, anchors,
+                           g.stage1 ? nullptr : tfm + b * 16, idx, score, c, keep, inr);
         keep = above && keep;
     }
     // warp-aggregated counters
@@ -225,8 +236,8 @@ __global__ void __launch_bounds__(128) pp_corners_kernel(const float* __restrict
     float c[8][3], score;
     bool keep, inr;
     decode_box(g, cls + (size_t)b * g.A * HW, reg + (size_t)b * g.A * 7 * HW,
-               g.has_dir ? dir + (size_t)b * g.A * g.num_bins * HW : nullptr, anchors, tfm + b * 16,
-               ws.sorted_idx[b * PP_MAX_TOPK + i], score, c, keep, inr);
+               g.has_dir ? dir + (size_t)b * g.A * g.num_bins * HW : nullptr, anchors, g.stage1 ? nullptr : tfm + b * 16,
+               ws.sorted_idx[b * PP_MAX_TOPK + i], score, c, keep, inr, ws.box7 + ((size_t)b * PP_MAX_TOPK + i) * 7);
     float* o = ws.boxes + ((size_t)b * PP_MAX_TOPK + i) * 24;
 #pragma unroll
     for (int k = 0; k < 8; ++k) { o[3 * k] = c[k][0]; o[3 * k + 1] = c[k][1]; o[3 * k + 2] = c[k][2]; }
@@ -337,7 +348,8 @@ __global__ void __launch_bounds__(64) pp_iou_mask_kernel(const PostGeom g, PostW
 // One CTA per scene: greedy NMS over the score-sorted boxes (warp 0, suppression matrix in shared memory), then the
 // range mask (mask_boxes_outside_range_numpy) and the ordered output.
 __global__ void __launch_bounds__(1024) pp_nms_scan_kernel(const PostGeom g, PostWs ws, float* __restrict__ out_boxes,
-                                                           float* __restrict__ out_scores, int* __restrict__ out_count) {
+                                                           float* __restrict__ out_scores, int* __restrict__ out_count,
+                                                           float* __restrict__ out_box7, int* __restrict__ out_index) {
     extern __shared__ unsigned long long smask[];              // [K][PP_WORDS]
     __shared__ short kept[PP_MAX_TOPK];
     __shared__ short outpos[PP_MAX_TOPK];
@@ -380,7 +392,17 @@ __global__ void __launch_bounds__(1024) pp_nms_scan_kernel(const PostGeom g, Pos
     }
     for (int t = tid; t < nk; t += blockDim.x) {
         const int pos = outpos[t];
-        if (pos >= 0) out_scores[(size_t)b * g.top_k + pos] = ws.sorted_score[b * PP_MAX_TOPK + kept[t]];
+        if (pos >= 0) {
+            out_scores[(size_t)b * g.top_k + pos] = ws.sorted_score[b * PP_MAX_TOPK + kept[t]];
+            if (out_index) out_index[(size_t)b * g.top_k + pos] = ws.sorted_idx[b * PP_MAX_TOPK + kept[t]];
+        }
+    }
+    if (out_box7) {
+        for (int e = tid; e < nk * 7; e += blockDim.x) {
+            const int t = e / 7, f = e - t * 7;
+            const int pos = outpos[t];
+            if (pos >= 0) out_box7[((size_t)b * g.top_k + pos) * 7 + f] = ws.box7[((size_t)b * PP_MAX_TOPK + kept[t]) * 7 + f];
+        }
     }
     if (tid == 0) {
         out_count[b * 2 + 0] = s_nout;
@@ -399,6 +421,7 @@ static size_t carve(int n_scenes, int cap, char* base, PostWs* ws) {
     const size_t o_sc = take((size_t)n_scenes * PP_MAX_TOPK * sizeof(float));
     const size_t o_box = take((size_t)n_scenes * PP_MAX_TOPK * 24 * sizeof(float));
     const size_t o_inr = take((size_t)n_scenes * PP_MAX_TOPK);
+    const size_t o_b7 = take((size_t)n_scenes * PP_MAX_TOPK * 7 * sizeof(float));
     const size_t o_mask = take((size_t)n_scenes * PP_MAX_TOPK * PP_WORDS * sizeof(unsigned long long));
     if (ws) {
         ws->counters = (int*)(base + o_cnt);
@@ -407,6 +430,7 @@ static size_t carve(int n_scenes, int cap, char* base, PostWs* ws) {
         ws->sorted_score = (float*)(base + o_sc);
         ws->boxes = (float*)(base + o_box);
         ws->in_range = (unsigned char*)(base + o_inr);
+        ws->box7 = (float*)(base + o_b7);
         ws->mask = (unsigned long long*)(base + o_mask);
     }
     return off;
@@ -419,14 +443,15 @@ extern "C" size_t cb_postprocess_workspace_bytes(int n_scenes, int H, int W, int
     return cb::carve(n_scenes, H * W * anchor_num, nullptr, nullptr);
 }
 
-extern "C" int cb_postprocess(const float* cls_preds, const float* reg_preds, const float* dir_preds, int n_scenes, int H,
-                              int W, int anchor_num, int num_bins, const float* anchors, const float* tfm,
-                              float score_threshold, float dir_offset, float nms_thresh, const double* gt_range,
-                              int order_hwl, int top_k, float* out_boxes, float* out_scores, int32_t* out_count,
-                              void* workspace, size_t workspace_bytes, void* stream) {
-    using namespace cb;
-    if (!cls_preds || !reg_preds || !anchors || !tfm || !gt_range || !out_boxes || !out_scores || !out_count || !workspace)
-        return CB_ERR_ARG;
+namespace cb {
+static int postprocess_impl(const float* cls_preds, const float* reg_preds, const float* dir_preds, int n_scenes, int H,
+                            int W, int anchor_num, int num_bins, const float* anchors, const float* tfm,
+                            float score_threshold, float dir_offset, float nms_thresh, const double* gt_range,
+                            int order_hwl, int top_k, float* out_boxes, float* out_scores, int32_t* out_count,
+                            void* workspace, size_t workspace_bytes, void* stream, int stage1, float* out_box7,
+                            int32_t* out_index) {
+    if (!cls_preds || !reg_preds || !anchors || !out_boxes || !out_scores || !out_count || !workspace) return CB_ERR_ARG;
+    if (!stage1 && (!tfm || !gt_range)) return CB_ERR_ARG;
     if (n_scenes < 1 || H < 1 || W < 1 || anchor_num < 1 || top_k < 1 || top_k > PP_MAX_TOPK) return CB_ERR_ARG;
     if (dir_preds && num_bins < 1) return CB_ERR_ARG;
     if ((long)H * W * anchor_num >= (1L << 31)) return CB_ERR_ARG;
@@ -436,7 +461,8 @@ extern "C" int cb_postprocess(const float* cls_preds, const float* reg_preds, co
     g.score_thr = score_threshold; g.dir_offset = dir_offset; g.nms_thr = nms_thresh;
     g.period = (float)(2.0 * 3.141592653589793 / (double)(num_bins > 0 ? num_bins : 1));
     g.two_pi = (float)(2.0 * 3.141592653589793);
-    for (int i = 0; i < 6; ++i) g.range[i] = gt_range[i];
+    g.stage1 = stage1 ? 1 : 0;
+    for (int i = 0; i < 6; ++i) g.range[i] = gt_range ? gt_range[i] : 0.0;
     PostWs ws;
     if (carve(n_scenes, g.cap, (char*)workspace, &ws) > workspace_bytes) return CB_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
@@ -454,8 +480,30 @@ extern "C" int cb_postprocess(const float* cls_preds, const float* reg_preds, co
     static cudaError_t attr_err = cudaFuncSetAttribute(pp_nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                        PP_MAX_TOPK * PP_WORDS * (int)sizeof(unsigned long long));
     if (attr_err != cudaSuccess) return (int)attr_err;
-    pp_nms_scan_kernel<<<n_scenes, 1024, (size_t)top_k * PP_WORDS * sizeof(unsigned long long), st>>>(g, ws, out_boxes,
-                                                                                                     out_scores, out_count);
+    pp_nms_scan_kernel<<<n_scenes, 1024, (size_t)top_k * PP_WORDS * sizeof(unsigned long long), st>>>(
+        g, ws, out_boxes, out_scores, out_count, out_box7, out_index);
     CB_CHECK_LAUNCH();
     return CB_OK;
+}
+}  // namespace cb
+
+extern "C" int cb_postprocess(const float* cls_preds, const float* reg_preds, const float* dir_preds, int n_scenes, int H,
+                              int W, int anchor_num, int num_bins, const float* anchors, const float* tfm,
+                              float score_threshold, float dir_offset, float nms_thresh, const double* gt_range,
+                              int order_hwl, int top_k, float* out_boxes, float* out_scores, int32_t* out_count,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+    return cb::postprocess_impl(cls_preds, reg_preds, dir_preds, n_scenes, H, W, anchor_num, num_bins, anchors, tfm,
+                                score_threshold, dir_offset, nms_thresh, gt_range, order_hwl, top_k, out_boxes, out_scores,
+                                out_count, workspace, workspace_bytes, stream, 0, nullptr, nullptr);
+}
+
+extern "C" int cb_postprocess_stage1(const float* cls_preds, const float* reg_preds, const float* dir_preds, int n_agents,
+                                     int H, int W, int anchor_num, int num_bins, const float* anchors,
+                                     float score_threshold, float dir_offset, float nms_thresh, int order_hwl, int top_k,
+                                     float* out_corners, float* out_boxes7, int32_t* out_index, float* out_scores,
+                                     int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!out_boxes7 || !out_index) return CB_ERR_ARG;
+    return cb::postprocess_impl(cls_preds, reg_preds, dir_preds, n_agents, H, W, anchor_num, num_bins, anchors, nullptr,
+                                score_threshold, dir_offset, nms_thresh, nullptr, order_hwl, top_k, out_corners, out_scores,
+                                out_count, workspace, workspace_bytes, stream, 1, out_boxes7, out_index);
 }

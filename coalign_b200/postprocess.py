@@ -145,3 +145,65 @@ class VoxelPostprocessorB200:
         (boxes, scores), = self.post_process_batch(cls, reg, dm, cav_content["anchor_box"],
                                                    cav_content["transformation_matrix"])
         return boxes, scores
+
+
+class UncertaintyVoxelPostprocessorB200(VoxelPostprocessorB200):
+    """Mirror of the reference's ``UncertaintyVoxelPostprocessor``
+    (/root/reference/opencood/data_utils/post_processor/uncertainty_voxel_postprocessor.py:27-118) for the stage-1 detector
+    (``point_pillar_uncertainty``): ``post_process_stage1`` turns the per-agent head outputs into the boxes +
+    uncertainties that ``pose_graph_pre_calc.py`` stores for the box-alignment pose graph.  Decode, direction fix and the
+    rotated NMS of every agent run in one ``cb_postprocess_stage1`` launch sequence; the uncertainties of the kept
+    anchors are gathered on the device from the returned anchor indices."""
+
+    @torch.no_grad()
+    def post_process_stage1(self, stage1_output_dict: dict, anchor_box):
+        lib = _lib.load(check_device=True)
+        cls_preds, reg_preds = stage1_output_dict["cls_preds"], stage1_output_dict["reg_preds"]
+        unc_preds = stage1_output_dict["unc_preds"]
+        dir_preds = stage1_output_dict.get("dir_preds")
+        dev = cls_preds.device
+        if dev.type != "cuda":
+            raise RuntimeError("coalign_b200 post-processing needs CUDA tensors (no CPU fallback)")
+        n, A, H, W = cls_preds.shape
+        if A != self.anchor_num or reg_preds.shape != (n, 7 * A, H, W) or unc_preds.shape[1] % A:
+            raise ValueError("cls_preds / reg_preds / unc_preds shapes do not match the anchor configuration")
+        ud = unc_preds.shape[1] // A                                         # :42
+        num_bins = 0
+        if dir_preds is not None:
+            num_bins = int(self.params["dir_args"]["num_bins"])
+            if dir_preds.shape != (n, num_bins * A, H, W):
+                raise ValueError("dir_preds shape does not match dir_args.num_bins")
+        anchors = self._device_anchors(anchor_box, dev)
+        if tuple(anchors.shape) != (H, W, A, 7):
+            raise ValueError("anchor_box must be (H, W, anchor_num, 7)")
+        cls_c, reg_c = cls_preds.float().contiguous(), reg_preds.float().contiguous()
+        dir_c = dir_preds.float().contiguous() if dir_preds is not None else None
+        need = int(lib.cb_postprocess_workspace_bytes(n, H, W, A))
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        corners = torch.empty(n, TOP_K, 8, 3, dtype=torch.float32, device=dev)
+        boxes7 = torch.empty(n, TOP_K, 7, dtype=torch.float32, device=dev)
+        index = torch.zeros(n, TOP_K, dtype=torch.int32, device=dev)
+        scores = torch.empty(n, TOP_K, dtype=torch.float32, device=dev)
+        counts = torch.zeros(n, 2, dtype=torch.int32, device=dev)
+        dir_offset = float(self.params["dir_args"]["dir_offset"]) if dir_preds is not None else 0.0
+        _lib.check(lib.cb_postprocess_stage1(cls_c.data_ptr(), reg_c.data_ptr(),
+                                             dir_c.data_ptr() if dir_c is not None else None, n, H, W, A, num_bins,
+                                             anchors.data_ptr(), float(self.params["target_args"]["score_threshold"]),
+                                             dir_offset, float(self.params["nms_thresh"]),
+                                             1 if self.params["order"] == "hwl" else 0, TOP_K,
+                                             corners.data_ptr(), boxes7.data_ptr(), index.data_ptr(), scores.data_ptr(),
+                                             counts.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
+                                             torch.cuda.current_stream(dev).cuda_stream), "cb_postprocess_stage1")
+        cnt = counts.cpu().numpy()                                           # the one device->host sync: result sizes
+        if int(cnt[:, 1].sum()) == 0:                                        # no anchor of any agent above the threshold (:87-88)
+            return None, None, None
+        # uncertainty of anchor idx = (h*W + w)*A + a, component k: unc_preds[n, a*ud + k, h, w]   (:45,55)
+        unc_flat = unc_preds.float().permute(0, 2, 3, 1).reshape(n, H * W * A, ud)
+        out_c, out_b, out_u = [], [], []
+        for b in range(n):
+            k = int(cnt[b, 0])
+            out_c.append(corners[b, :k])
+            out_b.append(boxes7[b, :k])
+            out_u.append(unc_flat[b][index[b, :k].long()])
+        return out_c, out_b, out_u

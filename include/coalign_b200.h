@@ -234,6 +234,21 @@ int cb_postprocess(const float* cls_preds, const float* reg_preds, const float* 
                    float* out_boxes, float* out_scores, int32_t* out_count,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* Stage-1 variant: UncertaintyVoxelPostprocessor.post_process_stage1
+ *   /root/reference/opencood/data_utils/post_processor/uncertainty_voxel_postprocessor.py:31-118
+ * Per agent: sigmoid + threshold, delta_to_boxes3d, direction-bin fix, corners in the agent's OWN frame (no projection),
+ * rotated NMS over the top_k candidates; no size / z filter and no range mask.  Next to the corners it returns the
+ * 7-parameter boxes and the flat anchor index (h*W + w)*A + a of every kept box, so that the caller gathers
+ * unc_preds[n, a*uncertainty_dim + k, h, w] without another pass (the reference masks unc_preds the same way, :42-56).
+ *   out_corners [n][top_k][8][3], out_boxes7 [n][top_k][7], out_index [n][top_k], out_scores [n][top_k], all in pick
+ *   order; out_count [n][2] = {boxes kept, anchors above score_threshold}. */
+int cb_postprocess_stage1(const float* cls_preds, const float* reg_preds, const float* dir_preds,
+                          int n_agents, int H, int W, int anchor_num, int num_bins,
+                          const float* anchors, float score_threshold, float dir_offset, float nms_thresh,
+                          int order_hwl, int top_k,
+                          float* out_corners, float* out_boxes7, int32_t* out_index, float* out_scores,
+                          int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
+
 /* --------------------------------------------------------------------------------------------
  * layout helpers (tests, debugging, interop): dense NCHW float32 <-> PF / PS bf16
  * ------------------------------------------------------------------------------------------ */

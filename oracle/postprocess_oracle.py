@@ -221,3 +221,39 @@ def post_process(params, anchor_box, tfm, cls_preds, reg_preds, dir_preds=None):
     m = ((pb >= lr[0:3]) & (pb <= lr[3:6])).all(axis=2)
     m = m.sum(axis=1) >= 8
     return torch.from_numpy(pb[m]), scores[m]
+
+
+def post_process_stage1(params, anchor_box, cls_preds, reg_preds, unc_preds, dir_preds=None):
+    """UncertaintyVoxelPostprocessor.post_process_stage1 (uncertainty_voxel_postprocessor.py:31-118): per-agent boxes in
+    the agent's own frame + their uncertainties, for the box-alignment pose graph.  Returns three lists (one entry per
+    agent): corners (K,8,3), boxes (K,7), uncertainty (K,ud) - or (None, None, None) when nothing passes the threshold."""
+    n = cls_preds.shape[0]
+    ud = unc_preds.shape[1] // cls_preds.shape[1]
+    prob = torch.sigmoid(cls_preds.permute(0, 2, 3, 1).contiguous())
+    unc = unc_preds.permute(0, 2, 3, 1).contiguous()
+    batch_box3d = delta_to_boxes3d(reg_preds, anchor_box)
+    mask = torch.gt(prob, params["target_args"]["score_threshold"])
+    counts = [int(m.sum()) for m in mask]
+    mask = mask.view(-1)
+    boxes3d = batch_box3d.view(-1, 7)[mask].view(-1, 7)
+    uncertainty = unc.view(-1, ud)[mask].view(-1, ud)
+    scores = prob.view(-1)[mask]
+    if dir_preds is not None and len(boxes3d) != 0:
+        dir_offset = params["dir_args"]["dir_offset"]
+        num_bins = params["dir_args"]["num_bins"]
+        dcp = dir_preds.permute(0, 2, 3, 1).contiguous().reshape(-1, num_bins)[mask]
+        dir_labels = torch.max(dcp, dim=-1)[1]
+        period = 2 * np.pi / num_bins
+        dir_rot = limit_period(boxes3d[..., 6] - dir_offset, 0, period)
+        boxes3d[..., 6] = dir_rot + dir_offset + period * dir_labels.to(boxes3d.dtype)
+        boxes3d[..., 6] = limit_period(boxes3d[..., 6], 0.5, 2 * np.pi)
+    if len(boxes3d) == 0:
+        return None, None, None
+    corners = boxes_to_corners_3d(boxes3d, order=params["order"])         # no projection at stage 1 (:80-82)
+    out_c, out_b, out_u, cur = [], [], [], 0
+    for k in counts:
+        c, b, s, u = corners[cur:cur + k], boxes3d[cur:cur + k], scores[cur:cur + k], uncertainty[cur:cur + k]
+        keep = nms_rotated(c, s, params["nms_thresh"])
+        out_c.append(c[keep]); out_b.append(b[keep]); out_u.append(u[keep])
+        cur += k
+    return out_c, out_b, out_u

@@ -67,7 +67,9 @@ sys.modules["opencood.utils.box_overlaps"] = bo
 
 from opencood.data_utils.post_processor.voxel_postprocessor import VoxelPostprocessor   # noqa: E402  (reference)
 
-from tests.golden_cases import post_params, post_case_inputs   # noqa: E402
+from opencood.data_utils.post_processor.uncertainty_voxel_postprocessor import UncertaintyVoxelPostprocessor   # noqa: E402
+
+from tests.golden_cases import post_params, post_case_inputs, stage1_case_inputs   # noqa: E402
 
 
 def run_case(name, H, W, **kw):
@@ -94,8 +96,30 @@ def run_case(name, H, W, **kw):
     print(f"{name}: candidates {n_cand} -> kept {n}")
 
 
+def run_stage1_case(name, H, W, n_agents, **kw):
+    """UncertaintyVoxelPostprocessor.post_process_stage1 of the UNMODIFIED reference -> post_stage1_<name>.npz"""
+    params = post_params(H_map=H, W_map=W)
+    pp = UncertaintyVoxelPostprocessor(params, train=False)
+    anchors = pp.generate_anchor_box()
+    inp = stage1_case_inputs(params, anchors, n_agents=n_agents, **kw)
+    out = {"cls_preds": torch.from_numpy(inp["cls"]), "reg_preds": torch.from_numpy(inp["reg"]),
+           "unc_preds": torch.from_numpy(inp["unc"]), "dir_preds": torch.from_numpy(inp["dir"])}
+    corners, boxes, unc = pp.post_process_stage1(out, torch.from_numpy(anchors))
+    res = {"has_result": np.array(corners is not None), "n_agents": np.int64(n_agents)}
+    if corners is not None:
+        for b in range(n_agents):
+            res[f"corners{b}"] = corners[b].numpy()
+            res[f"boxes{b}"] = boxes[b].numpy()
+            res[f"unc{b}"] = unc[b].numpy()
+    np.savez_compressed(os.path.join(HERE, f"post_stage1_{name}.npz"), **res)
+    print(f"stage1 {name}: kept", None if corners is None else [int(c.shape[0]) for c in corners])
+
+
 if __name__ == "__main__":
     PO.build_c()
+    run_stage1_case("typical", seed=11, H=24, W=40, n_agents=3, cls_bias=-3.0)
+    run_stage1_case("one_empty", seed=12, H=16, W=24, n_agents=3, cls_bias=-4.0, n_objects=3, empty_agents=(1,))
+    run_stage1_case("none", seed=13, H=16, W=24, n_agents=2, cls_bias=-12.0, n_objects=0)        # -> (None, None, None)
     run_case("typical", seed=1, H=24, W=40, cls_bias=-3.0)                 # a few dozen candidates, clustered
     run_case("many", seed=2, H=32, W=48, cls_bias=-0.3)                    # > 1000 candidates: top-1000 truncation
     run_case("none", seed=3, H=16, W=24, cls_bias=-12.0, n_objects=0)      # nothing above the threshold -> (None, None)

@@ -76,6 +76,18 @@ def post_case_inputs(params, anchors, seed, cls_bias=-3.0, n_objects=12, yaw_deg
             "tfm": tfm.astype(np.float32)}
 
 
+def stage1_case_inputs(params, anchors, seed, n_agents=3, uncertainty_dim=3, empty_agents=(), **kw):
+    """Head outputs of the stage-1 uncertainty detector for `n_agents` agents: post_case_inputs + unc_preds
+    (n, uncertainty_dim*A, H, W) ~ N(-1, 0.5) (log-variances); `empty_agents` get no anchor above the threshold."""
+    inp = post_case_inputs(params, anchors, seed, n_scenes=n_agents, **kw)
+    for b in empty_agents:
+        inp["cls"][b] = -20.0
+    H, W, A = anchors.shape[:3]
+    rng = np.random.default_rng(seed + 7000)
+    inp["unc"] = rng.normal(-1.0, 0.5, (n_agents, uncertainty_dim * A, H, W)).astype(np.float32)
+    return inp
+
+
 def single_case_inputs(n_frames, seed0, n_points=1800):
     """A batch of `n_frames` independent single-agent frames (the single-agent `point_pillar` model): reference collate
     format with the batch index in voxel_coords[:, 0]."""

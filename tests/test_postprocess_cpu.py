@@ -73,3 +73,39 @@ def test_host_mirror_anchors_and_abi_symbols():
     assert np.array_equal(a, PO.generate_anchor_box(params))
     lib = _lib.load()                                                  # symbols only; no compute without a GPU
     assert hasattr(lib, "cb_postprocess") and hasattr(lib, "cb_postprocess_workspace_bytes")
+
+
+STAGE1_CASES = {
+    "typical": dict(seed=11, H=24, W=40, n_agents=3, cls_bias=-3.0),
+    "one_empty": dict(seed=12, H=16, W=24, n_agents=3, cls_bias=-4.0, n_objects=3, empty_agents=(1,)),
+    "none": dict(seed=13, H=16, W=24, n_agents=2, cls_bias=-12.0, n_objects=0),
+}
+
+
+def stage1_case(name):
+    kw = dict(STAGE1_CASES[name])
+    H, W = kw.pop("H"), kw.pop("W")
+    params = G.post_params(H_map=H, W_map=W)
+    anchors = PO.generate_anchor_box(params)
+    return params, anchors, G.stage1_case_inputs(params, anchors, **kw)
+
+
+@pytest.mark.parametrize("name", list(STAGE1_CASES))
+def test_stage1_oracle_matches_reference_golden(name):
+    """UncertaintyVoxelPostprocessor.post_process_stage1 (boxes + uncertainties for the pose graph) -
+    oracle restatement against the unmodified reference (tests/golden/gen_golden_post.py::run_stage1_case)."""
+    g = np.load(os.path.join(GOLD, f"post_stage1_{name}.npz"))
+    params, anchors, inp = stage1_case(name)
+    c, b, u = PO.post_process_stage1(params, torch.from_numpy(anchors), torch.from_numpy(inp["cls"]),
+                                     torch.from_numpy(inp["reg"]), torch.from_numpy(inp["unc"]), torch.from_numpy(inp["dir"]))
+    if not bool(g["has_result"]):
+        assert c is None and b is None and u is None
+        return
+    assert len(c) == int(g["n_agents"])
+    for a in range(len(c)):
+        assert c[a].shape == g[f"corners{a}"].shape, (a, c[a].shape)
+        np.testing.assert_allclose(c[a].numpy(), g[f"corners{a}"], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(b[a].numpy(), g[f"boxes{a}"], rtol=0, atol=1e-6)
+        assert np.array_equal(u[a].numpy(), g[f"unc{a}"])              # a pure gather: same picks in the same order
+    if name == "one_empty":
+        assert c[1].shape[0] == 0 and c[0].shape[0] > 0

@@ -77,3 +77,26 @@ def test_batched_call_equals_single_calls_and_properties():
         for i in range(len(c) - 1):
             iou = PO.quad_iou_one_to_many(c[i, :4, :2], c[i + 1:, :4, :2])
             assert (iou <= params["nms_thresh"]).all()
+
+
+@pytest.mark.parametrize("name", ["typical", "one_empty", "none"])
+def test_stage1_cuda_matches_reference_golden(name):
+    """cb_postprocess_stage1 through UncertaintyVoxelPostprocessorB200.post_process_stage1 against the
+    unmodified reference's post_process_stage1 (corners, 7-parameter boxes and gathered uncertainties per agent)."""
+    from coalign_b200.postprocess import UncertaintyVoxelPostprocessorB200
+    from tests.test_postprocess_cpu import stage1_case
+    g = np.load(os.path.join(GOLD, f"post_stage1_{name}.npz"))
+    params, anchors, inp = stage1_case(name)
+    pp = UncertaintyVoxelPostprocessorB200(params, train=False)
+    out = {"cls_preds": torch.from_numpy(inp["cls"]).cuda(), "reg_preds": torch.from_numpy(inp["reg"]).cuda(),
+           "unc_preds": torch.from_numpy(inp["unc"]).cuda(), "dir_preds": torch.from_numpy(inp["dir"]).cuda()}
+    c, b, u = pp.post_process_stage1(out, torch.from_numpy(anchors))
+    if not bool(g["has_result"]):
+        assert c is None and b is None and u is None
+        return
+    assert len(c) == int(g["n_agents"])
+    for a in range(len(c)):
+        assert c[a].shape == g[f"corners{a}"].shape, (a, c[a].shape, g[f"corners{a}"].shape)
+        np.testing.assert_allclose(c[a].cpu().numpy(), g[f"corners{a}"], rtol=0, atol=2e-5)
+        np.testing.assert_allclose(b[a].cpu().numpy(), g[f"boxes{a}"], rtol=0, atol=2e-5)
+        assert np.array_equal(u[a].cpu().numpy(), g[f"unc{a}"])
