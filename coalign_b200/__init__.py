@@ -8,6 +8,7 @@ import os
 
 __all__ = ["register", "PointPillarCoalignB200", "PointPillarB200", "PointPillarUncertaintyB200"]
 PLUGIN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "opencood_plugin")
+LOSS_PLUGIN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "opencood_plugin_loss")
 
 
 def register():
@@ -16,6 +17,9 @@ def register():
     import opencood.models as m
     if PLUGIN_DIR not in list(m.__path__):
         m.__path__.append(PLUGIN_DIR)
+    import opencood.loss as lo                        # train_utils.create_loss: loss.core_method: point_pillar_loss_b200
+    if LOSS_PLUGIN_DIR not in list(lo.__path__):
+        lo.__path__.append(LOSS_PLUGIN_DIR)
 
 
 def __getattr__(name):

@@ -216,3 +216,43 @@ def post_params(lidar_range=None, voxel_size=None, H_map=None, W_map=None):
             "target_args": {"pos_threshold": 0.6, "neg_threshold": 0.45, "score_threshold": 0.20},
             "order": "hwl", "max_num": 100, "nms_thresh": 0.15,
             "dir_args": {"dir_offset": 0.7853, "num_bins": 2, "anchor_yaw": [0, 90]}}
+
+
+# ------------------------------------------------------------------------------------------
+# loss
+# ------------------------------------------------------------------------------------------
+def loss_args():
+    """yaml `loss.args` of opv2v/lidar_only_with_noise/coalign/pointpillar_coalign.yaml:132-147."""
+    return {"pos_cls_weight": 2.0,
+            "cls": {"type": "SigmoidFocalLoss", "alpha": 0.25, "gamma": 2.0, "weight": 2.0},
+            "reg": {"type": "WeightedSmoothL1Loss", "sigma": 3.0, "codewise": True, "weight": 2.0},
+            "dir": {"type": "WeightedSoftmaxClassificationLoss", "weight": 0.2,
+                    "args": {"dir_offset": 0.7853, "num_bins": 2, "anchor_yaw": [0, 90]}}}
+
+
+def loss_case(seed, n=2, H=12, W=20, A=2, n_pos=9, empty_samples=(), dtype=np.float64):
+    """Synthetic head outputs + label tensors with the structure `VoxelPostprocessor.generate_label` / `collate_batch`
+    produce (voxel_postprocessor.py:84-241): float64 (n,H,W,A) pos / neg masks (positives sparse, a don't-care band
+    around them, everything else negative), float64 (n,H,W,7A) regression targets that are non-zero on positives only."""
+    rng = np.random.default_rng(seed)
+    cls = rng.normal(-2.0, 2.0, (n, A, H, W)).astype(np.float32)
+    reg = rng.normal(0.0, 0.4, (n, 7 * A, H, W)).astype(np.float32)
+    dr = rng.normal(0.0, 1.5, (n, 2 * A, H, W)).astype(np.float32)
+    pos = np.zeros((n, H, W, A), dtype)
+    neg = np.ones((n, H, W, A), dtype)
+    tgt = np.zeros((n, H, W, 7 * A), dtype)
+    for b in range(n):
+        if b in empty_samples:
+            continue
+        for _ in range(n_pos):
+            h, w, a = int(rng.integers(1, H - 1)), int(rng.integers(1, W - 1)), int(rng.integers(0, A))
+            neg[b, h - 1:h + 2, w - 1:w + 2, :] = 0                       # don't-care band
+            pos[b, h, w, a] = 1
+            t = rng.normal(0.0, 0.3, 7)
+            t[6] = rng.uniform(-3.0, 3.0)                                   # yaw residual: exercises both direction bins
+            tgt[b, h, w, 7 * a:7 * a + 7] = t
+            cls[b, a, h, w] += 3.0
+    # a few large regression errors (linear branch of the smooth L1) and exact zeros (|diff| = 0)
+    reg[:, :, 0, 0] = 2.5
+    reg[:, :, 1, 1] = 0.0
+    return {"cls": cls, "reg": reg, "dir": dr, "pos": pos, "neg": neg, "tgt": tgt}

@@ -250,6 +250,29 @@ int cb_postprocess_stage1(const float* cls_preds, const float* reg_preds, const 
                           int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
 
 /* --------------------------------------------------------------------------------------------
+ * Training step, first piece: PointPillarLoss and its gradients w.r.t. the head outputs
+ *   /root/reference/opencood/loss/point_pillar_loss.py:36-116,119-158,201-245
+ * sigmoid focal classification loss + smooth-L1 regression loss on the sin-difference encoding + direction-bin cross
+ * entropy, normalised like the reference (per-sample positive count, / batch size, loss weights).
+ *   cls/reg/dir_preds : DEVICE float32 NCHW (n, A, H, W), (n, 7A, H, W), (n, num_bins*A, H, W); dir_preds may be NULL
+ *   pos_equal_one, neg_equal_one : DEVICE (n, H, W, A); targets (n, H, W, 7A); float64 when labels_f64 != 0 (what the
+ *                       reference's collate produces), else float32
+ *   anchor_yaw_rad    : HOST float64 [A] (dir.args.anchor_yaw in radians), read when dir_preds != NULL
+ *   out_losses        : DEVICE float32 [4] = {total_loss, reg_loss, cls_loss, dir_loss} (the reference's loss_dict)
+ *   grad_cls/reg/dir  : optional DEVICE float32 outputs, d(total_loss)/d(preds), same NCHW shapes as the inputs
+ * Two-stage reductions in a fixed order (bit-reproducible); three launches on the caller's stream.
+ * ------------------------------------------------------------------------------------------ */
+size_t cb_pointpillar_loss_workspace_bytes(int n, int H, int W, int anchor_num);
+int cb_pointpillar_loss(const float* cls_preds, const float* reg_preds, const float* dir_preds,
+                        const void* pos_equal_one, const void* neg_equal_one, const void* targets, int labels_f64,
+                        int n, int H, int W, int anchor_num, int num_bins,
+                        float pos_cls_weight, float alpha, float gamma, float cls_weight,
+                        float sigma, float reg_weight, float dir_weight, float dir_offset,
+                        const double* anchor_yaw_rad,
+                        float* out_losses, float* grad_cls, float* grad_reg, float* grad_dir,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* --------------------------------------------------------------------------------------------
  * layout helpers (tests, debugging, interop): dense NCHW float32 <-> PF / PS bf16
  * ------------------------------------------------------------------------------------------ */
 int cb_nchw_to_layout(const float* src, int n, int c, int h, int w, int to_ps,
