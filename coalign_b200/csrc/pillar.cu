@@ -11,7 +11,8 @@
 //   K2c  per chunk: ordered in-block scan + chunk prefix -> voxel ids, CSR offsets
 //   K3   CSR fill (arbitrary order inside a cell)
 //   K3b  thread per point: rank inside its cell (points with a smaller index), regroup into voxel-slot order
-//   K4   8 lanes per voxel: emit reference-format tensors, or PFN + canvas store.
+//   K4   8 lanes per voxel: emit reference-format tensors.
+// The hot path (cb_points_to_canvas) does not need the voxel ORDER and uses the v2 pipeline further down.
 #include <limits.h>
 #include "common.cuh"
 #include "../../include/coalign_b200.h"
@@ -35,9 +36,6 @@ struct VoxWs {            // workspace carve-up (device pointers)
     int* nvox;            // [n_agents+1]
     int2* chunk_tot;      // [n_agents][max_chunks]  (leaders, points) per chunk, then exclusive prefixes
     float4* vp;           // [sum_P]  points regrouped per voxel in slot order (first max_pts of each voxel)
-    int* perm;            // [n_agents][NCLS][vcap]  voxel ids bucketed by point-count class
-    int* bucket;          // [n_agents][NCLS]        bucket fill counters
-    float* coef;          // [PFN_NCOEF][64]         derived PFN coefficients (staging for the constant bank)
     int ncell, vcap, max_chunks;
 };
 
@@ -178,15 +176,8 @@ __global__ void __launch_bounds__(256) vox_chunk_assign_kernel(const __grid_cons
     int* cell2vox = ws.cell2vox + (long)a * ws.ncell;
     int* vox_off = ws.vox_off + (long)a * (ws.vcap + 1);
     int4* vox_meta = ws.vox_meta + (long)a * ws.vcap;
-    // processing order of the fused PFN kernel: pillars bucketed by point-count class.  Positions are claimed with
-    // shared-memory atomics inside the CTA and ONE global atomic per class and CTA.
-    __shared__ int s_cnt[NCLS], s_gbase[NCLS];
-    if (threadIdx.x < NCLS) s_cnt[threadIdx.x] = 0;
-    __syncthreads();
-    int lpos[4], lcls[4], lpv[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        lpos[j] = -1; lcls[j] = 0; lpv[j] = pv;
         if (lead[j]) {
             if (pv < max_voxels) {
                 cell2vox[cell[j]] = pv;
@@ -194,21 +185,12 @@ __global__ void __launch_bounds__(256) vox_chunk_assign_kernel(const __grid_cons
                 const int cx = cell[j] % g.gx, cyz = cell[j] / g.gx;
                 const int cy = cyz % g.gy, cz = cyz / g.gy;
                 vox_meta[pv] = make_int4(pc, cnt[j], cx | (cy << 12) | (cz << 24), chunk * CHUNK + (int)threadIdx.x * 4 + j);
-                lcls[j] = cnt[j] <= 1 ? 0 : (cnt[j] == 2 ? 1 : (cnt[j] <= 4 ? 2 : (cnt[j] <= 8 ? 3 : 4)));
-                lpos[j] = atomicAdd(&s_cnt[lcls[j]], 1);
             } else {
                 cell2vox[cell[j]] = -1;                    // refused: max_voxels reached
             }
             pv += 1; pc += cnt[j];
         }
     }
-    __syncthreads();
-    if (threadIdx.x < NCLS && s_cnt[threadIdx.x] > 0)
-        s_gbase[threadIdx.x] = atomicAdd(ws.bucket + a * NCLS + threadIdx.x, s_cnt[threadIdx.x]);
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-        if (lpos[j] >= 0) ws.perm[((long)a * NCLS + lcls[j]) * ws.vcap + s_gbase[lcls[j]] + lpos[j]] = lpv[j];
 }
 
 // K3 ------------------------------------------------------------------------------------------
@@ -402,23 +384,14 @@ __device__ __forceinline__ void pfn_thread_store(PointFn pt, const float4 p0, in
     pfn_store<NP>(best, canvas + row * 64 + GRP * 2 * NP, lo_off);
     if (dirty_slot && GRP == 0) *dirty_slot = row;
 }
-// grp (warp-uniform) -> compile-time channel group, so the constant-bank addresses are immediates
+// grp (warp-uniform: even / odd warps) -> compile-time channel half, so the constant-bank addresses are immediates
 template <int NP, class PointFn>
 __device__ __forceinline__ void pfn_thread_dispatch(int grp, PointFn pt, const float4 p0, int n, int max_pts, int a,
                                                     int cz, int cy, int cx, const PfnParams& pp, const CanvasGeom& cg,
                                                     __nv_bfloat16* canvas, long lo_off, long* dirty_slot) {
-    static_assert(NP == 16 || NP == 8, "2 or 4 channel groups");
-    if (NP == 16) {
-        if (grp == 0) pfn_thread_store<NP, 0>(pt, p0, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dirty_slot);
-        else          pfn_thread_store<NP, (NP == 16 ? 1 : 0)>(pt, p0, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dirty_slot);
-    } else {
-        switch (grp) {
-            case 0: pfn_thread_store<NP, 0>(pt, p0, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dirty_slot); break;
-            case 1: pfn_thread_store<NP, 1>(pt, p0, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dirty_slot); break;
-            case 2: pfn_thread_store<NP, (NP == 8 ? 2 : 0)>(pt, p0, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dirty_slot); break;
-            default: pfn_thread_store<NP, (NP == 8 ? 3 : 0)>(pt, p0, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dirty_slot); break;
-        }
-    }
+    static_assert(NP == 16, "two 32-channel halves per pillar");
+    if (grp == 0) pfn_thread_store<NP, 0>(pt, p0, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dirty_slot);
+    else          pfn_thread_store<NP, 1>(pt, p0, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dirty_slot);
 }
 
 // K4a: emit reference-format voxel tensors (8 lanes per voxel, voxels of all agents flattened) ---------
@@ -448,61 +421,6 @@ __global__ void __launch_bounds__(256) vox_emit_kernel(const __grid_constant__ A
             coords[row] = make_int4(a, (m.z >> 24) & 0xFF, (m.z >> 12) & 0xFFF, m.z & 0xFFF);
             num_points[row] = n;
         }
-    }
-}
-
-// K4b: fused PFN + scatter from the regrouped points: thread per (pillar, channel half) -------------------
-// Work items are the pillars of all agents flattened class-major (class, agent, index): every thread of the grid has
-// work and the pillars of a warp share a point-count class.
-__global__ void __launch_bounds__(256, 2) vox_pfn_kernel(const __grid_constant__ AgentOffsets ao, const VoxWs ws,
-                                                         int max_pts, const PfnParams pp, const CanvasGeom cg,
-                                                         __nv_bfloat16* canvas, long lo_off, long* dirty_rows) {
-    __shared__ int s_base[CB_MAX_AGENTS + 1];                      // first output voxel row of each agent
-    __shared__ int s_seg[NCLS * CB_MAX_AGENTS + 1];                // prefix over (class, agent) segments
-    const int nseg = NCLS * ao.n_agents;
-    if (threadIdx.x == 0) {
-        int b = 0;
-        for (int a = 0; a < ao.n_agents; ++a) { s_base[a] = b; b += ws.nvox[a]; }
-        int t = 0;
-        for (int sgm = 0; sgm < nseg; ++sgm) {
-            s_seg[sgm] = t;
-            t += ws.bucket[(sgm % ao.n_agents) * NCLS + sgm / ao.n_agents];
-        }
-        s_seg[nseg] = t;
-    }
-    __syncthreads();
-    const int total = s_seg[nseg];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int half = warp & 1;                                     // even warps: channels 0-31, odd warps: 32-63
-    const int slot = (blockIdx.x * 4 + (warp >> 1)) * 32 + lane;
-    const int nslot = gridDim.x * 4 * 32;
-    // one pillar per thread and iteration; the next pillar's (perm -> metadata -> first point) chain is fetched while
-    // the current one is computed
-    struct Item { int a, v; int4 m; float4 p0; };
-    auto fetch = [&](int gidx) {
-        Item it;
-        int lo = 0, hi = nseg;                                     // largest seg with s_seg[seg] <= gidx
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_seg[mid] <= gidx) lo = mid; else hi = mid; }
-        const int c = lo / ao.n_agents;
-        it.a = lo - c * ao.n_agents;
-        it.v = ws.perm[((long)it.a * NCLS + c) * ws.vcap + (gidx - s_seg[lo])];
-        it.m = __ldg(ws.vox_meta + (long)it.a * ws.vcap + it.v);
-        it.p0 = ws.vp[ao.off[it.a] + it.m.x];
-        return it;
-    };
-    Item cur;
-    if (slot < total) cur = fetch(slot);
-    for (int gidx = slot; gidx < total; gidx += nslot) {
-        Item nxt = cur;
-        if (gidx + nslot < total) nxt = fetch(gidx + nslot);
-        const int a = cur.a;
-        const int4 m = cur.m;
-        const int n = m.y < max_pts ? m.y : max_pts;
-        const float4* vpp = ws.vp + ao.off[a] + m.x;
-        const int cz = (m.z >> 24) & 0xFF, cy = (m.z >> 12) & 0xFFF, cx = m.z & 0xFFF;
-        long* dslot = dirty_rows ? dirty_rows + s_base[a] + cur.v : nullptr;
-        pfn_thread_dispatch<16>(half, [&](int k) { return vpp[k]; }, cur.p0, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dslot);
-        cur = nxt;
     }
 }
 
@@ -729,7 +647,7 @@ __global__ void __launch_bounds__(256) vox2_big_rank_kernel(const float4* __rest
 // V5: PFN + scatter, thread per (pillar, channel group of 2*NP channels); the 64/(2*NP) groups of a pillar are
 // consecutive warps of one CTA.  Work items are taken class-major so the pillars of a warp share a point-count class.
 template <int NP>
-__global__ void __launch_bounds__(256, (NP == 16 ? 2 : 3)) vox2_pfn_kernel(const Vox2Ws ws, int max_pts,
+__global__ void __launch_bounds__(256, 2) vox2_pfn_kernel(const Vox2Ws ws, int max_pts,
                                                                           const PfnParams pp, const CanvasGeom cg,
                                                                           __nv_bfloat16* canvas, long lo_off,
                                                                           long* dirty_rows, int* dirty_count) {
@@ -843,7 +761,6 @@ static int carve(VoxWs& ws, void* base, size_t bytes, int n_agents, int sum_poin
     size_t o_first_end = o;
     ws.count = (int*)take((size_t)n_agents * ncell * 4);
     ws.cursor = (int*)take((size_t)n_agents * vcap * 4);
-    ws.bucket = (int*)take((size_t)n_agents * NCLS * 4);
     size_t o_clear_end = o;
     ws.cell2vox = (int*)take((size_t)n_agents * ncell * 4);
     ws.vox_off = (int*)take((size_t)n_agents * (vcap + 1) * 4);
@@ -853,8 +770,6 @@ static int carve(VoxWs& ws, void* base, size_t bytes, int n_agents, int sum_poin
     ws.nvox = (int*)take(((size_t)n_agents + 1) * 4);
     ws.chunk_tot = (int2*)take((size_t)n_agents * max_chunks * 8);
     ws.vp = (float4*)take((size_t)sp * 16);
-    ws.perm = (int*)take((size_t)n_agents * NCLS * vcap * 4);
-    ws.coef = (float*)take((size_t)PFN_NCOEF * 64 * 4);
     ws.ncell = (int)ncell;
     ws.vcap = vcap;
     ws.max_chunks = max_chunks;
@@ -933,8 +848,7 @@ static int carve2(Vox2Ws& ws, void* base, size_t bytes, int n_agents, int sum_po
     ws.chunk_tot = (int*)take((size_t)n_agents * max_chunks * 4);
     ws.items = (int2*)take((size_t)NCLS * cap * 8);
     ws.coef = (float*)take((size_t)PFN_NCOEF * 64 * 4);
-    static const int s0_env = [] { const char* e = getenv("CB_SLOT_S0"); return e ? atoi(e) : V2_S0; }();
-    ws.S0 = s0_env >= 2 && s0_env <= 32 ? (s0_env & ~1) : V2_S0;
+    ws.S0 = V2_S0;
     ws.slots = (float4*)take((size_t)n_agents * ncell * ws.S0 * 16);
     ws.S2 = max_pts > ws.S0 ? ((max_pts - ws.S0 + 1) & ~1) : 0;   // 32-byte aligned second-tier records
     ws.slots2 = (float4*)take((size_t)n_agents * ncell * ws.S2 * 16);
@@ -1062,34 +976,13 @@ extern "C" int cb_points_to_canvas(const float* points, const int32_t* pt_offset
     if (cg.plane_rows * 4 >= (1L << 31)) return CB_ERR_ARG;
     const PfnParams pp = make_pfn(w, scale, shift, vsize, center_off);
     cudaError_t ce;
-    static const int front_ver = [] { const char* e = getenv("CB_FRONT_V"); return e ? atoi(e) : 2; }();
-    static const int pfn_np = [] { const char* e = getenv("CB_PFN_NP"); return e ? atoi(e) : 16; }();
-    if (front_ver >= 2) {
-        Vox2Ws ws2;
-        int rc2 = run_front2(points, pt_offset, n_agents, range, vsize, grid, max_pts, max_voxels, workspace,
-                             workspace_bytes, st, ws2, pp);
-        if (rc2) return rc2;
-        if (pfn_np == 8)
-            ce = launch_pdl(vox2_pfn_kernel<8>, dim3(148 * 4), dim3(256), 0, st, ws2, max_pts, pp, cg, (__nv_bfloat16*)canvas_ps,
-                            (long)lo_off, (long*)dirty_rows, (int*)dirty_count);
-        else
-            ce = launch_pdl(vox2_pfn_kernel<16>, dim3(148 * 2), dim3(256), 0, st, ws2, max_pts, pp, cg, (__nv_bfloat16*)canvas_ps,
-                            (long)lo_off, (long*)dirty_rows, (int*)dirty_count);
-        if (ce) return (int)ce;
-        CB_CHECK_LAUNCH();
-        return CB_OK;
-    }
-    AgentOffsets ao; VoxWs ws; Geom g;
-    int rc = run_front(points, pt_offset, n_agents, range, vsize, grid, max_pts, max_voxels, workspace,
-                       workspace_bytes, st, ao, ws, g, nullptr, dirty_count);
-    if (rc) return rc;
-    pfn_coef_kernel<<<1, 64, 0, st>>>(w, scale, shift, ws.coef);
-    CB_CHECK_LAUNCH();
-    ce = cudaMemcpyToSymbolAsync(c_pfn_k, ws.coef, sizeof(float) * PFN_NCOEF * 64, 0, cudaMemcpyDeviceToDevice, st);
+    Vox2Ws ws2;
+    int rc2 = run_front2(points, pt_offset, n_agents, range, vsize, grid, max_pts, max_voxels, workspace, workspace_bytes, st,
+                         ws2, pp);
+    if (rc2) return rc2;
+    ce = launch_pdl(vox2_pfn_kernel<16>, dim3(148 * 2), dim3(256), 0, st, ws2, max_pts, pp, cg, (__nv_bfloat16*)canvas_ps,
+                    (long)lo_off, (long*)dirty_rows, (int*)dirty_count);
     if (ce) return (int)ce;
-    vox_pfn_kernel<<<148 * 2, 256, 0, st>>>(ao, ws, max_pts, pp, cg, (__nv_bfloat16*)canvas_ps, (long)lo_off,
-                                            (long*)dirty_rows);
-    CB_CHECK_LAUNCH();
     return CB_OK;
 }
 

@@ -1,5 +1,5 @@
 """Development aid: time the pillar front-end alone (canvas clear + voxelise + PFN + scatter) for B scenes of 5 agents,
-eager launches and as a CUDA graph.  Env: CB_FRONT_V (1 = ordered-scan pipeline, 2 = cell-slot pipeline), CB_PFN_NP."""
+eager launches and as a CUDA graph (CB_NO_PDL=1 switches the programmatic dependent launches off)."""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -32,5 +32,5 @@ with torch.cuda.stream(side):
 torch.cuda.synchronize()
 t_graph = timeit(g.replay)
 by = B * 5 * (60000 * 16 + 200 * 704 * 64 * 2)
-print(f"front V={os.environ.get('CB_FRONT_V','2')} NP={os.environ.get('CB_PFN_NP','16')} B={B}: eager {t_eager:.1f} us, graph {t_graph:.1f} us "
+print(f"front-end B={B}: eager {t_eager:.1f} us, graph {t_graph:.1f} us "
       f"-> {by / t_graph / 1e3:.0f} GB/s algorithmic")

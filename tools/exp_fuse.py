@@ -1,5 +1,5 @@
 """Development aid: time the three warp+attention fusion launches of one step (B scenes of 5 agents, OPV2V shape), eager
-launches with CUDA events, inputs = the level outputs of a real forward.  Env: CB_FUSE_V, CB_FUSE_BLEND, CB_FUSE_TOUCH."""
+launches with CUDA events, inputs = the level outputs of a real forward.  Env: CB_FUSE_V (8 = the 8-channel-per-lane kernel), CB_FUSE_BLEND=32 (fp32 tap blend), CB_FUSE_OCC=3."""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -27,5 +27,5 @@ for r in range(reps + 2):
         torch.cuda.synchronize()
         if r >= 2: tot[i] += a.elapsed_time(b) * 1e3 / reps
 by = 6 * 3942400 * 2 * B
-print(f"fuse V={os.environ.get('CB_FUSE_V','9')} blend={os.environ.get('CB_FUSE_BLEND','16')} touch={os.environ.get('CB_FUSE_TOUCH','1')}: "
+print(f"fuse V={os.environ.get('CB_FUSE_V','9')} blend={os.environ.get('CB_FUSE_BLEND','16')} occ={os.environ.get('CB_FUSE_OCC','4')}: "
       + " + ".join(f"{t:.1f}" for t in tot) + f" = {sum(tot):.1f} us -> {by / sum(tot) / 1e3:.0f} GB/s algorithmic")
