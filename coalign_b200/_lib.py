@@ -90,7 +90,7 @@ def load(check_device: bool = False):
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(f"{LIB_PATH} is missing - run `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(coalign_b200 has no CPU fallback)")
-        lib = C.CDLL(LIB_PATH)
+        lib = C.CDLL(os.environ.get("COALIGN_B200_LIB", LIB_PATH))     # override: A/B timing of two builds (development)
         for name, (res, args) in EXPORTS.items():
             fn = getattr(lib, name)          # AttributeError if the symbol is not exported
             fn.restype = res
