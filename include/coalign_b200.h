@@ -86,7 +86,13 @@ int cb_pfn_scatter(const float* voxels, const int32_t* coords, const int32_t* nu
                    int64_t* dirty_rows, int32_t* dirty_count, void* stream);
 
 /* Same stages straight from raw points (A1..A5 fused; the (M,32,4) voxel tensor is never
- * materialised).  Uses the same workspace as cb_voxelize. */
+ * materialised).  Uses the same workspace as cb_voxelize (size from cb_voxelize_workspace_bytes).
+ * The canvas does not depend on the order of the voxels, so this path does not run the ordered scans of
+ * cb_voxelize unless a cap is hit (agents with more points than max_voxels; cells with more than max_pts
+ * points): results are identical to cb_voxelize + cb_pfn_scatter bit for bit.
+ * Thread safety: the derived PFN coefficients are staged in ONE constant-memory table per process, written on
+ * `stream` right before the kernel that reads it: calls with DIFFERENT PFN weights must not be in flight on
+ * different streams at the same time (same weights, or one stream: no restriction). */
 int cb_points_to_canvas(const float* points, const int32_t* pt_offset, int n_agents,
                         const float* range, const float* vsize, const int32_t* grid,
                         int max_pts, int max_voxels,
