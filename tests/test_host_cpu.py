@@ -180,3 +180,83 @@ def test_stage1_uncertainty_state_dict_contract_and_registry():
     assert found == [PointPillarUncertaintyB200]
     with pytest.raises(KeyError):
         PointPillarUncertaintyB200(synth.single_args())
+
+
+def test_c_abi_rejects_bad_arguments_without_a_device():
+    """Every entry point validates its arguments before the first CUDA call (returns CB_ERR_ARG = -1, never throws), so
+    this runs without a GPU; workspace queries are pure host arithmetic."""
+    import ctypes as C
+    import numpy as np
+    from coalign_b200 import _lib
+    lib = _lib.load(check_device=False)
+    grid = np.array([704, 200, 1], np.int32)
+    grid3 = np.array([704, 200, 2], np.int32)
+    rng = np.array([-140.8, -40, -3, 140.8, 40, 1], np.float32)
+    vs = np.array([0.4, 0.4, 4], np.float32)
+    off = np.array([0, 10], np.int32)
+    # workspace sizes: monotone in the agent count; the fused path (nz == 1) needs the per-cell slot arrays
+    w1 = lib.cb_voxelize_workspace_bytes(1, 60000, grid.ctypes.data, 70000)
+    w5 = lib.cb_voxelize_workspace_bytes(5, 300000, grid.ctypes.data, 70000)
+    assert w5 > w1 >= 200 * 704 * 32 * 16
+    assert lib.cb_voxelize_workspace_bytes(1, 60000, grid3.ctypes.data, 70000) < w1      # nz > 1: ordered pipeline only
+    dummy = C.c_void_p(256)                                     # non-null, 16-byte aligned, never dereferenced
+    # fused front-end: nz must be 1, canvas capacity >= agents, workspace / canvas non-null
+    assert lib.cb_points_to_canvas(dummy, off.ctypes.data, 1, rng.ctypes.data, vs.ctypes.data, grid3.ctypes.data, 32, 70000,
+                                   dummy, dummy, dummy, vs.ctypes.data, 1, dummy, 0, None, None, dummy, 1 << 20, None) == -1
+    assert lib.cb_points_to_canvas(dummy, off.ctypes.data, 2, rng.ctypes.data, vs.ctypes.data, grid.ctypes.data, 32, 70000,
+                                   dummy, dummy, dummy, vs.ctypes.data, 1, dummy, 0, None, None, dummy, 1 << 20, None) == -1
+    assert lib.cb_points_to_canvas(dummy, off.ctypes.data, 1, rng.ctypes.data, vs.ctypes.data, grid.ctypes.data, 33, 70000,
+                                   dummy, dummy, dummy, vs.ctypes.data, 1, dummy, 0, None, None, dummy, 1 << 20, None) == -1
+    # voxeliser: max_pts in [1, 32], workspace required
+    assert lib.cb_voxelize(dummy, off.ctypes.data, 1, rng.ctypes.data, vs.ctypes.data, grid.ctypes.data, 0, 70000, dummy,
+                           dummy, dummy, dummy, dummy, 1 << 20, None) == -1
+    assert lib.cb_voxelize(dummy, off.ctypes.data, 1, rng.ctypes.data, vs.ctypes.data, grid.ctypes.data, 32, 70000, dummy,
+                           dummy, dummy, dummy, None, 0, None) == -1
+    # fusion: channel count multiple of 64, method in {0, 1}
+    assert lib.cb_warp_att_fuse(dummy, 0, 0, 5, dummy, dummy, 1, 5, 100, 352, 48, 0, dummy, 0, None) == -1
+    assert lib.cb_warp_att_fuse(dummy, 0, 0, 5, dummy, dummy, 1, 5, 100, 352, 64, 2, dummy, 0, None) == -1
+    # post-processing: top_k <= 1024, outputs required
+    gt = np.zeros(6, np.float64)
+    assert lib.cb_postprocess(dummy, dummy, None, 1, 100, 352, 2, 0, dummy, dummy, 0.2, 0.0, 0.15, gt.ctypes.data, 1, 2000,
+                              dummy, dummy, dummy, dummy, 1 << 20, None) == -1
+    assert lib.cb_postprocess_stage1(dummy, dummy, None, 1, 100, 352, 2, 0, dummy, 0.2, 0.0, 0.15, 1, 1000,
+                                     dummy, None, None, dummy, dummy, dummy, 1 << 20, None) == -1
+    assert lib.cb_postprocess_workspace_bytes(0, 100, 352, 2) == 0
+
+
+def test_unmodified_reference_registries_resolve_the_plugins():
+    """With the reference tree present (build container), `train_utils.create_model` / `create_loss` of the UNMODIFIED
+    reference return our classes once `coalign_b200.register()` ran and only `core_method` changed in the hypes
+    (SURVEY 8b registry contract).  Runs in a subprocess (import-only stubs for open3d / matplotlib / box_overlaps)."""
+    import os
+    import subprocess
+    import sys
+    if not os.path.isdir("/root/reference/opencood"):
+        pytest.skip("reference tree not present on this machine")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, types
+import numpy as np
+sys.modules["open3d"] = types.ModuleType("open3d")
+import matplotlib
+cm = types.ModuleType("matplotlib.cm"); cm.get_cmap = lambda name: types.SimpleNamespace(colors=np.zeros((256, 3)))
+matplotlib.cm = cm; sys.modules["matplotlib.cm"] = cm
+bo = types.ModuleType("opencood.utils.box_overlaps"); bo.bbox_overlaps = None; sys.modules["opencood.utils.box_overlaps"] = bo
+import coalign_b200
+from coalign_b200 import synth
+from opencood.tools import train_utils
+coalign_b200.register()
+hypes = {"model": {"core_method": "point_pillar_coalign_b200", "args": synth.opv2v_args()},
+         "loss": {"core_method": "point_pillar_loss_b200", "args": synth.loss_args()}}
+names = [type(train_utils.create_model(hypes)).__name__, type(train_utils.create_loss(hypes)).__name__]
+hypes["model"] = {"core_method": "point_pillar_b200", "args": synth.single_args()}
+names.append(type(train_utils.create_model(hypes)).__name__)
+hypes["model"] = {"core_method": "point_pillar_uncertainty_b200", "args": synth.uncertainty_args()}
+names.append(type(train_utils.create_model(hypes)).__name__)
+print(",".join(names))
+'''
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(root, "tests", "golden", "_stubs"), "/root/reference", root]))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.strip().splitlines()[-1] == \
+        "PointPillarCoalignB200,PointPillarLossB200,PointPillarB200,PointPillarUncertaintyB200"
