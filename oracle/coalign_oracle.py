@@ -5,7 +5,10 @@ lines it follows (paths relative to /root/reference).  The restatement is *funct
 the reference ``state_dict`` (same key names) and the yaml ``model.args`` dict, so it can be
 checked against the reference module with identical weights (tests/golden/gen_golden.py).
 
-Inference (eval-mode BatchNorm) only.
+`forward` is the inference path (eval-mode BatchNorm, no autograd).  `forward_train` (bottom of the file) is the same graph
+with train-mode BatchNorm (batch statistics) and autograd enabled: the oracle of the training step,
+pinned by tests/golden/train_small.npz (losses, gradients and running-stat updates of the unmodified reference in
+`.train()` mode).
 """
 from __future__ import annotations
 
@@ -36,7 +39,21 @@ def bn_affine(sd: Dict[str, torch.Tensor], prefix: str, eps: float):
     return scale.float(), shift.float()
 
 
+# train-mode switch of the BatchNorm helpers (set by forward_train only): batch statistics instead of the running ones;
+# the batch mean / unbiased variance of every layer are recorded so that the running-stat update can be checked
+_TRAIN = {"on": False, "batch_stats": None}
+
+
+def _record_stats(prefix, x, dims):
+    if _TRAIN["batch_stats"] is not None:
+        with torch.no_grad():
+            _TRAIN["batch_stats"][prefix] = (x.mean(dims), x.var(dims, unbiased=True))
+
+
 def _bn2d(x, sd, prefix, eps):
+    if _TRAIN["on"]:                                    # nn.BatchNorm2d.forward in training mode
+        _record_stats(prefix, x, (0, 2, 3))
+        return F.batch_norm(x, None, None, sd[prefix + ".weight"], sd[prefix + ".bias"], True, 0.0, eps)
     # F.batch_norm in eval mode: (x-mean)/sqrt(var+eps)*w+b, exactly what nn.BatchNorm2d does.
     return F.batch_norm(x, sd[prefix + ".running_mean"], sd[prefix + ".running_var"],
                         sd[prefix + ".weight"], sd[prefix + ".bias"], False, 0.0, eps)
@@ -65,8 +82,14 @@ def pillar_vfe(sd, args, voxel_features, voxel_coords, voxel_num_points):
     feats = feats * mask
     w = sd["pillar_vfe.pfn_layers.0.linear.weight"]                             # (64,10) no bias, :24
     x = feats @ w.t()                                                           # :31-40
-    scale, shift = bn_affine(sd, "pillar_vfe.pfn_layers.0.norm", 1e-3)          # :25,41-44
-    x = x * scale + shift
+    if _TRAIN["on"]:                                    # BatchNorm1d(64) over (M, 64, 32): padded slots take part (:41-44)
+        pre = "pillar_vfe.pfn_layers.0.norm"
+        _record_stats(pre, x, (0, 1))
+        x = F.batch_norm(x.permute(0, 2, 1), None, None, sd[pre + ".weight"], sd[pre + ".bias"], True, 0.0,
+                         1e-3).permute(0, 2, 1)
+    else:
+        scale, shift = bn_affine(sd, "pillar_vfe.pfn_layers.0.norm", 1e-3)      # :25,41-44
+        x = x * scale + shift
     x = F.relu(x)                                                               # :45
     return x.max(dim=1)[0]                                                      # :46 (padded slots included)
 
@@ -230,6 +253,24 @@ def heads(sd, x):
 # --------------------------------------------------------------------------------------
 @torch.no_grad()
 def forward(sd, args, data_dict, stages: Optional[dict] = None):
+    return _forward(sd, args, data_dict, stages)
+
+
+def forward_train(sd, args, data_dict, stages: Optional[dict] = None):
+    """The reference forward in `.train()` mode (train.py:109-114): BatchNorm layers use batch statistics, autograd is on
+    (pass a state_dict whose parameters require grad).  Returns (output dict, {bn prefix: (batch mean, unbiased batch
+    var)}); the running statistics a step would leave behind are  (1-m)*running + m*batch  with m = 0.1 inside the
+    BasicBlocks (nn.BatchNorm2d default, resblock.py:38-39) and 0.01 for the PFN norm and the deblocks
+    (pillar_vfe.py:25, base_bev_backbone_resnet.py:62-63)."""
+    _TRAIN["on"], _TRAIN["batch_stats"] = True, {}
+    try:
+        out = _forward(sd, args, data_dict, stages)
+        return out, _TRAIN["batch_stats"]
+    finally:
+        _TRAIN["on"], _TRAIN["batch_stats"] = False, None
+
+
+def _forward(sd, args, data_dict, stages: Optional[dict] = None):
     pl = data_dict["processed_lidar"]
     vf, vc, vn = pl["voxel_features"], pl["voxel_coords"], pl["voxel_num_points"]
     record_len = data_dict["record_len"]
