@@ -260,3 +260,43 @@ print(",".join(names))
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout.strip().splitlines()[-1] == \
         "PointPillarCoalignB200,PointPillarLossB200,PointPillarB200,PointPillarUncertaintyB200"
+
+
+def test_collate_restatement_matches_the_reference_static_method():
+    """A2 (collate_batch_dict, sp_voxel_preprocessor.py:145-174) is plain numpy inside the reference tree: with the tree
+    present, the oracle's `collate` is checked against the unmodified static method (A1, the spconv generator itself,
+    stays unpinned - the package is absent).  Subprocess: import-only stubs (icecream, open3d, pypcd, matplotlib, box_overlaps)."""
+    import os
+    import subprocess
+    import sys
+    if not os.path.isdir("/root/reference/opencood"):
+        pytest.skip("reference tree not present on this machine")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, types
+import numpy as np
+sys.modules["open3d"] = types.ModuleType("open3d")
+pp = types.ModuleType("pypcd"); pp.pypcd = types.ModuleType("pypcd.pypcd"); sys.modules["pypcd"] = pp; sys.modules["pypcd.pypcd"] = pp.pypcd
+import matplotlib
+cm = types.ModuleType("matplotlib.cm"); cm.get_cmap = lambda name: types.SimpleNamespace(colors=np.zeros((256, 3)))
+matplotlib.cm = cm; sys.modules["matplotlib.cm"] = cm
+bo = types.ModuleType("opencood.utils.box_overlaps"); bo.bbox_overlaps = None; sys.modules["opencood.utils.box_overlaps"] = bo
+from opencood.data_utils.pre_processor.sp_voxel_preprocessor import SpVoxelPreprocessor
+from coalign_b200 import synth
+from oracle import voxelize_np as V
+rng = np.random.default_rng(0)
+R, VS = [-11.2, -4.8, -3, 11.2, 4.8, 1], [0.4, 0.4, 4]
+per_agent = [V.voxelize_c(synth.lidar_cloud(rng, n, R, sigma=5.0), R, VS, 32, 70000) for n in (700, 1, 1500)]
+ref = SpVoxelPreprocessor.collate_batch_dict({"voxel_features": [a[0] for a in per_agent],
+                                              "voxel_coords": [a[1] for a in per_agent],
+                                              "voxel_num_points": [a[2] for a in per_agent]})
+vf, vc, vn = V.collate(per_agent)
+assert np.array_equal(ref["voxel_features"].numpy(), vf)
+assert np.array_equal(ref["voxel_coords"].numpy(), vc) and ref["voxel_coords"].shape[1] == 4
+assert np.array_equal(ref["voxel_num_points"].numpy(), vn)
+print("collate ok", vc.shape)
+'''
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(root, "tests", "golden", "_stubs"), "/root/reference", root]))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "collate ok" in r.stdout
