@@ -75,3 +75,37 @@ def test_stage1_uncertainty_plan_reproduces_reference_golden():
         a, b = out[k].numpy().astype(np.float64), g[k].astype(np.float64)
         err = np.abs(a - b)
         assert (err <= 1e-3 * np.abs(b) + 1e-3 * np.sqrt((b * b).mean())).all(), (k, err.max())
+
+
+def test_engine_batch_validation_and_agent_offsets_on_cpu():
+    """Host logic of the engine that needs no device: batch-shape validation (same errors a malformed collate output would
+    hit in the reference as shape mismatches deep inside regroup / warp) and the agent-offset prefix sums the fusion
+    kernel consumes (regroup, fusion_in_one.py:21-24)."""
+    import pytest
+    import torch
+    from coalign_b200.engine import CoAlignEngine
+    args = synth.make_args(G.SMALL_RANGE, [0.4, 0.4, 4])
+    sd = synth.random_state_dict(args, 0)
+    eng = CoAlignEngine(args, sd, 6, 3, device="cpu", precise=False, plan_only=True)
+    pw = torch.eye(4, dtype=torch.float64).repeat(2, 5, 5, 1, 1)
+    eng._set_scene_meta((2, 3), pw)
+    assert eng.agent_off.tolist() == [0, 2, 5, 5]                       # padded with the total: empty trailing scenes
+    assert torch.equal(eng.pairwise[:2], pw)
+    with pytest.raises(ValueError):
+        eng._set_scene_meta((2, 3, 2), torch.eye(4, dtype=torch.float64).repeat(3, 5, 5, 1, 1))    # 7 agents > capacity 6
+    with pytest.raises(ValueError):
+        eng._set_scene_meta((1, 1, 1, 1), torch.eye(4, dtype=torch.float64).repeat(4, 5, 5, 1, 1))  # 4 scenes > capacity 3
+    with pytest.raises(ValueError):
+        eng._set_scene_meta((0, 2), pw)                                                            # empty scene
+    with pytest.raises(ValueError):
+        eng._set_scene_meta((6,), torch.eye(4, dtype=torch.float64).repeat(1, 5, 5, 1, 1))          # 6 agents > max_cav 5
+    with pytest.raises(ValueError):
+        eng._set_scene_meta((2, 3), torch.eye(4, dtype=torch.float64).repeat(2, 4, 4, 1, 1))        # wrong L
+    with pytest.raises(RuntimeError):
+        eng._launch_ops([], 1, 0)                                                                  # plan-only: no launches
+    single = CoAlignEngine(synth.single_args(G.SMALL_RANGE, G.SMALL_VOXEL),
+                           synth.random_state_dict(synth.single_args(G.SMALL_RANGE, G.SMALL_VOXEL), 0, backbone="plain"),
+                           2, 2, device="cpu", plan_only=True, backbone="plain", fusion=False)
+    single._set_scene_meta((1, 1), None)
+    with pytest.raises(ValueError):
+        single._set_scene_meta((2,), None)                                                         # one agent per frame
