@@ -67,7 +67,7 @@ def pillar_vfe(sd, args, voxel_features, voxel_coords, voxel_num_points):
     vx, vy, vz = [float(v) for v in args["voxel_size"]]
     rng = [float(v) for v in args["lidar_range"]]
     x_off, y_off, z_off = vx / 2 + rng[0], vy / 2 + rng[1], vz / 2 + rng[2]   # pillar_vfe.py:87-89
-    vf = voxel_features.float()
+    vf = voxel_features.to(sd["pillar_vfe.pfn_layers.0.linear.weight"].dtype)   # float32 (float64 state_dict: exactness checks)
     n = voxel_num_points.to(vf.dtype).view(-1, 1, 1)
     mean = vf[:, :, :3].sum(dim=1, keepdim=True) / n                           # :118-120
     f_cluster = vf[:, :, :3] - mean                                             # :121
