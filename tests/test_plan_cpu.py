@@ -109,3 +109,43 @@ def test_engine_batch_validation_and_agent_offsets_on_cpu():
     single._set_scene_meta((1, 1), None)
     with pytest.raises(ValueError):
         single._set_scene_meta((2,), None)                                                         # one agent per frame
+
+
+def test_wgrad_and_dgrad_as_row_shifted_gemms_over_the_padded_flat_index():
+    """DESIGN §8 plan for the training step, checked numerically: in the PF layout (zero halo) the weight gradient of a
+    3x3/s1 convolution is nine plain GEMMs over the flattened padded pixel index with one constant row shift per tap, and
+    the input gradient is the forward's shifted-GEMM form on dZ with the per-tap weights transposed and the shifts negated."""
+    import torch
+    from torch.nn.grad import conv2d_input, conv2d_weight
+    g = torch.Generator().manual_seed(0)
+    n, cin, cout, H, W = 2, 8, 16, 5, 7
+    x = torch.randn(n, cin, H, W, generator=g, dtype=torch.float64)
+    dz = torch.randn(n, cout, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(cout, cin, 3, 3, generator=g, dtype=torch.float64)
+    Wp = W + 2
+
+    def to_pf(t):                                                       # (n,C,H,W) -> [n*(H+2)*(W+2)][C], zero halo
+        p = torch.zeros(t.shape[0], H + 2, Wp, t.shape[1], dtype=t.dtype)
+        p[:, 1:H + 1, 1:W + 1, :] = t.permute(0, 2, 3, 1)
+        return p.reshape(-1, t.shape[1])
+
+    def shifted(a, s):                                                  # rows q -> a[q + s], zero outside (TMA OOB fill)
+        out = torch.zeros_like(a)
+        if s >= 0:
+            out[:a.shape[0] - s] = a[s:]
+        else:
+            out[-s:] = a[:s]
+        return out
+
+    xp, dzp = to_pf(x), to_pf(dz)
+    ref_dw = conv2d_weight(x, w.shape, dz, padding=1)
+    ref_dx = conv2d_input(x.shape, w, dz, padding=1)
+    dxp = torch.zeros_like(xp)
+    for r in range(3):
+        for s in range(3):
+            shift = (r - 1) * Wp + (s - 1)                              # the forward's row shift of tap (r, s)
+            dw_tap = dzp.t() @ shifted(xp, shift)                       # [cout][cin]: one MN-major GEMM, K = all rows
+            assert torch.allclose(dw_tap, ref_dw[:, :, r, s], atol=1e-10), (r, s)
+            dxp += shifted(dzp, -shift) @ w[:, :, r, s]                 # [rows][cin]
+    dx = dxp.reshape(n, H + 2, Wp, cin)[:, 1:H + 1, 1:W + 1, :].permute(0, 3, 1, 2)
+    assert torch.allclose(dx, ref_dx, atol=1e-10)
