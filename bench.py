@@ -171,6 +171,8 @@ def run_ours(opt):
     torch.cuda.set_device(local)
     dist_utils.init("nccl", device_id=torch.device("cuda", local))
     B = opt.scenes_per_step
+    if B < 1 or B * N_AGENTS > 64:
+        raise SystemExit("--scenes-per-step must be in [1, %d] (CB_MAX_AGENTS = 64 agents per launch)" % (64 // N_AGENTS))
     NB = 8                                                   # rotating input batches (> L2 together with activations)
     args, batches = make_batches(NB, B, seed0=1000 * rank)
     sd = synth.random_state_dict(args, 0)
