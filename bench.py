@@ -112,21 +112,49 @@ def make_batches(n_batches, scenes_per_step, seed0):
 # ----------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference algorithm on the host cores
 # ----------------------------------------------------------------------------------------------------------
+_REF_MODEL = {}
+
+
+def cpu_arm_kind():
+    from oracle import build_ref
+    return "reference" if build_ref.available() else "port"
+
+
 def cpu_scene_seconds(args, sd, scene, threads):
+    """One 5-agent scene on the host cores: voxelisation (oracle/voxelize.c - spconv is not part of the reference tree) +
+    the forward.  The forward is the UNMODIFIED reference model (oracle/_ref, staged by oracle/build_ref.py, created through
+    the reference's own yaml + registry) when it is staged, else the oracle port."""
     import torch
+    from oracle import build_ref
     from oracle import coalign_oracle as O
     from tests.golden_cases import scenes_to_batch, to_torch_batch
     torch.set_num_threads(threads)
+    model = None
+    if build_ref.available():
+        model = _REF_MODEL.get("m")
+        if model is None:
+            model = _REF_MODEL["m"] = build_ref.build_reference_model(args, sd)
     t0 = time.perf_counter()
     inp = scenes_to_batch([scene], args["lidar_range"], args["voxel_size"], 32, 70000)      # oracle/voxelize.c
-    out = O.forward(sd, args, to_torch_batch(inp))
+    batch = to_torch_batch(inp)
+    if model is not None:
+        with torch.no_grad():
+            out = model(batch)                      # PointPillarBaselineMultiscale.forward, eval mode, fp32
+    else:
+        out = O.forward(sd, args, batch)
     dt = time.perf_counter() - t0
     return dt, out
 
 
+def cpu_threads(opt):
+    """Threads for the CPU arm: all host threads up to 32 - on the 128-thread GPU box 32 measured fastest for this
+    conv-dominated forward (16: 0.9x, 64: 0.6x, 128: 0.07x; tests/dev_cpu_threads_sweep.py), --cpu-threads overrides."""
+    return opt.cpu_threads or min(os.cpu_count() or 1, 32)
+
+
 def run_reference(opt):
-    """--impl reference: per step one 5-agent 60k-pt scene through the CPU restatement (oracle/) of the reference's
-    PyTorch path, fp32, all host threads torch will use.  Rank 0 only."""
+    """--impl reference: per step one 5-agent 60k-pt scene through the reference's own CPU PyTorch path (oracle/_ref: the
+    unmodified model created by train_utils.create_model; the oracle port if it is not staged), fp32.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -134,25 +162,30 @@ def run_reference(opt):
     from coalign_b200 import synth
     args, batches = make_batches(1, 1, seed0=0)
     sd = synth.random_state_dict(args, 0)
-    threads = opt.cpu_threads or min(os.cpu_count() or 1, 32)
+    threads = cpu_threads(opt)
+    kind = cpu_arm_kind()
     scene = batches[0][2][0]
-    for _ in range(min(opt.warmup, 2)):               # ~2 s per scene: keep the whole run within a few minutes
+    for _ in range(min(opt.warmup, 2)):               # seconds per scene: keep the whole run within a few minutes
         cpu_scene_seconds(args, sd, scene, threads)
-    opt.steps = min(opt.steps, 30)
+    opt.steps = max(3, min(opt.steps, 20))
     t0 = time.perf_counter()
     for _ in range(opt.steps):
         cpu_scene_seconds(args, sd, scene, threads)
     dt = time.perf_counter() - t0
     v = opt.steps / dt
+    what = ("the UNMODIFIED reference model (oracle/_ref, created through the reference's yaml + registry)" if kind == "reference"
+            else "CPU restatement of the reference PyTorch path (oracle/)")
     print(json.dumps({
         "impl": "reference", "metric": "scenes_per_sec", "value": v, "unit": "scenes/s", "n_gpus": opt.gpus,
         "steps": opt.steps, "warmup": opt.warmup, "ms_per_step": dt / opt.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "scenes_per_step": 1, "agents_per_scene": N_AGENTS,
                    "points_per_agent": N_POINTS, "canvas": "200x704",
-                   "parallelism": "CPU only, rank 0; a step is a bounded sample (one scene) of the same workload",
-                   "note": "CPU restatement of the reference PyTorch path (oracle/), voxelisation by oracle/voxelize.c"},
-        "cpu_baseline": {"value": v, "unit": "scenes/s", "cores": threads, "kind": "port",
+                   "parallelism": "CPU only, rank 0 (one process whatever --gpus says); a step is a bounded sample (one "
+                                  "scene) of the same workload; scenes/s is a rate, so 1 scene/step here vs 12/step on the "
+                                  "GPU arm compares like with like",
+                   "note": what + ", voxelisation by oracle/voxelize.c (spconv is not in the reference tree)"},
+        "cpu_baseline": {"value": v, "unit": "scenes/s", "cores": threads, "host_threads": os.cpu_count(), "kind": kind,
                          "sample": f"{opt.steps} x one 5-agent scene"},
         "e2e": {"value": v, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -355,15 +388,113 @@ def run_ours(opt):
     h2d = int(host_pts[0].numel() * 4 + host_pw[0].numel() * 8)
     d2h = int(sum(v.numel() * 4 for v in host_out.values()))
 
-    # ---- CPU baseline beside it (rank 0, N=1 only): one scene through the oracle port
-    cpu = None
+    # ---- frames whose clouds differ in size from step to step (real sweeps do): same API, same captured graph
+    vary = None
+    if rank == 0 and world == 1 and not opt.no_extras:
+        rng = np.random.default_rng(7)
+        vb = []
+        for p_np, w_np, _ in batches[:4]:
+            cnt = rng.integers(int(0.75 * N_POINTS), N_POINTS + 1, size=B * N_AGENTS)
+            parts = [p_np[a * N_POINTS:a * N_POINTS + int(c)] for a, c in enumerate(cnt)]
+            o = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+            vb.append((torch.from_numpy(np.concatenate(parts)).pin_memory(), o, torch.from_numpy(w_np).pin_memory()))
+        g0 = len(eng._graphs)
+        nv = max(8, min(opt.steps, 40))
+        last = None
+        for i in range(4):
+            last = runner.submit(vb[i % 4][0], vb[i % 4][1], rl, vb[i % 4][2])
+        runner.result(last); runner.drain(); torch.cuda.synchronize()
+        g1 = len(eng._graphs)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(runner.s_in)
+        prev = None
+        for i in range(nv):
+            t = runner.submit(vb[i % 4][0], vb[i % 4][1], rl, vb[i % 4][2])
+            if prev is not None:
+                runner.result(prev)
+            prev = t
+        runner.result(prev)
+        e1.record(runner.s_out)
+        runner.drain(); torch.cuda.synchronize()
+        vary = {"value": B * nv / (e0.elapsed_time(e1) * 1e-3), "unit": "scenes/s", "steps": nv,
+                "points_per_agent": "uniform in [45000, 60000], different every step",
+                "graphs_captured_for_these_frames": g1 - g0, "graphs_captured_during_timed_steps": len(eng._graphs) - g1,
+                "note": "per-agent point offsets live in a device array (cb_points_to_canvas_dev): one CUDA graph per batch "
+                        "signature and capacity bucket, not per frame"}
+
+    # ---- the literal drop-in call: model(batch['ego']) with reference-schema HOST tensors (voxel tensors from the
+    # dataloader's collate) -> H2D -> PointPillarCoalignB200.forward -> D2H of cls/reg/dir, every step
+    plug = None
+    if rank == 0 and world == 1 and not opt.no_extras:
+        from coalign_b200.model import PointPillarCoalignB200
+        Bp = 2
+        model = PointPillarCoalignB200(args)
+        model.load_state_dict(sd, strict=True)
+        model = model.cuda().eval()
+        hb = []
+        for bi in range(2):
+            p_np, w_np, _ = batches[bi]
+            npts = Bp * N_AGENTS * N_POINTS
+            vf, vc, vn, _nv = eng.voxelize(torch.from_numpy(p_np[:npts]).cuda(), off[:Bp * N_AGENTS + 1])
+            hb.append({"processed_lidar": {"voxel_features": vf.cpu().pin_memory(), "voxel_coords": vc.cpu().pin_memory(),
+                                           "voxel_num_points": vn.cpu().pin_memory()},
+                       "record_len": torch.tensor([N_AGENTS] * Bp, dtype=torch.int64),
+                       "pairwise_t_matrix": torch.from_numpy(w_np[:Bp]).pin_memory()})
+        hout = None
+
+        def plug_step(i):
+            nonlocal hout
+            b = hb[i % 2]
+            dev_b = {"processed_lidar": {k: v.cuda(non_blocking=True) for k, v in b["processed_lidar"].items()},
+                     "record_len": b["record_len"], "pairwise_t_matrix": b["pairwise_t_matrix"].cuda(non_blocking=True)}
+            with torch.no_grad():
+                o = model(dev_b)
+            if hout is None:
+                hout = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in o.items()}
+            for k, v in o.items():
+                hout[k].copy_(v, non_blocking=True)
+            torch.cuda.current_stream().synchronize()            # the caller reads the maps (post-processing) every step
+        np_ = max(5, min(opt.steps, 30))
+        for i in range(3):
+            plug_step(i)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(np_):
+            plug_step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        pl0 = hb[0]["processed_lidar"]
+        plug = {"value": Bp * np_ / (e0.elapsed_time(e1) * 1e-3), "unit": "scenes/s", "scenes_per_step": Bp, "steps": np_,
+                "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in pl0.values())
+                                          + hb[0]["pairwise_t_matrix"].numel() * 8),
+                "d2h_bytes_per_step": int(sum(v.numel() * 4 for v in hout.values())),
+                "api": "PointPillarCoalignB200.forward(batch['ego']) - the registry drop-in, reference input schema: "
+                       "(M,32,4) voxel tensors in pinned host memory -> H2D -> forward -> D2H, serial like "
+                       "inference.py:125-143; the voxel tensors are 75x the bytes of the raw clouds"}
+        del model
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): one scene through the reference's CPU path; its head maps are also
+    # the parity check of THIS run's GPU output for the same scene (the benchmarked configuration itself)
+    cpu, parity = None, None
     if rank == 0 and world == 1 and not opt.no_cpu_baseline:
-        threads = opt.cpu_threads or min(os.cpu_count() or 1, 32)
+        threads = cpu_threads(opt)
         scene = batches[0][2][0]
         cpu_scene_seconds(args, sd, scene, threads)             # warm-up
-        dts = [cpu_scene_seconds(args, sd, scene, threads)[0] for _ in range(2)]
-        cpu = {"value": 1.0 / float(np.median(dts)), "unit": "scenes/s", "cores": threads, "kind": "port",
-               "sample": "2 timed forwards of one 5-agent 60k-pt scene (1 warm-up), fp32, oracle/ restatement"}
+        runs = [cpu_scene_seconds(args, sd, scene, threads) for _ in range(3)]
+        dts = [r[0] for r in runs]
+        cpu = {"value": 1.0 / float(np.median(dts)), "unit": "scenes/s", "cores": threads, "host_threads": os.cpu_count(),
+               "kind": cpu_arm_kind(),
+               "sample": "3 timed forwards of one 5-agent 60k-pt scene (1 warm-up), fp32, voxelisation included"}
+        ref_out = runs[-1][1]
+        gpu_out = step_resident(0)                               # batch 0: its scene 0 is `scene`
+        torch.cuda.synchronize()
+        parity = {"mode": "bf16x3 (precise)" if opt.precise else "bf16", "scene": "scene 0 of batch 0 (12-scene launch)",
+                  "against": cpu["kind"], "rel_l2": {}, "max_abs_over_rms": {}}
+        for k, r in ref_out.items():
+            a = gpu_out[k][0].float().cpu().numpy().astype(np.float64)
+            b = r[0].detach().numpy().astype(np.float64)
+            parity["rel_l2"][k] = float(np.linalg.norm(a - b) / np.linalg.norm(b))
+            parity["max_abs_over_rms"][k] = float(np.abs(a - b).max() / np.sqrt((b * b).mean()))
 
     if rank == 0:
         line = {
@@ -380,7 +511,8 @@ def run_ours(opt):
                     "api": "coalign_b200.runtime.PipelinedRunner.submit/result (pinned host in/out every step; "
                            "H2D, forward and D2H of neighbouring steps overlap on 3 streams)"},
             "gpu_launches": launches_per_step * opt.steps,
-            "clocks": clocks, "roofline": roof, "roofline_hbm": hbm_roofs, "cpu_baseline": cpu, "postprocess": post,
+            "clocks": clocks, "roofline": roof, "roofline_hbm": hbm_roofs, "cpu_baseline": cpu, "parity": parity,
+            "postprocess": post, "e2e_varying_clouds": vary, "plugin_api": plug,
         }
         sys.stdout.flush()
         print(json.dumps(line), flush=True)
@@ -401,6 +533,7 @@ def main():
     ap.add_argument("--block-n", type=int, default=256)
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the varying-cloud-size and plugin-API measurements")
     ap.add_argument("--no-pair", action="store_true", help="single-CTA conv kernel instead of CTA pairs")
     opt = ap.parse_args()
     if opt.warmup < 3 and opt.impl == "ours":

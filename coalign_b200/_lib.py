@@ -48,6 +48,11 @@ EXPORTS = {
                                       C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                       C.c_void_p]),
+    "cb_points_to_canvas_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                          C.c_void_p]),
+    "cb_upload_i32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "cb_conv_gemm": (C.c_int, [C.POINTER(ConvDesc), C.c_int, C.c_void_p]),
     "cb_conv_gemm_pair": (C.c_int, [C.POINTER(ConvDesc), C.c_int, C.c_void_p]),
     "cb_conv_gemm_t": (C.c_int, [C.POINTER(ConvDesc), C.c_int, C.c_void_p]),
@@ -87,10 +92,11 @@ def load(check_device: bool = False):
     """Load the CUDA library (raises if it was not built).  With check_device, also require sm_100."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise RuntimeError(f"{LIB_PATH} is missing - run `python -c 'import __graft_entry__ as g; g.build()'` "
-                               "(coalign_b200 has no CPU fallback)")
-        lib = C.CDLL(os.environ.get("COALIGN_B200_LIB", LIB_PATH))     # override: A/B timing of two builds (development)
+        path = os.environ.get("COALIGN_B200_LIB", LIB_PATH)            # override: A/B timing of two builds (development)
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing - run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(the .so is git-ignored; coalign_b200 has no CPU fallback)")
+        lib = C.CDLL(path)
         for name, (res, args) in EXPORTS.items():
             fn = getattr(lib, name)          # AttributeError if the symbol is not exported
             fn.restype = res

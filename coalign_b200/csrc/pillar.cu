@@ -23,6 +23,12 @@ constexpr int CHUNK = 1024;       // points per scan chunk (256 threads x 4)
 constexpr int NCLS = 5;           // pillar classes by point count: 1 | 2 | 3-4 | 5-8 | 9+
 
 struct AgentOffsets { int n_agents; int off[CB_MAX_AGENTS + 1]; };
+// View of the per-agent point offsets: either the by-value kernel parameter (host-array entry points) or a device array
+// (cb_points_to_canvas_dev: offsets change every frame without changing the kernel arguments of a captured CUDA graph).
+struct AoView { int n_agents; const int* off; };
+__device__ __forceinline__ AoView ao_view(const AgentOffsets& v, const int* off_dev) {
+    AoView a; a.n_agents = v.n_agents; a.off = off_dev ? off_dev : v.off; return a;
+}
 
 struct VoxWs {            // workspace carve-up (device pointers)
     int* first;           // [n_agents][ncell]   min point index per cell (0x7f7f7f7f = empty)
@@ -463,17 +469,19 @@ __device__ __forceinline__ float4* slot_ptr(const Vox2Ws& ws, long gc, int k) {
     return k < ws.S0 ? ws.slots + gc * ws.S0 + k : ws.slots2 + gc * ws.S2 + (k - ws.S0);
 }
 
-__device__ __forceinline__ int find_agent_bs(const AgentOffsets& ao, int i) {      // largest a with off[a] <= i
+__device__ __forceinline__ int find_agent_bs(const AoView& ao, int i) {      // largest a with off[a] <= i
     int lo = 0, hi = ao.n_agents;
     while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ao.off[mid] <= i) lo = mid; else hi = mid; }
     return lo;
 }
 
 __global__ void __launch_bounds__(256) vox2_assign_kernel(const float4* __restrict__ pts,
-                                                          const __grid_constant__ AgentOffsets ao, const Geom g,
+                                                          const __grid_constant__ AgentOffsets ao_val,
+                                                          const int* __restrict__ off_dev, const Geom g,
                                                           const Vox2Ws ws, int max_pts, int use_first) {
     pdl_launch_dependents();
     pdl_wait();
+    const AoView ao = ao_view(ao_val, off_dev);
     const int total = ao.off[ao.n_agents];
     const int i = blockIdx.x * 256 + threadIdx.x;
     const int a_lo = find_agent_bs(ao, blockIdx.x * 256);          // CTA-uniform
@@ -506,7 +514,7 @@ __global__ void __launch_bounds__(256) vox2_assign_kernel(const float4* __restri
 }
 
 // V2a/b: max_voxels cap.  "Leader" = the first point of its cell; voxel rank = number of leaders before it.
-__device__ __forceinline__ int cap_leaders(const AgentOffsets& ao, const Vox2Ws& ws, int a, int chunk, long (&gc)[4]) {
+__device__ __forceinline__ int cap_leaders(const AoView& ao, const Vox2Ws& ws, int a, int chunk, long (&gc)[4]) {
     const int p0 = ao.off[a], np = ao.off[a + 1] - p0;
     int mask = 0;
 #pragma unroll
@@ -523,10 +531,12 @@ __device__ __forceinline__ int cap_leaders(const AgentOffsets& ao, const Vox2Ws&
     }
     return mask;
 }
-__global__ void __launch_bounds__(256) vox2_cap_count_kernel(const __grid_constant__ AgentOffsets ao, const Vox2Ws ws,
+__global__ void __launch_bounds__(256) vox2_cap_count_kernel(const __grid_constant__ AgentOffsets ao_val,
+                                                             const int* __restrict__ off_dev, const Vox2Ws ws,
                                                              int max_voxels) {
     pdl_launch_dependents();
     pdl_wait();
+    const AoView ao = ao_view(ao_val, off_dev);
     const int a = blockIdx.y, chunk = blockIdx.x;
     if (ws.scal[V2_SCAL + a] <= max_voxels) return;                 // uniform: this agent is under the cap
     long gc[4];
@@ -535,10 +545,12 @@ __global__ void __launch_bounds__(256) vox2_cap_count_kernel(const __grid_consta
     block_scan2(__popc(mask), 0, ev, ec, tv, tc);
     if (threadIdx.x == 0) ws.chunk_tot[(long)a * ws.max_chunks + chunk] = tv;
 }
-__global__ void __launch_bounds__(256) vox2_cap_refuse_kernel(const __grid_constant__ AgentOffsets ao, const Vox2Ws ws,
+__global__ void __launch_bounds__(256) vox2_cap_refuse_kernel(const __grid_constant__ AgentOffsets ao_val,
+                                                              const int* __restrict__ off_dev, const Vox2Ws ws,
                                                               int max_voxels) {
     pdl_launch_dependents();
     pdl_wait();
+    const AoView ao = ao_view(ao_val, off_dev);
     const int a = blockIdx.y, chunk = blockIdx.x;
     if (ws.scal[V2_SCAL + a] <= max_voxels) return;
     int part = 0;
@@ -607,9 +619,11 @@ __global__ void __launch_bounds__(256) vox2_cells_kernel(const Vox2Ws ws, unsign
 }
 
 // V4a/b: cells with more than max_pts points (grid-stride; the whole grid exits at once when there are none)
-__global__ void __launch_bounds__(256) vox2_big_fill_kernel(const __grid_constant__ AgentOffsets ao, const Vox2Ws ws) {
+__global__ void __launch_bounds__(256) vox2_big_fill_kernel(const __grid_constant__ AgentOffsets ao_val,
+                                                            const int* __restrict__ off_dev, const Vox2Ws ws) {
     pdl_launch_dependents();
     pdl_wait();
+    const AoView ao = ao_view(ao_val, off_dev);
     if (ws.scal[6] == 0) return;
     const int total = ao.off[ao.n_agents];
     for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
@@ -623,10 +637,12 @@ __global__ void __launch_bounds__(256) vox2_big_fill_kernel(const __grid_constan
     }
 }
 __global__ void __launch_bounds__(256) vox2_big_rank_kernel(const float4* __restrict__ pts,
-                                                            const __grid_constant__ AgentOffsets ao, const Vox2Ws ws,
+                                                            const __grid_constant__ AgentOffsets ao_val,
+                                                            const int* __restrict__ off_dev, const Vox2Ws ws,
                                                             int max_pts) {
     pdl_launch_dependents();
     pdl_wait();
+    const AoView ao = ao_view(ao_val, off_dev);
     if (ws.scal[6] == 0) return;
     const int total = ao.off[ao.n_agents];
     for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
@@ -861,8 +877,11 @@ static int carve2(Vox2Ws& ws, void* base, size_t bytes, int n_agents, int sum_po
     return CB_OK;
 }
 
-// v2 front half (V1..V4) of the fused path.  pt_offset is a HOST array.
-static int run_front2(const float* points, const int32_t* pt_offset, int n_agents, const float* range,
+// v2 front half (V1..V4) of the fused path.  Offsets come either from a HOST array (pt_offset, baked into the kernel
+// arguments) or from a DEVICE array (off_dev; then `total_cap` / `agent_cap` bound the grid sizes and the launch
+// sequence depends only on those capacities, so a captured CUDA graph serves every frame).
+static int run_front2(const float* points, const int32_t* pt_offset, const int32_t* off_dev, int total_cap, int agent_cap,
+                      int n_agents, const float* range,
                       const float* vsize, const int32_t* grid, int max_pts, int max_voxels, void* workspace,
                       size_t workspace_bytes, cudaStream_t st, Vox2Ws& ws, const PfnParams& pp) {
     if (n_agents < 1 || n_agents > CB_MAX_AGENTS || max_pts < 1 || max_pts > 32 || max_voxels < 1) return CB_ERR_ARG;
@@ -870,14 +889,23 @@ static int run_front2(const float* points, const int32_t* pt_offset, int n_agent
     if (grid[0] > 4096 || grid[1] > 4096 || grid[2] != 1) return CB_ERR_ARG;          // packed work items; nz == 1
     AgentOffsets ao; Geom g;
     ao.n_agents = n_agents;
-    for (int i = 0; i <= n_agents; ++i) ao.off[i] = pt_offset[i];
-    if (ao.off[0] != 0) return CB_ERR_ARG;
-    int max_np = 0;
-    for (int i = 0; i < n_agents; ++i) {
-        if (ao.off[i + 1] < ao.off[i]) return CB_ERR_ARG;
-        if (ao.off[i + 1] - ao.off[i] > max_np) max_np = ao.off[i + 1] - ao.off[i];
+    int max_np = 0, total = 0, may_cap = 0;
+    if (off_dev) {
+        if (total_cap < 0 || agent_cap < 0) return CB_ERR_ARG;
+        for (int i = 0; i <= n_agents; ++i) ao.off[i] = 0;
+        total = total_cap; max_np = agent_cap < total_cap ? agent_cap : total_cap;
+        may_cap = max_np > max_voxels;
+    } else {
+        for (int i = 0; i <= n_agents; ++i) ao.off[i] = pt_offset[i];
+        if (ao.off[0] != 0) return CB_ERR_ARG;
+        for (int i = 0; i < n_agents; ++i) {
+            if (ao.off[i + 1] < ao.off[i]) return CB_ERR_ARG;
+            if (ao.off[i + 1] - ao.off[i] > max_np) max_np = ao.off[i + 1] - ao.off[i];
+        }
+        total = ao.off[n_agents];
+        // an agent with no more points than max_voxels can never hit the voxel cap: then `first` and V2a/b are not needed
+        for (int i = 0; i < n_agents; ++i) may_cap |= (ao.off[i + 1] - ao.off[i]) > max_voxels;
     }
-    const int total = ao.off[n_agents];
     size_t clr[2];
     int rc = carve2(ws, workspace, workspace_bytes, n_agents, total, grid, max_pts, max_voxels, clr, nullptr);
     if (rc) return rc;
@@ -885,9 +913,6 @@ static int run_front2(const float* points, const int32_t* pt_offset, int n_agent
     g.r0 = range[0]; g.r1 = range[1]; g.r2 = range[2];
     g.v0 = vsize[0]; g.v1 = vsize[1]; g.v2 = vsize[2];
     g.gx = grid[0]; g.gy = grid[1]; g.gz = grid[2];
-    // an agent with no more points than max_voxels can never hit the voxel cap: then `first` and V2a/b are not needed
-    int may_cap = 0;
-    for (int i = 0; i < n_agents; ++i) may_cap |= (ao.off[i + 1] - ao.off[i]) > max_voxels;
     // PFN coefficient table -> constant bank first, so that the kernel chain below is kernel -> kernel only (programmatic
     // dependent launches: the launch latency of kernel n+1 overlaps the tail of kernel n)
     cudaError_t e;
@@ -900,18 +925,18 @@ static int run_front2(const float* points, const int32_t* pt_offset, int n_agent
     if (total > 0) {
         const unsigned pblocks = (unsigned)((total + 255) / 256);
         const unsigned sblocks = pblocks < 148u * 4u ? pblocks : 148u * 4u;
-        vox2_assign_kernel<<<pblocks, 256, 0, st>>>((const float4*)points, ao, g, ws, max_pts, may_cap);
+        vox2_assign_kernel<<<pblocks, 256, 0, st>>>((const float4*)points, ao, off_dev, g, ws, max_pts, may_cap);
         CB_CHECK_LAUNCH();
         if (may_cap) {
             const dim3 cgrid((unsigned)((max_np + CHUNK - 1) / CHUNK), (unsigned)n_agents);
-            e = launch_pdl(vox2_cap_count_kernel, cgrid, dim3(256), 0, st, ao, ws, max_voxels);       if (e) return (int)e;
-            e = launch_pdl(vox2_cap_refuse_kernel, cgrid, dim3(256), 0, st, ao, ws, max_voxels);      if (e) return (int)e;
+            e = launch_pdl(vox2_cap_count_kernel, cgrid, dim3(256), 0, st, ao, off_dev, ws, max_voxels);   if (e) return (int)e;
+            e = launch_pdl(vox2_cap_refuse_kernel, cgrid, dim3(256), 0, st, ao, off_dev, ws, max_voxels);  if (e) return (int)e;
         }
         const unsigned total_cells = (unsigned)n_agents * (unsigned)ws.ncell;
         e = launch_pdl(vox2_cells_kernel, dim3((total_cells + 1023u) / 1024u), dim3(256), 0, st, ws, total_cells, (int)grid[0],
                        max_pts);                                                                       if (e) return (int)e;
-        e = launch_pdl(vox2_big_fill_kernel, dim3(sblocks), dim3(256), 0, st, ao, ws);                if (e) return (int)e;
-        e = launch_pdl(vox2_big_rank_kernel, dim3(sblocks), dim3(256), 0, st, (const float4*)points, ao, ws, max_pts);
+        e = launch_pdl(vox2_big_fill_kernel, dim3(sblocks), dim3(256), 0, st, ao, off_dev, ws);       if (e) return (int)e;
+        e = launch_pdl(vox2_big_rank_kernel, dim3(sblocks), dim3(256), 0, st, (const float4*)points, ao, off_dev, ws, max_pts);
         if (e) return (int)e;
     }
     return CB_OK;
@@ -963,12 +988,13 @@ extern "C" int cb_voxelize(const float* points, const int32_t* pt_offset, int n_
     return CB_OK;
 }
 
-extern "C" int cb_points_to_canvas(const float* points, const int32_t* pt_offset, int n_agents, const float* range,
-                                   const float* vsize, const int32_t* grid, int max_pts, int max_voxels,
-                                   const float* w, const float* scale, const float* shift,
-                                   const float* center_off, int canvas_agents, void* canvas_ps,
-                                   int64_t lo_off, int64_t* dirty_rows, int32_t* dirty_count,
-                                   void* workspace, size_t workspace_bytes, void* stream) {
+static int points_to_canvas_impl(const float* points, const int32_t* pt_offset, const int32_t* off_dev, int total_cap,
+                                 int agent_cap, int n_agents, const float* range,
+                                 const float* vsize, const int32_t* grid, int max_pts, int max_voxels,
+                                 const float* w, const float* scale, const float* shift,
+                                 const float* center_off, int canvas_agents, void* canvas_ps,
+                                 int64_t lo_off, int64_t* dirty_rows, int32_t* dirty_count,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
     using namespace cb;
     if (grid[2] != 1 || !canvas_ps || canvas_agents < n_agents) return CB_ERR_ARG;   // nz == 1 (point_pillar_scatter.py:13)
     cudaStream_t st = (cudaStream_t)stream;
@@ -977,12 +1003,55 @@ extern "C" int cb_points_to_canvas(const float* points, const int32_t* pt_offset
     const PfnParams pp = make_pfn(w, scale, shift, vsize, center_off);
     cudaError_t ce;
     Vox2Ws ws2;
-    int rc2 = run_front2(points, pt_offset, n_agents, range, vsize, grid, max_pts, max_voxels, workspace, workspace_bytes, st,
-                         ws2, pp);
+    int rc2 = run_front2(points, pt_offset, off_dev, total_cap, agent_cap, n_agents, range, vsize, grid, max_pts, max_voxels,
+                         workspace, workspace_bytes, st, ws2, pp);
     if (rc2) return rc2;
     ce = launch_pdl(vox2_pfn_kernel<16>, dim3(148 * 2), dim3(256), 0, st, ws2, max_pts, pp, cg, (__nv_bfloat16*)canvas_ps,
                     (long)lo_off, (long*)dirty_rows, (int*)dirty_count);
     if (ce) return (int)ce;
+    return CB_OK;
+}
+
+extern "C" int cb_points_to_canvas(const float* points, const int32_t* pt_offset, int n_agents, const float* range,
+                                   const float* vsize, const int32_t* grid, int max_pts, int max_voxels,
+                                   const float* w, const float* scale, const float* shift,
+                                   const float* center_off, int canvas_agents, void* canvas_ps,
+                                   int64_t lo_off, int64_t* dirty_rows, int32_t* dirty_count,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+    if (!pt_offset) return CB_ERR_ARG;
+    return points_to_canvas_impl(points, pt_offset, nullptr, 0, 0, n_agents, range, vsize, grid, max_pts, max_voxels, w, scale,
+                                 shift, center_off, canvas_agents, canvas_ps, lo_off, dirty_rows, dirty_count, workspace,
+                                 workspace_bytes, stream);
+}
+
+extern "C" int cb_points_to_canvas_dev(const float* points, const int32_t* pt_offset_dev, int n_agents, int point_capacity,
+                                       int agent_capacity, const float* range,
+                                       const float* vsize, const int32_t* grid, int max_pts, int max_voxels,
+                                       const float* w, const float* scale, const float* shift,
+                                       const float* center_off, int canvas_agents, void* canvas_ps,
+                                       int64_t lo_off, int64_t* dirty_rows, int32_t* dirty_count,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
+    if (!pt_offset_dev) return CB_ERR_ARG;
+    return points_to_canvas_impl(points, nullptr, pt_offset_dev, point_capacity, agent_capacity, n_agents, range, vsize, grid,
+                                 max_pts, max_voxels, w, scale, shift, center_off, canvas_agents, canvas_ps, lo_off, dirty_rows,
+                                 dirty_count, workspace, workspace_bytes, stream);
+}
+
+namespace cb {
+struct I32Pack { int n; int v[CB_MAX_AGENTS + 1]; };
+__global__ void upload_i32_kernel(const __grid_constant__ I32Pack p, int* __restrict__ dst) {
+    const int i = threadIdx.x;
+    if (i < p.n) dst[i] = p.v[i];
+}
+}  // namespace cb
+
+extern "C" int cb_upload_i32(const int32_t* host_vals, int n, int32_t* dst_dev, void* stream) {
+    if (!host_vals || !dst_dev || n < 1 || n > CB_MAX_AGENTS + 1) return CB_ERR_ARG;
+    cb::I32Pack p;
+    p.n = n;
+    for (int i = 0; i < n; ++i) p.v[i] = host_vals[i];
+    cb::upload_i32_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(p, dst_dev);
+    CB_CHECK_LAUNCH();
     return CB_OK;
 }
 

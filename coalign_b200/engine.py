@@ -11,6 +11,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 import os
+from collections import OrderedDict
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -155,7 +156,8 @@ class CoAlignEngine:
                 raise ValueError("deblock outputs do not line up (torch.cat would fail in the reference too)")
         self._pack_weights(state_dict)
         self._alloc()
-        self._graphs: Dict[tuple, dict] = {}
+        self._graphs: "OrderedDict[tuple, dict]" = OrderedDict()       # LRU, bounded by max_graphs
+        self.max_graphs = 16
         self._stream = None if self.plan_only else torch.cuda.Stream(device=self.device)
 
     # ------------------------------------------------------------------ weights
@@ -260,6 +262,7 @@ class CoAlignEngine:
         self.dirty_rows = torch.zeros(self._dirty_cap, dtype=torch.int64, device=dev)
         self.dirty_count = torch.zeros(1, dtype=torch.int32, device=dev)
         self.pts_buf = None
+        self.pt_off_dev = torch.zeros(self.max_agents + 1, dtype=torch.int32, device=dev)   # per-agent point offsets
 
     # ------------------------------------------------------------------ descriptors
     def _expand(self, steps, lo_rows, k_hi):
@@ -492,6 +495,10 @@ class CoAlignEngine:
         if ent is None:
             ent = {"ops": self.build_descs(n_img, n_scenes), "graph": None}
             self._graphs[key] = ent
+            while len(self._graphs) > self.max_graphs:        # least recently used signature goes (graph + descriptors)
+                self._graphs.popitem(last=False)
+        else:
+            self._graphs.move_to_end(key)
         cur = torch.cuda.current_stream(self.device)
 
         def run(stream_ptr):
@@ -529,7 +536,11 @@ class CoAlignEngine:
         off[n_scenes + 1:] = off[n_scenes]
         key = tuple(record_len)
         if getattr(self, "_off_key", None) != key:
-            self.agent_off.copy_(torch.from_numpy(off), non_blocking=False)
+            if self.plan_only or self.max_scenes + 1 > _lib.CB_MAX_AGENTS + 1:
+                self.agent_off.copy_(torch.from_numpy(off), non_blocking=False)
+            else:
+                _lib.check(self.lib.cb_upload_i32(off.ctypes.data, self.max_scenes + 1, self.agent_off.data_ptr(),
+                                                  torch.cuda.current_stream(self.device).cuda_stream), "cb_upload_i32")
             self._off_key = key
 
     def _outputs(self, n_scenes: int, clone: bool):
@@ -600,27 +611,38 @@ class CoAlignEngine:
         if points.dtype != torch.float32 or points.dim() != 2 or points.shape[1] != 4 or points.shape[0] < total:
             raise TypeError("points must be float32 (sum_P, 4)")
         if self.pts_buf is None or self.pts_buf.shape[0] < total:
-            self.pts_buf = torch.empty(max(total, 1), 4, dtype=torch.float32, device=self.device)
-            self._graphs = {k: v for k, v in self._graphs.items() if k[0] != "pts"}
+            # capacity = the caller's buffer (a serving loop passes its largest-frame staging buffer): no regrowth later
+            self.pts_buf = torch.empty(max(total, int(points.shape[0]), 1), 4, dtype=torch.float32, device=self.device)
+            for k in [k for k in self._graphs if k[0] == "pts"]:
+                del self._graphs[k]
         if points.data_ptr() != self.pts_buf.data_ptr():
             self.pts_buf[:total].copy_(points[:total], non_blocking=True)     # static address for the graph
-        ws = self._ws(n_img, total, max_voxels)
+        if po[0] != 0 or (np.diff(po) < 0).any():
+            raise ValueError("pt_offset must start at 0 and be non-decreasing")
+        # The per-agent offsets live in a device array the kernels read, and the launch geometry depends only on the two
+        # capacities below: one captured graph serves every frame of this batch signature, whatever the clouds' sizes
+        # (real sweeps differ from frame to frame; a key on the offsets themselves would re-capture every step).
+        pt_cap = int(self.pts_buf.shape[0])
+        agent_cap = min(pt_cap, (int(np.diff(po).max(initial=0)) + 16383) // 16384 * 16384)
+        ws = self._ws(n_img, pt_cap, max_voxels)
+        cur = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.cb_upload_i32(po.ctypes.data, n_img + 1, self.pt_off_dev.data_ptr(), cur), "cb_upload_i32")
         if getattr(self, "_canvas_untracked", False):
-            self._clear_canvas(torch.cuda.current_stream(self.device).cuda_stream)     # full memset, outside the graph
-        po_keep = po.copy()
+            self._clear_canvas(cur)                                           # full memset, outside the graph
 
         def front(stream_ptr):
             self._clear_canvas(stream_ptr)
-            _lib.check(self.lib.cb_points_to_canvas(self.pts_buf.data_ptr(), po_keep.ctypes.data, n_img,
-                                                    self._range_f.ctypes.data, self._vsize_f.ctypes.data,
-                                                    self._grid_i.ctypes.data, max_pts, max_voxels,
-                                                    self.pfn_w.data_ptr(), self.pfn_scale.data_ptr(),
-                                                    self.pfn_shift.data_ptr(), self._center_off_f.ctypes.data,
-                                                    self.canvas.n_cap, self.canvas.ptr, self.canvas.lo_off,
-                                                    self.dirty_rows.data_ptr(), self.dirty_count.data_ptr(),
-                                                    ws.data_ptr(), ws.numel(), stream_ptr), "cb_points_to_canvas")
+            _lib.check(self.lib.cb_points_to_canvas_dev(self.pts_buf.data_ptr(), self.pt_off_dev.data_ptr(), n_img,
+                                                        pt_cap, agent_cap,
+                                                        self._range_f.ctypes.data, self._vsize_f.ctypes.data,
+                                                        self._grid_i.ctypes.data, max_pts, max_voxels,
+                                                        self.pfn_w.data_ptr(), self.pfn_scale.data_ptr(),
+                                                        self.pfn_shift.data_ptr(), self._center_off_f.ctypes.data,
+                                                        self.canvas.n_cap, self.canvas.ptr, self.canvas.lo_off,
+                                                        self.dirty_rows.data_ptr(), self.dirty_count.data_ptr(),
+                                                        ws.data_ptr(), ws.numel(), stream_ptr), "cb_points_to_canvas_dev")
 
-        key = ("pts", record_len, tuple(int(v) for v in po), int(max_pts), int(max_voxels), ws.data_ptr())
+        key = ("pts", record_len, pt_cap, agent_cap, int(max_pts), int(max_voxels), ws.data_ptr())
         self._graphed(key, record_len, front)
         return self._outputs(len(record_len), clone)
 

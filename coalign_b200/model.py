@@ -95,6 +95,17 @@ class PointPillarCoalignB200(nn.Module):
     def __init__(self, args):
         super().__init__()
         self.args = args
+        if not args["base_bev_backbone"].get("resnet", True):
+            # point_pillar_baseline_multiscale.py:31-34 builds BaseBEVBackbone for resnet: false; CoAlign's yamls all set true
+            raise NotImplementedError("point_pillar_coalign_b200 implements base_bev_backbone.resnet: true")
+        if "fusion_method" not in args:                    # the reference indexes args['fusion_method'] (:36-41)
+            raise KeyError("model.args.fusion_method is required ('att' or 'max')")
+        if args["fusion_method"] == "att":
+            fd = list(args.get("att", {}).get("feat_dim", args["base_bev_backbone"]["num_filters"]))
+            if fd != list(args["base_bev_backbone"]["num_filters"]):
+                # ScaledDotProductAttention(feat_dim[i]) scales the scores by 1/sqrt(feat_dim[i]) (att_fuse.py:40-44); the
+                # fusion kernel uses the channel count of the level, which every shipped yaml makes equal
+                raise NotImplementedError("att.feat_dim must equal base_bev_backbone.num_filters on the B200 path")
         self.pillar_vfe = _PillarVFE(args["pillar_vfe"])
         self.backbone = _Backbone(args["base_bev_backbone"])
         self.fusion_net = nn.ModuleList()            # parameter-free (fusion_in_one.py:91-136)
@@ -109,7 +120,7 @@ class PointPillarCoalignB200(nn.Module):
             self.dir_head = nn.Conv2d(out_c, args["dir_args"]["num_bins"] * an, 1)
         self.max_cav = int(args.get("max_cav", 5))
         self.precise = bool(args.get("b200_precise", False))
-        self.block_n_cap = int(args.get("b200_block_n", 128))
+        self.block_n_cap = int(args.get("b200_block_n", 256))     # 256-wide tiles run on CTA pairs (the benchmarked engine)
         self._engine = None
         self._engine_key = None
         if args.get("backbone_fix", False):
@@ -221,7 +232,7 @@ class PointPillarB200(nn.Module):
         if "dir_args" in args:
             self.dir_head = nn.Conv2d(out_c, args["dir_args"]["num_bins"] * an, 1)
         self.precise = bool(args.get("b200_precise", False))
-        self.block_n_cap = int(args.get("b200_block_n", 128))
+        self.block_n_cap = int(args.get("b200_block_n", 256))     # 256-wide tiles run on CTA pairs (the benchmarked engine)
         self._engine = None
         self._engine_key = None
 

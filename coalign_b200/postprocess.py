@@ -63,9 +63,14 @@ class VoxelPostprocessorB200:
 
     # ------------------------------------------------------------------ CUDA path
     def _device_anchors(self, anchor_box, device) -> torch.Tensor:
+        """Device copy of the anchors, cached by CONTENT (a strided 257-element sample + shape + the total): an address
+        can be reused by a different array, and per-batch collated anchor tensors are new objects with the same values."""
         if isinstance(anchor_box, np.ndarray):
             anchor_box = torch.from_numpy(anchor_box)
-        key = (anchor_box.data_ptr(), tuple(anchor_box.shape), str(device))
+        flat = anchor_box.reshape(-1)
+        step = max(1, flat.numel() // 257)
+        sample = flat[::step].detach().to("cpu", torch.float64)
+        key = (tuple(anchor_box.shape), str(device), float(flat.detach().double().sum()), tuple(sample.tolist()))
         t = self._anchor_cache.get(key)
         if t is None:
             t = anchor_box.to(device=device, dtype=torch.float32).contiguous()     # `.float()` of delta_to_boxes3d

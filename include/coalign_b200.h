@@ -101,6 +101,22 @@ int cb_points_to_canvas(const float* points, const int32_t* pt_offset, int n_age
                         int64_t* dirty_rows, int32_t* dirty_count,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* cb_points_to_canvas with the per-agent point offsets in DEVICE memory (int32 [n_agents+1], off[0] = 0, non-decreasing,
+ * off[n_agents] <= point_capacity, no agent with more than agent_capacity points): grid sizes and the launch sequence
+ * depend only on the two capacities, so a CUDA graph captured once serves frames whose clouds have different sizes
+ * (real LiDAR sweeps do; sp_voxel_preprocessor.py:62-85 is called per cloud).  Results are identical to
+ * cb_points_to_canvas on the same offsets.  The max_voxels path runs whenever agent_capacity > max_voxels. */
+int cb_points_to_canvas_dev(const float* points, const int32_t* pt_offset_dev, int n_agents, int point_capacity,
+                            int agent_capacity, const float* range, const float* vsize, const int32_t* grid,
+                            int max_pts, int max_voxels,
+                            const float* w, const float* scale, const float* shift,
+                            const float* center_off, int canvas_agents, void* canvas_ps, int64_t lo_off,
+                            int64_t* dirty_rows, int32_t* dirty_count,
+                            void* workspace, size_t workspace_bytes, void* stream);
+/* Stream-ordered upload of up to CB_MAX_AGENTS+1 int32 values (they travel as kernel arguments: no pinned staging buffer
+ * whose lifetime the caller would have to manage).  Used for the offsets above and the scene prefix sums. */
+int cb_upload_i32(const int32_t* host_vals, int n, int32_t* dst_dev, void* stream);
+
 /* Sparse canvas reset: zero the cells listed in dirty_rows[0..*dirty_count) (DEVICE arrays written by the two
  * entry points above when their dirty_rows/dirty_count arguments are non-NULL: one canvas row per pillar, -1 =
  * skipped).  Replaces the full-canvas memset between frames (the canvas is ~80 % zeros). */

@@ -441,6 +441,95 @@ def test_full_size_dairv2x_two_agents_pose_noise_vs_oracle():
     _full_size_case(synth.dairv2x_args(), 2, seed=12, pose_noise=True)
 
 
+def test_full_size_opv2v_five_agents_vs_oracle():
+    """BASELINE configs[2], the benchmarked configuration: 5 agents, pose noise, full 200x704 canvas, 60k points/agent."""
+    _full_size_case(synth.opv2v_args(), 5, seed=13, pose_noise=True)
+
+
+def test_bench_launch_60_agents_equals_single_scene_launches():
+    """The bench runs 12 scenes x 5 agents in ONE launch sequence.  Scene by scene it must give what a single-scene launch
+    gives: bit for bit in bf16 mode (every output pixel sees the same operands in the same K order whatever tile it falls
+    into), and the first scene additionally within bf16 drift of the fp32 oracle."""
+    from oracle import coalign_oracle as O
+    torch.set_num_threads(min(32, os.cpu_count() or 1))
+    args = synth.opv2v_args()
+    sd = synth.random_state_dict(args, 0)
+    B, NA, P = 12, 5, 60000
+    scenes = [synth.make_scene(2000 + s, NA, P, args["lidar_range"], max_cav=5, pose_noise=True) for s in range(B)]
+    pts = torch.from_numpy(np.concatenate([p for sc in scenes for p in sc["points"]]).astype(np.float32)).cuda()
+    pw = torch.from_numpy(np.stack([sc["pairwise_t_matrix"] for sc in scenes])).cuda()
+    off = (np.arange(B * NA + 1) * P).astype(np.int32)
+    eng = make_engine(args, sd, B * NA, B, precise=False, block_n_cap=256)
+    big = {k: v.cpu().numpy() for k, v in eng.forward_points(pts, off, [NA] * B, pw).items()}
+    for s in (0, 5, 11):
+        one = eng.forward_points(pts[s * NA * P:(s + 1) * NA * P].contiguous(), off[:NA + 1], [NA], pw[s:s + 1])
+        for k in big:
+            assert np.array_equal(one[k][0].cpu().numpy(), big[k][s]), (s, k)
+    inp = G.scenes_to_batch([scenes[0]], args["lidar_range"], args["voxel_size"])
+    ref = O.forward(sd, args, G.to_torch_batch(inp))
+    for k in ref:
+        assert rel_l2(big[k][0], ref[k][0].numpy()) < 3e-2, (k, rel_l2(big[k][0], ref[k][0].numpy()))
+
+
+def test_bf16_mode_against_bf16_rounded_interpreter():
+    """Like-for-like check of the production (bf16) mode: the launch-plan interpreter (tests/plan_interpreter.py) evaluates
+    the SAME descriptors on the CPU with the same bf16-packed weights and a bf16 rounding at every activation store, fp32
+    accumulation in between.  What is left between it and the GPU is accumulation order inside a K loop, the packed-bf16
+    tap blend of the fusion kernel and roundings that flip on ties: an order of magnitude below the drift against the fp32
+    oracle (5e-2 bound), so a bug at the 1e-2 level cannot hide behind "bf16 noise"."""
+    from coalign_b200.engine import CoAlignEngine
+    from tests import plan_interpreter as PI
+    seed = 1
+    args = G.small_args("att")
+    sd = synth.random_state_dict(args, seed)
+    rl = [3, 2]
+    inp = G.small_case_inputs(rl, seed0=100 + seed)
+    cpu_eng = CoAlignEngine(args, sd, 5, 2, device="cpu", precise=False, plan_only=True)
+    ref = PI.run_plan(cpu_eng, sd, args, G.to_torch_batch(inp))
+    eng = make_engine(args, sd, 5, 2, precise=False)
+    out = eng.forward_voxels(*cuda_batch(inp))
+    torch.cuda.synchronize()
+    for i in range(3):
+        got = eng.read_act(eng.lvl[i]["out"], 5).cpu().numpy()
+        want = PI.act_to_nchw(cpu_eng.lvl[i]["out"], cpu_eng.lvl[i]["out"].n_cap)[:5].numpy()
+        assert rel_l2(got, want) < 6e-3, (f"feat{i}", rel_l2(got, want))
+    for k in ("cls_preds", "reg_preds", "dir_preds"):
+        r = rel_l2(out[k].cpu().numpy(), ref[k].numpy())
+        assert r < 8e-3, (k, r)
+
+
+def test_varying_cloud_sizes_reuse_one_graph():
+    """Frames whose clouds differ in size (real sweeps do): the per-agent offsets travel through a device array, so the
+    second and later frames replay the graph captured for the first, and every frame equals the result of the
+    host-offset entry point (cb_points_to_canvas + voxel-tensor path) on the same clouds."""
+    args = G.small_args("att")
+    sd = synth.random_state_dict(args, 8)
+    eng = make_engine(args, sd, 5, 2, precise=False)
+    ref_eng = make_engine(args, sd, 5, 2, precise=False, use_graph=False)
+    rng = np.random.default_rng(0)
+    cap = None
+    for frame in range(5):
+        scenes = G.small_case_scenes([3, 2], 700 + 10 * frame, n_points=1800)
+        clouds = [p[:int(rng.integers(900, 1801))] for sc in scenes for p in sc["points"]]
+        if frame == 3:
+            clouds[1] = clouds[1][:0]                                   # an agent with an empty cloud
+        off = np.concatenate([[0], np.cumsum([c.shape[0] for c in clouds])]).astype(np.int32)
+        flat = np.concatenate(clouds).astype(np.float32)
+        if cap is None:
+            cap = torch.zeros(5 * 1800, 4, device="cuda")               # the serving loop's staging buffer: fixed capacity
+        cap[:flat.shape[0]] = torch.from_numpy(flat).cuda()
+        pw = torch.from_numpy(np.stack([sc["pairwise_t_matrix"] for sc in scenes])).cuda()
+        out = {k: v.clone() for k, v in eng.forward_points(cap, off, [3, 2], pw).items()}
+        n_graphs = len(eng._graphs)
+        assert n_graphs == 1, n_graphs
+        # host-offset reference: reference-format voxel tensors from cb_voxelize, then the voxel entry
+        vf, vc, vn, _ = ref_eng.voxelize(torch.from_numpy(flat).cuda(), off)
+        want = ref_eng.forward_voxels(vf, vc, vn, [3, 2], pw)
+        torch.cuda.synchronize()
+        for k in out:
+            assert torch.equal(out[k], want[k]), (frame, k)
+
+
 def test_single_agent_pointpillar_matches_reference_golden():
     """BASELINE configs[0]: single-agent `point_pillar` (BaseBEVBackbone, no fusion) through the nn.Module twin:
     precise mode within rtol 1e-3 of the unmodified reference's outputs; bf16 mode at bf16-level drift; raw-point entry
