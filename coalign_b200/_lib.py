@@ -33,7 +33,52 @@ class ConvDesc(C.Structure):
     ]
 
 
+CB_WGRAD_MAX_BOXES, CB_WGRAD_MAX_UNITS = 4, 28
+
+
+class WgradBox(C.Structure):
+    _fields_ = [("row_off", C.c_int32), ("out_ld", C.c_int32), ("out_off", C.c_int64), ("col", C.c_uint16),
+                ("x_sel", C.c_uint16), ("pad_", C.c_uint32)]
+
+
+class WgradUnit(C.Structure):
+    _fields_ = [("m0", C.c_int32), ("a_row_off", C.c_int32), ("m_valid", C.c_int32), ("n_boxes", C.c_int32),
+                ("box", WgradBox * CB_WGRAD_MAX_BOXES)]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [("dz_ptr", C.c_void_p), ("dz_lo_ptr", C.c_void_p), ("dz_pitch", C.c_int32), ("k_splits", C.c_int32),
+                ("rows_total", C.c_int64), ("x_ptr", C.c_void_p * 2), ("x_rows", C.c_int64 * 2), ("x_pitch", C.c_int32 * 2),
+                ("x_lo_rows", C.c_int32 * 2), ("dw", C.c_void_p), ("n_units", C.c_int32), ("pad_", C.c_int32),
+                ("units", WgradUnit * CB_WGRAD_MAX_UNITS)]
+
+
+class Map(C.Structure):
+    _fields_ = [("n_img", C.c_int32), ("Hp", C.c_int32), ("Wp", C.c_int32), ("c_total", C.c_int32), ("c_mod", C.c_int32),
+                ("y_mode", C.c_int32), ("y_pitch", C.c_int32), ("y_ch_off", C.c_int32), ("up_k", C.c_int32),
+                ("y_Hp", C.c_int32), ("y_Wp", C.c_int32), ("y_plane_rows", C.c_int64)]
+
+
+_P, _I, _L, _F, _D = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
+
 EXPORTS = {
+    "cb_wgrad": (C.c_int, [C.POINTER(WgradDesc), _I, _P]),
+    "cb_wgrad_simt": (C.c_int, [C.POINTER(WgradDesc), _P]),
+    "cb_bn_stats": (C.c_int, [_P, _L, C.POINTER(Map), _P, _P]),
+    "cb_bn_finalize": (C.c_int, [_P, _I, _D, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "cb_bn_apply": (C.c_int, [_P, _L, _P, _P, _P, _L, _P, _P, _P, C.c_int32, _L, _I, C.POINTER(Map), _P, _L, _P]),
+    "cb_bn_bwd_reduce": (C.c_int, [_P, _L, _P, _L, _I, _P, _L, _P, _P, C.POINTER(Map), _P, _P]),
+    "cb_bn_bwd_apply": (C.c_int, [_P, _L, _P, _L, _I, _P, _L, _P, _P, _P, _P, _D, C.POINTER(Map), _P, _L, _P, _L, _P, _P, _P]),
+    "cb_heads_grad_pack": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _L, _P, _P]),
+    "cb_warp_att_fuse_bwd": (C.c_int, [_P, _I, _L, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _L, _P, _P]),
+    "cb_grad_combine": (C.c_int, [_P, _P, _L, _I, _I, _I, _I, _I, _I, _P, _L, _P]),
+    "cb_pfn_train_stats": (C.c_int, [_P, _P, _P, _I, _P, _I, _P, _P, _P, _P]),
+    "cb_pfn_train_finalize": (C.c_int, [_P, _P, _I, _I, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
+    "cb_pfn_bwd": (C.c_int, [_P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P, _P]),
+    "cb_pfn_bwd_finalize": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "cb_pack_weight": (C.c_int, [_P, _I, _I, _I, _I, _L, _L, _L, _L, _P, _I, _I, _I, _P]),
+    "cb_permute_f32": (C.c_int, [_P, _I, _I, _I, _I, _L, _L, _L, _L, _F, _P, _P]),
+    "cb_adam_step": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _P, _I, _P]),
     "cb_version": (C.c_int, []),
     "cb_device_check": (C.c_int, []),
     "cb_voxelize_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_void_p, C.c_int]),

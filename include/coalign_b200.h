@@ -23,6 +23,7 @@
 #ifndef COALIGN_B200_H
 #define COALIGN_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -293,6 +294,163 @@ int cb_pointpillar_loss(const float* cls_preds, const float* reg_preds, const fl
                         const double* anchor_yaw_rad,
                         float* out_losses, float* grad_cls, float* grad_reg, float* grad_dir,
                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Training step, device side: autograd of the forward above, train-mode BatchNorm, Adam.
+ * Reference: the loop body /root/reference/opencood/tools/train.py:105-125 (model.train(); forward; criterion;
+ * backward; optimizer.step) with torch.optim.Adam from train_utils.setup_optimizer (train_utils.py:196-206) and
+ * nn.BatchNorm2d / BatchNorm1d in training mode (batch statistics, running-stat update with the layer's momentum:
+ * resblock.py:38-39, base_bev_backbone_resnet.py:62-63, pillar_vfe.py:25,41-44).
+ *
+ * Division of labour:
+ *   - forward convolutions run through cb_conv_gemm* with RAW (unfolded) weights, bias 0, no ReLU -> z (bf16 PF);
+ *   - cb_bn_stats / cb_bn_finalize / cb_bn_apply turn z into y = relu(bn(z) [+ bn_b(z_b)] [+ residual]) in the layout
+ *     the next consumer wants (PF, PS, or pixel-shuffled into the concat buffer);
+ *   - backward: cb_bn_bwd_reduce + cb_bn_bwd_apply give dz from dy (ReLU mask from y, batch-norm adjoint), the input
+ *     gradient is the FORWARD kernel on dz with transposed/flipped packed weights (cb_conv_gemm*), the weight gradient is
+ *     cb_wgrad (MN-major tcgen05 GEMM over the pixel index, split-K);
+ *   - cb_warp_att_fuse_bwd is the adjoint of cb_warp_att_fuse (soft-max backward over the agents + scatter-add of the
+ *     four bilinear taps), cb_pfn_* the train-mode PFN (statistics over all M*32 slots, arg-max routing);
+ *   - cb_adam_step is torch.optim.Adam (L2 weight decay folded into the gradient) on flat fp32 buffers.
+ * All of them: raw device pointers, caller-owned workspaces, enqueue-only on `stream`, CUDA-graph capturable.
+ * ------------------------------------------------------------------------------------------ */
+
+/* ---- weight gradient: dW[m][..] += sum_q dZ[q + a_row_off][m0 + m] * X[q + row_off][col + c]  (see csrc/wgrad.cu) */
+#define CB_WGRAD_MAX_BOXES 4
+#define CB_WGRAD_MAX_UNITS 28
+typedef struct cb_wgrad_box {
+    int32_t row_off;      /* row shift (tap) + plane offset of the X operand, rows of the X tensor */
+    int32_t out_ld;       /* floats between consecutive m (dZ channels) in dw */
+    int64_t out_off;      /* float offset in dw of (m = 0, c = 0) of this 64-channel block */
+    uint16_t col;         /* first X channel of the block */
+    uint16_t x_sel;       /* which X tensor (0/1) */
+    uint32_t pad_;
+} cb_wgrad_box;
+typedef struct cb_wgrad_unit {
+    int32_t m0;           /* first dZ channel (128 per unit; channels past dz_pitch read as zero) */
+    int32_t a_row_off;    /* row shift of the dZ operand */
+    int32_t m_valid;      /* rows of the 128 that are stored (<= 128) */
+    int32_t n_boxes;      /* 1..CB_WGRAD_MAX_BOXES 64-channel X blocks (GEMM N = 64 * n_boxes) */
+    cb_wgrad_box box[CB_WGRAD_MAX_BOXES];
+} cb_wgrad_unit;
+typedef struct cb_wgrad_desc {
+    const void* dz_ptr;        /* bf16 [rows_total][dz_pitch] PF row space of the conv output; halo rows zero */
+    const void* dz_lo_ptr;     /* precise mode: lo plane of dZ (same shape) or NULL */
+    int32_t dz_pitch;
+    int32_t k_splits;          /* <= 0: chosen so that units * splits fills the SMs once */
+    int64_t rows_total;        /* n_img * Hp * Wp */
+    const void* x_ptr[2];      /* bf16 [x_rows][x_pitch] (PF, PS planes, ...); rows outside read as zero */
+    int64_t x_rows[2];
+    int32_t x_pitch[2];
+    int32_t x_lo_rows[2];      /* precise mode: row offset of the lo plane inside x (counted in x_rows) */
+    float* dw;                 /* fp32, accumulated into (zero it first) */
+    int32_t n_units;
+    int32_t pad_;
+    cb_wgrad_unit units[CB_WGRAD_MAX_UNITS];
+} cb_wgrad_desc;
+int cb_wgrad(const cb_wgrad_desc* desc, int max_ctas, void* stream);
+/* SIMT evaluation of the same descriptor (validation of the tensor-core kernel; tests only). */
+int cb_wgrad_simt(const cb_wgrad_desc* desc, void* stream);
+
+/* ---- train-mode BatchNorm around the conv GEMMs.
+ * Row mapping ("y side") shared by cb_bn_apply / cb_bn_bwd_*: z is always PF [n_img][Hp][Wp][c_total] in the GEMM's row
+ * space; the activation y (and its gradient dy) lives in
+ *   CB_OUT_PF       the same rows, channels [y_ch_off, y_ch_off + c_total)
+ *   CB_OUT_PS       4 parity planes (y_Hp, y_Wp, y_plane_rows as in cb_conv_desc)
+ *   CB_OUT_UPSAMPLE pixel-shuffled: column block ab = col / c_mod goes to pixel (k*h + a, k*w + b), channel col % c_mod
+ * Channel statistics are indexed by col % c_mod (c_total = k*k*c_mod for the transposed convolutions). */
+typedef struct cb_map {
+    int32_t n_img, Hp, Wp;       /* z row space: rows_total = n_img*Hp*Wp, interior 1..Hp-2 x 1..Wp-2 */
+    int32_t c_total, c_mod;
+    int32_t y_mode;              /* CB_OUT_PF / CB_OUT_PS / CB_OUT_UPSAMPLE */
+    int32_t y_pitch, y_ch_off, up_k, y_Hp, y_Wp;
+    int64_t y_plane_rows;
+} cb_map;
+
+/* sums[0..c_mod) += sum z, sums[c_mod..2c_mod) += sum z*z over the interior pixels (fp64). */
+int cb_bn_stats(const void* z, int64_t z_lo_off, const cb_map* map, double* sums, void* stream);
+/* Batch statistics -> per-channel affine (scale = gamma*inv_std, shift = beta - mean*scale), saved mean / inv_std for the
+ * backward, running-stat update: running = (1-momentum)*running + momentum*(mean | unbiased var).  count = elements per
+ * channel.  gamma == NULL: identity (scale 1, shift = bias or 0). */
+int cb_bn_finalize(const double* sums, int c, double count, float eps, float momentum,
+                   const float* gamma, const float* beta, float* running_mean, float* running_var,
+                   float* scale, float* shift, float* mean, float* inv_std, void* stream);
+/* y = [relu]( z*scale + shift [+ z_b*scale_b + shift_b] [+ residual] ) written through `map` (bf16, + lo plane when
+ * y_lo_off != 0).  residual: bf16 PF in z's row space, pitch res_pitch. */
+int cb_bn_apply(const void* z, int64_t z_lo_off, const float* scale, const float* shift,
+                const void* z_b, int64_t z_b_lo_off, const float* scale_b, const float* shift_b,
+                const void* residual, int32_t res_pitch, int64_t res_lo_off, int relu,
+                const cb_map* map, void* y, int64_t y_lo_off, void* stream);
+/* dyr = dy * (y > 0 if relu);  sums[0..c) += sum dyr, sums[c..2c) += sum dyr * x_hat, x_hat = (z - mean) * inv_std
+ * (mean == NULL: no BatchNorm, only the first half = bias gradient). */
+int cb_bn_bwd_reduce(const void* dy, int64_t dy_lo_off, const void* y, int64_t y_lo_off, int relu,
+                     const void* z, int64_t z_lo_off, const float* mean, const float* inv_std,
+                     const cb_map* map, double* sums, void* stream);
+/* dz = gamma*inv_std * (dyr - sums[c]/count - x_hat * sums[c_mod + c]/count)  (no BatchNorm: dz = dyr), bf16 PF in z's
+ * row space, interior rows only (halo rows stay zero).  Also writes d_gamma / d_beta (fp32 [c_mod]) when non-NULL, and
+ * dsum_pf = dyr as bf16 PF (pitch c_total) when non-NULL (the identity branch of a residual block). */
+int cb_bn_bwd_apply(const void* dy, int64_t dy_lo_off, const void* y, int64_t y_lo_off, int relu,
+                    const void* z, int64_t z_lo_off, const float* mean, const float* inv_std, const float* gamma,
+                    const double* sums, double count, const cb_map* map,
+                    void* dz, int64_t dz_lo_off, void* dsum_pf, int64_t dsum_lo_off,
+                    float* d_gamma, float* d_beta, void* stream);
+
+/* ---- heads: d(loss)/d(cls, reg, dir) fp32 NCHW (from cb_pointpillar_loss) -> bf16 PF [n][Hp][Wp][64] (zero padded
+ * columns) for the dgrad / wgrad GEMMs, and the bias gradients d_bias[c] = sum over pixels (fp32, [sum of head_cn]). */
+int cb_heads_grad_pack(const float* const* grads, const int32_t* head_cn, int n_heads, int n, int H, int W,
+                       void* g_pf, int64_t g_lo_off, float* d_bias, void* stream);
+
+/* ---- adjoint of cb_warp_att_fuse: d_feat (fp32, dense [sum_agents][H][W][C], ACCUMULATED with vector reductions; zero it
+ * first) from d_fused (bf16 PF [n_scenes][H+2][W+2][C]) - soft-max backward over the agents (att_fuse.py:44-46), gradient of
+ * the ego query, scatter-add through the four bilinear taps (torch_transformation_utils.py:322-331); method 1 = MaxFusion
+ * (gradient to the first arg-max agent, fusion_in_one.py:83-86). */
+int cb_warp_att_fuse_bwd(const void* feat, int in_ps, int64_t in_lo_off, int sum_agents,
+                         const double* affine, const int32_t* agent_off, int n_scenes, int max_cav,
+                         int H, int W, int C, int method,
+                         const void* d_fused_pf, int64_t d_fused_lo_off, float* d_feat, void* stream);
+/* out(layout) = bf16( acc_fp32 [n][H][W][C] + addend(layout, optional) ): closes the gradient of a level map (fusion
+ * branch + the next level's first block) in the layout its producer's backward reads (PF or PS, + lo plane). */
+int cb_grad_combine(const float* acc, const void* addend, int64_t addend_lo_off, int to_ps, int n_cap, int n, int H, int W,
+                    int C, void* out, int64_t out_lo_off, void* stream);
+
+/* ---- PFN in training mode, reference-format voxel tensors (what train.py's dataloader delivers).
+ * cb_pfn_train_stats: sums[0..10) = sum of the 10 augmented features over all valid points, sums[10..110) = their 10x10
+ * Gram matrix (fp64, accumulated).  With them mean / E[x^2] of linear(f) over ALL M*max_pts slots (padded slots are zero
+ * rows, pillar_vfe.py:41-44) follow in closed form: cb_pfn_train_finalize writes scale / shift (+ mean, inv_std, running
+ * stats with momentum 0.01), after which cb_pfn_scatter runs the forward unchanged.
+ * cb_pfn_bwd: arg-max routing of d_canvas (PS layout) to the slot that won the max, ReLU mask, and the reductions
+ * bsum[0..64) = d_beta, [64..128) = d_gamma, [128..768) = sum dy * f (fp64); cb_pfn_bwd_finalize turns them into the
+ * gradients of linear.weight (64x10), norm.weight, norm.bias. */
+int cb_pfn_train_stats(const float* voxels, const int32_t* coords, const int32_t* num_points, int n_rows_cap,
+                       const int32_t* n_voxels_dev, int max_pts, const float* vsize, const float* center_off,
+                       double* sums, void* stream);
+int cb_pfn_train_finalize(const double* sums, const int32_t* n_voxels_dev, int n_rows_cap, int max_pts,
+                          const float* w, const float* gamma, const float* beta, float eps, float momentum,
+                          float* running_mean, float* running_var, float* scale, float* shift, float* mean, float* inv_std,
+                          void* stream);
+int cb_pfn_bwd(const float* voxels, const int32_t* coords, const int32_t* num_points, int n_rows_cap,
+               const int32_t* n_voxels_dev, int max_pts, const float* w, const float* scale, const float* shift,
+               const float* mean, const float* inv_std, const float* vsize, const float* center_off,
+               const void* d_canvas_ps, int64_t d_canvas_lo_off, int canvas_agents, int ny, int nx,
+               double* bsum, void* stream);
+int cb_pfn_bwd_finalize(const double* stats_sums, const double* bsum, const int32_t* n_voxels_dev, int n_rows_cap,
+                        int max_pts, const float* w, const float* gamma, const float* mean, const float* inv_std,
+                        float* d_w, float* d_gamma, float* d_beta, void* stream);
+
+/* ---- layout permutations of parameters / gradients: dst[(r1,r0)][(k1,k0)] = src[r1*s_r1 + r0*s_r0 + k1*s_k1 + k0*s_k0].
+ * cb_pack_weight: fp32 -> bf16 [R1*R0][dst_ld] at column k_off (hi; + lo part at column k_off + lo_col_off when non-zero).
+ * cb_permute_f32: fp32 -> fp32 [R1*R0][K1*K0] (gradient back to the parameter's own layout), scaled by `alpha`. */
+int cb_pack_weight(const float* src, int R1, int R0, int K1, int K0, int64_t s_r1, int64_t s_r0, int64_t s_k1, int64_t s_k0,
+                   void* dst, int dst_ld, int k_off, int lo_col_off, void* stream);
+int cb_permute_f32(const float* src, int R1, int R0, int K1, int K0, int64_t s_r1, int64_t s_r0, int64_t s_k1, int64_t s_k0,
+                   float alpha, float* dst, void* stream);
+
+/* ---- torch.optim.Adam step on flat fp32 buffers (train_utils.py:196-206: lr, eps, weight_decay from the yaml):
+ *   g += wd*p;  m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g*g;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+ * `step` is the 1-based step count in DEVICE memory (int32, incremented by the kernel's caller via cb_adam_step's
+ * `inc_step`), so that a captured graph can be replayed every iteration; grad_scale multiplies g first (1/world). */
+int cb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                 float weight_decay, float grad_scale, int32_t* step_dev, int inc_step, void* stream);
 
 /* --------------------------------------------------------------------------------------------
  * layout helpers (tests, debugging, interop): dense NCHW float32 <-> PF / PS bf16
