@@ -56,7 +56,8 @@ class WgradDesc(C.Structure):
 class Map(C.Structure):
     _fields_ = [("n_img", C.c_int32), ("Hp", C.c_int32), ("Wp", C.c_int32), ("c_total", C.c_int32), ("c_mod", C.c_int32),
                 ("y_mode", C.c_int32), ("y_pitch", C.c_int32), ("y_ch_off", C.c_int32), ("up_k", C.c_int32),
-                ("y_Hp", C.c_int32), ("y_Wp", C.c_int32), ("y_plane_rows", C.c_int64)]
+                ("y_Hp", C.c_int32), ("y_Wp", C.c_int32), ("z_at_y", C.c_int32), ("z_pitch", C.c_int32),
+                ("y_plane_rows", C.c_int64)]
 
 
 _P, _I, _L, _F, _D = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double

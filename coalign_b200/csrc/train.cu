@@ -9,7 +9,7 @@ namespace cb {
 
 // ------------------------------------------------------------------------------------------------ helpers
 struct MapP {
-    int n_img, Hp, Wp, c_total, c_mod, y_mode, y_pitch, y_ch_off, up_k, y_Hp, y_Wp;
+    int n_img, Hp, Wp, c_total, c_mod, y_mode, y_pitch, y_ch_off, up_k, y_Hp, y_Wp, z_at_y, z_pitch;
     long y_plane_rows, rows_total;
 };
 
@@ -24,6 +24,8 @@ static int fill_map(const cb_map* m, MapP& p) {
     p.n_img = m->n_img; p.Hp = m->Hp; p.Wp = m->Wp; p.c_total = m->c_total; p.c_mod = m->c_mod; p.y_mode = m->y_mode;
     p.y_pitch = m->y_pitch; p.y_ch_off = m->y_ch_off; p.up_k = m->up_k; p.y_Hp = m->y_Hp; p.y_Wp = m->y_Wp;
     p.y_plane_rows = m->y_plane_rows;
+    p.z_at_y = m->z_at_y; p.z_pitch = m->z_pitch;
+    if (p.z_at_y && (p.z_pitch < p.c_mod || p.z_pitch % 8)) return CB_ERR_ARG;
     p.rows_total = (long)m->n_img * m->Hp * m->Wp;
     if (p.rows_total >= (1L << 31)) return CB_ERR_ARG;
     return CB_OK;
@@ -47,6 +49,13 @@ __device__ __forceinline__ long y_offset(const MapP& m, unsigned q, int col) {
     const int a = ab / m.up_k, b = ab - a * m.up_k;
     const long row = (long)((int)n * m.y_Hp + m.up_k * h + a + 1) * m.y_Wp + (m.up_k * w + b + 1);
     return row * m.y_pitch + m.y_ch_off + c;
+}
+
+// element offset of the saved forward z for (row q, column col): GEMM row space, or - z_at_y - the y position with z's pitch
+__device__ __forceinline__ long z_offset(const MapP& m, long q, int col, long yo) {
+    if (!m.z_at_y) return q * m.c_total + col;
+    const long yrow = (yo - m.y_ch_off - (col % m.c_mod)) / m.y_pitch;
+    return yrow * m.z_pitch + (col % m.c_mod);
 }
 
 // 8 bf16 (hi [+ lo plane]) -> 8 floats
@@ -230,7 +239,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(
             }
             if (has_bn) {
                 float v[8];
-                load8(z, q * m.c_total + col, z_lo_off, v);
+                load8(z, z_offset(m, q, col, yo), z_lo_off, v);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) a1[j] = fmaf(g[j], (v[j] - mu[j]) * iv[j], a1[j]);
             }
@@ -285,7 +294,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(
         if (dsum) store8(dsum, q * m.c_total + col, dsum_lo_off, g);
         if (has_bn) {
             float v[8];
-            load8(z, q * m.c_total + col, z_lo_off, v);
+            load8(z, z_offset(m, q, col, yo), z_lo_off, v);
 #pragma unroll
             for (int j = 0; j < 8; ++j) g[j] = gi[j] * (g[j] - k0[j] - (v[j] - mu[j]) * iv[j] * k1[j]);
         }

@@ -30,7 +30,7 @@ def _half_up(x: int) -> int:          # output size of a k3/s2/p1 (and k1/s2/p0)
 class Act:
     """One activation buffer in HBM.  layout 'pf' = padded flat, 'ps' = phase split (4 parity planes)."""
 
-    def __init__(self, n_cap: int, H: int, W: int, C_: int, layout: str, precise: bool, device):
+    def __init__(self, n_cap: int, H: int, W: int, C_: int, layout: str, precise: bool, device, dtype=BF16):
         self.n_cap, self.H, self.W, self.C, self.layout = n_cap, H, W, C_, layout
         if layout == "pf":
             self.Hp, self.Wp = H + 2, W + 2
@@ -41,7 +41,8 @@ class Act:
             self.plane_rows = n_cap * self.Hp * self.Wp
             self.rows = 4 * self.plane_rows
         self.precise = precise
-        self.t = torch.zeros(self.rows * (2 if precise else 1), C_, dtype=BF16, device=device)
+        # dtype other than bf16: CPU plan checks only (tests/train_plan_interpreter.py runs the plan in exact fp32)
+        self.t = torch.zeros(self.rows * (2 if precise else 1), C_, dtype=dtype, device=device)
         self.lo_off = self.rows * C_ if precise else 0                 # element offset of the lo plane
         self.lo_rows = self.rows if precise else 0
 

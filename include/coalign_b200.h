@@ -364,6 +364,9 @@ typedef struct cb_map {
     int32_t c_total, c_mod;
     int32_t y_mode;              /* CB_OUT_PF / CB_OUT_PS / CB_OUT_UPSAMPLE */
     int32_t y_pitch, y_ch_off, up_k, y_Hp, y_Wp;
+    int32_t z_at_y;              /* backward kernels only: 1 = the saved forward z is stored at the y position (pixel-shuffled
+                                    PF tensor of c_mod channels, pitch z_pitch) instead of in the GEMM's row space */
+    int32_t z_pitch;
     int64_t y_plane_rows;
 } cb_map;
 

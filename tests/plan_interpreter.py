@@ -20,7 +20,7 @@ def _f32(act):
 
 def _store(act, rows_idx, ch0, vals):
     """Write float32 `vals` [n, c] into Act rows (hi/lo split in precise mode, bf16 rounding otherwise)."""
-    hi = vals.to(torch.bfloat16)
+    hi = vals.to(act.t.dtype)
     c = vals.shape[1]
     act.t[rows_idx, ch0:ch0 + c] = hi
     if act.precise:
