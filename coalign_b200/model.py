@@ -8,8 +8,11 @@ checkpoints load with train_utils.load_saved_model), same `forward(data_dict)` i
 dict.  The forward itself runs entirely on our CUDA library - there is no PyTorch/CPU fallback:
 constructing the engine without the built library or without a B200 raises.
 
-Scope: inference / eval mode.  `.train()` forward raises NotImplementedError (training
-kernels are a later row of SURVEY 8f).
+`.eval()` forward = CoAlignEngine (eval-mode BatchNorm folded into the packed weights, one CUDA graph per batch
+signature).  `.train()` forward = coalign_b200.train_engine.TrainEngine behind a torch.autograd.Function: batch-statistics
+BatchNorm with running-stat updates, and `loss.backward()` runs our backward kernels and hands every parameter its gradient,
+so the loop body of /root/reference/opencood/tools/train.py:105-125 (zero_grad, forward, criterion, backward,
+torch.optim.Adam.step) and DistributedDataParallel's gradient hooks (train_ddp.py:104-109) work unchanged.
 """
 from __future__ import annotations
 
@@ -89,6 +92,33 @@ class _Shrink(nn.Module):                      # downsample_conv.py:30-50
             cin = d
 
 
+class _TrainStep(torch.autograd.Function):
+    """Autograd bridge of the train-mode forward: inputs are the module's parameters (so that autograd, optimizers and DDP
+    hooks see them), outputs the head maps; backward runs TrainEngine.backward and returns one gradient per parameter."""
+
+    @staticmethod
+    def forward(ctx, module, data_dict, names, *params):
+        eng = module._train_engine(data_dict)
+        pl = data_dict["processed_lidar"]
+        out = eng.forward_train(pl["voxel_features"].float(), pl["voxel_coords"], pl["voxel_num_points"],
+                                [int(v) for v in data_dict["record_len"].tolist()], data_dict["pairwise_t_matrix"])
+        ctx.eng, ctx.names, ctx.need = eng, names, [p.requires_grad for p in params]
+        ctx.head_names = list(eng.head_names)
+        for b in module.buffers():                                   # nn.BatchNorm bookkeeping (num_batches_tracked)
+            if b.dtype == torch.int64 and b.dim() == 0:
+                b += 1
+        return tuple(out[k].clone() for k in eng.head_names)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        eng = ctx.eng
+        grads = {}
+        for k, g, ref in zip(ctx.head_names, gouts, eng.head_out):
+            grads[k] = g.contiguous().float() if g is not None else torch.zeros_like(ref[:len(eng._last[0])])
+        G = eng.backward(grads)
+        return (None, None, None) + tuple(G[n].clone() if need else None for n, need in zip(ctx.names, ctx.need))
+
+
 class PointPillarCoalignB200(nn.Module):
     """core_method: point_pillar_coalign_b200 (registry rule: train_utils.py:127-146)."""
 
@@ -123,6 +153,7 @@ class PointPillarCoalignB200(nn.Module):
         self.block_n_cap = int(args.get("b200_block_n", 256))     # 256-wide tiles run on CTA pairs (the benchmarked engine)
         self._engine = None
         self._engine_key = None
+        self._train_eng = None
         if args.get("backbone_fix", False):
             self.backbone_fix()
 
@@ -138,11 +169,42 @@ class PointPillarCoalignB200(nn.Module):
 
     def invalidate(self):
         self._engine = None
+        self._train_eng = None
 
     def load_state_dict(self, *a, **k):
         r = super().load_state_dict(*a, **k)
         self.invalidate()
         return r
+
+    def _apply(self, fn, *a, **k):                   # .to() / .cuda(): parameter storage moves, engines are rebuilt
+        self.invalidate()
+        return super()._apply(fn, *a, **k)
+
+    def _train_engine(self, data_dict):
+        """TrainEngine whose flat parameter / running-stat buffers ARE the storage of this module's parameters and buffers
+        (`p.data` is re-pointed once), so optimizer updates reach the kernels without copies."""
+        from .train_engine import TrainEngine
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("PointPillarCoalignB200 runs on a B200 only: call .to('cuda') (no CPU fallback)")
+        rl = [int(v) for v in data_dict["record_len"].tolist()]
+        m = int(data_dict["processed_lidar"]["voxel_features"].shape[0])
+        e = getattr(self, "_train_eng", None)
+        if e is None or e.max_agents < sum(rl) or e.max_scenes < len(rl) or e.max_voxels_total < m or e.device != dev:
+            cap_s = max(len(rl), e.max_scenes if e is not None else 1)
+            cap_a = max(sum(rl), e.max_agents if e is not None else 1)
+            cap_v = max(m * 5 // 4, e.max_voxels_total if e is not None else 1)
+            self._train_eng = None
+            e = TrainEngine(self.args, self.state_dict(), cap_a, cap_s, device=dev, precise=self.precise,
+                            max_cav=self.max_cav, max_voxels_total=cap_v,
+                            max_pts=int(data_dict["processed_lidar"]["voxel_features"].shape[1]))
+            for name, p in self.named_parameters():
+                p.data = e.P[name]
+            for name, b in self.named_buffers():
+                if name in e.R:
+                    b.data = e.R[name]
+            self._train_eng = e
+        return e
 
     def engine(self, n_agents: int, n_scenes: int):
         from .engine import CoAlignEngine
@@ -161,15 +223,16 @@ class PointPillarCoalignB200(nn.Module):
         return self._engine
 
     def forward(self, data_dict: Dict):
-        if self.training:
-            raise NotImplementedError("coalign_b200: training-mode forward/backward is not implemented yet "
-                                      "(inference path only; see DESIGN.md)")
-        pl = data_dict["processed_lidar"]
-        record_len = [int(v) for v in data_dict["record_len"].tolist()]
         pw = data_dict["pairwise_t_matrix"]
         if pw.shape[1] != self.max_cav:
             self.max_cav = int(pw.shape[1])
             self.invalidate()
+        if self.training:
+            names, params = zip(*self.named_parameters())
+            outs = _TrainStep.apply(self, data_dict, names, *params)
+            return dict(zip(self._train_eng.head_names, outs))
+        pl = data_dict["processed_lidar"]
+        record_len = [int(v) for v in data_dict["record_len"].tolist()]
         eng = self.engine(sum(record_len), len(record_len))
         vc = pl["voxel_coords"]
         vn = pl["voxel_num_points"]

@@ -3,8 +3,10 @@ here?": no - datasets, open3d, spconv are absent - so the drop-in is demonstrate
 
   inference.py:123-143 + inference_utils.inference_intermediate_fusion:   output = model(batch['ego']);
                                                                            boxes, scores = post_processor.post_process(...)
-  train.py:105-118 (forward + criterion + logging; backward stops at the head outputs):
+  train.py:105-125 (the whole iteration, on the device):                 model.train(); model.zero_grad(); optimizer.zero_grad()
+                                                                           output = model(batch['ego'])
                                                                            loss = criterion(output, label_dict)
+                                                                           loss.backward(); optimizer.step()
 
 With the reference tree on PYTHONPATH (build container) the model and the loss are created by the reference's own
 registries from a reference yaml with only `core_method` changed; without it (GPU box) the same classes are instantiated
@@ -82,6 +84,29 @@ def main():
         gn = float(sum((v.grad ** 2).sum() for v in heads.values()) ** 0.5)
         print(f"scene {it}: cls {tuple(out['cls_preds'].shape)}, {n_box} boxes after NMS, forward + post-process {dt:.1f} ms "
               f"(first call includes graph capture), |dL/dheads| = {gn:.4f}")
+    # ---- train.py:105-125: a few iterations of the reference's loop body with torch.optim.Adam (train_utils.py:196-206)
+    model.train()
+    optimizer = torch.optim.Adam(model.parameters(), lr=2e-3, eps=1e-10, weight_decay=1e-4)
+    scene = synth.make_scene(500, opt.agents, opt.points, args["lidar_range"], pose_noise=True)
+    eng = model.engine(opt.agents, 1)
+    off = (np.arange(opt.agents + 1) * opt.points).astype(np.int32)
+    vf, vc, vn, _ = eng.voxelize(torch.from_numpy(np.concatenate(scene["points"]).astype(np.float32)).cuda(), off, 32, 32000)
+    batch = {"processed_lidar": {"voxel_features": vf, "voxel_coords": vc, "voxel_num_points": vn},
+             "record_len": torch.tensor([opt.agents]), "pairwise_t_matrix": torch.from_numpy(scene["pairwise_t_matrix"][None]).cuda()}
+    H, W = out["cls_preds"].shape[2:]
+    case = synth.loss_case(seed=9, n=1, H=H, W=W, n_pos=20)
+    label = {"pos_equal_one": torch.from_numpy(case["pos"]).cuda(), "neg_equal_one": torch.from_numpy(case["neg"]).cuda(),
+             "targets": torch.from_numpy(case["tgt"]).cuda()}
+    for it in range(4):
+        model.zero_grad()
+        optimizer.zero_grad()
+        output = model(batch)
+        loss = criterion(output, label)
+        criterion.logging(0, it, 4)
+        loss.backward()
+        optimizer.step()
+    n_grad = sum(p.grad is not None for p in model.parameters())
+    print(f"train loop: 4 iterations, {n_grad} parameters received gradients from the device backward")
     print("demo ok")
 
 
