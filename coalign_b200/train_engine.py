@@ -63,6 +63,15 @@ class TrainPack:
         self.jobs.append((src, R1, R0, K1, K0, s_r1, s_r0, s_k1, s_k0, row_off, k_off))
 
 
+class PackRows:
+    """Rows [r0, r0 + n) of a TrainPack as a GEMM weight matrix of its own (a GEMM whose N exceeds what one launch's
+    epilogue supports is split into column blocks)."""
+
+    def __init__(self, pk: TrainPack, r0: int, n: int):
+        self.w, self.bias = pk.w[r0:r0 + n], pk.bias[r0:r0 + n]
+        self.rows, self.k, self.k_total = n, pk.k, pk.k_total
+
+
 class TrainEngine(CoAlignEngine):
     """Training-mode engine.  `state_dict` provides the initial parameters and BatchNorm running statistics; afterwards the
     engine owns them in two flat fp32 buffers (`pflat`, `gflat` for the gradients, same layout, ordered in the order the
@@ -418,7 +427,12 @@ class TrainEngine(CoAlignEngine):
         fwd: List[Tuple[str, dict]] = []
         bwd: List[Tuple[str, dict]] = []
         conv = lambda d: ("conv", {"desc": d})        # noqa: E731
-        bn_ = self._bn_for
+
+        def bn_(c):                                   # widest tile that divides the GEMM's N (384 -> 128)
+            for b in (256, 128, 64, 32):
+                if b <= max(self.block_n_cap, 64) and c % b == 0:
+                    return b
+            raise ValueError(f"no tile width divides {c}")
         # ============================================================ forward
         fwd.append(("zero_fwd", {}))
         fwd.append(("pack_all", {}))
@@ -509,8 +523,10 @@ class TrainEngine(CoAlignEngine):
             bwd += self._wgrad(dzb, [xin, None], boxes, n_sc, s["cout"], s["name"] + ".weight", 9 * s["cin"])
             bwd.append(self._unpack(s["name"] + ".weight", "conv", cout=s["cout"], cin=s["cin"], taps=9))
             dx = self.d_shrink[si - 1] if si > 0 else self.d_cat
-            bwd.append(conv(self._desc([dzb, None], s["d"], self._steps_dgrad_3x3_s1(s["cout"], dzb.Wp), n_sc, dx.Hp, dx.Wp,
-                                       s["cin"], bn_(s["cin"]), s["cin"], False, dx, CB_OUT_PF)))
+            nblk = 256 if s["cin"] % 256 == 0 else 128            # the epilogue stages at most 256 bias / channel slots
+            for c0 in range(0, s["cin"], nblk):
+                bwd.append(conv(self._desc([dzb, None], PackRows(s["d"], c0, nblk), self._steps_dgrad_3x3_s1(s["cout"], dzb.Wp),
+                                           n_sc, dx.Hp, dx.Wp, nblk, bn_(nblk), nblk, False, dx, CB_OUT_PF, out_ch_off=c0)))
         for li in reversed(range(len(self.deconvs))):
             dc = self.deconvs[li]
             k, cu, cin = dc["k"], dc["cout"], dc["cin"]
