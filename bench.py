@@ -191,6 +191,90 @@ def run_reference(opt):
 
 
 # ----------------------------------------------------------------------------------------------------------
+# training step: forward + loss + backward + NCCL gradient all-reduce + Adam, all on the device
+# ----------------------------------------------------------------------------------------------------------
+TRAIN_GFLOP_PER_SCENE = 3.0 * CONV_GFLOP_PER_SCENE          # forward + dgrad + wgrad of every convolution
+
+
+def run_train(opt, args, sd, eng, batches, rank, local, world):
+    """`--train-scenes` (default 4 = the reference's batch_size, pointpillar_coalign.yaml:17) 5-agent scenes per GPU and
+    iteration through coalign_b200.trainer.Trainer: voxel tensors (reference schema, max_voxel_train 32000 per agent) resident
+    in HBM, one CUDA-graph replay per backward segment, the 51.6 MB of fp32 gradients all-reduced with NCCL in 5 buckets that
+    overlap the rest of the backward pass.  Returns the `train` object of the JSON line."""
+    import torch
+    import torch.distributed as dist
+    from coalign_b200 import dist_utils, synth
+    from coalign_b200.trainer import Trainer
+    Bt = opt.train_scenes
+    na = Bt * N_AGENTS
+    off = (np.arange(na + 1) * N_POINTS).astype(np.int32)
+    vox = []
+    for bi in range(2):
+        p_np, w_np, _ = batches[bi]
+        vf, vc, vn, _nv = eng.voxelize(torch.from_numpy(p_np[:na * N_POINTS]).cuda(), off, 32, 32000)
+        vox.append({"voxel_features": vf, "voxel_coords": vc, "voxel_num_points": vn, "record_len": [N_AGENTS] * Bt,
+                    "pairwise_t_matrix": torch.from_numpy(w_np[:Bt]).cuda()})
+    mv = max(int(v["voxel_features"].shape[0]) for v in vox)
+    H, W = 100, 352
+    case = synth.loss_case(seed=rank, n=Bt, H=H, W=W, n_pos=40)
+    labels = {"pos_equal_one": torch.from_numpy(case["pos"]).cuda(), "neg_equal_one": torch.from_numpy(case["neg"]).cuda(),
+              "targets": torch.from_numpy(case["tgt"]).cuda()}
+    res = {}
+    for mode in (["ddp", "local"] if world > 1 else ["local"]):
+        tr = Trainer(args, sd, synth.loss_args(), max_agents=na, max_scenes=Bt, max_voxels_total=mv + 1024, lr=2e-3, eps=1e-10,
+                     weight_decay=1e-4, precise=opt.precise, use_graph=True, distributed=(mode == "ddp"))
+        k = max(5, min(opt.steps, 30))
+        for i in range(4):
+            tr.step(vox[i % 2], labels)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            loss = tr.step(vox[i % 2], labels)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            ms = dist_utils.max_over_ranks(ms, device="cuda")
+            dist.barrier()
+        res[mode] = (ms / k, float(loss), k)
+        n_flat = tr.eng.n_flat
+        buckets = [b - a for a, b in tr.eng.buckets]
+        if mode == "ddp":                                   # the collective alone: all five buckets back to back
+            for _ in range(2):
+                for a, b in tr.eng.buckets:
+                    dist.all_reduce(tr.eng.gflat[a:b])
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                for a, b in tr.eng.buckets:
+                    dist.all_reduce(tr.eng.gflat[a:b])
+            e1.record()
+            torch.cuda.synchronize()
+            res["allreduce_ms"] = dist_utils.max_over_ranks(e0.elapsed_time(e1) / 5, device="cuda")
+        del tr
+        torch.cuda.empty_cache()
+    key = "ddp" if world > 1 else "local"
+    ms_step = res[key][0]
+    out = {"metric": "train_scenes_per_sec", "value": world * Bt / (ms_step * 1e-3), "unit": "scenes/s", "ms_per_step": ms_step,
+           "scenes_per_step_per_gpu": Bt, "steps": res[key][2], "loss_last": res[key][1],
+           "dtype": "bf16x3 (fp32-class)" if opt.precise else "bf16 activations / fp32 master weights, gradients and optimizer",
+           "conv_tflops": TRAIN_GFLOP_PER_SCENE * 1e9 * Bt / (ms_step * 1e-3) / 1e12,
+           "gradient_bytes": n_flat * 4, "buckets_bytes": [4 * b for b in buckets],
+           "what": "forward (train-mode BatchNorm) + cb_pointpillar_loss + backward (dgrad / wgrad on tcgen05) + NCCL all-reduce "
+                   "of the flat fp32 gradient buffer + cb_adam_step; voxel tensors resident in HBM (reference input schema)"}
+    if world > 1:
+        comm_exposed = res["ddp"][0] - res["local"][0]
+        out.update({"ms_per_step_without_allreduce": res["local"][0], "allreduce_ms_alone": res["allreduce_ms"],
+                    "allreduce_exposed_ms": comm_exposed,
+                    "overlap_fraction": max(0.0, min(1.0, 1.0 - comm_exposed / max(res["allreduce_ms"], 1e-6))),
+                    "nccl_ranks": world})
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------
 def run_ours(opt):
@@ -479,6 +563,11 @@ def run_ours(opt):
                        "inference.py:125-143; the voxel tensors are 75x the bytes of the raw clouds"}
         del model
 
+    # ---- the training iteration (every rank: the all-reduce is a collective)
+    train = None
+    if not opt.no_train and not opt.precise:
+        train = run_train(opt, args, sd, eng, batches, rank, local, world)
+
     # ---- CPU baseline beside it (rank 0, N=1 only): one scene through the reference's CPU path; its head maps are also
     # the parity check of THIS run's GPU output for the same scene (the benchmarked configuration itself)
     cpu, parity = None, None
@@ -518,7 +607,7 @@ def run_ours(opt):
                            "H2D, forward and D2H of neighbouring steps overlap on 3 streams)"},
             "gpu_launches": launches_per_step * opt.steps,
             "clocks": clocks, "roofline": roof, "roofline_hbm": hbm_roofs, "cpu_baseline": cpu, "parity": parity,
-            "postprocess": post, "e2e_varying_clouds": vary, "plugin_api": plug,
+            "postprocess": post, "e2e_varying_clouds": vary, "plugin_api": plug, "train": train,
         }
         sys.stdout.flush()
         print(json.dumps(line), flush=True)
@@ -540,6 +629,8 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the varying-cloud-size and plugin-API measurements")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-iteration measurement (`train` object)")
+    ap.add_argument("--train-scenes", type=int, default=4, help="scenes per GPU per training iteration (reference batch_size 4)")
     ap.add_argument("--no-pair", action="store_true", help="single-CTA conv kernel instead of CTA pairs")
     opt = ap.parse_args()
     if opt.warmup < 3 and opt.impl == "ours":

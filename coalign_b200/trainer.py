@@ -24,6 +24,19 @@ from . import _lib
 from .train_engine import TrainEngine
 
 
+def allreduce_buckets(flat: torch.Tensor, buckets: Sequence, upto: Optional[int] = None, start: int = 0, async_op: bool = True):
+    """All-reduce (sum) the slices buckets[start:upto] of the flat gradient buffer, in order; returns the work handles.
+    Bucket i holds the gradients the i-th backward segment completes, so calling this right after enqueueing segment i
+    overlaps the collective with segments i+1.. (the role of DistributedDataParallel's reducer, train_ddp.py:104-109)."""
+    import torch.distributed as dist
+    works = []
+    for a, b in buckets[start:upto]:
+        w = dist.all_reduce(flat[a:b], async_op=async_op)
+        if async_op:
+            works.append(w)
+    return works
+
+
 class Trainer:
     def __init__(self, args: dict, state_dict: Dict[str, torch.Tensor], loss_args: dict, max_agents: int, max_scenes: int,
                  max_voxels_total: int = 0, lr: float = 2e-3, eps: float = 1e-10, weight_decay: float = 1e-4,
@@ -154,9 +167,7 @@ class Trainer:
             else:
                 g["fns"][i]()
             if self.distributed and i < len(e.buckets):
-                import torch.distributed as dist
-                a, b = e.buckets[i]
-                works.append(dist.all_reduce(e.gflat[a:b], async_op=True))
+                works += allreduce_buckets(e.gflat, e.buckets, upto=i + 1, start=i)
         for w in works:
             w.wait()                                   # stream-level wait: the optimizer runs after the collectives
         self._adam()
