@@ -11,6 +11,8 @@ LIB_PATH = os.path.join(HERE, "lib", "libcoalign_b200.so")
 CB_MAX_KSTEPS = 168
 CB_MAX_AGENTS = 64
 CB_OUT_PF, CB_OUT_PS, CB_OUT_UPSAMPLE, CB_OUT_HEADS = 0, 1, 2, 3
+(CB_OPT_NO_PDL, CB_OPT_EPI_DIRECT, CB_OPT_TMA_STORE, CB_OPT_HALO_BO, CB_OPT_FUSE_VERSION, CB_OPT_FUSE_BLEND_FP32,
+ CB_OPT_FUSE_OCC3, CB_OPT_CONV_DEBUG) = range(8)
 
 
 class KStep(C.Structure):
@@ -81,6 +83,8 @@ EXPORTS = {
     "cb_permute_f32": (C.c_int, [_P, _I, _I, _I, _I, _L, _L, _L, _L, _F, _P, _P]),
     "cb_adam_step": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _P, _I, _P]),
     "cb_version": (C.c_int, []),
+    "cb_set_option": (C.c_int, [C.c_int, C.c_int]),
+    "cb_get_option": (C.c_int, [C.c_int]),
     "cb_device_check": (C.c_int, []),
     "cb_voxelize_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "cb_voxelize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,

@@ -282,11 +282,12 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 }  // namespace cb
 
 namespace cb {
-// Host: launch `kernel` with the PDL attribute (falls back to a plain launch when disabled via CB_NO_PDL=1).
+int opt_get(int option);        // option table (layout.cu), see cb_set_option in include/coalign_b200.h
+// Host: launch `kernel` with the PDL attribute (plain launch when CB_OPT_NO_PDL is set).
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                               Args&&... args) {
-    static const bool enabled = [] { const char* e = getenv("CB_NO_PDL"); return !(e && e[0] == '1'); }();
+    const bool enabled = opt_get(0 /* CB_OPT_NO_PDL */) == 0;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];

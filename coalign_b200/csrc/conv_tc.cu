@@ -1047,10 +1047,7 @@ static int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t col
     return r == CUDA_SUCCESS ? CB_OK : CB_ERR_DRIVER;
 }
 
-static int dbg_flags() {
-    const char* e = getenv("CB_DEBUG");
-    return e ? atoi(e) : 0;
-}
+static int dbg_flags() { return cb::opt_get(CB_OPT_CONV_DEBUG); }
 
 template <int BN, int KPS, int ST>
 static int launch_st(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& tout,
@@ -1161,9 +1158,9 @@ static int build_halo_items(const cb_conv_desc* d, cb::HaloItems& items) {
 }
 
 // Direct epilogue (two 256-bit stores per thread and 32-column chunk instead of the shared-memory transposition):
-// bf16 outputs whose rows and channel offsets keep every 64-byte chunk 32-byte aligned.  CB_EPI_DIRECT=0 disables it.
+// bf16 outputs whose rows and channel offsets keep every 64-byte chunk 32-byte aligned.  cb_set_option(CB_OPT_EPI_DIRECT, 0) disables it.
 static bool epi_direct_ok(const cb_conv_desc* d) {
-    static const bool enabled = [] { const char* e = getenv("CB_EPI_DIRECT"); return !(e && e[0] == '0'); }();
+    const bool enabled = cb::opt_get(CB_OPT_EPI_DIRECT) != 0;
     return enabled && d->out_mode != CB_OUT_HEADS && d->out_lo_off == 0 && d->res_lo_off == 0 && d->out_pitch % 16 == 0 &&
            d->out_ch_off % 16 == 0 && ((uintptr_t)d->out % 32) == 0 && d->block_n >= 64;
 }
@@ -1200,8 +1197,8 @@ static int conv_gemm_impl(const cb_conv_desc* d, int max_ctas, void* stream, boo
     int use_tma = 0;
     {
         // TMA-store epilogue: measured slower than the transposed 64-byte STG path on the residual layers (BN=64: 127 vs
-        // 107 us) and equal elsewhere (profiles/r1_exp_halo.txt), so it is opt-in (CB_TMA_STORE=1)
-        static const bool no_tma_store = [] { const char* e = getenv("CB_TMA_STORE"); return !(e && e[0] == '1'); }();
+        // 107 us) and equal elsewhere (profiles/r1_exp_halo.txt), so it is opt-in (CB_OPT_TMA_STORE)
+        const bool no_tma_store = cb::opt_get(CB_OPT_TMA_STORE) == 0;
         if (!no_tma_store && d->out_mode == CB_OUT_PF && d->out_lo_off == 0 && d->res_lo_off == 0 && d->block_n >= 64 &&
             !(dbg_flags() & 7)) {
             rc = make_tmap(&tout, d->out, p.rows_total, d->out_pitch, d->out_pitch, BM, d->block_n >= 128 ? 64 : 32);
@@ -1313,7 +1310,7 @@ extern "C" int cb_conv_gemm_halo(const cb_conv_desc* d, int max_ctas, void* stre
     if (rc) return rc;
     CUtensorMap tout = tw;
     int use_tma = 0;
-    static const bool no_tma_store = [] { const char* e = getenv("CB_TMA_STORE"); return !(e && e[0] == '1'); }();
+    const bool no_tma_store = cb::opt_get(CB_OPT_TMA_STORE) == 0;
     if (d->out_mode == CB_OUT_PF && !no_tma_store) {
         rc = make_tmap(&tout, d->out, p.rows_total, d->out_pitch, d->out_pitch, BM, 32);
         if (rc) return rc;
@@ -1334,8 +1331,7 @@ extern "C" int cb_conv_gemm_halo(const cb_conv_desc* d, int max_ctas, void* stre
     const int cap = max_ctas > 0 ? max_ctas : sms;
     if (grid > cap) grid = cap;
     if (!use_tma && epi_direct_ok(d)) use_tma = 2;
-    const char* e = getenv("CB_HALO_BO");
-    const int bo_mode = e ? atoi(e) : 0;
+    const int bo_mode = cb::opt_get(CB_OPT_HALO_BO);
     cudaError_t le = launch_pdl(conv_gemm_halo64_kernel, dim3(grid), dim3(TC_THREADS), Halo64Cfg::SMEM_BYTES,
                                 (cudaStream_t)stream, ta0, ta1, tw, tout, p, items, m_tiles, bo_mode, use_tma);
     return le == cudaSuccess ? CB_OK : (int)le;
@@ -1390,8 +1386,7 @@ extern "C" int cb_conv_gemm_t_halo(const cb_conv_desc* d, int max_ctas, void* st
     int grid = m_tiles;
     const int cap = max_ctas > 0 ? max_ctas : sms;
     if (grid > cap) grid = cap;
-    const char* e = getenv("CB_HALO_BO");
-    const int bo_mode = e ? atoi(e) : 0;
+    const int bo_mode = cb::opt_get(CB_OPT_HALO_BO);
     cudaError_t le = launch_pdl(conv_gemm_tct_halo_kernel, dim3(grid), dim3(TC_THREADS), TctHaloCfg::SMEM_BYTES,
                                 (cudaStream_t)stream, ta0, ta1, ta0t, ta1t, tw, p, items, m_tiles, bo_mode);
     return le == cudaSuccess ? CB_OK : (int)le;

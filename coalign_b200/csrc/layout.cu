@@ -108,3 +108,25 @@ extern "C" int cb_layout_to_nchw(const void* src, int64_t lo_off, int from_ps, i
     CB_CHECK_LAUNCH();
     return CB_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// option table (include/coalign_b200.h: cb_set_option)
+// ---------------------------------------------------------------------------------------------------------------
+#include <atomic>
+namespace cb {
+static std::atomic<int> g_opts[CB_OPT_COUNT] = {{0}, {1}, {0}, {0}, {9}, {0}, {0}, {0}};
+int opt_get(int option) {
+    if (option < 0 || option >= CB_OPT_COUNT) return 0;
+    return g_opts[option].load(std::memory_order_relaxed);
+}
+}  // namespace cb
+
+extern "C" int cb_set_option(int option, int value) {
+    if (option < 0 || option >= CB_OPT_COUNT) return CB_ERR_ARG;
+    return cb::g_opts[option].exchange(value, std::memory_order_relaxed);
+}
+extern "C" int cb_get_option(int option) {
+    if (option < 0 || option >= CB_OPT_COUNT) return CB_ERR_ARG;
+    return cb::opt_get(option);
+}

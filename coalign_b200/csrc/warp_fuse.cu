@@ -583,7 +583,7 @@ extern "C" int cb_warp_att_fuse(const void* feat, int in_ps, int64_t in_lo_off, 
     cudaStream_t st = (cudaStream_t)stream;
     const __nv_bfloat16* f = (const __nv_bfloat16*)feat;
     __nv_bfloat16* o = (__nv_bfloat16*)out_pf;
-    if (C == 64 || C == 128 || C == 256) {
+    if ((C == 64 || C == 128 || C == 256) && opt_get(CB_OPT_FUSE_VERSION) >= 8) {
         const int ppw = 256 / C;                                    // pixels per warp
         long nb = (total + 8L * ppw - 1) / (8L * ppw);
         if (nb > 148 * 24) nb = 148 * 24;
@@ -594,11 +594,11 @@ extern "C" int cb_warp_att_fuse(const void* feat, int in_ps, int64_t in_lo_off, 
                        f, (long)in_lo_off, affine, agent_off, n_scenes, max_cav, g, method, o, (long)out_lo_off); \
         else launch_pdl(warp_att_fuse_v8_kernel<LPP_, MAXN_, false>, dim3((unsigned)nb), dim3(256), 0, st, \
                        f, (long)in_lo_off, affine, agent_off, n_scenes, max_cav, g, method, o, (long)out_lo_off); } while (0)
-        static const int fuse_ver = [] { const char* e = getenv("CB_FUSE_V"); return e ? atoi(e) : 9; }();
-        // bf16 maps (no lo plane): blend the bilinear taps with packed bf16 FMAs; CB_FUSE_BLEND=32 keeps the fp32 blend
-        static const bool bf16_blend = [] { const char* e = getenv("CB_FUSE_BLEND"); return !(e && atoi(e) == 32); }();
-        // 64 registers / 4 CTAs per SM (two taps in flight at a time) measured 4 % faster than 80 / 3; CB_FUSE_OCC=3 selects the latter
-        static const bool occ4 = [] { const char* e = getenv("CB_FUSE_OCC"); return !(e && atoi(e) == 3); }();
+        const int fuse_ver = opt_get(CB_OPT_FUSE_VERSION);
+        // bf16 maps (no lo plane): blend the bilinear taps with packed bf16 FMAs; CB_OPT_FUSE_BLEND_FP32 keeps the fp32 blend
+        const bool bf16_blend = opt_get(CB_OPT_FUSE_BLEND_FP32) == 0;
+        // 64 registers / 4 CTAs per SM (two taps in flight at a time) measured 4 % faster than 80 / 3 (CB_OPT_FUSE_OCC3)
+        const bool occ4 = opt_get(CB_OPT_FUSE_OCC3) == 0;
         const bool small = max_cav <= 5;
         // v9 indexes tap rows by 32-bit BYTE offsets and needs 32-byte aligned buffers
         const bool v9_ok = fuse_ver >= 9 && (long)sum_agents * g.Hp * g.Wp * (in_ps ? 4 : 1) * (long)(2 * C) < (1L << 32) &&

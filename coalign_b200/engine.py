@@ -100,7 +100,8 @@ class CoAlignEngine:
     def __init__(self, args: dict, state_dict: Dict[str, torch.Tensor], max_agents: int, max_scenes: int,
                  device="cuda", precise: bool = False, max_cav: int = 5, block_n_cap: int = 128,
                  use_graph: bool = True, simt_conv: bool = False, pair: bool = True, plan_only: bool = False,
-                 backbone: str = "resnet", fusion: bool = True):
+                 backbone: str = "resnet", fusion: bool = True, chan_major: bool = True, pair_min_bn: int = 256,
+                 halo: bool = True):
         # backbone "resnet": ResNetBEVBackbone (CoAlign); "plain": BaseBEVBackbone conv stacks (single-agent point_pillar,
         # /root/reference/opencood/models/sub_modules/base_bev_backbone.py).  fusion=False: every agent is its own
         # scene and the per-level maps go straight to the deblocks (point_pillar.py:52-84).
@@ -116,9 +117,9 @@ class CoAlignEngine:
         self.use_graph = use_graph
         self.simt_conv = simt_conv            # validation only: evaluate the descriptors with the SIMT kernel
         self.pair = pair                      # CTA-pair (cta_group::2) conv kernel ...
-        self.chan_major = os.environ.get('CB_CHAN_MAJOR', '1') != '0'      # Cout=128 layers: channel-major 128x256 tiles
-        self.pair_min_bn = int(os.environ.get('CB_PAIR_MIN_BN', '256'))   # ... for tiles at least this wide (measured)
-        self.halo = os.environ.get('CB_HALO', '1') != '0'                 # halo-box kernels for the Cout=64/128 layers
+        self.chan_major = bool(chan_major)                                # Cout=128 layers: channel-major 128x256 tiles
+        self.pair_min_bn = int(pair_min_bn)                               # ... for tiles at least this wide (measured)
+        self.halo = bool(halo)                                            # halo-box kernels for the Cout=64/128 layers
         nx, ny, nz = [int(v) for v in args["point_pillar_scatter"]["grid_size"]]
         if nz != 1:
             raise ValueError("PointPillarScatter requires nz == 1")

@@ -7,8 +7,9 @@
  *   - returns 0 on success, a positive cudaError_t, or a negative CB_ERR_* argument/driver error;
  *   - never allocates and never synchronises: the caller owns inputs, outputs and workspaces,
  *     all work is enqueued on `stream` (CUDA-graph capturable);
- *   - no global state except the lazily resolved cuTensorMapEncodeTiled entry point and
- *     per-kernel shared-memory attributes (idempotent, thread-safe).
+ *   - no hidden global state: the lazily resolved cuTensorMapEncodeTiled entry point, per-kernel shared-memory
+ *     attributes (idempotent, thread-safe) and the explicit option table below (cb_set_option; no environment variables
+ *     are read anywhere in the library).
  *
  * Activation layouts (bf16, channels innermost):
  *   PF  "padded flat": [n][H+2][W+2][C]; the 1-pixel halo is zero and is never written.
@@ -38,6 +39,22 @@ extern "C" {
  * cb_version / cb_device_check
  * ------------------------------------------------------------------------------------------ */
 int cb_version(void);
+/* Process-wide kernel-selection options (development / validation switches; defaults = the measured-best product path).
+ * Explicit calls replace the environment variables of round 1.  Set them before launching; they are read at launch time
+ * (atomic loads), so changing one between launches is well defined, changing one DURING stream capture is not. */
+enum {
+    CB_OPT_NO_PDL = 0,        /* 1: launch without programmatic dependent launch                         (default 0) */
+    CB_OPT_EPI_DIRECT = 1,    /* conv epilogue: 1 = two 256-bit stores per thread where alignment allows (default 1) */
+    CB_OPT_TMA_STORE = 2,     /* conv epilogue: 1 = TMA store for PF outputs (measured slower on residual layers; default 0) */
+    CB_OPT_HALO_BO = 3,       /* halo kernels: UMMA descriptor base-offset mode experiment               (default 0) */
+    CB_OPT_FUSE_VERSION = 4,  /* fusion kernel: 9 = tiled v9 (default), 8 = v8, 1 = first version          */
+    CB_OPT_FUSE_BLEND_FP32 = 5, /* 1: fp32 tap blend in bf16 mode instead of packed bf16 FMAs             (default 0) */
+    CB_OPT_FUSE_OCC3 = 6,     /* 1: 3 CTAs/SM variant of v9 instead of 4                                  (default 0) */
+    CB_OPT_CONV_DEBUG = 7,    /* conv kernel experiment flags (profiles/r1_conv_analysis.md)              (default 0) */
+    CB_OPT_COUNT = 8
+};
+int cb_set_option(int option, int value);     /* returns the previous value, or CB error (< 0) for an unknown option */
+int cb_get_option(int option);
 /* 0 when the current device is sm_100 (B200); negative otherwise.  The Python side raises - there is
  * no CPU or generic-GPU fallback. */
 int cb_device_check(void);

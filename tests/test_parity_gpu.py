@@ -244,11 +244,25 @@ def test_voxelize_bit_exact_and_fused_path():
             assert np.array_equal(c1, c2), (max_pts, max_vox, rep, np.abs(c1 - c2).max(), (c1 != c2).sum())
 
 
-def test_warp_fuse_op_golden():
-    """A11/A12 op-level: fused warp+attention kernel vs the reference's AttFusion/MaxFusion on 64-channel maps."""
+@pytest.mark.parametrize("version", [9, 8, 1])
+def test_warp_fuse_op_golden(version):
+    """A11/A12 op-level: fused warp+attention kernel vs the reference's AttFusion/MaxFusion on 64-channel maps - the tiled
+    v9 kernel (product path) and the two earlier kernels it falls back to (v8: buffers that are not 32-byte aligned or
+    too large for 32-bit byte offsets; v1: channel counts other than 64/128/256), selected through cb_set_option."""
     from coalign_b200 import _lib
     from oracle import coalign_oracle as O
     lib = _lib.load(True)
+    prev = lib.cb_set_option(_lib.CB_OPT_FUSE_VERSION, version)
+    try:
+        _warp_fuse_op_case(lib)
+    finally:
+        lib.cb_set_option(_lib.CB_OPT_FUSE_VERSION, prev)
+    assert lib.cb_get_option(_lib.CB_OPT_FUSE_VERSION) == prev
+
+
+def _warp_fuse_op_case(lib):
+    from coalign_b200 import _lib
+    from oracle import coalign_oracle as O
     g = torch.Generator().manual_seed(3)
     H, W, Cc = 9, 14, 64
     x = torch.randn(5, Cc, H, W, generator=g)
