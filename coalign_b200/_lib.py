@@ -70,8 +70,9 @@ EXPORTS = {
     "cb_bn_stats": (C.c_int, [_P, _L, C.POINTER(Map), _P, _P]),
     "cb_bn_finalize": (C.c_int, [_P, _I, _D, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "cb_bn_apply": (C.c_int, [_P, _L, _P, _P, _P, _L, _P, _P, _P, C.c_int32, _L, _I, C.POINTER(Map), _P, _L, _P]),
-    "cb_bn_bwd_reduce": (C.c_int, [_P, _L, _P, _L, _I, _P, _L, _P, _P, C.POINTER(Map), _P, _P]),
-    "cb_bn_bwd_apply": (C.c_int, [_P, _L, _P, _L, _I, _P, _L, _P, _P, _P, _P, _D, C.POINTER(Map), _P, _L, _P, _L, _P, _P, _P]),
+    "cb_bn_bwd_reduce": (C.c_int, [_P, _L, _P, _L, _I, _P, _L, _P, _P, _P, _P, C.POINTER(Map), _P, _P]),
+    "cb_bn_bwd_apply": (C.c_int, [_P, _L, _P, _L, _I, _P, _L, _P, _P, _P, _P, _P, _P, _D, C.POINTER(Map), _P, _L, _P, _L, _P,
+                                  _P, _P]),
     "cb_heads_grad_pack": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _L, _P, _P]),
     "cb_warp_att_fuse_bwd": (C.c_int, [_P, _I, _L, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _L, _P, _P]),
     "cb_grad_combine": (C.c_int, [_P, _P, _L, _I, _I, _I, _I, _I, _I, _P, _L, _P]),

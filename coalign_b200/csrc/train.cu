@@ -51,13 +51,6 @@ __device__ __forceinline__ long y_offset(const MapP& m, unsigned q, int col) {
     return row * m.y_pitch + m.y_ch_off + c;
 }
 
-// element offset of the saved forward z for (row q, column col): GEMM row space, or - z_at_y - the y position with z's pitch
-__device__ __forceinline__ long z_offset(const MapP& m, long q, int col, long yo) {
-    if (!m.z_at_y) return q * m.c_total + col;
-    const long yrow = (yo - m.y_ch_off - (col % m.c_mod)) / m.y_pitch;
-    return yrow * m.z_pitch + (col % m.c_mod);
-}
-
 // 8 bf16 (hi [+ lo plane]) -> 8 floats
 __device__ __forceinline__ void load8(const __nv_bfloat16* base, long off, long lo_off, float (&v)[8]) {
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + off));
@@ -83,7 +76,7 @@ __device__ __forceinline__ void store8(__nv_bfloat16* base, long off, long lo_of
 }
 
 constexpr int EW_THREADS = 256;
-constexpr int EW_BLOCKS = 148 * 4;
+constexpr int EW_BLOCKS = 148 * 6;
 
 // Per-block reduction of per-thread partial sums (8 channels each, two quantities) into fp64 global sums.
 // s_acc: [2][256] floats of shared memory (zeroed here); channel of element j of this thread = cbase + j.
@@ -103,7 +96,8 @@ __device__ __forceinline__ void block_reduce_to_global(float (&a0)[8], float (&a
     }
 }
 
-// Thread layout shared by the row-wise kernels: a thread owns one 8-channel chunk (fixed) and walks rows.
+// Thread layout shared by the row-wise kernels: a thread owns one 8-channel chunk (fixed) and walks rows with a
+// division-free cursor (n, hp, wp advance by the decomposed row step); two rows are in flight per iteration.
 struct RowWalk { int chunk, cpr, row0, row_step; };
 __device__ __forceinline__ RowWalk row_walk(int c_total) {
     RowWalk r;
@@ -115,6 +109,45 @@ __device__ __forceinline__ RowWalk row_walk(int c_total) {
     r.row_step = gridDim.x * rpi;
     return r;
 }
+struct ColInfo { int col, cb, a, b; };                       // column, channel (col % c_mod), sub-pixel of CB_OUT_UPSAMPLE
+__device__ __forceinline__ ColInfo col_info(const MapP& m, int col) {
+    ColInfo c;
+    c.col = col; c.cb = col % m.c_mod; c.a = c.b = 0;
+    if (m.y_mode == CB_OUT_UPSAMPLE) { const int ab = col / m.c_mod; c.a = ab / m.up_k; c.b = ab - c.a * m.up_k; }
+    return c;
+}
+struct RowCur { long q; int n, hp, wp, dn, dh, dw, step; };
+__device__ __forceinline__ RowCur cur_init(const MapP& m, int q0, int step) {
+    RowCur c;
+    const int plane = m.Hp * m.Wp;
+    c.q = q0; c.step = step;
+    c.n = q0 / plane; int rem = q0 - c.n * plane; c.hp = rem / m.Wp; c.wp = rem - c.hp * m.Wp;
+    c.dn = step / plane; rem = step - c.dn * plane; c.dh = rem / m.Wp; c.dw = rem - c.dh * m.Wp;
+    return c;
+}
+__device__ __forceinline__ void cur_next(const MapP& m, RowCur& c) {
+    c.q += c.step;
+    c.wp += c.dw; if (c.wp >= m.Wp) { c.wp -= m.Wp; ++c.hp; }
+    c.hp += c.dh; if (c.hp >= m.Hp) { c.hp -= m.Hp; ++c.n; }
+    c.n += c.dn;
+}
+// y-side element offset of the cursor's row for this thread's 8 channels; -1 = halo row or past the end
+__device__ __forceinline__ long y_off_cur(const MapP& m, const RowCur& c, const ColInfo& ci) {
+    if (c.q >= m.rows_total || c.hp < 1 || c.hp > m.Hp - 2 || c.wp < 1 || c.wp > m.Wp - 2) return -1;
+    const int h = c.hp - 1, w = c.wp - 1;
+    if (m.y_mode == CB_OUT_PF) return c.q * m.y_pitch + m.y_ch_off + ci.col;
+    if (m.y_mode == CB_OUT_PS) {
+        const int ph = (h & 1) * 2 + (w & 1);
+        const long row = (long)ph * m.y_plane_rows + (long)(c.n * m.y_Hp + (h >> 1) + 1) * m.y_Wp + (w >> 1) + 1;
+        return row * m.y_pitch + m.y_ch_off + ci.col;
+    }
+    const long row = (long)(c.n * m.y_Hp + m.up_k * h + ci.a + 1) * m.y_Wp + (m.up_k * w + ci.b + 1);
+    return row * m.y_pitch + m.y_ch_off + ci.cb;
+}
+__device__ __forceinline__ long z_off_cur(const MapP& m, const RowCur& c, const ColInfo& ci, long yo) {
+    if (!m.z_at_y) return c.q * m.c_total + ci.col;
+    return (yo - m.y_ch_off - ci.cb) / m.y_pitch * m.z_pitch + ci.cb;
+}
 
 // ------------------------------------------------------------------------------------------------ BatchNorm forward
 __global__ void __launch_bounds__(EW_THREADS) bn_stats_kernel(const __nv_bfloat16* __restrict__ z, long z_lo_off,
@@ -123,18 +156,20 @@ __global__ void __launch_bounds__(EW_THREADS) bn_stats_kernel(const __nv_bfloat1
     pdl_launch_dependents();
     pdl_wait();
     const RowWalk rw = row_walk(m.c_total);
-    const int col = rw.chunk * 8;
+    const ColInfo ci = col_info(m, rw.chunk * 8);
     float a0[8] = {}, a1[8] = {};
     if (rw.row0 >= 0) {
-        for (long q = rw.row0; q < m.rows_total; q += rw.row_step) {
-            if (y_offset(m, (unsigned)q, col) < 0) continue;             // halo rows hold zeros, but skip the loads
-            float v[8];
-            load8(z, q * m.c_total + col, z_lo_off, v);
+        RowCur c0 = cur_init(m, rw.row0, 2 * rw.row_step), c1 = cur_init(m, rw.row0 + rw.row_step, 2 * rw.row_step);
+        for (; c0.q < m.rows_total; cur_next(m, c0), cur_next(m, c1)) {
+            const bool k0 = y_off_cur(m, c0, ci) >= 0, k1 = y_off_cur(m, c1, ci) >= 0;   // halo rows hold zeros: skip the loads
+            float v[8] = {}, u[8] = {};
+            if (k0) load8(z, c0.q * m.c_total + ci.col, z_lo_off, v);
+            if (k1) load8(z, c1.q * m.c_total + ci.col, z_lo_off, u);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { a0[j] += v[j]; a1[j] = fmaf(v[j], v[j], a1[j]); }
+            for (int j = 0; j < 8; ++j) { a0[j] += v[j] + u[j]; a1[j] = fmaf(v[j], v[j], fmaf(u[j], u[j], a1[j])); }
         }
     }
-    block_reduce_to_global(a0, a1, col % m.c_mod, m.c_mod, true, s_acc, sums);
+    block_reduce_to_global(a0, a1, ci.cb, m.c_mod, true, s_acc, sums);
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, int c, double count, float eps, float momentum,
@@ -176,84 +211,106 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(
     pdl_wait();
     const RowWalk rw = row_walk(m.c_total);
     if (rw.row0 < 0) return;
-    const int col = rw.chunk * 8, cb_ = col % m.c_mod;
+    const ColInfo ci = col_info(m, rw.chunk * 8);
+    const int col = ci.col;
     float sc[8], sh[8], scb[8], shb[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        sc[j] = scale[cb_ + j]; sh[j] = shift[cb_ + j];
-        scb[j] = zb ? scale_b[cb_ + j] : 0.f; shb[j] = zb ? shift_b[cb_ + j] : 0.f;
+        sc[j] = scale[ci.cb + j]; sh[j] = shift[ci.cb + j];
+        scb[j] = zb ? scale_b[ci.cb + j] : 0.f; shb[j] = zb ? shift_b[ci.cb + j] : 0.f;
     }
-    for (long q = rw.row0; q < m.rows_total; q += rw.row_step) {
-        const long yo = y_offset(m, (unsigned)q, col);
-        if (yo < 0) continue;
-        float v[8];
-        load8(z, q * m.c_total + col, z_lo_off, v);
+    RowCur c[2] = {cur_init(m, rw.row0, 2 * rw.row_step), cur_init(m, rw.row0 + rw.row_step, 2 * rw.row_step)};
+    for (; c[0].q < m.rows_total; cur_next(m, c[0]), cur_next(m, c[1])) {
+        long yo[2];
+        float v[2][8], ub[2][8], ur[2][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
-        if (zb) {
-            float u[8];
-            load8(zb, q * m.c_total + col, zb_lo_off, u);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += fmaf(u[j], scb[j], shb[j]);
+        for (int r = 0; r < 2; ++r) {
+            yo[r] = y_off_cur(m, c[r], ci);
+            if (yo[r] >= 0) {
+                load8(z, c[r].q * m.c_total + col, z_lo_off, v[r]);
+                if (zb) load8(zb, c[r].q * m.c_total + col, zb_lo_off, ub[r]);
+                if (res) load8(res, c[r].q * (long)res_pitch + col, res_lo_off, ur[r]);
+            }
         }
-        if (res) {
-            float u[8];
-            load8(res, q * (long)res_pitch + col, res_lo_off, u);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += u[j];
-        }
-        if (relu) {
+        for (int r = 0; r < 2; ++r) {
+            if (yo[r] < 0) continue;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+            for (int j = 0; j < 8; ++j) {
+                float t = fmaf(v[r][j], sc[j], sh[j]);
+                if (zb) t += fmaf(ub[r][j], scb[j], shb[j]);
+                if (res) t += ur[r][j];
+                v[r][j] = relu ? fmaxf(t, 0.f) : t;
+            }
+            store8(y, yo[r], y_lo_off, v[r]);
         }
-        store8(y, yo, y_lo_off, v);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ BatchNorm backward
+// ReLU mask: from y (the stored activation) or - mask_scale != NULL, the plain conv + BN + ReLU case - recomputed from the z
+// that is loaded anyway (sign of z*scale + shift), which saves one tensor read in both backward passes.
 __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(
     const __nv_bfloat16* __restrict__ dy, long dy_lo_off, const __nv_bfloat16* __restrict__ y, long y_lo_off, int relu,
     const __nv_bfloat16* __restrict__ z, long z_lo_off, const float* __restrict__ mean, const float* __restrict__ inv_std,
-    const MapP m, double* __restrict__ sums) {
+    const float* __restrict__ mask_scale, const float* __restrict__ mask_shift, const MapP m, double* __restrict__ sums) {
     __shared__ float s_acc[2 * 256];
     pdl_launch_dependents();
     pdl_wait();
+    __shared__ float s_mu[256], s_ms[256], s_mh[256];
     const RowWalk rw = row_walk(m.c_total);
-    const int col = rw.chunk * 8, cb_ = col % m.c_mod;
+    const ColInfo ci = col_info(m, rw.chunk * 8);
     const bool has_bn = mean != nullptr;
-    float mu[8], iv[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { mu[j] = has_bn ? mean[cb_ + j] : 0.f; iv[j] = has_bn ? inv_std[cb_ + j] : 0.f; }
+    const bool zmask = relu && mask_scale != nullptr && has_bn;
+    for (int c = threadIdx.x; c < m.c_mod; c += EW_THREADS) {
+        s_mu[c] = has_bn ? mean[c] : 0.f;
+        s_ms[c] = zmask ? mask_scale[c] : 0.f;
+        s_mh[c] = zmask ? mask_shift[c] : 0.f;
+    }
+    __syncthreads();
+    const float* mu = s_mu + ci.cb;
+    const float* ms = s_ms + ci.cb;
+    const float* mh = s_mh + ci.cb;
     float a0[8] = {}, a1[8] = {};
     if (rw.row0 >= 0) {
-        for (long q = rw.row0; q < m.rows_total; q += rw.row_step) {
-            const long yo = y_offset(m, (unsigned)q, col);
-            if (yo < 0) continue;
-            float g[8];
-            load8(dy, yo, dy_lo_off, g);
-            if (relu) {
-                float yv[8];
-                load8(y, yo, y_lo_off, yv);
+        RowCur c[2] = {cur_init(m, rw.row0, 2 * rw.row_step), cur_init(m, rw.row0 + rw.row_step, 2 * rw.row_step)};
+        for (; c[0].q < m.rows_total; cur_next(m, c[0]), cur_next(m, c[1])) {
+            long yo[2];
+            float g[2][8], yv[2][8], v[2][8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
-            }
-            if (has_bn) {
-                float v[8];
-                load8(z, z_offset(m, q, col, yo), z_lo_off, v);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) a1[j] = fmaf(g[j], (v[j] - mu[j]) * iv[j], a1[j]);
+            for (int r = 0; r < 2; ++r) {
+                yo[r] = y_off_cur(m, c[r], ci);
+                if (yo[r] >= 0) {
+                    load8(dy, yo[r], dy_lo_off, g[r]);
+                    if (relu && !zmask) load8(y, yo[r], y_lo_off, yv[r]);
+                    if (has_bn) load8(z, z_off_cur(m, c[r], ci, yo[r]), z_lo_off, v[r]);
+                }
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) a0[j] += g[j];
+            for (int r = 0; r < 2; ++r) {
+                if (yo[r] < 0) continue;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float gj = g[r][j];
+                    if (relu) gj = (zmask ? fmaf(v[r][j], ms[j], mh[j]) : yv[r][j]) > 0.f ? gj : 0.f;
+                    a0[j] += gj;
+                    if (has_bn) a1[j] = fmaf(gj, v[r][j] - mu[j], a1[j]);       // x_hat = (z - mean) * inv_std: scaled below
+                }
+            }
         }
     }
-    block_reduce_to_global(a0, a1, cb_, m.c_mod, has_bn, s_acc, sums);
+    if (has_bn) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a1[j] *= inv_std[ci.cb + j];
+    }
+    block_reduce_to_global(a0, a1, ci.cb, m.c_mod, has_bn, s_acc, sums);
 }
 
 __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(
     const __nv_bfloat16* __restrict__ dy, long dy_lo_off, const __nv_bfloat16* __restrict__ y, long y_lo_off, int relu,
     const __nv_bfloat16* __restrict__ z, long z_lo_off, const float* __restrict__ mean, const float* __restrict__ inv_std,
-    const float* __restrict__ gamma, const double* __restrict__ sums, double count, const MapP m,
+    const float* __restrict__ gamma, const float* __restrict__ mask_scale, const float* __restrict__ mask_shift,
+    const double* __restrict__ sums, double count, const MapP m,
     __nv_bfloat16* __restrict__ dz, long dz_lo_off, __nv_bfloat16* __restrict__ dsum, long dsum_lo_off,
     float* __restrict__ d_gamma, float* __restrict__ d_beta) {
     pdl_launch_dependents();
@@ -265,40 +322,59 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(
             if (d_gamma && has_bn) d_gamma[c] = (float)sums[m.c_mod + c];
         }
     }
+    // dz = gamma*inv * (g - s0/n - (z - mean)*inv * s1/n) = A*g + B*z + C per channel
+    __shared__ float s_A[256], s_B[256], s_C[256], s_ms[256], s_mh[256];
+    const bool zmask = relu && mask_scale != nullptr && has_bn;
+    for (int c = threadIdx.x; c < m.c_mod; c += EW_THREADS) {
+        float A = 1.f, B = 0.f, Cc = 0.f;
+        if (has_bn) {
+            const double iv = (double)inv_std[c], gi = (double)gamma[c] * iv;
+            const double k0 = sums[c] / count, k1 = sums[m.c_mod + c] / count;
+            A = (float)gi;
+            B = (float)(-gi * iv * k1);
+            Cc = (float)(-gi * k0 + gi * iv * k1 * (double)mean[c]);
+        }
+        s_A[c] = A; s_B[c] = B; s_C[c] = Cc;
+        s_ms[c] = zmask ? mask_scale[c] : 0.f;
+        s_mh[c] = zmask ? mask_shift[c] : 0.f;
+    }
+    __syncthreads();
     const RowWalk rw = row_walk(m.c_total);
     if (rw.row0 < 0) return;
-    const int col = rw.chunk * 8, cb_ = col % m.c_mod;
-    float mu[8], iv[8], gi[8], k0[8], k1[8];
+    const ColInfo ci = col_info(m, rw.chunk * 8);
+    const int col = ci.col;
+    const float* cA = s_A + ci.cb;
+    const float* cB = s_B + ci.cb;
+    const float* cC = s_C + ci.cb;
+    const float* ms = s_ms + ci.cb;
+    const float* mh = s_mh + ci.cb;
+    RowCur c[2] = {cur_init(m, rw.row0, 2 * rw.row_step), cur_init(m, rw.row0 + rw.row_step, 2 * rw.row_step)};
+    for (; c[0].q < m.rows_total; cur_next(m, c[0]), cur_next(m, c[1])) {
+        long yo[2];
+        float g[2][8], yv[2][8], v[2][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        if (has_bn) {
-            mu[j] = mean[cb_ + j]; iv[j] = inv_std[cb_ + j];
-            gi[j] = gamma[cb_ + j] * iv[j];
-            k0[j] = (float)(sums[cb_ + j] / count);
-            k1[j] = (float)(sums[m.c_mod + cb_ + j] / count);
-        } else {
-            mu[j] = iv[j] = k0[j] = k1[j] = 0.f; gi[j] = 1.f;
+        for (int r = 0; r < 2; ++r) {
+            yo[r] = y_off_cur(m, c[r], ci);
+            if (yo[r] >= 0) {
+                load8(dy, yo[r], dy_lo_off, g[r]);
+                if (relu && !zmask) load8(y, yo[r], y_lo_off, yv[r]);
+                if (has_bn) load8(z, z_off_cur(m, c[r], ci, yo[r]), z_lo_off, v[r]);
+            }
         }
-    }
-    for (long q = rw.row0; q < m.rows_total; q += rw.row_step) {
-        const long yo = y_offset(m, (unsigned)q, col);
-        if (yo < 0) continue;
-        float g[8];
-        load8(dy, yo, dy_lo_off, g);
-        if (relu) {
-            float yv[8];
-            load8(y, yo, y_lo_off, yv);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
-        }
-        if (dsum) store8(dsum, q * m.c_total + col, dsum_lo_off, g);
-        if (has_bn) {
-            float v[8];
-            load8(z, z_offset(m, q, col, yo), z_lo_off, v);
+        for (int r = 0; r < 2; ++r) {
+            if (yo[r] < 0) continue;
+            if (relu) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) g[j] = gi[j] * (g[j] - k0[j] - (v[j] - mu[j]) * iv[j] * k1[j]);
+                for (int j = 0; j < 8; ++j) g[r][j] = (zmask ? fmaf(v[r][j], ms[j], mh[j]) : yv[r][j]) > 0.f ? g[r][j] : 0.f;
+            }
+            if (dsum) store8(dsum, c[r].q * m.c_total + col, dsum_lo_off, g[r]);
+            if (has_bn) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) g[r][j] = fmaf(cA[j], g[r][j], fmaf(cB[j], v[r][j], cC[j]));
+            }
+            store8(dz, c[r].q * m.c_total + col, dz_lo_off, g[r]);
         }
-        store8(dz, q * m.c_total + col, dz_lo_off, g);
     }
 }
 
@@ -890,31 +966,37 @@ extern "C" int cb_bn_apply(const void* z, int64_t z_lo_off, const float* scale, 
 }
 
 extern "C" int cb_bn_bwd_reduce(const void* dy, int64_t dy_lo_off, const void* y, int64_t y_lo_off, int relu, const void* z,
-                                int64_t z_lo_off, const float* mean, const float* inv_std, const cb_map* map, double* sums,
-                                void* stream) {
+                                int64_t z_lo_off, const float* mean, const float* inv_std, const float* mask_scale,
+                                const float* mask_shift, const cb_map* map, double* sums, void* stream) {
     MapP m;
     int rc = fill_map(map, m);
     if (rc) return rc;
-    if (!dy || !sums || (relu && !y) || (mean && (!z || !inv_std))) return CB_ERR_ARG;
+    const bool zmask = mask_scale && mask_shift && mean;
+    if (!zmask) mask_scale = mask_shift = nullptr;
+    if (!dy || !sums || (relu && !y && !zmask) || (mean && (!z || !inv_std))) return CB_ERR_ARG;
     const int rpi = EW_THREADS / (m.c_total >> 3);
     cudaError_t e = launch_pdl(bn_bwd_reduce_kernel, dim3(ew_grid((m.rows_total + rpi - 1) / rpi * EW_THREADS / 4)),
                                dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(dy), (long)dy_lo_off, BF(y), (long)y_lo_off, relu,
-                               BF(z), (long)z_lo_off, mean, inv_std, m, sums);
+                               BF(z), (long)z_lo_off, mean, inv_std, mask_scale, mask_shift, m, sums);
     return e == cudaSuccess ? CB_OK : (int)e;
 }
 
 extern "C" int cb_bn_bwd_apply(const void* dy, int64_t dy_lo_off, const void* y, int64_t y_lo_off, int relu, const void* z,
                                int64_t z_lo_off, const float* mean, const float* inv_std, const float* gamma,
+                               const float* mask_scale, const float* mask_shift,
                                const double* sums, double count, const cb_map* map, void* dz, int64_t dz_lo_off,
                                void* dsum_pf, int64_t dsum_lo_off, float* d_gamma, float* d_beta, void* stream) {
     MapP m;
     int rc = fill_map(map, m);
     if (rc) return rc;
-    if (!dy || !dz || !sums || (relu && !y) || (mean && (!z || !inv_std || !gamma || count <= 0))) return CB_ERR_ARG;
+    const bool zmask = mask_scale && mask_shift && mean;
+    if (!zmask) mask_scale = mask_shift = nullptr;
+    if (!dy || !dz || !sums || (relu && !y && !zmask) || (mean && (!z || !inv_std || !gamma || count <= 0))) return CB_ERR_ARG;
     const int rpi = EW_THREADS / (m.c_total >> 3);
     cudaError_t e = launch_pdl(bn_bwd_apply_kernel, dim3(ew_grid((m.rows_total + rpi - 1) / rpi * EW_THREADS / 2)),
                                dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(dy), (long)dy_lo_off, BF(y), (long)y_lo_off, relu,
-                               BF(z), (long)z_lo_off, mean, inv_std, gamma, sums, count, m, BFW(dz), (long)dz_lo_off,
+                               BF(z), (long)z_lo_off, mean, inv_std, gamma, mask_scale, mask_shift, sums, count, m, BFW(dz),
+                               (long)dz_lo_off,
                                BFW(dsum_pf), (long)dsum_lo_off, d_gamma, d_beta);
     return e == cudaSuccess ? CB_OK : (int)e;
 }

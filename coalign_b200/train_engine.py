@@ -532,7 +532,7 @@ class TrainEngine(CoAlignEngine):
             k, cu, cin = dc["k"], dc["cout"], dc["cin"]
             f, dfu = self.lvl[li]["fused"], self.lvl[li]["d_fused"]
             bwd.append(("bn_bwd", {"bn": dc["bn"], "has_bn": True, "dy": self.d_cat, "y": self.cat, "relu": 1, "z": dc["zu"],
-                                   "map": dc["map"], "count": float(n_sc * H0 * W0), "dz": dc["dzu"], "dsum": None,
+                                   "map": dc["map"], "count": float(n_sc * H0 * W0), "dz": dc["dzu"], "dsum": None, "zmask": True,
                                    "d_gamma": self.G[dc["bn"] + ".weight"], "d_beta": self.G[dc["bn"] + ".bias"]}))
             bwd += self._wgrad(dc["dzu"], [f, None], [(0, 0, cb * 64, cb * 64) for cb in range(cin // 64)], n_sc, k * k * cu,
                                dc["name"], cin)
@@ -574,7 +574,7 @@ class TrainEngine(CoAlignEngine):
                                            cout, bn_(cout), cout, False, d_o1, CB_OUT_PF)))
                 # o1 = relu(bn1(z1))
                 bwd.append(("bn_bwd", {"bn": p + ".bn1", "has_bn": True, "dy": d_o1, "y": B["o1"], "relu": 1, "z": B["z1"],
-                                       "map": B["m1"], "count": cnt, "dz": dz, "dsum": None,
+                                       "map": B["m1"], "count": cnt, "dz": dz, "dsum": None, "zmask": True,
                                        "d_gamma": self.G[p + ".bn1.weight"], "d_beta": self.G[p + ".bn1.bias"]}))
                 if blk["stride"] == 2:
                     taps = self._s2_taps()
@@ -660,11 +660,15 @@ class TrainEngine(CoAlignEngine):
                 sums = self.redv(o["bn"], 1).data_ptr()
                 mean = self.bnv(o["bn"], 2).data_ptr() if hb else None
                 inv = self.bnv(o["bn"], 3).data_ptr() if hb else None
+                zm = bool(o.get("zmask")) and hb               # y = relu(bn(z)) with nothing added: mask from z
+                msc = self.bnv(o["bn"], 0).data_ptr() if zm else None
+                msh = self.bnv(o["bn"], 1).data_ptr() if zm else None
                 ck(lib.cb_bn_bwd_reduce(dy.ptr, dy.lo_off, y.ptr, y.lo_off, o["relu"], z.ptr if hb else None,
-                                        z.lo_off if hb else 0, mean, inv, C.byref(o["map"]), sums, sp), "cb_bn_bwd_reduce")
+                                        z.lo_off if hb else 0, mean, inv, msc, msh, C.byref(o["map"]), sums, sp),
+                   "cb_bn_bwd_reduce")
                 ck(lib.cb_bn_bwd_apply(dy.ptr, dy.lo_off, y.ptr, y.lo_off, o["relu"], z.ptr if hb else None,
                                        z.lo_off if hb else 0, mean, inv,
-                                       self.P[o["bn"] + ".weight"].data_ptr() if hb else None, sums, o["count"],
+                                       self.P[o["bn"] + ".weight"].data_ptr() if hb else None, msc, msh, sums, o["count"],
                                        C.byref(o["map"]), dz.ptr, dz.lo_off, dsum.ptr if dsum is not None else None,
                                        dsum.lo_off if dsum is not None else 0,
                                        o["d_gamma"].data_ptr() if o["d_gamma"] is not None else None,

@@ -402,15 +402,19 @@ int cb_bn_apply(const void* z, int64_t z_lo_off, const float* scale, const float
                 const void* residual, int32_t res_pitch, int64_t res_lo_off, int relu,
                 const cb_map* map, void* y, int64_t y_lo_off, void* stream);
 /* dyr = dy * (y > 0 if relu);  sums[0..c) += sum dyr, sums[c..2c) += sum dyr * x_hat, x_hat = (z - mean) * inv_std
- * (mean == NULL: no BatchNorm, only the first half = bias gradient). */
+ * (mean == NULL: no BatchNorm, only the first half = bias gradient).  mask_scale / mask_shift non-NULL (plain
+ * conv + BN + ReLU, i.e. y = relu(z*scale + shift) with nothing added): the ReLU mask is recomputed from z instead of
+ * reading y - one tensor read less in each of the two backward passes. */
 int cb_bn_bwd_reduce(const void* dy, int64_t dy_lo_off, const void* y, int64_t y_lo_off, int relu,
                      const void* z, int64_t z_lo_off, const float* mean, const float* inv_std,
+                     const float* mask_scale, const float* mask_shift,
                      const cb_map* map, double* sums, void* stream);
 /* dz = gamma*inv_std * (dyr - sums[c]/count - x_hat * sums[c_mod + c]/count)  (no BatchNorm: dz = dyr), bf16 PF in z's
  * row space, interior rows only (halo rows stay zero).  Also writes d_gamma / d_beta (fp32 [c_mod]) when non-NULL, and
  * dsum_pf = dyr as bf16 PF (pitch c_total) when non-NULL (the identity branch of a residual block). */
 int cb_bn_bwd_apply(const void* dy, int64_t dy_lo_off, const void* y, int64_t y_lo_off, int relu,
                     const void* z, int64_t z_lo_off, const float* mean, const float* inv_std, const float* gamma,
+                    const float* mask_scale, const float* mask_shift,
                     const double* sums, double count, const cb_map* map,
                     void* dz, int64_t dz_lo_off, void* dsum_pf, int64_t dsum_lo_off,
                     float* d_gamma, float* d_beta, void* stream);

@@ -135,11 +135,11 @@ def test_train_mode_batchnorm_forward_backward_pf():
     dyp = pf_from_nchw(dy)
     bs = torch.zeros(2 * c, dtype=torch.float64, device="cuda")
     _lib.check(L.cb_bn_bwd_reduce(dyp.data_ptr(), 0, y.data_ptr(), 0, 1, zp.data_ptr(), 0, mean.data_ptr(), inv.data_ptr(),
-                                  C.byref(m), bs.data_ptr(), sp()))
+                                  None, None, C.byref(m), bs.data_ptr(), sp()))
     dz, dsum = torch.zeros_like(zp), torch.zeros_like(zp)
     dg, db = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
     _lib.check(L.cb_bn_bwd_apply(dyp.data_ptr(), 0, y.data_ptr(), 0, 1, zp.data_ptr(), 0, mean.data_ptr(), inv.data_ptr(),
-                                 gamma.data_ptr(), bs.data_ptr(), float(n * H * W), C.byref(m), dz.data_ptr(), 0,
+                                 gamma.data_ptr(), None, None, bs.data_ptr(), float(n * H * W), C.byref(m), dz.data_ptr(), 0,
                                  dsum.data_ptr(), 0, dg.data_ptr(), db.data_ptr(), sp()))
     mask = (got > 0).float()
     torch.cuda.synchronize()
