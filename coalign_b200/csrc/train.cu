@@ -7,6 +7,10 @@
 
 namespace cb {
 
+// Programmatic dependent launch: these kernels run several waves of CTAs, so they do NOT trigger their dependents early
+// (CTAs of the next kernel would occupy SM slots spinning in griddepcontrol.wait while later waves of this one still need
+// them); griddepcontrol.wait is kept so that they may follow a kernel that does trigger early (the GEMM kernels).
+
 // ------------------------------------------------------------------------------------------------ helpers
 struct MapP {
     int n_img, Hp, Wp, c_total, c_mod, y_mode, y_pitch, y_ch_off, up_k, y_Hp, y_Wp, z_at_y, z_pitch;
@@ -79,20 +83,33 @@ constexpr int EW_THREADS = 256;
 constexpr int EW_BLOCKS = 148 * 6;
 
 // Per-block reduction of per-thread partial sums (8 channels each, two quantities) into fp64 global sums.
-// s_acc: [2][256] floats of shared memory (zeroed here); channel of element j of this thread = cbase + j.
-__device__ __forceinline__ void block_reduce_to_global(float (&a0)[8], float (&a1)[8], int cbase, int c_mod, bool two,
-                                                       float* s_acc, double* sums) {
-    for (int i = threadIdx.x; i < 2 * 256; i += EW_THREADS) s_acc[i] = 0.f;
+// s_part: [2][2048] floats of shared memory; slot of element j of this thread = tslot*8 + j with tslot = threadIdx.x
+// (256 threads x 8 channels).  Thread c < c_mod then adds up every slot whose channel is c (fixed order: deterministic per
+// block) and issues ONE fp64 atomic per quantity.  (Shared-memory float atomics compile to CAS spin loops on sm_100.)
+__device__ __forceinline__ void block_reduce_to_global(float (&a0)[8], float (&a1)[8], int c_total, int c_mod, bool two,
+                                                       float* s_part, double* sums) {
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        atomicAdd(&s_acc[cbase + j], a0[j]);
-        if (two) atomicAdd(&s_acc[256 + cbase + j], a1[j]);
+        s_part[threadIdx.x * 8 + j] = a0[j];
+        if (two) s_part[2048 + threadIdx.x * 8 + j] = a1[j];
     }
     __syncthreads();
+    // thread t owns chunk (t % cpr) -> columns [8*(t%cpr), +8); channel = column % c_mod
+    const int cpr = c_total >> 3;
+    const int rpi = EW_THREADS / cpr;                                 // row lanes per block (threads >= rpi*cpr hold zeros)
     for (int c = threadIdx.x; c < c_mod; c += EW_THREADS) {
-        atomicAdd(sums + c, (double)s_acc[c]);
-        if (two) atomicAdd(sums + c_mod + c, (double)s_acc[256 + c]);
+        float t0 = 0.f, t1 = 0.f;
+        for (int col = c; col < c_total; col += c_mod) {
+            const int chunk = col >> 3, j = col & 7;
+            for (int rl = 0; rl < rpi; ++rl) {
+                const int t = rl * cpr + chunk;
+                t0 += s_part[t * 8 + j];
+                if (two) t1 += s_part[2048 + t * 8 + j];
+            }
+        }
+        atomicAdd(sums + c, (double)t0);
+        if (two) atomicAdd(sums + c_mod + c, (double)t1);
     }
 }
 
@@ -152,24 +169,31 @@ __device__ __forceinline__ long z_off_cur(const MapP& m, const RowCur& c, const 
 // ------------------------------------------------------------------------------------------------ BatchNorm forward
 __global__ void __launch_bounds__(EW_THREADS) bn_stats_kernel(const __nv_bfloat16* __restrict__ z, long z_lo_off,
                                                               const MapP m, double* __restrict__ sums) {
-    __shared__ float s_acc[2 * 256];
-    pdl_launch_dependents();
+    __shared__ float s_part[2 * 2048];
     pdl_wait();
     const RowWalk rw = row_walk(m.c_total);
     const ColInfo ci = col_info(m, rw.chunk * 8);
     float a0[8] = {}, a1[8] = {};
     if (rw.row0 >= 0) {
-        RowCur c0 = cur_init(m, rw.row0, 2 * rw.row_step), c1 = cur_init(m, rw.row0 + rw.row_step, 2 * rw.row_step);
-        for (; c0.q < m.rows_total; cur_next(m, c0), cur_next(m, c1)) {
-            const bool k0 = y_off_cur(m, c0, ci) >= 0, k1 = y_off_cur(m, c1, ci) >= 0;   // halo rows hold zeros: skip the loads
-            float v[8] = {}, u[8] = {};
-            if (k0) load8(z, c0.q * m.c_total + ci.col, z_lo_off, v);
-            if (k1) load8(z, c1.q * m.c_total + ci.col, z_lo_off, u);
+        // four rows in flight per thread; loads are unconditional (rows past the end re-read row 0 and are masked out; halo
+        // rows hold zeros), so that the four 16-byte loads issue back to back
+        RowCur c[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { a0[j] += v[j] + u[j]; a1[j] = fmaf(v[j], v[j], fmaf(u[j], u[j], a1[j])); }
+        for (int r = 0; r < 4; ++r) c[r] = cur_init(m, rw.row0 + r * rw.row_step, 4 * rw.row_step);
+        for (; c[0].q < m.rows_total;) {
+            float v[4][8];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) load8(z, (c[r].q < m.rows_total ? c[r].q : 0) * m.c_total + ci.col, z_lo_off, v[r]);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float k = (c[r].q < m.rows_total && y_off_cur(m, c[r], ci) >= 0) ? 1.f : 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const float t = v[r][j] * k; a0[j] += t; a1[j] = fmaf(t, t, a1[j]); }
+                cur_next(m, c[r]);
+            }
         }
     }
-    block_reduce_to_global(a0, a1, ci.cb, m.c_mod, true, s_acc, sums);
+    block_reduce_to_global(a0, a1, m.c_total, m.c_mod, true, s_part, sums);
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, int c, double count, float eps, float momentum,
@@ -177,7 +201,6 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int c, doubl
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
                                    float* __restrict__ inv_out) {
-    pdl_launch_dependents();
     pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c) return;
@@ -207,7 +230,6 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(
     const __nv_bfloat16* __restrict__ zb, long zb_lo_off, const float* __restrict__ scale_b, const float* __restrict__ shift_b,
     const __nv_bfloat16* __restrict__ res, int res_pitch, long res_lo_off, int relu, const MapP m,
     __nv_bfloat16* __restrict__ y, long y_lo_off) {
-    pdl_launch_dependents();
     pdl_wait();
     const RowWalk rw = row_walk(m.c_total);
     if (rw.row0 < 0) return;
@@ -224,13 +246,12 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(
         long yo[2];
         float v[2][8], ub[2][8], ur[2][8];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < 2; ++r) {                                            // unconditional loads (row 0 for dead rows)
             yo[r] = y_off_cur(m, c[r], ci);
-            if (yo[r] >= 0) {
-                load8(z, c[r].q * m.c_total + col, z_lo_off, v[r]);
-                if (zb) load8(zb, c[r].q * m.c_total + col, zb_lo_off, ub[r]);
-                if (res) load8(res, c[r].q * (long)res_pitch + col, res_lo_off, ur[r]);
-            }
+            const long qz = yo[r] >= 0 ? c[r].q : 0;
+            load8(z, qz * m.c_total + col, z_lo_off, v[r]);
+            if (zb) load8(zb, qz * m.c_total + col, zb_lo_off, ub[r]);
+            if (res) load8(res, qz * (long)res_pitch + col, res_lo_off, ur[r]);
         }
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
@@ -254,8 +275,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(
     const __nv_bfloat16* __restrict__ dy, long dy_lo_off, const __nv_bfloat16* __restrict__ y, long y_lo_off, int relu,
     const __nv_bfloat16* __restrict__ z, long z_lo_off, const float* __restrict__ mean, const float* __restrict__ inv_std,
     const float* __restrict__ mask_scale, const float* __restrict__ mask_shift, const MapP m, double* __restrict__ sums) {
-    __shared__ float s_acc[2 * 256];
-    pdl_launch_dependents();
+    __shared__ float s_part[2 * 2048];
     pdl_wait();
     __shared__ float s_mu[256], s_ms[256], s_mh[256];
     const RowWalk rw = row_walk(m.c_total);
@@ -278,20 +298,19 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(
             long yo[2];
             float g[2][8], yv[2][8], v[2][8];
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
+            for (int r = 0; r < 2; ++r) {                                        // unconditional loads (masked below)
                 yo[r] = y_off_cur(m, c[r], ci);
-                if (yo[r] >= 0) {
-                    load8(dy, yo[r], dy_lo_off, g[r]);
-                    if (relu && !zmask) load8(y, yo[r], y_lo_off, yv[r]);
-                    if (has_bn) load8(z, z_off_cur(m, c[r], ci, yo[r]), z_lo_off, v[r]);
-                }
+                const long yl = yo[r] >= 0 ? yo[r] : (long)(m.y_ch_off + ci.cb);
+                load8(dy, yl, dy_lo_off, g[r]);
+                if (relu && !zmask) load8(y, yl, y_lo_off, yv[r]);
+                if (has_bn) load8(z, yo[r] >= 0 ? z_off_cur(m, c[r], ci, yo[r]) : (long)ci.cb, z_lo_off, v[r]);
             }
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
-                if (yo[r] < 0) continue;
+                const bool live = yo[r] >= 0;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    float gj = g[r][j];
+                    float gj = live ? g[r][j] : 0.f;
                     if (relu) gj = (zmask ? fmaf(v[r][j], ms[j], mh[j]) : yv[r][j]) > 0.f ? gj : 0.f;
                     a0[j] += gj;
                     if (has_bn) a1[j] = fmaf(gj, v[r][j] - mu[j], a1[j]);       // x_hat = (z - mean) * inv_std: scaled below
@@ -303,7 +322,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(
 #pragma unroll
         for (int j = 0; j < 8; ++j) a1[j] *= inv_std[ci.cb + j];
     }
-    block_reduce_to_global(a0, a1, ci.cb, m.c_mod, has_bn, s_acc, sums);
+    block_reduce_to_global(a0, a1, m.c_total, m.c_mod, has_bn, s_part, sums);
 }
 
 __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(
@@ -313,7 +332,6 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(
     const double* __restrict__ sums, double count, const MapP m,
     __nv_bfloat16* __restrict__ dz, long dz_lo_off, __nv_bfloat16* __restrict__ dsum, long dsum_lo_off,
     float* __restrict__ d_gamma, float* __restrict__ d_beta) {
-    pdl_launch_dependents();
     pdl_wait();
     const bool has_bn = mean != nullptr;
     if (blockIdx.x == 0) {
@@ -353,13 +371,12 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(
         long yo[2];
         float g[2][8], yv[2][8], v[2][8];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < 2; ++r) {                                            // unconditional loads
             yo[r] = y_off_cur(m, c[r], ci);
-            if (yo[r] >= 0) {
-                load8(dy, yo[r], dy_lo_off, g[r]);
-                if (relu && !zmask) load8(y, yo[r], y_lo_off, yv[r]);
-                if (has_bn) load8(z, z_off_cur(m, c[r], ci, yo[r]), z_lo_off, v[r]);
-            }
+            const long yl = yo[r] >= 0 ? yo[r] : (long)(m.y_ch_off + ci.cb);
+            load8(dy, yl, dy_lo_off, g[r]);
+            if (relu && !zmask) load8(y, yl, y_lo_off, yv[r]);
+            if (has_bn) load8(z, yo[r] >= 0 ? z_off_cur(m, c[r], ci, yo[r]) : (long)ci.cb, z_lo_off, v[r]);
         }
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
@@ -385,7 +402,6 @@ __global__ void __launch_bounds__(256) heads_grad_pack_kernel(const HeadsP hd, i
                                                               __nv_bfloat16* __restrict__ out, long lo_off,
                                                               float* __restrict__ d_bias) {
     __shared__ float s_b[64];
-    pdl_launch_dependents();
     pdl_wait();
     if (threadIdx.x < 64) s_b[threadIdx.x] = 0.f;
     __syncthreads();
@@ -455,7 +471,6 @@ __global__ void __launch_bounds__(256) warp_att_fuse_bwd_kernel(
     const __nv_bfloat16* __restrict__ feat, long in_lo_off, const double* __restrict__ affine,
     const int* __restrict__ agent_off, int n_scenes, int L, const FuseBG g, int method,
     const __nv_bfloat16* __restrict__ dfused, long dfused_lo_off, float* __restrict__ dfeat) {
-    pdl_launch_dependents();
     pdl_wait();
     constexpr int PPW = 32 / LPP;
     const int lane = threadIdx.x & 31;
@@ -586,7 +601,6 @@ __global__ void __launch_bounds__(256) warp_att_fuse_bwd_kernel(
 __global__ void __launch_bounds__(256) grad_combine_kernel(const float* __restrict__ acc, const __nv_bfloat16* __restrict__ addend,
                                                            long addend_lo_off, int to_ps, int n_cap, int n, int H, int W, int C,
                                                            __nv_bfloat16* __restrict__ out, long out_lo_off) {
-    pdl_launch_dependents();
     pdl_wait();
     const int cpr = C >> 3;
     const long total = (long)n * H * W * cpr;
@@ -652,7 +666,6 @@ __global__ void __launch_bounds__(256) pfn_train_stats_kernel(const float4* __re
                                                               double* __restrict__ sums) {
     __shared__ float s_f[8][32][10];
     __shared__ double s_red[PFN_NQ];
-    pdl_launch_dependents();
     pdl_wait();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     int n_rows = n_voxels_dev ? *n_voxels_dev : n_rows_cap;
@@ -714,7 +727,6 @@ __global__ void pfn_train_finalize_kernel(const double* __restrict__ sums, const
                                           float* __restrict__ running_mean, float* __restrict__ running_var,
                                           float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
                                           float* __restrict__ inv_out) {
-    pdl_launch_dependents();
     pdl_wait();
     const int c = threadIdx.x;
     if (c >= 64) return;
@@ -758,7 +770,6 @@ __global__ void __launch_bounds__(256) pfn_bwd_kernel(const float4* __restrict__
                                                       double* __restrict__ bsum) {
     __shared__ float s_f[8][32][10];
     __shared__ double s_red[64 * 12];
-    pdl_launch_dependents();
     pdl_wait();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     int n_rows = n_voxels_dev ? *n_voxels_dev : n_rows_cap;
@@ -845,7 +856,6 @@ __global__ void pfn_bwd_finalize_kernel(const double* __restrict__ st, const dou
                                         const float* __restrict__ w, const float* __restrict__ gamma,
                                         const float* __restrict__ mean, const float* __restrict__ inv_std,
                                         float* __restrict__ d_w, float* __restrict__ d_gamma, float* __restrict__ d_beta) {
-    pdl_launch_dependents();
     pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 640) return;
@@ -867,7 +877,6 @@ __global__ void pfn_bwd_finalize_kernel(const double* __restrict__ st, const dou
 __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ src, int R0, int K0, long rows, int K,
                                                           long s_r1, long s_r0, long s_k1, long s_k0,
                                                           __nv_bfloat16* __restrict__ dst, int dst_ld, int k_off, int lo_col_off) {
-    pdl_launch_dependents();
     pdl_wait();
     const long total = rows * K;
     for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
@@ -885,7 +894,6 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
 __global__ void __launch_bounds__(256) permute_f32_kernel(const float* __restrict__ src, int R0, int K0, long rows, int K,
                                                           long s_r1, long s_r0, long s_k1, long s_k0, float alpha,
                                                           float* __restrict__ dst) {
-    pdl_launch_dependents();
     pdl_wait();
     const long total = rows * K;
     for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
@@ -901,7 +909,6 @@ __global__ void __launch_bounds__(256) permute_f32_kernel(const float* __restric
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, long n, float lr, float b1, float b2, float eps,
                                                    float wd, float gscale, const int* __restrict__ step_dev) {
-    pdl_launch_dependents();
     pdl_wait();
     const int step = *step_dev;
     const float bc1 = 1.f - powf(b1, (float)step);
