@@ -166,8 +166,29 @@ __device__ __forceinline__ long z_off_cur(const MapP& m, const RowCur& c, const 
     return (yo - m.y_ch_off - ci.cb) / m.y_pitch * m.z_pitch + ci.cb;
 }
 
-// ------------------------------------------------------------------------------------------------ BatchNorm forward
-__global__ void __launch_bounds__(EW_THREADS) bn_stats_kernel(const __nv_bfloat16* __restrict__ z, long z_lo_off,
+// ------------------------------------------------------------------------------------------------ BatchNorm kernels
+// All four are latency-bound streaming kernels: at 100-130 registers only 16 warps fit on an SM, so every thread keeps R
+// rows x up to 3 tensors of 16-byte loads in flight (raw bf16 words, converted only when consumed): ~50-100 KB per SM, what
+// HBM3e needs to stay busy (ncu of the first version: 16 KB in flight, 1.9 TB/s).  Loads are unconditional - rows past the
+// end or halo rows re-read a valid dummy row and are masked - so that they issue back to back.
+template <bool LO> struct Raw8 { uint4 hi, lo; };
+template <bool LO>
+__device__ __forceinline__ void ld_raw(const __nv_bfloat16* base, long off, long lo_off, Raw8<LO>& r) {
+    r.hi = __ldg(reinterpret_cast<const uint4*>(base + off));
+    if (LO) r.lo = __ldg(reinterpret_cast<const uint4*>(base + lo_off + off));
+}
+template <bool LO>
+__device__ __forceinline__ void cvt_raw(const Raw8<LO>& r, float (&v)[8]) {
+    v[0] = bf16_lo(r.hi.x); v[1] = bf16_hi(r.hi.x); v[2] = bf16_lo(r.hi.y); v[3] = bf16_hi(r.hi.y);
+    v[4] = bf16_lo(r.hi.z); v[5] = bf16_hi(r.hi.z); v[6] = bf16_lo(r.hi.w); v[7] = bf16_hi(r.hi.w);
+    if (LO) {
+        v[0] += bf16_lo(r.lo.x); v[1] += bf16_hi(r.lo.x); v[2] += bf16_lo(r.lo.y); v[3] += bf16_hi(r.lo.y);
+        v[4] += bf16_lo(r.lo.z); v[5] += bf16_hi(r.lo.z); v[6] += bf16_lo(r.lo.w); v[7] += bf16_hi(r.lo.w);
+    }
+}
+
+template <int R, bool LO>
+__global__ void __launch_bounds__(EW_THREADS, 2) bn_stats_kernel(const __nv_bfloat16* __restrict__ z, long z_lo_off,
                                                               const MapP m, double* __restrict__ sums) {
     __shared__ float s_part[2 * 2048];
     pdl_wait();
@@ -175,20 +196,20 @@ __global__ void __launch_bounds__(EW_THREADS) bn_stats_kernel(const __nv_bfloat1
     const ColInfo ci = col_info(m, rw.chunk * 8);
     float a0[8] = {}, a1[8] = {};
     if (rw.row0 >= 0) {
-        // four rows in flight per thread; loads are unconditional (rows past the end re-read row 0 and are masked out; halo
-        // rows hold zeros), so that the four 16-byte loads issue back to back
-        RowCur c[4];
+        RowCur c[R];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) c[r] = cur_init(m, rw.row0 + r * rw.row_step, 4 * rw.row_step);
-        for (; c[0].q < m.rows_total;) {
-            float v[4][8];
+        for (int r = 0; r < R; ++r) c[r] = cur_init(m, rw.row0 + r * rw.row_step, R * rw.row_step);
+        while (c[0].q < m.rows_total) {
+            Raw8<LO> raw[R];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) load8(z, (c[r].q < m.rows_total ? c[r].q : 0) * m.c_total + ci.col, z_lo_off, v[r]);
+            for (int r = 0; r < R; ++r) ld_raw<LO>(z, (c[r].q < m.rows_total ? c[r].q : 0) * m.c_total + ci.col, z_lo_off, raw[r]);
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const float k = (c[r].q < m.rows_total && y_off_cur(m, c[r], ci) >= 0) ? 1.f : 0.f;
+            for (int r = 0; r < R; ++r) {
+                const float k = y_off_cur(m, c[r], ci) >= 0 ? 1.f : 0.f;             // halo rows hold zeros anyway
+                float v[8];
+                cvt_raw<LO>(raw[r], v);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { const float t = v[r][j] * k; a0[j] += t; a1[j] = fmaf(t, t, a1[j]); }
+                for (int j = 0; j < 8; ++j) { const float t = v[j] * k; a0[j] += t; a1[j] = fmaf(t, t, a1[j]); }
                 cur_next(m, c[r]);
             }
         }
@@ -225,63 +246,84 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int c, doubl
     }
 }
 
-__global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(
+template <int R, bool LO>
+__global__ void __launch_bounds__(EW_THREADS, 2) bn_apply_kernel(
     const __nv_bfloat16* __restrict__ z, long z_lo_off, const float* __restrict__ scale, const float* __restrict__ shift,
     const __nv_bfloat16* __restrict__ zb, long zb_lo_off, const float* __restrict__ scale_b, const float* __restrict__ shift_b,
     const __nv_bfloat16* __restrict__ res, int res_pitch, long res_lo_off, int relu, const MapP m,
     __nv_bfloat16* __restrict__ y, long y_lo_off) {
+    __shared__ float s_sc[256], s_sh[256], s_scb[256], s_shb[256];
     pdl_wait();
+    for (int c = threadIdx.x; c < m.c_mod; c += EW_THREADS) {
+        s_sc[c] = scale[c]; s_sh[c] = shift[c];
+        s_scb[c] = zb ? scale_b[c] : 0.f; s_shb[c] = zb ? shift_b[c] : 0.f;
+    }
+    __syncthreads();
     const RowWalk rw = row_walk(m.c_total);
     if (rw.row0 < 0) return;
     const ColInfo ci = col_info(m, rw.chunk * 8);
     const int col = ci.col;
-    float sc[8], sh[8], scb[8], shb[8];
+    const float* sc = s_sc + ci.cb;
+    const float* sh = s_sh + ci.cb;
+    const float* scb = s_scb + ci.cb;
+    const float* shb = s_shb + ci.cb;
+    RowCur c[R];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        sc[j] = scale[ci.cb + j]; sh[j] = shift[ci.cb + j];
-        scb[j] = zb ? scale_b[ci.cb + j] : 0.f; shb[j] = zb ? shift_b[ci.cb + j] : 0.f;
-    }
-    RowCur c[2] = {cur_init(m, rw.row0, 2 * rw.row_step), cur_init(m, rw.row0 + rw.row_step, 2 * rw.row_step)};
-    for (; c[0].q < m.rows_total; cur_next(m, c[0]), cur_next(m, c[1])) {
-        long yo[2];
-        float v[2][8], ub[2][8], ur[2][8];
+    for (int r = 0; r < R; ++r) c[r] = cur_init(m, rw.row0 + r * rw.row_step, R * rw.row_step);
+    while (c[0].q < m.rows_total) {
+        long yo[R];
+        Raw8<LO> rz[R], rb[R], rr[R];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {                                            // unconditional loads (row 0 for dead rows)
+        for (int r = 0; r < R; ++r) {
             yo[r] = y_off_cur(m, c[r], ci);
             const long qz = yo[r] >= 0 ? c[r].q : 0;
-            load8(z, qz * m.c_total + col, z_lo_off, v[r]);
-            if (zb) load8(zb, qz * m.c_total + col, zb_lo_off, ub[r]);
-            if (res) load8(res, qz * (long)res_pitch + col, res_lo_off, ur[r]);
+            ld_raw<LO>(z, qz * m.c_total + col, z_lo_off, rz[r]);
+            if (zb) ld_raw<LO>(zb, qz * m.c_total + col, zb_lo_off, rb[r]);
+            if (res) ld_raw<LO>(res, qz * (long)res_pitch + col, res_lo_off, rr[r]);
         }
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            if (yo[r] < 0) continue;
+        for (int r = 0; r < R; ++r) {
+            if (yo[r] >= 0) {
+                float v[8], u[8];
+                cvt_raw<LO>(rz[r], v);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float t = fmaf(v[r][j], sc[j], sh[j]);
-                if (zb) t += fmaf(ub[r][j], scb[j], shb[j]);
-                if (res) t += ur[r][j];
-                v[r][j] = relu ? fmaxf(t, 0.f) : t;
+                for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+                if (zb) {
+                    cvt_raw<LO>(rb[r], u);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] += fmaf(u[j], scb[j], shb[j]);
+                }
+                if (res) {
+                    cvt_raw<LO>(rr[r], u);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] += u[j];
+                }
+                if (relu) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                store8(y, yo[r], LO ? y_lo_off : 0, v);
             }
-            store8(y, yo[r], y_lo_off, v[r]);
+            cur_next(m, c[r]);
         }
     }
 }
 
-// ------------------------------------------------------------------------------------------------ BatchNorm backward
 // ReLU mask: from y (the stored activation) or - mask_scale != NULL, the plain conv + BN + ReLU case - recomputed from the z
 // that is loaded anyway (sign of z*scale + shift), which saves one tensor read in both backward passes.
-__global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(
+template <int R, bool LO>
+__global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_reduce_kernel(
     const __nv_bfloat16* __restrict__ dy, long dy_lo_off, const __nv_bfloat16* __restrict__ y, long y_lo_off, int relu,
     const __nv_bfloat16* __restrict__ z, long z_lo_off, const float* __restrict__ mean, const float* __restrict__ inv_std,
     const float* __restrict__ mask_scale, const float* __restrict__ mask_shift, const MapP m, double* __restrict__ sums) {
     __shared__ float s_part[2 * 2048];
-    pdl_wait();
     __shared__ float s_mu[256], s_ms[256], s_mh[256];
+    pdl_wait();
     const RowWalk rw = row_walk(m.c_total);
     const ColInfo ci = col_info(m, rw.chunk * 8);
     const bool has_bn = mean != nullptr;
     const bool zmask = relu && mask_scale != nullptr && has_bn;
+    const bool ymask = relu && !zmask;
     for (int c = threadIdx.x; c < m.c_mod; c += EW_THREADS) {
         s_mu[c] = has_bn ? mean[c] : 0.f;
         s_ms[c] = zmask ? mask_scale[c] : 0.f;
@@ -293,28 +335,37 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(
     const float* mh = s_mh + ci.cb;
     float a0[8] = {}, a1[8] = {};
     if (rw.row0 >= 0) {
-        RowCur c[2] = {cur_init(m, rw.row0, 2 * rw.row_step), cur_init(m, rw.row0 + rw.row_step, 2 * rw.row_step)};
-        for (; c[0].q < m.rows_total; cur_next(m, c[0]), cur_next(m, c[1])) {
-            long yo[2];
-            float g[2][8], yv[2][8], v[2][8];
+        RowCur c[R];
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {                                        // unconditional loads (masked below)
+        for (int r = 0; r < R; ++r) c[r] = cur_init(m, rw.row0 + r * rw.row_step, R * rw.row_step);
+        while (c[0].q < m.rows_total) {
+            long yo[R];
+            Raw8<LO> rg[R], ry[R], rz[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
                 yo[r] = y_off_cur(m, c[r], ci);
                 const long yl = yo[r] >= 0 ? yo[r] : (long)(m.y_ch_off + ci.cb);
-                load8(dy, yl, dy_lo_off, g[r]);
-                if (relu && !zmask) load8(y, yl, y_lo_off, yv[r]);
-                if (has_bn) load8(z, yo[r] >= 0 ? z_off_cur(m, c[r], ci, yo[r]) : (long)ci.cb, z_lo_off, v[r]);
+                ld_raw<LO>(dy, yl, dy_lo_off, rg[r]);
+                if (ymask) ld_raw<LO>(y, yl, y_lo_off, ry[r]);
+                if (has_bn) ld_raw<LO>(z, yo[r] >= 0 ? z_off_cur(m, c[r], ci, yo[r]) : (long)ci.cb, z_lo_off, rz[r]);
             }
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const bool live = yo[r] >= 0;
+            for (int r = 0; r < R; ++r) {
+                if (yo[r] >= 0) {
+                    float g[8], v[8], yv[8];
+                    cvt_raw<LO>(rg[r], g);
+                    if (has_bn) cvt_raw<LO>(rz[r], v);
+                    if (ymask) cvt_raw<LO>(ry[r], yv);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float gj = live ? g[r][j] : 0.f;
-                    if (relu) gj = (zmask ? fmaf(v[r][j], ms[j], mh[j]) : yv[r][j]) > 0.f ? gj : 0.f;
-                    a0[j] += gj;
-                    if (has_bn) a1[j] = fmaf(gj, v[r][j] - mu[j], a1[j]);       // x_hat = (z - mean) * inv_std: scaled below
+                    for (int j = 0; j < 8; ++j) {
+                        float gj = g[j];
+                        if (zmask) gj = fmaf(v[j], ms[j], mh[j]) > 0.f ? gj : 0.f;
+                        if (ymask) gj = yv[j] > 0.f ? gj : 0.f;
+                        a0[j] += gj;
+                        if (has_bn) a1[j] = fmaf(gj, v[j] - mu[j], a1[j]);       // x_hat = (z - mean) * inv_std: scaled below
+                    }
                 }
+                cur_next(m, c[r]);
             }
         }
     }
@@ -325,13 +376,16 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(
     block_reduce_to_global(a0, a1, m.c_total, m.c_mod, has_bn, s_part, sums);
 }
 
-__global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(
+template <int R, bool LO>
+__global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_apply_kernel(
     const __nv_bfloat16* __restrict__ dy, long dy_lo_off, const __nv_bfloat16* __restrict__ y, long y_lo_off, int relu,
     const __nv_bfloat16* __restrict__ z, long z_lo_off, const float* __restrict__ mean, const float* __restrict__ inv_std,
     const float* __restrict__ gamma, const float* __restrict__ mask_scale, const float* __restrict__ mask_shift,
     const double* __restrict__ sums, double count, const MapP m,
     __nv_bfloat16* __restrict__ dz, long dz_lo_off, __nv_bfloat16* __restrict__ dsum, long dsum_lo_off,
     float* __restrict__ d_gamma, float* __restrict__ d_beta) {
+    // dz = gamma*inv * (g - s0/n - (z - mean)*inv * s1/n) = A*g + B*z + C per channel
+    __shared__ float s_A[256], s_B[256], s_C[256], s_ms[256], s_mh[256];
     pdl_wait();
     const bool has_bn = mean != nullptr;
     if (blockIdx.x == 0) {
@@ -340,9 +394,8 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(
             if (d_gamma && has_bn) d_gamma[c] = (float)sums[m.c_mod + c];
         }
     }
-    // dz = gamma*inv * (g - s0/n - (z - mean)*inv * s1/n) = A*g + B*z + C per channel
-    __shared__ float s_A[256], s_B[256], s_C[256], s_ms[256], s_mh[256];
     const bool zmask = relu && mask_scale != nullptr && has_bn;
+    const bool ymask = relu && !zmask;
     for (int c = threadIdx.x; c < m.c_mod; c += EW_THREADS) {
         float A = 1.f, B = 0.f, Cc = 0.f;
         if (has_bn) {
@@ -366,31 +419,40 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(
     const float* cC = s_C + ci.cb;
     const float* ms = s_ms + ci.cb;
     const float* mh = s_mh + ci.cb;
-    RowCur c[2] = {cur_init(m, rw.row0, 2 * rw.row_step), cur_init(m, rw.row0 + rw.row_step, 2 * rw.row_step)};
-    for (; c[0].q < m.rows_total; cur_next(m, c[0]), cur_next(m, c[1])) {
-        long yo[2];
-        float g[2][8], yv[2][8], v[2][8];
+    RowCur c[R];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {                                            // unconditional loads
+    for (int r = 0; r < R; ++r) c[r] = cur_init(m, rw.row0 + r * rw.row_step, R * rw.row_step);
+    while (c[0].q < m.rows_total) {
+        long yo[R];
+        Raw8<LO> rg[R], ry[R], rz[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
             yo[r] = y_off_cur(m, c[r], ci);
             const long yl = yo[r] >= 0 ? yo[r] : (long)(m.y_ch_off + ci.cb);
-            load8(dy, yl, dy_lo_off, g[r]);
-            if (relu && !zmask) load8(y, yl, y_lo_off, yv[r]);
-            if (has_bn) load8(z, yo[r] >= 0 ? z_off_cur(m, c[r], ci, yo[r]) : (long)ci.cb, z_lo_off, v[r]);
+            ld_raw<LO>(dy, yl, dy_lo_off, rg[r]);
+            if (ymask) ld_raw<LO>(y, yl, y_lo_off, ry[r]);
+            if (has_bn) ld_raw<LO>(z, yo[r] >= 0 ? z_off_cur(m, c[r], ci, yo[r]) : (long)ci.cb, z_lo_off, rz[r]);
         }
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            if (yo[r] < 0) continue;
-            if (relu) {
+        for (int r = 0; r < R; ++r) {
+            if (yo[r] >= 0) {
+                float g[8], v[8], yv[8];
+                cvt_raw<LO>(rg[r], g);
+                if (has_bn) cvt_raw<LO>(rz[r], v);
+                if (ymask) cvt_raw<LO>(ry[r], yv);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) g[r][j] = (zmask ? fmaf(v[r][j], ms[j], mh[j]) : yv[r][j]) > 0.f ? g[r][j] : 0.f;
-            }
-            if (dsum) store8(dsum, c[r].q * m.c_total + col, dsum_lo_off, g[r]);
-            if (has_bn) {
+                for (int j = 0; j < 8; ++j) {
+                    if (zmask) g[j] = fmaf(v[j], ms[j], mh[j]) > 0.f ? g[j] : 0.f;
+                    if (ymask) g[j] = yv[j] > 0.f ? g[j] : 0.f;
+                }
+                if (dsum) store8(dsum, c[r].q * m.c_total + col, LO ? dsum_lo_off : 0, g);
+                if (has_bn) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) g[r][j] = fmaf(cA[j], g[r][j], fmaf(cB[j], v[r][j], cC[j]));
+                    for (int j = 0; j < 8; ++j) g[j] = fmaf(cA[j], g[j], fmaf(cB[j], v[j], cC[j]));
+                }
+                store8(dz, c[r].q * m.c_total + col, LO ? dz_lo_off : 0, g);
             }
-            store8(dz, c[r].q * m.c_total + col, dz_lo_off, g[r]);
+            cur_next(m, c[r]);
         }
     }
 }
@@ -943,8 +1005,11 @@ extern "C" int cb_bn_stats(const void* z, int64_t z_lo_off, const cb_map* map, d
     int rc = fill_map(map, m);
     if (rc || !z || !sums) return rc ? rc : CB_ERR_ARG;
     const int rpi = EW_THREADS / (m.c_total >> 3);
-    cudaError_t e = launch_pdl(bn_stats_kernel, dim3(ew_grid((m.rows_total + rpi - 1) / rpi * EW_THREADS / 4)), dim3(EW_THREADS),
-                               0, (cudaStream_t)stream, BF(z), (long)z_lo_off, m, sums);
+    const dim3 grid(ew_grid((m.rows_total + rpi - 1) / rpi * EW_THREADS / 8));
+    cudaError_t e = z_lo_off ? launch_pdl(bn_stats_kernel<4, true>, grid, dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(z),
+                                          (long)z_lo_off, m, sums)
+                             : launch_pdl(bn_stats_kernel<8, false>, grid, dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(z),
+                                          (long)z_lo_off, m, sums);
     return e == cudaSuccess ? CB_OK : (int)e;
 }
 
@@ -966,9 +1031,14 @@ extern "C" int cb_bn_apply(const void* z, int64_t z_lo_off, const float* scale, 
     if (rc) return rc;
     if (!z || !scale || !shift || !y || (z_b && (!scale_b || !shift_b)) || (residual && res_pitch % 8)) return CB_ERR_ARG;
     const int rpi = EW_THREADS / (m.c_total >> 3);
-    cudaError_t e = launch_pdl(bn_apply_kernel, dim3(ew_grid((m.rows_total + rpi - 1) / rpi * EW_THREADS / 2)), dim3(EW_THREADS), 0,
-                               (cudaStream_t)stream, BF(z), (long)z_lo_off, scale, shift, BF(z_b), (long)z_b_lo_off, scale_b,
-                               shift_b, BF(residual), (int)res_pitch, (long)res_lo_off, relu, m, BFW(y), (long)y_lo_off);
+    const dim3 grid(ew_grid((m.rows_total + rpi - 1) / rpi * EW_THREADS / 4));
+    const bool lo = z_lo_off || y_lo_off || z_b_lo_off || res_lo_off;
+    cudaError_t e = lo ? launch_pdl(bn_apply_kernel<2, true>, grid, dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(z),
+                                    (long)z_lo_off, scale, shift, BF(z_b), (long)z_b_lo_off, scale_b, shift_b, BF(residual),
+                                    (int)res_pitch, (long)res_lo_off, relu, m, BFW(y), (long)y_lo_off)
+                       : launch_pdl(bn_apply_kernel<4, false>, grid, dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(z),
+                                    (long)z_lo_off, scale, shift, BF(z_b), (long)z_b_lo_off, scale_b, shift_b, BF(residual),
+                                    (int)res_pitch, (long)res_lo_off, relu, m, BFW(y), (long)y_lo_off);
     return e == cudaSuccess ? CB_OK : (int)e;
 }
 
@@ -982,9 +1052,14 @@ extern "C" int cb_bn_bwd_reduce(const void* dy, int64_t dy_lo_off, const void* y
     if (!zmask) mask_scale = mask_shift = nullptr;
     if (!dy || !sums || (relu && !y && !zmask) || (mean && (!z || !inv_std))) return CB_ERR_ARG;
     const int rpi = EW_THREADS / (m.c_total >> 3);
-    cudaError_t e = launch_pdl(bn_bwd_reduce_kernel, dim3(ew_grid((m.rows_total + rpi - 1) / rpi * EW_THREADS / 4)),
-                               dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(dy), (long)dy_lo_off, BF(y), (long)y_lo_off, relu,
-                               BF(z), (long)z_lo_off, mean, inv_std, mask_scale, mask_shift, m, sums);
+    const dim3 grid(ew_grid((m.rows_total + rpi - 1) / rpi * EW_THREADS / 4));
+    const bool lo = dy_lo_off || y_lo_off || z_lo_off;
+    cudaError_t e = lo ? launch_pdl(bn_bwd_reduce_kernel<2, true>, grid, dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(dy),
+                                    (long)dy_lo_off, BF(y), (long)y_lo_off, relu, BF(z), (long)z_lo_off, mean, inv_std,
+                                    mask_scale, mask_shift, m, sums)
+                       : launch_pdl(bn_bwd_reduce_kernel<4, false>, grid, dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(dy),
+                                    (long)dy_lo_off, BF(y), (long)y_lo_off, relu, BF(z), (long)z_lo_off, mean, inv_std,
+                                    mask_scale, mask_shift, m, sums);
     return e == cudaSuccess ? CB_OK : (int)e;
 }
 
@@ -1000,11 +1075,16 @@ extern "C" int cb_bn_bwd_apply(const void* dy, int64_t dy_lo_off, const void* y,
     if (!zmask) mask_scale = mask_shift = nullptr;
     if (!dy || !dz || !sums || (relu && !y && !zmask) || (mean && (!z || !inv_std || !gamma || count <= 0))) return CB_ERR_ARG;
     const int rpi = EW_THREADS / (m.c_total >> 3);
-    cudaError_t e = launch_pdl(bn_bwd_apply_kernel, dim3(ew_grid((m.rows_total + rpi - 1) / rpi * EW_THREADS / 2)),
-                               dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(dy), (long)dy_lo_off, BF(y), (long)y_lo_off, relu,
-                               BF(z), (long)z_lo_off, mean, inv_std, gamma, mask_scale, mask_shift, sums, count, m, BFW(dz),
-                               (long)dz_lo_off,
-                               BFW(dsum_pf), (long)dsum_lo_off, d_gamma, d_beta);
+    const dim3 grid(ew_grid((m.rows_total + rpi - 1) / rpi * EW_THREADS / 4));
+    const bool lo = dy_lo_off || y_lo_off || z_lo_off || dz_lo_off || dsum_lo_off;
+    cudaError_t e = lo ? launch_pdl(bn_bwd_apply_kernel<2, true>, grid, dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(dy),
+                                    (long)dy_lo_off, BF(y), (long)y_lo_off, relu, BF(z), (long)z_lo_off, mean, inv_std, gamma,
+                                    mask_scale, mask_shift, sums, count, m, BFW(dz), (long)dz_lo_off, BFW(dsum_pf),
+                                    (long)dsum_lo_off, d_gamma, d_beta)
+                       : launch_pdl(bn_bwd_apply_kernel<4, false>, grid, dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(dy),
+                                    (long)dy_lo_off, BF(y), (long)y_lo_off, relu, BF(z), (long)z_lo_off, mean, inv_std, gamma,
+                                    mask_scale, mask_shift, sums, count, m, BFW(dz), (long)dz_lo_off, BFW(dsum_pf),
+                                    (long)dsum_lo_off, d_gamma, d_beta);
     return e == cudaSuccess ? CB_OK : (int)e;
 }
 

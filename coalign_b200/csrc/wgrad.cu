@@ -267,8 +267,9 @@ extern "C" int cb_wgrad(const cb_wgrad_desc* d, int max_ctas, void* stream) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int cap = max_ctas > 0 ? max_ctas : sms;
     int ks = d->k_splits;
-    if (ks <= 0) {                                   // one wave of CTAs, at least 8 K blocks per work item
-        ks = (cap + d->n_units - 1) / d->n_units;
+    if (ks <= 0) {                                   // exactly one wave of CTAs (units * splits <= SMs: a second, partial
+        ks = cap / d->n_units;                       // wave would double the kernel's duration), >= 8 K blocks per work item
+        if (ks < 1) ks = 1;
         const int lim = p.n_kblocks / 8 > 0 ? p.n_kblocks / 8 : 1;
         if (ks > lim) ks = lim;
     }

@@ -391,9 +391,11 @@ class TrainEngine(CoAlignEngine):
         else:
             dst_t, dst_off = dst, 0
         units = []
-        for m0 in range(0, m_total, 128):
-            for i in range(0, len(boxes), _lib.CB_WGRAD_MAX_BOXES):
-                units.append((m0, min(128, m_total - m0), boxes[i:i + _lib.CB_WGRAD_MAX_BOXES]))
+        nu = (len(boxes) + _lib.CB_WGRAD_MAX_BOXES - 1) // _lib.CB_WGRAD_MAX_BOXES
+        cuts = [len(boxes) * i // nu for i in range(nu + 1)]          # equally sized units (9 boxes -> 3+3+3, not 4+4+1):
+        for m0 in range(0, m_total, 128):                              # every work item of the launch takes the same time
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                units.append((m0, min(128, m_total - m0), boxes[a:b]))
         ops = []
         for u0 in range(0, len(units), _lib.CB_WGRAD_MAX_UNITS):
             d = WgradDesc()
