@@ -830,14 +830,11 @@ __global__ void __launch_bounds__(256) pfn_bwd_kernel(const float4* __restrict__
                                                       const float* __restrict__ inv_std, const PfnT t,
                                                       const __nv_bfloat16* __restrict__ dcanvas, long dc_lo_off, const CanvasG cg,
                                                       double* __restrict__ bsum) {
-    __shared__ float s_f[8][32][10];
-    __shared__ double s_red[64 * 12];
+    __shared__ float s_f[8][32][24];                                     // features [..][10]; reused for the final reduction
     pdl_wait();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     int n_rows = n_voxels_dev ? *n_voxels_dev : n_rows_cap;
     if (n_rows > n_rows_cap) n_rows = n_rows_cap;
-    for (int i = threadIdx.x; i < 64 * 12; i += 256) s_red[i] = 0.0;
-    __syncthreads();
     float wl[2][10], sc[2], sh[2], mu[2], iv[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -851,7 +848,6 @@ __global__ void __launch_bounds__(256) pfn_bwd_kernel(const float4* __restrict__
     for (int r = 0; r < 2; ++r)
 #pragma unroll
         for (int i = 0; i < 12; ++i) acc[r][i] = 0.f;
-    int flush = 0;
     for (long m = (long)blockIdx.x * 8 + wib; m < n_rows; m += (long)gridDim.x * 8) {
         int n = __ldg(num_points + m);
         n = n < max_pts ? n : max_pts;
@@ -893,23 +889,23 @@ __global__ void __launch_bounds__(256) pfn_bwd_kernel(const float4* __restrict__
                 }
             }
         }
-        if (++flush == 64) {                                             // bound the fp32 partial sums
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-#pragma unroll
-                for (int i = 0; i < 12; ++i) { atomicAdd(&s_red[(lane + 32 * r) * 12 + i], (double)acc[r][i]); acc[r][i] = 0.f; }
-            flush = 0;
-        }
     }
+    // per-warp fp32 partials (<= a few hundred pillars each) -> shared memory -> one fp64 global atomic per entry and CTA
+    // (shared-memory double atomics are CAS loops on sm_100: no periodic flushes through them)
+    __syncthreads();
+    float* s_w = &s_f[0][0][0];                                          // reuse: 8 warps x 768 floats = 24 KB
 #pragma unroll
     for (int r = 0; r < 2; ++r)
 #pragma unroll
-        for (int i = 0; i < 12; ++i) atomicAdd(&s_red[(lane + 32 * r) * 12 + i], (double)acc[r][i]);
+        for (int i = 0; i < 12; ++i) s_w[wib * 768 + (lane + 32 * r) * 12 + i] = acc[r][i];
     __syncthreads();
     for (int i = threadIdx.x; i < 64 * 12; i += 256) {
+        double t = 0.0;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) t += (double)s_w[w8 * 768 + i];
         const int c = i / 12, k = i - c * 12;
         const int dst = k == 0 ? c : (k == 1 ? 64 + c : 128 + c * 10 + (k - 2));
-        atomicAdd(bsum + dst, s_red[i]);
+        atomicAdd(bsum + dst, t);
     }
 }
 
