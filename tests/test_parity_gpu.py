@@ -324,8 +324,11 @@ def test_plugin_through_reference_style_call():
         out = m(batch)
     for k in ("cls_preds", "reg_preds", "dir_preds"):
         assert_close(out[k].cpu().numpy(), g[k], 1e-3, 1e-3, k)
+    # .train() runs the device training path (tests/test_train_gpu.py); the single-agent twins stay inference-only
+    from coalign_b200.model import PointPillarB200
+    single = PointPillarB200(synth.single_args(G.SMALL_RANGE, G.SMALL_VOXEL)).cuda()
     with pytest.raises(NotImplementedError):
-        m.train()(batch)
+        single.train()(batch)
 
 
 def test_ragged_batches_and_empty_agent_same_engine():
