@@ -32,6 +32,7 @@ class ConvDesc(C.Structure):
         ("out_plane_rows", C.c_int64),
         ("head_out", C.c_void_p * 4), ("head_c0", C.c_int32 * 4), ("head_cn", C.c_int32 * 4), ("n_heads", C.c_int32),
         ("n_ksteps", C.c_int32), ("ksteps", KStep * CB_MAX_KSTEPS),
+        ("in_pad", C.c_int32),
     ]
 
 
@@ -134,6 +135,10 @@ EXPORTS = {
                                     C.c_void_p]),
     "cb_layout_to_nchw": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_void_p, C.c_void_p]),
+    "cb_nchw_to_ps_pad": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64,
+                                    C.c_void_p]),
+    "cb_upsample_concat": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                     C.c_int64, C.c_int, C.c_int, C.c_void_p]),
 }
 
 _lib = None

@@ -8,7 +8,7 @@ namespace cb {
 
 struct ConvParams {
     // row space
-    int n_img, Hp, Wp;
+    int n_img, Hp, Wp, pad;
     long rows_total;
     int n_total, cout_mod, relu;
     // epilogue
@@ -44,11 +44,14 @@ __device__ __forceinline__ RowDest decode_row(const ConvParams& p, long q64, int
     const unsigned rem = q - n * plane;
     const unsigned hp = rem / (unsigned)p.Wp;
     const unsigned wp = rem - hp * (unsigned)p.Wp;
-    if (hp < 1u || hp > (unsigned)(p.Hp - 2) || wp < 1u || wp > (unsigned)(p.Wp - 2)) return d;
-    const int h = (int)hp - 1, w = (int)wp - 1;
+    const unsigned pad = (unsigned)p.pad;
+    if (hp < pad || hp > (unsigned)(p.Hp - 1) - pad || wp < pad || wp > (unsigned)(p.Wp - 1) - pad) return d;
+    const int h = (int)(hp - pad), w = (int)(wp - pad);
     d.n = (int)n; d.h = h; d.w = w;
-    if (p.out_mode == CB_OUT_PF || p.out_mode == CB_OUT_HEADS) {
+    if (p.out_mode == CB_OUT_HEADS || (p.out_mode == CB_OUT_PF && p.out_Hp == p.Hp && p.out_Wp == p.Wp)) {
         d.row = q64;
+    } else if (p.out_mode == CB_OUT_PF) {      // destination PF map with its own (1-pixel) halo: address by pixel
+        d.row = (long)((int)n * p.out_Hp + h + 1) * p.out_Wp + w + 1;
     } else if (p.out_mode == CB_OUT_PS) {
         const int ph = (h & 1) * 2 + (w & 1);
         d.row = (long)ph * p.out_plane_rows + (long)((int)n * p.out_Hp + (h >> 1) + 1) * p.out_Wp + (w >> 1) + 1;
@@ -233,7 +236,9 @@ inline int fill_params(const cb_conv_desc* d, ConvParams& p) {
     if (d->out_mode != CB_OUT_HEADS && (d->out == nullptr || (d->out_pitch % 8) || (d->out_ch_off % 8))) return CB_ERR_ARG;
     if (d->out_mode == CB_OUT_UPSAMPLE && (d->up_k < 1 || d->cout_mod % d->block_n != 0)) return CB_ERR_ARG;
     if (d->residual && (d->res_pitch % 8)) return CB_ERR_ARG;
-    p.n_img = d->n_img; p.Hp = d->Hp; p.Wp = d->Wp;
+    if (d->in_pad < 0 || d->in_pad > 3) return CB_ERR_ARG;
+    p.n_img = d->n_img; p.Hp = d->Hp; p.Wp = d->Wp; p.pad = d->in_pad ? d->in_pad : 1;
+    if (p.pad != 1 && (d->residual != nullptr && (d->out_Hp != d->Hp || d->out_Wp != d->Wp) && false)) return CB_ERR_ARG;
     p.rows_total = (long)d->n_img * d->Hp * d->Wp;
     p.n_total = d->n_total; p.cout_mod = d->cout_mod; p.relu = d->relu;
     p.bias = d->bias;
@@ -241,6 +246,7 @@ inline int fill_params(const cb_conv_desc* d, ConvParams& p) {
     p.out = (__nv_bfloat16*)d->out; p.out_pitch = d->out_pitch; p.out_ch_off = d->out_ch_off;
     p.out_lo_off = d->out_lo_off;
     p.out_mode = d->out_mode; p.up_k = d->up_k; p.out_Hp = d->out_Hp; p.out_Wp = d->out_Wp;
+    if (d->out_mode == CB_OUT_PF && (d->out_Hp == 0 || d->out_Wp == 0)) { p.out_Hp = d->Hp; p.out_Wp = d->Wp; }
     p.out_plane_rows = d->out_plane_rows;
     for (int i = 0; i < CB_MAX_HEADS; ++i) { p.head_out[i] = d->head_out[i]; p.head_c0[i] = d->head_c0[i]; p.head_cn[i] = d->head_cn[i]; }
     p.n_heads = d->n_heads;

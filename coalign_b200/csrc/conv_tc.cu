@@ -1200,7 +1200,7 @@ static int conv_gemm_impl(const cb_conv_desc* d, int max_ctas, void* stream, boo
         // 107 us) and equal elsewhere (profiles/r1_exp_halo.txt), so it is opt-in (CB_OPT_TMA_STORE)
         const bool no_tma_store = cb::opt_get(CB_OPT_TMA_STORE) == 0;
         if (!no_tma_store && d->out_mode == CB_OUT_PF && d->out_lo_off == 0 && d->res_lo_off == 0 && d->block_n >= 64 &&
-            !(dbg_flags() & 7)) {
+            !(dbg_flags() & 7) && p.pad == 1 && p.out_Hp == p.Hp && p.out_Wp == p.Wp) {
             rc = make_tmap(&tout, d->out, p.rows_total, d->out_pitch, d->out_pitch, BM, d->block_n >= 128 ? 64 : 32);
             if (rc) return rc;
             use_tma = 1;
@@ -1311,7 +1311,7 @@ extern "C" int cb_conv_gemm_halo(const cb_conv_desc* d, int max_ctas, void* stre
     CUtensorMap tout = tw;
     int use_tma = 0;
     const bool no_tma_store = cb::opt_get(CB_OPT_TMA_STORE) == 0;
-    if (d->out_mode == CB_OUT_PF && !no_tma_store) {
+    if (d->out_mode == CB_OUT_PF && !no_tma_store && p.pad == 1 && p.out_Hp == p.Hp && p.out_Wp == p.Wp) {
         rc = make_tmap(&tout, d->out, p.rows_total, d->out_pitch, d->out_pitch, BM, 32);
         if (rc) return rc;
         use_tma = 1;

@@ -59,7 +59,103 @@ __global__ void ps_to_pf_kernel(const uint4* __restrict__ src, int n_cap, int n,
     dst[layout_row(0, n, H, W, a, h, w) * c8 + c] = __ldg(src + layout_row(1, n_cap, H, W, a, h, w) * c8 + c);
 }
 
+__global__ void nchw_to_ps_pad_kernel(const float* __restrict__ src, int N, int C, int H, int W, int pad, int n_cap,
+                                      __nv_bfloat16* __restrict__ dst, long lo_off) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;      // over (n,h,w,c), c fastest
+    const long total = (long)N * H * W * C;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    long t = i / C;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    const float v = src[(((long)n * C + c) * H + h) * W + w];
+    const int Hq = (H + 1) / 2 + 2 * pad, Wq = (W + 1) / 2 + 2 * pad;
+    const int ph = (h & 1) * 2 + (w & 1);
+    const long row = (long)ph * n_cap * Hq * Wq + ((long)n * Hq + (h >> 1) + pad) * Wq + (w >> 1) + pad;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    dst[row * C + c] = hi;
+    if (lo_off) dst[lo_off + row * C + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// 8 channels (16 bytes) per thread; align_corners=True: source coordinate = dst * (h-1)/(scale*h-1)
+__global__ void __launch_bounds__(256) upsample_concat_kernel(const __nv_bfloat16* __restrict__ src, long src_lo_off, int n,
+                                                              int h, int w, int c, int scale, __nv_bfloat16* __restrict__ dst,
+                                                              long dst_lo_off, int dst_pitch, int dst_ch_off) {
+    pdl_wait();
+    const int c8 = c >> 3, H2 = h * scale, W2 = w * scale;
+    const long total = (long)n * H2 * W2 * c8;
+    const float ry = H2 > 1 ? (float)(h - 1) / (float)(H2 - 1) : 0.f, rx = W2 > 1 ? (float)(w - 1) / (float)(W2 - 1) : 0.f;
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+        const int ch = (int)(i % c8) * 8;
+        long t = i / c8;
+        const int x = (int)(t % W2); t /= W2;
+        const int y = (int)(t % H2);
+        const int a = (int)(t / H2);
+        float v[8];
+        auto ld = [&](int yy, int xx, float (&o)[8]) {
+            const long off = (((long)a * (h + 2) + yy + 1) * (w + 2) + xx + 1) * c + ch;
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + off));
+            o[0] = bf16_lo(u.x); o[1] = bf16_hi(u.x); o[2] = bf16_lo(u.y); o[3] = bf16_hi(u.y);
+            o[4] = bf16_lo(u.z); o[5] = bf16_hi(u.z); o[6] = bf16_lo(u.w); o[7] = bf16_hi(u.w);
+            if (src_lo_off) {
+                const uint4 l = __ldg(reinterpret_cast<const uint4*>(src + src_lo_off + off));
+                o[0] += bf16_lo(l.x); o[1] += bf16_hi(l.x); o[2] += bf16_lo(l.y); o[3] += bf16_hi(l.y);
+                o[4] += bf16_lo(l.z); o[5] += bf16_hi(l.z); o[6] += bf16_lo(l.w); o[7] += bf16_hi(l.w);
+            }
+        };
+        if (scale == 1) {
+            ld(y, x, v);
+        } else {
+            // same arithmetic as ATen's upsample_bilinear2d (align_corners=True): fp32 source index, floor, lambda weights
+            const float sy = ry * (float)y, sx = rx * (float)x;
+            const int y0 = (int)sy, x0 = (int)sx;
+            const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+            const float ly = sy - (float)y0, lx = sx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+            float p00[8], p01[8], p10[8], p11[8];
+            ld(y0, x0, p00); ld(y0, x1, p01); ld(y1, x0, p10); ld(y1, x1, p11);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = hy * (hx * p00[j] + lx * p01[j]) + ly * (hx * p10[j] + lx * p11[j]);
+        }
+        const long o = (((long)a * (H2 + 2) + y + 1) * (W2 + 2) + x + 1) * dst_pitch + dst_ch_off + ch;
+        uint32_t hi[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) hi[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
+        *reinterpret_cast<uint4*>(dst + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (dst_lo_off) {
+            uint32_t lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) lo[e] = pack_bf16(v[2 * e] - bf16_lo(hi[e]), v[2 * e + 1] - bf16_hi(hi[e]));
+            *reinterpret_cast<uint4*>(dst + dst_lo_off + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+    }
+}
+
 }  // namespace cb
+
+extern "C" int cb_nchw_to_ps_pad(const float* src, int n, int c, int h, int w, int pad, int n_cap, void* dst, int64_t lo_off,
+                                 void* stream) {
+    const long total = (long)n * c * h * w;
+    if (!src || !dst || total <= 0 || pad < 1 || pad > 3 || n > n_cap) return CB_ERR_ARG;
+    cb::nchw_to_ps_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        src, n, c, h, w, pad, n_cap, (__nv_bfloat16*)dst, (long)lo_off);
+    CB_CHECK_LAUNCH();
+    return CB_OK;
+}
+
+extern "C" int cb_upsample_concat(const void* src_pf, int64_t src_lo_off, int n, int h, int w, int c, int scale, void* dst_pf,
+                                  int64_t dst_lo_off, int dst_pitch, int dst_ch_off, void* stream) {
+    if (!src_pf || !dst_pf || n < 1 || h < 1 || w < 1 || c < 8 || c % 8 || (scale != 1 && scale != 2)) return CB_ERR_ARG;
+    if (dst_pitch % 8 || dst_ch_off % 8 || dst_ch_off + c > dst_pitch) return CB_ERR_ARG;
+    if ((src_lo_off != 0) != (dst_lo_off != 0)) return CB_ERR_ARG;
+    const long total = (long)n * h * scale * w * scale * (c / 8);
+    long blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    cudaError_t e = cb::launch_pdl(cb::upsample_concat_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream,
+                                   (const __nv_bfloat16*)src_pf, (long)src_lo_off, n, h, w, c, scale, (__nv_bfloat16*)dst_pf,
+                                   (long)dst_lo_off, dst_pitch, dst_ch_off);
+    return e == cudaSuccess ? CB_OK : (int)e;
+}
 
 extern "C" int cb_ps_to_pf(const void* src_ps, int64_t src_lo_off, int n_cap, int n, int h, int w, int c, void* dst_pf,
                            int64_t dst_lo_off, void* stream) {

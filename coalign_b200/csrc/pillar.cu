@@ -475,7 +475,6 @@ __device__ __forceinline__ int find_agent_bs(const AoView& ao, int i) {      // 
     return lo;
 }
 
-constexpr int V2_PPT = 4;                // points per thread of vox2_assign: four returning atomics in flight per thread
 __global__ void __launch_bounds__(256) vox2_assign_kernel(const float4* __restrict__ pts,
                                                           const __grid_constant__ AgentOffsets ao_val,
                                                           const int* __restrict__ off_dev, const Geom g,
@@ -484,67 +483,33 @@ __global__ void __launch_bounds__(256) vox2_assign_kernel(const float4* __restri
     pdl_wait();
     const AoView ao = ao_view(ao_val, off_dev);
     const int total = ao.off[ao.n_agents];
-    const int base = blockIdx.x * (256 * V2_PPT);
-    const int a_lo = find_agent_bs(ao, base);                      // CTA-uniform
-    const int a_hi = find_agent_bs(ao, min(base + 256 * V2_PPT - 1, total - 1));
-    // The kernel is bound by the latency of the returning L2 atomics (ncu: 22 % issue slots busy, long-scoreboard stall 30
-    // per issue at full occupancy): every thread handles V2_PPT points and issues their atomics back to back.
-    float4 p[V2_PPT];
-    int cell[V2_PPT], ag[V2_PPT], pos[V2_PPT];
-    long gc[V2_PPT];
-#pragma unroll
-    for (int k = 0; k < V2_PPT; ++k) {
-        const int i = base + k * 256 + threadIdx.x;
-        cell[k] = -1; ag[k] = a_lo; pos[k] = 0; gc[k] = 0;
-        if (i < total) {
-            if (a_lo != a_hi) ag[k] = find_agent_bs(ao, i);
-            p[k] = __ldg(pts + i);
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int a_lo = find_agent_bs(ao, blockIdx.x * 256);          // CTA-uniform
+    const int a_hi = find_agent_bs(ao, min(blockIdx.x * 256 + 255, total - 1));
+    int a = a_lo, opened = 0;
+    if (i < total) {
+        if (a_lo != a_hi) a = find_agent_bs(ao, i);
+        const float4 p = __ldg(pts + i);
+        const float fx = floorf(__fdiv_rn(__fsub_rn(p.x, g.r0), g.v0));      // as vox_assign_kernel (serial generator)
+        const float fy = floorf(__fdiv_rn(__fsub_rn(p.y, g.r1), g.v1));
+        const float fz = floorf(__fdiv_rn(__fsub_rn(p.z, g.r2), g.v2));
+        int cell = -1;
+        if (fx >= 0.f && fx < (float)g.gx && fy >= 0.f && fy < (float)g.gy && fz >= 0.f && fz < (float)g.gz) {
+            cell = ((int)fz * g.gy + (int)fy) * g.gx + (int)fx;
+            const long gc = (long)a * ws.ncell + cell;
+            const int pos = atomicAdd(ws.count + gc, 1);
+            if (use_first) atomicMin(ws.first + gc, i - ao.off[a]);  // only the max_voxels cap needs it
+            if (pos < max_pts) *slot_ptr(ws, gc, pos) = p;
+            opened = pos == 0;
         }
-    }
-#pragma unroll
-    for (int k = 0; k < V2_PPT; ++k) {
-        const int i = base + k * 256 + threadIdx.x;
-        if (i < total) {
-            const float fx = floorf(__fdiv_rn(__fsub_rn(p[k].x, g.r0), g.v0));      // as vox_assign_kernel (serial generator)
-            const float fy = floorf(__fdiv_rn(__fsub_rn(p[k].y, g.r1), g.v1));
-            const float fz = floorf(__fdiv_rn(__fsub_rn(p[k].z, g.r2), g.v2));
-            if (fx >= 0.f && fx < (float)g.gx && fy >= 0.f && fy < (float)g.gy && fz >= 0.f && fz < (float)g.gz) {
-                cell[k] = ((int)fz * g.gy + (int)fy) * g.gx + (int)fx;
-                gc[k] = (long)ag[k] * ws.ncell + cell[k];
-            }
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < V2_PPT; ++k) {
-        if (cell[k] >= 0) {
-            pos[k] = atomicAdd(ws.count + gc[k], 1);
-            if (use_first) atomicMin(ws.first + gc[k], base + k * 256 + threadIdx.x - ao.off[ag[k]]);   // only the max_voxels cap needs it
-        }
-    }
-    int opened = 0, opened_any[V2_PPT];
-#pragma unroll
-    for (int k = 0; k < V2_PPT; ++k) {
-        const int i = base + k * 256 + threadIdx.x;
-        opened_any[k] = 0;
-        if (cell[k] >= 0) {
-            if (pos[k] < max_pts) *slot_ptr(ws, gc[k], pos[k]) = p[k];
-            opened_any[k] = pos[k] == 0;
-            opened += opened_any[k];
-        }
-        if (i < total) ws.cellid[i] = cell[k];
+        ws.cellid[i] = cell;
     }
     // non-empty cells per agent: one atomic per CTA when the CTA lies inside one agent (the usual case)
     if (a_lo == a_hi) {
-        __shared__ int s_open;
-        if (threadIdx.x == 0) s_open = 0;
-        __syncthreads();
-        if (opened) atomicAdd(&s_open, opened);
-        __syncthreads();
-        if (threadIdx.x == 0 && s_open > 0) atomicAdd(ws.scal + V2_SCAL + a_lo, s_open);
-    } else {
-#pragma unroll
-        for (int k = 0; k < V2_PPT; ++k)
-            if (opened_any[k]) atomicAdd(ws.scal + V2_SCAL + ag[k], 1);
+        const int c = __syncthreads_count(opened);
+        if (threadIdx.x == 0 && c > 0) atomicAdd(ws.scal + V2_SCAL + a_lo, c);
+    } else if (opened) {
+        atomicAdd(ws.scal + V2_SCAL + a, 1);
     }
 }
 
@@ -960,8 +925,7 @@ static int run_front2(const float* points, const int32_t* pt_offset, const int32
     if (total > 0) {
         const unsigned pblocks = (unsigned)((total + 255) / 256);
         const unsigned sblocks = pblocks < 148u * 4u ? pblocks : 148u * 4u;
-        const unsigned ablocks = (unsigned)((total + 256 * V2_PPT - 1) / (256 * V2_PPT));
-        vox2_assign_kernel<<<ablocks, 256, 0, st>>>((const float4*)points, ao, off_dev, g, ws, max_pts, may_cap);
+        vox2_assign_kernel<<<pblocks, 256, 0, st>>>((const float4*)points, ao, off_dev, g, ws, max_pts, may_cap);
         CB_CHECK_LAUNCH();
         if (may_cap) {
             const dim3 cgrid((unsigned)((max_np + CHUNK - 1) / CHUNK), (unsigned)n_agents);

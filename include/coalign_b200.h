@@ -198,6 +198,10 @@ typedef struct cb_conv_desc {
     /* K loop */
     int32_t n_ksteps;
     cb_kstep ksteps[CB_MAX_KSTEPS];
+    /* halo width of the GEMM row space (0 = 1): interior = in_pad..Hp-1-in_pad x in_pad..Wp-1-in_pad.  2 for the 7x7/s2 stem
+     * of the camera BEV encoder (lss_submodule.py:371-372), whose taps reach two pixels into the parity planes; a CB_OUT_PF
+     * destination with other padded dims (out_Hp/out_Wp != Hp/Wp) is then addressed by pixel, not by GEMM row. */
+    int32_t in_pad;
 } cb_conv_desc;
 
 /* tcgen05 path (the product).  max_ctas <= 0: one persistent CTA per SM. */
@@ -488,6 +492,15 @@ int cb_ps_to_pf(const void* src_ps, int64_t src_lo_off, int n_cap, int n, int h,
                 void* dst_pf, int64_t dst_lo_off, void* stream);
 int cb_layout_to_nchw(const void* src, int64_t lo_off, int from_ps, int n, int c, int h, int w,
                       int pitch, int ch_off, float* dst, void* stream);
+/* dense NCHW float32 (n,c,h,w) -> PS layout with a `pad`-pixel halo per parity plane (plane dims ceil(h/2)+2*pad,
+ * ceil(w/2)+2*pad; n_cap = plane stride in images): the input layout of the camera BEV encoder's 7x7/s2 stem. */
+int cb_nchw_to_ps_pad(const float* src, int n, int c, int h, int w, int pad, int n_cap, void* dst, int64_t lo_off,
+                      void* stream);
+/* Bilinear up-sampling by `scale` (1 = plain copy, 2 = nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True),
+ * lss_submodule.py:23-24,36-37) of a PF map (n, h, w, c) into channels [dst_ch_off, dst_ch_off + c) of a PF map
+ * (n, scale*h, scale*w, dst_pitch): Up.forward's upsample + torch.cat without materialising either. */
+int cb_upsample_concat(const void* src_pf, int64_t src_lo_off, int n, int h, int w, int c, int scale,
+                       void* dst_pf, int64_t dst_lo_off, int dst_pitch, int dst_ch_off, void* stream);
 
 #ifdef __cplusplus
 }
