@@ -30,14 +30,14 @@ def _half_up(x: int) -> int:          # output size of a k3/s2/p1 (and k1/s2/p0)
 class Act:
     """One activation buffer in HBM.  layout 'pf' = padded flat, 'ps' = phase split (4 parity planes)."""
 
-    def __init__(self, n_cap: int, H: int, W: int, C_: int, layout: str, precise: bool, device, dtype=BF16):
-        self.n_cap, self.H, self.W, self.C, self.layout = n_cap, H, W, C_, layout
+    def __init__(self, n_cap: int, H: int, W: int, C_: int, layout: str, precise: bool, device, dtype=BF16, pad: int = 1):
+        self.n_cap, self.H, self.W, self.C, self.layout, self.pad = n_cap, H, W, C_, layout, pad
         if layout == "pf":
-            self.Hp, self.Wp = H + 2, W + 2
+            self.Hp, self.Wp = H + 2 * pad, W + 2 * pad
             self.plane_rows = 0
             self.rows = n_cap * self.Hp * self.Wp
         else:
-            self.Hp, self.Wp = _half_up(H) + 2, _half_up(W) + 2       # padded dims of each parity plane
+            self.Hp, self.Wp = _half_up(H) + 2 * pad, _half_up(W) + 2 * pad      # padded dims of each parity plane
             self.plane_rows = n_cap * self.Hp * self.Wp
             self.rows = 4 * self.plane_rows
         self.precise = precise

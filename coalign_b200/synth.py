@@ -256,3 +256,70 @@ def loss_case(seed, n=2, H=12, W=20, A=2, n_pos=9, empty_samples=(), dtype=np.fl
     reg[:, :, 0, 0] = 2.5
     reg[:, :, 1, 1] = 0.0
     return {"cls": cls, "reg": reg, "dir": dr, "pos": pos, "neg": neg, "tgt": tgt}
+
+
+# ------------------------------------------------------------------------------------------
+# camera BEV half (BASELINE configs[4]): BevEncodeMSFusion on the splat output
+# ------------------------------------------------------------------------------------------
+def random_camera_bev_state_dict(seed=0, in_channels=128) -> Dict[str, torch.Tensor]:
+    """Random-init weights with the key names / shapes of the reference's BevEncodeMSFusion (lss_submodule.py:357-388:
+    7x7/s2 stem, resnet18 layer1-3, two Up blocks, down_layer); BatchNorm statistics randomised like random_state_dict."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def bn(prefix, c):
+        sd[prefix + ".weight"] = torch.rand(c, generator=g) * 0.8 + 0.6
+        sd[prefix + ".bias"] = torch.randn(c, generator=g) * 0.1
+        sd[prefix + ".running_mean"] = torch.randn(c, generator=g) * 0.1
+        sd[prefix + ".running_var"] = torch.rand(c, generator=g) * 0.8 + 0.6
+        sd[prefix + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.int64)
+
+    def conv(name, cout, cin, k):
+        sd[name] = torch.randn(cout, cin, k, k, generator=g) * math.sqrt(2.0 / (cin * k * k))
+
+    conv("conv1.weight", 64, in_channels, 7)
+    bn("bn1", 64)
+    cin = 64
+    for li, c in ((1, 64), (2, 128), (3, 256)):
+        for b in range(2):
+            p = f"layer{li}.{b}"
+            conv(p + ".conv1.weight", c, cin if b == 0 else c, 3)
+            bn(p + ".bn1", c)
+            conv(p + ".conv2.weight", c, c, 3)
+            bn(p + ".bn2", c)
+            if b == 0 and cin != c:
+                conv(p + ".downsample.0.weight", c, cin, 1)
+                bn(p + ".downsample.1", c)
+        cin = c
+    for name, ci in (("up_layer2", 128 + 256), ("up_layer1", 64 + 256)):
+        conv(name + ".conv.0.weight", 256, ci, 3)
+        bn(name + ".conv.1", 256)
+        conv(name + ".conv.3.weight", 256, 256, 3)
+        bn(name + ".conv.4", 256)
+    conv("down_layer.0.weight", 256, 256, 3)
+    sd["down_layer.0.bias"] = torch.randn(256, generator=g) * 0.05
+    conv("down_layer.2.weight", 128, 256, 3)
+    sd["down_layer.2.bias"] = torch.randn(128, generator=g) * 0.05
+    return sd
+
+
+def camera_bev_case(record_len, seed, hw=240, in_channels=128, max_cav=5, voxel=0.4):
+    """Synthetic splat output (sumN, 128, hw, hw) float32 (sparse-ish, non-negative like a pooled frustum feature map) and
+    pairwise_t_matrix (B, L, L, 4, 4) float64 for agents spread inside the [-hw*voxel/2, hw*voxel/2] grid."""
+    rng = np.random.default_rng(5000 + seed)
+    n = int(sum(record_len))
+    x = rng.standard_normal((n, in_channels, hw, hw)).astype(np.float32)
+    x *= (rng.random((n, 1, hw, hw)) < 0.6).astype(np.float32)
+    half = hw * voxel / 2
+    pws = []
+    for k in record_len:
+        poses = [[0, 0, 0, 0, 0, 0]] + [[float(rng.uniform(-half / 2, half / 2)), float(rng.uniform(-half / 2, half / 2)), 0, 0,
+                                         float(rng.uniform(-180, 180)), 0] for _ in range(k - 1)]
+        ts = [_pose_matrix(p) for p in poses]
+        pw = np.tile(np.eye(4), (max_cav, max_cav, 1, 1))
+        for i in range(k):
+            for j in range(k):
+                if i != j:
+                    pw[i, j] = np.linalg.solve(ts[j], ts[i])
+        pws.append(pw)
+    return x, np.stack(pws)

@@ -36,10 +36,11 @@ def nchw_to_act(x, act):
 
 
 def act_rows(act, n, h, w):
+    pad = getattr(act, "pad", 1)
     if act.layout == "pf":
-        return (n * act.Hp + h + 1) * act.Wp + w + 1
+        return (n * act.Hp + h + pad) * act.Wp + w + pad
     ph = (h & 1) * 2 + (w & 1)
-    return ph * act.plane_rows + (n * act.Hp + (h >> 1) + 1) * act.Wp + (w >> 1) + 1
+    return ph * act.plane_rows + (n * act.Hp + (h >> 1) + pad) * act.Wp + (w >> 1) + pad
 
 
 def act_to_nchw(act, n):
@@ -68,10 +69,12 @@ def run_conv(eng, d):
     n = q // (d.Hp * d.Wp)
     rem = q % (d.Hp * d.Wp)
     hp, wp = rem // d.Wp, rem % d.Wp
-    inter = (hp >= 1) & (hp <= d.Hp - 2) & (wp >= 1) & (wp <= d.Wp - 2)
-    h, w = hp - 1, wp - 1
+    pad = d.in_pad if d.in_pad else 1
+    inter = (hp >= pad) & (hp <= d.Hp - 1 - pad) & (wp >= pad) & (wp <= d.Wp - 1 - pad)
+    h, w = hp - pad, wp - pad
     cols = torch.arange(d.n_total)
-    v = acc + pc.bias[cols % d.cout_mod].view(1, -1)
+    bias = reg[d.bias].bias if d.bias in reg else pc.bias          # a K-split launch shares the weights, not the bias
+    v = acc + bias[cols % d.cout_mod].view(1, -1)
     if d.residual:
         v = v + _f32(reg[d.residual])[:rows_total, :d.n_total]
     if d.relu:
@@ -85,7 +88,11 @@ def run_conv(eng, d):
         return
     out = reg[d.out]
     if d.out_mode == CB_OUT_PF:
-        _store(out, qi, d.out_ch_off, v[inter])
+        if d.out_Hp == d.Hp and d.out_Wp == d.Wp:
+            _store(out, qi, d.out_ch_off, v[inter])
+        else:                                               # destination with its own halo: addressed by pixel
+            rows = (n * d.out_Hp + h + 1) * d.out_Wp + w + 1
+            _store(out, rows[inter], d.out_ch_off, v[inter])
     elif d.out_mode == CB_OUT_PS:
         ph = (h & 1) * 2 + (w & 1)
         rows = ph * d.out_plane_rows + (n * d.out_Hp + (h >> 1) + 1) * d.out_Wp + (w >> 1) + 1

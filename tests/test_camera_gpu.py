@@ -1,0 +1,65 @@
+"""GPU parity of the camera model's BEV half: BevEncoderEngine through the C ABI against golden vectors of
+the UNMODIFIED reference `BevEncodeMSFusion` (tests/golden/camera_bev_small*.npz) - precise mode within 1e-3, bf16 at bf16
+drift - plus the two new layout kernels against PyTorch."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from coalign_b200 import _lib, synth
+from tests.test_camera_cpu import CASES, _load
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+@pytest.mark.parametrize("name,method", CASES)
+def test_camera_bev_encoder_matches_reference_golden(name, method):
+    from coalign_b200.camera import BevEncoderEngine
+    g, rl, sd, x, pw = _load(name)
+    for precise in (True, False):
+        eng = BevEncoderEngine(sd, 48, 48, sum(rl), len(rl), discrete_ratio=0.4, method=method, precise=precise)
+        for rep in range(2):                              # second call replays the captured graph
+            xs, xf = eng.forward(x.cuda(), rl, pw.cuda())
+        torch.cuda.synchronize()
+        for got, key in ((xs, "x_single"), (xf, "x_fuse")):
+            ref = g[key]
+            got = got.cpu().numpy()
+            if precise:
+                err = np.abs(got - ref)
+                assert (err <= 1e-3 * np.abs(ref) + 1e-3 * np.sqrt((ref * ref).mean())).all(), (key, err.max())
+            else:
+                assert rel_l2(got, ref) < 3e-2, (key, rel_l2(got, ref))
+
+
+def test_upsample_concat_matches_torch():
+    """cb_upsample_concat == nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) + torch.cat (lss_submodule.py:
+    23-24,36-37) on bf16-rounded inputs."""
+    lib = _lib.load(True)
+    sp = torch.cuda.current_stream().cuda_stream
+    torch.manual_seed(0)
+    n, h, w, c1, c2 = 2, 6, 9, 64, 128
+    a = torch.randn(n, c1, 2 * h, 2 * w, device="cuda").to(torch.bfloat16).float()
+    b = torch.randn(n, c2, h, w, device="cuda").to(torch.bfloat16).float()
+
+    def to_pf(t):
+        nn_, cc, hh, ww = t.shape
+        p = torch.zeros(nn_, hh + 2, ww + 2, cc, dtype=torch.bfloat16, device="cuda")
+        p[:, 1:-1, 1:-1] = t.permute(0, 2, 3, 1).to(torch.bfloat16)
+        return p.reshape(-1, cc).contiguous()
+    pa, pb_ = to_pf(a), to_pf(b)
+    dst = torch.zeros(n * (2 * h + 2) * (2 * w + 2), c1 + c2, dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.cb_upsample_concat(pa.data_ptr(), 0, n, 2 * h, 2 * w, c1, 1, dst.data_ptr(), 0, c1 + c2, 0, sp))
+    _lib.check(lib.cb_upsample_concat(pb_.data_ptr(), 0, n, h, w, c2, 2, dst.data_ptr(), 0, c1 + c2, c1, sp))
+    torch.cuda.synchronize()
+    got = dst.float().reshape(n, 2 * h + 2, 2 * w + 2, c1 + c2)[:, 1:-1, 1:-1].permute(0, 3, 1, 2)
+    ref = torch.cat([a, F.interpolate(b, scale_factor=2, mode="bilinear", align_corners=True)], 1)
+    assert torch.equal(got[:, :c1], a)
+    assert (got[:, c1:] - ref[:, c1:]).abs().max().item() < 2e-2          # one bf16 rounding of the interpolated value
+    assert dst.reshape(n, 2 * h + 2, 2 * w + 2, -1)[:, 0].abs().max().item() == 0
