@@ -563,6 +563,33 @@ def run_ours(opt):
                        "inference.py:125-143; the voxel tensors are 75x the bytes of the raw clouds"}
         del model
 
+    # ---- BASELINE configs[4], BEV half: BevEncodeMSFusion on a splat-output-shaped input (5 agents x 128 x 240 x 240 / scene)
+    cam = None
+    if rank == 0 and world == 1 and not opt.no_extras and not opt.precise:
+        from coalign_b200.camera import BevEncoderEngine
+        Bc = 2
+        csd = synth.random_camera_bev_state_dict(0)
+        ceng = BevEncoderEngine(csd, 240, 240, Bc * N_AGENTS, Bc, discrete_ratio=0.4, method="att", device=f"cuda:{local}")
+        cx, cpw = synth.camera_bev_case([N_AGENTS] * Bc, 0, hw=240)
+        cxd, cpwd = torch.from_numpy(cx).cuda(), torch.from_numpy(cpw).cuda()
+        for _ in range(3):
+            ceng.forward(cxd, [N_AGENTS] * Bc, cpwd)
+        kc = max(5, min(opt.steps, 30))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(kc):
+            ceng.forward(cxd, [N_AGENTS] * Bc, cpwd)
+        e1.record()
+        torch.cuda.synchronize()
+        msc = e0.elapsed_time(e1) / kc
+        cam = {"value": Bc / (msc * 1e-3), "unit": "scenes/s", "ms_per_step": msc, "scenes_per_step": Bc,
+               "conv_tflops": 562.85e9 * Bc / (msc * 1e-3) / 1e12,
+               "workload": "BEV half of BASELINE configs[4]: BevEncodeMSFusion (7x7/s2 stem, resnet18 layer1-3, AttFusion at "
+                           "(64,120,120) (128,60,60) (256,30,30), two Up blocks, down_layer) on 5 x (128,240,240) splat-shaped "
+                           "maps per scene, x_single + x_fuse; lift / splat and the EfficientNet camera encoder are not built"}
+        del ceng, cxd
+        torch.cuda.empty_cache()
+
     # ---- the training iteration (every rank: the all-reduce is a collective)
     train = None
     if not opt.no_train and not opt.precise:
@@ -607,7 +634,7 @@ def run_ours(opt):
                            "H2D, forward and D2H of neighbouring steps overlap on 3 streams)"},
             "gpu_launches": launches_per_step * opt.steps,
             "clocks": clocks, "roofline": roof, "roofline_hbm": hbm_roofs, "cpu_baseline": cpu, "parity": parity,
-            "postprocess": post, "e2e_varying_clouds": vary, "plugin_api": plug, "train": train,
+            "postprocess": post, "e2e_varying_clouds": vary, "plugin_api": plug, "train": train, "camera_bev": cam,
         }
         sys.stdout.flush()
         print(json.dumps(line), flush=True)

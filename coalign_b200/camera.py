@@ -262,3 +262,69 @@ class BevEncoderEngine(CoAlignEngine):
         xs = self.read_act(self.dec["x_single"], n_img)
         xf = self.read_act(self.dec["x_fuse"], n_sc)
         return xs, xf
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# drop-in twin of the reference sub-module
+# ----------------------------------------------------------------------------------------------------------------------
+import torch.nn as nn       # noqa: E402
+
+
+class _Block(nn.Module):                          # torchvision BasicBlock parameter container
+    def __init__(self, cin, cout, has_ds):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, 2 if has_ds else 1, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(cout)
+        self.conv2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(cout)
+        if has_ds:
+            self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, 2, bias=False), nn.BatchNorm2d(cout))
+
+
+class _Up(nn.Module):                             # lss_submodule.Up parameter container (conv.0/1/3/4)
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv = nn.Sequential(nn.Conv2d(cin, cout, 3, padding=1, bias=False), nn.BatchNorm2d(cout), nn.ReLU(inplace=True),
+                                  nn.Conv2d(cout, cout, 3, padding=1, bias=False), nn.BatchNorm2d(cout), nn.ReLU(inplace=True))
+
+
+class BevEncodeMSFusionB200(nn.Module):
+    """state_dict-compatible twin of the reference's `BevEncodeMSFusion` (lss_submodule.py:357-417): same constructor
+    argument (`fusion_args` with `core_method` in {att_ms, max_ms} and `args.in_channels` / `args.voxel_size`), same 118
+    state_dict entries, same `forward(x, record_len, pairwise_t_matrix) -> (x_single, x_fuse)`.  Inference only, B200 only."""
+
+    def __init__(self, fusion_args):
+        super().__init__()
+        args = fusion_args["args"]
+        self.method = {"att_ms": "att", "max_ms": "max"}.get(fusion_args["core_method"])
+        if self.method is None:
+            raise NotImplementedError("BevEncodeMSFusion: core_method must be att_ms or max_ms")     # the reference raises too
+        self.discrete_ratio = float(args["voxel_size"][0])
+        self.precise = bool(args.get("b200_precise", False))
+        inC = int(args["in_channels"])
+        self.conv1 = nn.Conv2d(inC, 64, 7, 2, 3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.layer1 = nn.Sequential(_Block(64, 64, False), _Block(64, 64, False))
+        self.layer2 = nn.Sequential(_Block(64, 128, True), _Block(128, 128, False))
+        self.layer3 = nn.Sequential(_Block(128, 256, True), _Block(256, 256, False))
+        self.up_layer1 = _Up(64 + 256, 256)
+        self.up_layer2 = _Up(128 + 256, 256)
+        self.down_layer = nn.Sequential(nn.Conv2d(256, 256, 3, 1, 1), nn.ReLU(inplace=True), nn.Conv2d(256, 128, 3, 1, 1),
+                                        nn.ReLU(inplace=True))
+        self._eng, self._key = None, None
+
+    def forward(self, x, record_len, pairwise_t_matrix):
+        if self.training:
+            raise NotImplementedError("BevEncodeMSFusionB200 is inference-only (the training kernels cover the LiDAR model)")
+        rl = [int(v) for v in (record_len.tolist() if torch.is_tensor(record_len) else record_len)]
+        _, _c, H, W = x.shape
+        key = (x.device, H, W, int(pairwise_t_matrix.shape[1]), tuple(int(p._version) for p in self.parameters()))
+        e = self._eng
+        if e is None or self._key != key or e.max_agents < sum(rl) or e.max_scenes < len(rl):
+            self._eng = None
+            e = BevEncoderEngine(self.state_dict(), H, W, max(sum(rl), e.max_agents if e is not None else 1),
+                                 max(len(rl), e.max_scenes if e is not None else 1), discrete_ratio=self.discrete_ratio,
+                                 method=self.method, device=x.device, precise=self.precise,
+                                 max_cav=int(pairwise_t_matrix.shape[1]))
+            self._eng, self._key = e, key
+        return e.forward(x.float().contiguous(), rl, pairwise_t_matrix)

@@ -63,3 +63,23 @@ def test_upsample_concat_matches_torch():
     assert torch.equal(got[:, :c1], a)
     assert (got[:, c1:] - ref[:, c1:]).abs().max().item() < 2e-2          # one bf16 rounding of the interpolated value
     assert dst.reshape(n, 2 * h + 2, 2 * w + 2, -1)[:, 0].abs().max().item() == 0
+
+
+def test_bev_encode_ms_fusion_twin_matches_engine_and_golden():
+    """The nn.Module twin of the reference sub-module (same constructor argument, same 118 state_dict entries, same forward
+    signature) in precise mode against the reference golden."""
+    from coalign_b200.camera import BevEncodeMSFusionB200
+    g, rl, sd, x, pw = _load("camera_bev_small")
+    m = BevEncodeMSFusionB200({"core_method": "att_ms", "args": {"in_channels": 128, "voxel_size": [0.4, 0.4, 20],
+                                                               "b200_precise": True}})
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        xs, xf = m(x.cuda(), torch.tensor(rl).cuda(), pw.cuda())
+    torch.cuda.synchronize()
+    for got, key in ((xs, "x_single"), (xf, "x_fuse")):
+        ref = g[key]
+        err = np.abs(got.cpu().numpy() - ref)
+        assert (err <= 1e-3 * np.abs(ref) + 1e-3 * np.sqrt((ref * ref).mean())).all(), (key, err.max())
+    with pytest.raises(NotImplementedError):
+        m.train()(x.cuda(), torch.tensor(rl).cuda(), pw.cuda())
