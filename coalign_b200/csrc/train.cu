@@ -80,7 +80,7 @@ __device__ __forceinline__ void store8(__nv_bfloat16* base, long off, long lo_of
 }
 
 constexpr int EW_THREADS = 256;
-constexpr int EW_BLOCKS = 148 * 6;
+constexpr int EW_BLOCKS = 148 * 2;   // one resident wave of the 2-CTA/SM streaming kernels (several waves re-run their prologues and ramps)
 
 // Per-block reduction of per-thread partial sums (8 channels each, two quantities) into fp64 global sums.
 // s_part: [2][2048] floats of shared memory; slot of element j of this thread = tslot*8 + j with tslot = threadIdx.x
