@@ -137,6 +137,9 @@ EXPORTS = {
                                     C.c_int, C.c_void_p, C.c_void_p]),
     "cb_nchw_to_ps_pad": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64,
                                     C.c_void_p]),
+    "cb_nhwc_to_ps_pad": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64,
+                                    C.c_void_p]),
+    "cb_lift_splat": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 6 + [C.c_void_p] * 5),
     "cb_upsample_concat": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                      C.c_int64, C.c_int, C.c_int, C.c_void_p]),
 }

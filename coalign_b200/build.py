@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "lib", "obj")
 LIB = os.path.join(HERE, "lib", "libcoalign_b200.so")
-SOURCES = ["conv_tc.cu", "conv_simt.cu", "pillar.cu", "warp_fuse.cu", "layout.cu", "postprocess.cu", "loss.cu", "wgrad.cu", "train.cu"]
+SOURCES = ["conv_tc.cu", "conv_simt.cu", "pillar.cu", "warp_fuse.cu", "layout.cu", "postprocess.cu", "loss.cu", "wgrad.cu", "train.cu", "lift_splat.cu"]
 HEADERS = ["common.cuh", "conv_common.cuh", os.path.join("..", "..", "include", "coalign_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

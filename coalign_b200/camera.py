@@ -224,15 +224,18 @@ class BevEncoderEngine(CoAlignEngine):
                 raise RuntimeError("unknown op " + kind)
 
     @torch.no_grad()
-    def forward(self, x: torch.Tensor, record_len: Sequence[int], pairwise: torch.Tensor, clone: bool = True):
-        """x (sumN, inC, H, W) float32 on the device (the splat output); returns (x_single, x_fuse) float32 NCHW."""
+    def forward(self, x: torch.Tensor, record_len: Sequence[int], pairwise: torch.Tensor, clone: bool = True,
+                channels_last: bool = False):
+        """x (sumN, inC, H, W) float32 on the device (the splat output; channels_last: (sumN, H, W, inC), what
+        LiftSplatB200 produces); returns (x_single, x_fuse) float32 NCHW."""
         record_len = tuple(int(v) for v in record_len)
         n_img, n_sc = sum(record_len), len(record_len)
-        if tuple(x.shape) != (n_img, self.in_c, self.ny, self.nx) or x.dtype != torch.float32:
-            raise ValueError("x must be float32 (sum(record_len), in_channels, H, W)")
+        want = (n_img, self.ny, self.nx, self.in_c) if channels_last else (n_img, self.in_c, self.ny, self.nx)
+        if tuple(x.shape) != want or x.dtype != torch.float32:
+            raise ValueError("x must be float32 %s" % (want,))
         self._set_scene_meta(record_len, pairwise)
-        self.in_f32[:n_img].copy_(x, non_blocking=True)
-        key = ("bev", record_len)
+        self.in_f32.view(-1)[:x.numel()].copy_(x.reshape(-1), non_blocking=True)
+        key = ("bev", record_len, bool(channels_last))
         ent = self._graphs.get(key)
         if ent is None:
             ent = {"ops": self.build_bev_ops(n_img, n_sc), "graph": None}
@@ -241,8 +244,9 @@ class BevEncoderEngine(CoAlignEngine):
                 self._graphs.popitem(last=False)
 
         def run(sp):
-            _lib.check(self.lib.cb_nchw_to_ps_pad(self.in_f32.data_ptr(), n_img, self.in_c, self.ny, self.nx, 2,
-                                                  self.x_in.n_cap, self.x_in.ptr, self.x_in.lo_off, sp), "cb_nchw_to_ps_pad")
+            to_ps = self.lib.cb_nhwc_to_ps_pad if channels_last else self.lib.cb_nchw_to_ps_pad
+            _lib.check(to_ps(self.in_f32.data_ptr(), n_img, self.in_c, self.ny, self.nx, 2, self.x_in.n_cap, self.x_in.ptr,
+                             self.x_in.lo_off, sp), "cb_n*_to_ps_pad")
             _lib.check(self.lib.cb_normalize_affine(self.pairwise.data_ptr(), n_sc, self.max_cav, self.ny, self.nx,
                                                     float(self.voxel_size[0]), self.affine.data_ptr(), sp), "cb_normalize_affine")
             self._launch_bev(ent["ops"], n_sc, sp)
@@ -328,3 +332,58 @@ class BevEncodeMSFusionB200(nn.Module):
                                  max_cav=int(pairwise_t_matrix.shape[1]))
             self._eng, self._key = e, key
         return e.forward(x.float().contiguous(), rl, pairwise_t_matrix)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# lift + splat (the camera front-end between the image encoder and the BEV encoder)
+# ----------------------------------------------------------------------------------------------------------------------
+class LiftSplatB200:
+    """Device replacement of `LiftSplatShoot.get_geometry` + the lift of `CamEncode.forward` + `voxel_pooling`
+    (/root/reference/opencood/models/lift_splat_shoot.py:64-169, lss_submodule.py:134-136): depth logits and image features of
+    every camera in, BEV feature map out.  Constructor arguments are the yaml's `grid_conf`, `data_aug_conf.final_dim` and
+    `img_downsample` (lss_coalign_fusion.yaml:28-43,99).  The geometry's 3x3 inverses are host plumbing (torch.inverse on B*N
+    tiny matrices, as in the reference); everything per frustum point runs in `cb_lift_splat`."""
+
+    def __init__(self, grid_conf: dict, final_dim, downsample: int, device="cuda"):
+        self.lib = _lib.load(check_device=True)
+        self.device = torch.device(device)
+        gc = grid_conf
+        self.dx = np.asarray([row[2] for row in (gc["xbound"], gc["ybound"], gc["zbound"])], np.float32)          # gen_dx_bx
+        self.bx = np.asarray([row[0] + row[2] / 2.0 for row in (gc["xbound"], gc["ybound"], gc["zbound"])], np.float32)
+        self.nx = np.asarray([int((row[1] - row[0]) / row[2]) for row in (gc["xbound"], gc["ybound"], gc["zbound"])], np.int32)
+        ogfH, ogfW = final_dim
+        self.fH, self.fW = ogfH // downsample, ogfW // downsample
+        d_min, d_max, nb = gc["ddiscr"]
+        if gc["mode"] == "UD":
+            ds = d_min + (d_max - d_min) / nb * np.arange(nb)
+        elif gc["mode"] == "LID":
+            ds = d_min + 2 * (d_max - d_min) / (nb * (1 + nb)) * (np.arange(nb) * np.arange(1, 1 + nb)) / 2
+        else:
+            raise NotImplementedError(gc["mode"])
+        self.D = int(nb)
+        self.ds = torch.tensor(ds, dtype=torch.float).to(self.device)                                   # create_frustum (:69-74)
+        self.xs = torch.linspace(0, ogfW - 1, self.fW, dtype=torch.float).to(self.device)
+        self.ys = torch.linspace(0, ogfH - 1, self.fH, dtype=torch.float).to(self.device)
+
+    @torch.no_grad()
+    def __call__(self, depth_logit, x_img, rots, trans, intrins, post_rots, post_trans, out: torch.Tensor = None):
+        """depth_logit (B*N, D, fH, fW), x_img (B*N, C, fH, fW) float32 CUDA; camera tensors (B, N, 3[, 3]).  Returns the BEV
+        accumulator (B, ny, nx, nz*C) float32 channels-last (== voxel_pooling's output permuted to NHWC)."""
+        B, N = int(trans.shape[0]), int(trans.shape[1])
+        BN, C = int(x_img.shape[0]), int(x_img.shape[1])
+        if BN != B * N or tuple(depth_logit.shape) != (BN, self.D, self.fH, self.fW) or tuple(x_img.shape[2:]) != (self.fH, self.fW):
+            raise ValueError("lift_splat: inconsistent shapes")
+        f = lambda t: t.to(self.device, torch.float32)      # noqa: E731
+        cam = torch.cat([torch.inverse(f(post_rots)).reshape(BN, 9), f(post_trans).reshape(BN, 3),
+                         f(rots).matmul(torch.inverse(f(intrins))).reshape(BN, 9), f(trans).reshape(BN, 3)], 1).contiguous()
+        ny, nxx, nz = int(self.nx[1]), int(self.nx[0]), int(self.nx[2])
+        if out is None:
+            out = torch.zeros(B, ny, nxx, nz * C, dtype=torch.float32, device=self.device)
+        else:
+            out.zero_()
+        dl, xi = depth_logit.float().contiguous(), x_img.float().contiguous()
+        _lib.check(self.lib.cb_lift_splat(dl.data_ptr(), xi.data_ptr(), cam.data_ptr(), self.xs.data_ptr(), self.ys.data_ptr(),
+                                          self.ds.data_ptr(), B, N, self.D, self.fH, self.fW, C, self.dx.ctypes.data,
+                                          self.bx.ctypes.data, self.nx.ctypes.data, out.data_ptr(),
+                                          torch.cuda.current_stream(self.device).cuda_stream), "cb_lift_splat")
+        return out

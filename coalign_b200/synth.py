@@ -323,3 +323,33 @@ def camera_bev_case(record_len, seed, hw=240, in_channels=128, max_cav=5, voxel=
                     pw[i, j] = np.linalg.solve(ts[j], ts[i])
         pws.append(pw)
     return x, np.stack(pws)
+
+
+def lift_splat_case(seed=0, B=2, N=4, C=64, final_dim=(96, 128), downsample=8, n_bins=16):
+    """Small lift + splat problem with the structure of the camera yaml (lss_coalign_fusion.yaml:28-43): N pinhole cameras
+    looking outwards from the agent, LID depth bins, a square BEV grid.  Returns numpy arrays + the config dicts."""
+    rng = np.random.default_rng(7000 + seed)
+    grid_conf = {"xbound": [-16.0, 16.0, 0.4], "ybound": [-16.0, 16.0, 0.4], "zbound": [-10.0, 10.0, 20.0],
+                 "ddiscr": [2, 18, n_bins], "mode": "LID"}
+    fH, fW = final_dim[0] // downsample, final_dim[1] // downsample
+    rots = np.zeros((B, N, 3, 3), np.float32)
+    trans = np.zeros((B, N, 3), np.float32)
+    intr = np.zeros((B, N, 3, 3), np.float32)
+    post_rots = np.zeros((B, N, 3, 3), np.float32)
+    post_trans = np.zeros((B, N, 3), np.float32)
+    cam_to_ego = np.array([[0, 0, 1.0], [-1.0, 0, 0], [0, -1.0, 0]])          # camera (x right, y down, z fwd) -> ego (x fwd, y left, z up)
+    for b in range(B):
+        for n in range(N):
+            yaw = np.deg2rad(90.0 * n + rng.uniform(-10, 10))
+            rz = np.array([[np.cos(yaw), -np.sin(yaw), 0], [np.sin(yaw), np.cos(yaw), 0], [0, 0, 1.0]])
+            rots[b, n] = (rz @ cam_to_ego).astype(np.float32)
+            trans[b, n] = [rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(1.2, 1.8)]
+            f = rng.uniform(0.9, 1.1) * final_dim[1] / 2
+            intr[b, n] = [[f, 0, final_dim[1] / 2], [0, f, final_dim[0] / 2], [0, 0, 1]]
+            sc = rng.uniform(0.8, 0.85)
+            post_rots[b, n] = np.diag([sc, sc, 1.0]).astype(np.float32)
+            post_trans[b, n] = [rng.uniform(-8, 0), rng.uniform(-8, 0), 0]
+    return {"grid_conf": grid_conf, "final_dim": list(final_dim), "downsample": downsample,
+            "depth_logit": rng.standard_normal((B * N, n_bins, fH, fW)).astype(np.float32) * 2.0,
+            "x_img": rng.standard_normal((B * N, C, fH, fW)).astype(np.float32),
+            "rots": rots, "trans": trans, "intrins": intr, "post_rots": post_rots, "post_trans": post_trans}

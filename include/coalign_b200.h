@@ -496,6 +496,21 @@ int cb_layout_to_nchw(const void* src, int64_t lo_off, int from_ps, int n, int c
  * ceil(w/2)+2*pad; n_cap = plane stride in images): the input layout of the camera BEV encoder's 7x7/s2 stem. */
 int cb_nchw_to_ps_pad(const float* src, int n, int c, int h, int w, int pad, int n_cap, void* dst, int64_t lo_off,
                       void* stream);
+/* fp32 channels-last (n, h, w, c) -> the same PS / pad layout (the BEV accumulator of cb_lift_splat feeds the stem). */
+int cb_nhwc_to_ps_pad(const float* src, int n, int c, int h, int w, int pad, int n_cap, void* dst, int64_t lo_off,
+                      void* stream);
+/* Lift + splat of the camera model: depth soft-max (x) image features, summed into the BEV voxels of their frustum points.
+ *   CamEncode.get_depth_dist + the outer product of CamEncode.forward   lss_submodule.py:60-61,134-136
+ *   LiftSplatShoot.get_geometry / voxel_pooling                         lift_splat_shoot.py:80-105,115-169
+ * depth_logit DEVICE f32 [B*N][D][fH][fW]; feat DEVICE f32 [B*N][C][fH][fW]; cam_mats DEVICE f32 [B*N][24] = inverse(post_rots)
+ * (9, row major), post_trans (3), rots * inverse(intrins) (9), trans (3); xs [fW], ys [fH], ds [D] DEVICE f32 = the frustum's
+ * image-plane coordinates and depth bins (create_frustum, :64-78); dx, bx HOST f32 [3], nx HOST i32 [3] from gen_dx_bx.
+ * acc: DEVICE f32 [B][ny][nx][nz*C] channels-last, ACCUMULATED (zero it first); equals voxel_pooling's `final` with the z
+ * planes concatenated along the channels (:163-165), i.e. final[b, z*C + c, y, x] = acc[b][y][x][z*C + c].
+ * The lifted (B*N, C, D, fH, fW) tensor, the sort by voxel rank and the cumsum trick are never materialised. */
+int cb_lift_splat(const float* depth_logit, const float* feat, const float* cam_mats, const float* xs, const float* ys,
+                  const float* ds, int B, int N, int D, int fH, int fW, int C, const float* dx, const float* bx,
+                  const int32_t* nx, float* acc, void* stream);
 /* Bilinear up-sampling by `scale` (1 = plain copy, 2 = nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True),
  * lss_submodule.py:23-24,36-37) of a PF map (n, h, w, c) into channels [dst_ch_off, dst_ch_off + c) of a PF map
  * (n, scale*h, scale*w, dst_pitch): Up.forward's upsample + torch.cat without materialising either. */

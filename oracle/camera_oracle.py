@@ -58,3 +58,70 @@ def bev_encode_ms_fusion(sd: Dict[str, torch.Tensor], x, record_len, pairwise_t_
     if stages is not None:
         stages.update(feats=feats, fused=fused)
     return x_single, x_fuse
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# lift + splat: /root/reference/opencood/models/lift_splat_shoot.py:64-169 (create_frustum, get_geometry, get_cam_feats'
+# reshape, voxel_pooling) and the "lift" line of CamEncode.forward (lss_submodule.py:134-136: depth softmax (x) features);
+# depth_discretization / gen_dx_bx from utils/camera_utils.py:129-135,186-195.
+# ----------------------------------------------------------------------------------------------------------------------
+import numpy as np      # noqa: E402
+
+
+def depth_bins(d_min, d_max, num_bins, mode):
+    if mode == "UD":
+        return d_min + (d_max - d_min) / num_bins * np.arange(num_bins)
+    if mode == "LID":
+        bin_size = 2 * (d_max - d_min) / (num_bins * (1 + num_bins))
+        return d_min + bin_size * (np.arange(num_bins) * np.arange(1, 1 + num_bins)) / 2
+    raise NotImplementedError(mode)
+
+
+def gen_dx_bx(xbound, ybound, zbound):
+    dx = torch.Tensor([row[2] for row in [xbound, ybound, zbound]])
+    bx = torch.Tensor([row[0] + row[2] / 2.0 for row in [xbound, ybound, zbound]])
+    nx = torch.LongTensor([(row[1] - row[0]) / row[2] for row in [xbound, ybound, zbound]])
+    return dx, bx, nx
+
+
+def frustum(grid_conf, final_dim, downsample):
+    ogfH, ogfW = final_dim
+    fH, fW = ogfH // downsample, ogfW // downsample
+    ds = torch.tensor(depth_bins(*grid_conf["ddiscr"], grid_conf["mode"]), dtype=torch.float).view(-1, 1, 1).expand(-1, fH, fW)
+    D = ds.shape[0]
+    xs = torch.linspace(0, ogfW - 1, fW, dtype=torch.float).view(1, 1, fW).expand(D, fH, fW)
+    ys = torch.linspace(0, ogfH - 1, fH, dtype=torch.float).view(1, fH, 1).expand(D, fH, fW)
+    return torch.stack((xs, ys, ds), -1)
+
+
+def geometry(fr, rots, trans, intrins, post_rots, post_trans):
+    B, N, _ = trans.shape
+    points = fr - post_trans.view(B, N, 1, 1, 1, 3)
+    points = torch.inverse(post_rots).view(B, N, 1, 1, 1, 3, 3).matmul(points.unsqueeze(-1))
+    points = torch.cat((points[:, :, :, :, :, :2] * points[:, :, :, :, :, 2:3], points[:, :, :, :, :, 2:3]), 5)
+    combine = rots.matmul(torch.inverse(intrins))
+    points = combine.view(B, N, 1, 1, 1, 3, 3).matmul(points).squeeze(-1)
+    return points + trans.view(B, N, 1, 1, 1, 3)
+
+
+@torch.no_grad()
+def lift_splat(depth_logit, x_img, rots, trans, intrins, post_rots, post_trans, grid_conf, final_dim, downsample):
+    """depth_logit (B*N, D, fH, fW), x_img (B*N, C, fH, fW) -> BEV (B, C*nz, ny, nx): soft-max over depth, outer product with
+    the features, and the sum of all frustum points that fall into each voxel.  The sum is an exact index_add in float64 (the
+    reference's sort + float32 cumsum + difference computes the same sums with cancellation noise)."""
+    B, N, _ = trans.shape
+    BN, C, fH, fW = x_img.shape
+    dx, bx, nx = gen_dx_bx(grid_conf["xbound"], grid_conf["ybound"], grid_conf["zbound"])
+    fr = frustum(grid_conf, final_dim, downsample)
+    D = fr.shape[0]
+    geom = geometry(fr, rots, trans, intrins, post_rots, post_trans)                       # (B,N,D,fH,fW,3)
+    depth = torch.softmax(depth_logit, dim=1)
+    x = (depth.unsqueeze(1) * x_img.unsqueeze(2)).view(B, N, C, D, fH, fW).permute(0, 1, 3, 4, 5, 2)   # (B,N,D,fH,fW,C)
+    idx = ((geom - (bx - dx / 2.)) / dx).long().view(-1, 3)                                 # truncation toward zero, like .long()
+    bix = torch.arange(B).view(B, 1).expand(B, N * D * fH * fW).reshape(-1)
+    kept = ((idx[:, 0] >= 0) & (idx[:, 0] < nx[0]) & (idx[:, 1] >= 0) & (idx[:, 1] < nx[1]) & (idx[:, 2] >= 0) & (idx[:, 2] < nx[2]))
+    flat = ((bix * nx[2] + idx[:, 2]) * nx[1] + idx[:, 1]) * nx[0] + idx[:, 0]             # (b, z, y, x)
+    out = torch.zeros(B * int(nx[2]) * int(nx[1]) * int(nx[0]), C, dtype=torch.float64)
+    out.index_add_(0, flat[kept], x.reshape(-1, C)[kept].double())
+    out = out.view(B, int(nx[2]), int(nx[1]), int(nx[0]), C).permute(0, 4, 1, 2, 3)        # (B, C, nz, ny, nx)
+    return torch.cat(out.unbind(dim=2), 1).float()                                          # collapse z like the reference

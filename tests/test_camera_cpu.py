@@ -75,3 +75,18 @@ def test_camera_bev_launch_plan_reproduces_reference_golden(name, method):
         ref = g[key]
         err = np.abs(got.numpy() - ref)
         assert (err <= 1e-3 * np.abs(ref) + 1e-3 * np.sqrt((ref * ref).mean())).all(), (key, err.max())
+
+
+def test_lift_splat_oracle_matches_reference_golden():
+    """oracle.camera_oracle.lift_splat (exact float64 index_add) against the UNMODIFIED reference's create_frustum /
+    get_geometry / voxel_pooling (tests/golden/gen_golden_lift.py); the reference's float32 cumsum trick carries its own
+    cancellation noise, hence 1e-4 of the map's scale."""
+    g = np.load(os.path.join(GOLD, "lift_splat_small.npz"))
+    case = synth.lift_splat_case(seed=int(g["seed"]))
+    t = {k: torch.from_numpy(v) for k, v in case.items() if isinstance(v, np.ndarray)}
+    bev = CO.lift_splat(t["depth_logit"], t["x_img"], t["rots"], t["trans"], t["intrins"], t["post_rots"], t["post_trans"],
+                        case["grid_conf"], case["final_dim"], case["downsample"])
+    ref = g["bev"]
+    assert bev.shape == ref.shape
+    assert np.abs(bev.numpy() - ref).max() <= 1e-4 * np.abs(ref).max()
+    assert (ref != 0).mean() > 0.05                                        # the case actually fills a part of the grid
