@@ -8,8 +8,9 @@
 Everything is the existing machinery - tcgen05 implicit-GEMM convolutions (`cb_conv_gemm*`), `cb_warp_att_fuse`, eval-mode
 BatchNorm folded into the packed weights - plus three small additions of this round: `cb_conv_desc.in_pad` (the 7x7 stem's
 taps reach two pixels into the parity planes of its PS-layout input), `cb_nchw_to_ps_pad` (that input layout) and
-`cb_upsample_concat` (`Up`'s bilinear x2 + `torch.cat` written straight into the concat buffer).  Lift / splat (the camera
-front-end proper, lift_splat_shoot.py:80-169) is NOT built: this engine starts from the splat output.
+`cb_upsample_concat` (`Up`'s bilinear x2 + `torch.cat` written straight into the concat buffer).  Lift + splat
+(lift_splat_shoot.py:64-169) is `LiftSplatB200` at the bottom of this file (`cb_lift_splat`); the EfficientNet image encoder
+that produces its inputs is not built.
 """
 from __future__ import annotations
 
