@@ -654,6 +654,9 @@ def run_ours(opt):
         line = {
             "metric": "scenes_per_sec", "value": value, "unit": "scenes/s", "n_gpus": world, "steps": opt.steps,
             "warmup": opt.warmup, "ms_per_step": ms / opt.steps, "higher_is_better": True, "scaling": "weak",
+            "timed_region_s": ms * 1e-3,
+            "timed_region_note": (None if ms >= 1000.0 else "timed region shorter than 1 s: the SM clock has not settled under the "
+                                  "board's power cap yet; steady state is ~5 % lower (profiles/r1_bench_final_n1.json, 200 steps)"),
             "vs_baseline": None, "dtype": "bf16x3 (fp32-class)" if opt.precise else "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "scenes_per_step": B, "agents_per_scene": N_AGENTS, "points_per_agent": N_POINTS,

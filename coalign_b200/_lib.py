@@ -56,6 +56,12 @@ class WgradDesc(C.Structure):
                 ("units", WgradUnit * CB_WGRAD_MAX_UNITS)]
 
 
+class PackJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("s_r1", C.c_int64), ("s_r0", C.c_int64), ("s_k1", C.c_int64),
+                ("s_k0", C.c_int64), ("first", C.c_int64), ("R0", C.c_int32), ("K0", C.c_int32), ("rows", C.c_int32),
+                ("K", C.c_int32), ("dst_ld", C.c_int32), ("k_off", C.c_int32), ("lo_col_off", C.c_int32), ("pad_", C.c_int32)]
+
+
 class Map(C.Structure):
     _fields_ = [("n_img", C.c_int32), ("Hp", C.c_int32), ("Wp", C.c_int32), ("c_total", C.c_int32), ("c_mod", C.c_int32),
                 ("y_mode", C.c_int32), ("y_pitch", C.c_int32), ("y_ch_off", C.c_int32), ("up_k", C.c_int32),
@@ -82,6 +88,7 @@ EXPORTS = {
     "cb_pfn_bwd": (C.c_int, [_P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P, _P]),
     "cb_pfn_bwd_finalize": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "cb_pack_weight": (C.c_int, [_P, _I, _I, _I, _I, _L, _L, _L, _L, _P, _I, _I, _I, _P]),
+    "cb_pack_weights_batch": (C.c_int, [_P, _I, _L, _P]),
     "cb_permute_f32": (C.c_int, [_P, _I, _I, _I, _I, _L, _L, _L, _L, _F, _P, _P]),
     "cb_adam_step": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _P, _I, _P]),
     "cb_version": (C.c_int, []),

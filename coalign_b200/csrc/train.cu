@@ -528,8 +528,25 @@ __device__ __forceinline__ void red_add_v4f(float* p, float a, float b, float c,
 }
 
 // LPP lanes per pixel, 8 channels per lane (C = 8*LPP).  A warp covers 32/LPP consecutive pixels of a row-major scan.
-template <int LPP>
-__global__ void __launch_bounds__(256) warp_att_fuse_bwd_kernel(
+// Register budget (the first version held every agent's warped vector, tap record and gradient at once: 213-255 registers,
+// one CTA per SM): only the warped vectors v_j stay live; the tap geometry is recomputed for the scatter pass (a dozen
+// float ops per agent) and each agent's gradient is formed and scattered on the fly.
+struct FbTap { int x0, y0; float wx, wy; };
+__device__ __forceinline__ FbTap fb_tap(const double* __restrict__ A, double xs, double ys, const FuseBG& g) {
+    FbTap t;
+    const float gx = (float)(A[0] * xs + A[1] * ys + A[2]);
+    const float gy = (float)(A[3] * xs + A[4] * ys + A[5]);
+    const float ix = ((gx + 1.f) * g.W - 1.f) * 0.5f;
+    const float iy = ((gy + 1.f) * g.H - 1.f) * 0.5f;
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    t.wx = ix - fx0; t.wy = iy - fy0;
+    t.x0 = (int)fminf(fmaxf(fx0, -2.f), (float)g.W + 1.f);
+    t.y0 = (int)fminf(fmaxf(fy0, -2.f), (float)g.H + 1.f);
+    return t;
+}
+
+template <int LPP, int MAXN>
+__global__ void __launch_bounds__(256, 2) warp_att_fuse_bwd_kernel(
     const __nv_bfloat16* __restrict__ feat, long in_lo_off, const double* __restrict__ affine,
     const int* __restrict__ agent_off, int n_scenes, int L, const FuseBG g, int method,
     const __nv_bfloat16* __restrict__ dfused, long dfused_lo_off, float* __restrict__ dfeat) {
@@ -549,31 +566,21 @@ __global__ void __launch_bounds__(256) warp_att_fuse_bwd_kernel(
         const int h = rem / g.W, w = rem - h * g.W;
         const int a0 = agent_off[b];
         int n = agent_off[b + 1] - a0;
-        n = n < FB_MAX_AGENTS ? n : FB_MAX_AGENTS;
+        n = n < MAXN ? n : MAXN;
         const double xs = (2.0 * w + 1.0) / g.W - 1.0;
         const double ys = (2.0 * h + 1.0) / g.H - 1.0;
-        float v[FB_MAX_AGENTS][8];
-        int tx0[FB_MAX_AGENTS], ty0[FB_MAX_AGENTS];
-        float twx[FB_MAX_AGENTS], twy[FB_MAX_AGENTS];
+        const double* Ab = affine + (long)b * L * 6;
+        float v[MAXN][8];
 #pragma unroll
-        for (int j = 0; j < FB_MAX_AGENTS; ++j) {
+        for (int j = 0; j < MAXN; ++j) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[j][e] = 0.f;
-            tx0[j] = ty0[j] = 0; twx[j] = twy[j] = 0.f;
             if (j < n) {
-                const double* A = affine + ((long)b * L + j) * 6;
-                const float gx = (float)(A[0] * xs + A[1] * ys + A[2]);
-                const float gy = (float)(A[3] * xs + A[4] * ys + A[5]);
-                const float ix = ((gx + 1.f) * g.W - 1.f) * 0.5f;
-                const float iy = ((gy + 1.f) * g.H - 1.f) * 0.5f;
-                const float fx0 = floorf(ix), fy0 = floorf(iy);
-                twx[j] = ix - fx0; twy[j] = iy - fy0;
-                tx0[j] = (int)fminf(fmaxf(fx0, -2.f), (float)g.W + 1.f);
-                ty0[j] = (int)fminf(fmaxf(fy0, -2.f), (float)g.H + 1.f);
+                const FbTap t = fb_tap(Ab + j * 6, xs, ys, g);
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int xx = tx0[j] + (t & 1), yy = ty0[j] + (t >> 1);
-                    const float wt = ((t & 1) ? twx[j] : 1.f - twx[j]) * ((t >> 1) ? twy[j] : 1.f - twy[j]);
+                for (int k = 0; k < 4; ++k) {
+                    const int xx = t.x0 + (k & 1), yy = t.y0 + (k >> 1);
+                    const float wt = ((k & 1) ? t.wx : 1.f - t.wx) * ((k >> 1) ? t.wy : 1.f - t.wy);
                     if (xx >= 0 && xx < g.W && yy >= 0 && yy < g.H) {
                         float u[8];
                         load8(feat, fb_in_row(g, a0 + j, yy, xx) * g.C + c0, in_lo_off, u);
@@ -585,24 +592,30 @@ __global__ void __launch_bounds__(256) warp_att_fuse_bwd_kernel(
         }
         float go[8];
         load8(dfused, (((long)b * (g.H + 2) + h + 1) * (g.W + 2) + w + 1) * g.C + c0, dfused_lo_off, go);
-        float dv[FB_MAX_AGENTS][8];
+        // per-agent coefficients of  dv_j = ca_j * go + cs_j * v_0  (+ d0 for the ego), or the arg-max mask of MaxFusion
+        float ca[MAXN], cs[MAXN], d0[8];
+        unsigned amask[MAXN];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d0[e] = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAXN; ++j) { ca[j] = 0.f; cs[j] = 0.f; amask[j] = 0u; }
         if (method == 1) {                                               // MaxFusion: first arg-max agent per channel
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 float best = v[0][e];
                 int bj = 0;
 #pragma unroll
-                for (int j = 1; j < FB_MAX_AGENTS; ++j)
+                for (int j = 1; j < MAXN; ++j)
                     if (j < n && v[j][e] > best) { best = v[j][e]; bj = j; }
 #pragma unroll
-                for (int j = 0; j < FB_MAX_AGENTS; ++j) dv[j][e] = (j == bj) ? go[e] : 0.f;
+                for (int j = 0; j < MAXN; ++j) amask[j] |= (j == bj) ? (1u << e) : 0u;
             }
         } else {
-            float sc[FB_MAX_AGENTS], da[FB_MAX_AGENTS];
+            float da[MAXN];
             float smax = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < FB_MAX_AGENTS; ++j) {
-                sc[j] = 0.f; da[j] = 0.f;
+            for (int j = 0; j < MAXN; ++j) {
+                da[j] = 0.f;
                 if (j < n) {
                     float d = 0.f, e2 = 0.f;
 #pragma unroll
@@ -612,47 +625,48 @@ __global__ void __launch_bounds__(256) warp_att_fuse_bwd_kernel(
                         d += __shfl_xor_sync(0xffffffffu, d, o);
                         e2 += __shfl_xor_sync(0xffffffffu, e2, o);
                     }
-                    sc[j] = d * g.inv_sqrt_c;
+                    ca[j] = d * g.inv_sqrt_c;                            // score for now
                     da[j] = e2;
-                    smax = fmaxf(smax, sc[j]);
+                    smax = fmaxf(smax, ca[j]);
                 }
             }
             float den = 0.f;
 #pragma unroll
-            for (int j = 0; j < FB_MAX_AGENTS; ++j)
-                if (j < n) { sc[j] = __expf(sc[j] - smax); den += sc[j]; }
+            for (int j = 0; j < MAXN; ++j)
+                if (j < n) { ca[j] = __expf(ca[j] - smax); den += ca[j]; }
             const float rden = 1.f / den;
             float tsum = 0.f;
 #pragma unroll
-            for (int j = 0; j < FB_MAX_AGENTS; ++j)
-                if (j < n) { sc[j] *= rden; tsum = fmaf(sc[j], da[j], tsum); }          // sc = attention weights now
-            float d0[8] = {};
+            for (int j = 0; j < MAXN; ++j)
+                if (j < n) { ca[j] *= rden; tsum = fmaf(ca[j], da[j], tsum); }           // ca = attention weights now
 #pragma unroll
-            for (int j = 0; j < FB_MAX_AGENTS; ++j) {
+            for (int j = 0; j < MAXN; ++j) {
                 if (j < n) {
-                    const float ds = sc[j] * (da[j] - tsum) * g.inv_sqrt_c;              // d loss / d score_j
+                    cs[j] = ca[j] * (da[j] - tsum) * g.inv_sqrt_c;                         // d loss / d score_j
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        dv[j][e] = fmaf(sc[j], go[e], ds * v[0][e]);
-                        d0[e] = fmaf(ds, v[j][e], d0[e]);
-                    }
+                    for (int e = 0; e < 8; ++e) d0[e] = fmaf(cs[j], v[j][e], d0[e]);
                 }
             }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) dv[0][e] += d0[e];
         }
         if (!live) continue;
 #pragma unroll
-        for (int j = 0; j < FB_MAX_AGENTS; ++j) {
+        for (int j = 0; j < MAXN; ++j) {
             if (j < n) {
+                float dv[8];
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int xx = tx0[j] + (t & 1), yy = ty0[j] + (t >> 1);
-                    const float wt = ((t & 1) ? twx[j] : 1.f - twx[j]) * ((t >> 1) ? twy[j] : 1.f - twy[j]);
+                for (int e = 0; e < 8; ++e) {
+                    if (method == 1) dv[e] = (amask[j] >> e) & 1u ? go[e] : 0.f;
+                    else dv[e] = fmaf(ca[j], go[e], cs[j] * v[0][e]) + (j == 0 ? d0[e] : 0.f);
+                }
+                const FbTap t = fb_tap(Ab + j * 6, xs, ys, g);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int xx = t.x0 + (k & 1), yy = t.y0 + (k >> 1);
+                    const float wt = ((k & 1) ? t.wx : 1.f - t.wx) * ((k >> 1) ? t.wy : 1.f - t.wy);
                     if (xx >= 0 && xx < g.W && yy >= 0 && yy < g.H && wt != 0.f) {
                         float* dst = dfeat + ((((long)(a0 + j) * g.H + yy) * g.W + xx) * g.C + c0);
-                        red_add_v4f(dst, wt * dv[j][0], wt * dv[j][1], wt * dv[j][2], wt * dv[j][3]);
-                        red_add_v4f(dst + 4, wt * dv[j][4], wt * dv[j][5], wt * dv[j][6], wt * dv[j][7]);
+                        red_add_v4f(dst, wt * dv[0], wt * dv[1], wt * dv[2], wt * dv[3]);
+                        red_add_v4f(dst + 4, wt * dv[4], wt * dv[5], wt * dv[6], wt * dv[7]);
                     }
                 }
             }
@@ -822,7 +836,7 @@ __global__ void pfn_train_finalize_kernel(const double* __restrict__ sums, const
 struct CanvasG { int ny, nx, Hq, Wq; long plane_rows; };
 
 // lane owns channels (lane, lane + 32); bsum layout: [0,64) d_beta, [64,128) d_gamma, [128, 128 + 640) sum dy*f [c][10]
-__global__ void __launch_bounds__(256) pfn_bwd_kernel(const float4* __restrict__ voxels, const int* __restrict__ coords,
+__global__ void __launch_bounds__(256, 4) pfn_bwd_kernel(const float4* __restrict__ voxels, const int* __restrict__ coords,
                                                       const int* __restrict__ num_points, int n_rows_cap,
                                                       const int* __restrict__ n_voxels_dev, int max_pts,
                                                       const float* __restrict__ w, const float* __restrict__ scale,
@@ -835,12 +849,15 @@ __global__ void __launch_bounds__(256) pfn_bwd_kernel(const float4* __restrict__
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     int n_rows = n_voxels_dev ? *n_voxels_dev : n_rows_cap;
     if (n_rows > n_rows_cap) n_rows = n_rows_cap;
-    float wl[2][10], sc[2], sh[2], mu[2], iv[2];
+    // the kernel is bound by the latency of its dependent loads (count -> points -> coords -> gradient row): the linear
+    // layer's weights live in shared memory (row stride 11: conflict-free) so that four CTAs fit on an SM
+    __shared__ float s_w[64 * 11];
+    for (int i = threadIdx.x; i < 640; i += 256) s_w[(i / 10) * 11 + (i % 10)] = w[i];
+    __syncthreads();
+    float sc[2], sh[2], mu[2], iv[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         const int c = lane + 32 * r;
-#pragma unroll
-        for (int i = 0; i < 10; ++i) wl[r][i] = w[c * 10 + i];
         sc[r] = scale[c]; sh[r] = shift[c]; mu[r] = mean[c]; iv[r] = inv_std[c];
     }
     float acc[2][12];
@@ -872,7 +889,7 @@ __global__ void __launch_bounds__(256) pfn_bwd_kernel(const float4* __restrict__
             for (int k = 0; k < n; ++k) {
                 float lin = 0.f;
 #pragma unroll
-                for (int i = 0; i < 10; ++i) lin = fmaf(s_f[wib][k][i], wl[r][i], lin);
+                for (int i = 0; i < 10; ++i) lin = fmaf(s_f[wib][k][i], s_w[c * 11 + i], lin);
                 const float yv = fmaxf(fmaf(lin, sc[r], sh[r]), 0.f);
                 if (yv > best) { best = yv; bk = k; best_lin = lin; }
             }
@@ -893,16 +910,16 @@ __global__ void __launch_bounds__(256) pfn_bwd_kernel(const float4* __restrict__
     // per-warp fp32 partials (<= a few hundred pillars each) -> shared memory -> one fp64 global atomic per entry and CTA
     // (shared-memory double atomics are CAS loops on sm_100: no periodic flushes through them)
     __syncthreads();
-    float* s_w = &s_f[0][0][0];                                          // reuse: 8 warps x 768 floats = 24 KB
+    float* s_acc = &s_f[0][0][0];                                         // reuse: 8 warps x 768 floats = 24 KB
 #pragma unroll
     for (int r = 0; r < 2; ++r)
 #pragma unroll
-        for (int i = 0; i < 12; ++i) s_w[wib * 768 + (lane + 32 * r) * 12 + i] = acc[r][i];
+        for (int i = 0; i < 12; ++i) s_acc[wib * 768 + (lane + 32 * r) * 12 + i] = acc[r][i];
     __syncthreads();
     for (int i = threadIdx.x; i < 64 * 12; i += 256) {
         double t = 0.0;
 #pragma unroll
-        for (int w8 = 0; w8 < 8; ++w8) t += (double)s_w[w8 * 768 + i];
+        for (int w8 = 0; w8 < 8; ++w8) t += (double)s_acc[w8 * 768 + i];
         const int c = i / 12, k = i - c * 12;
         const int dst = k == 0 ? c : (k == 1 ? 64 + c : 128 + c * 10 + (k - 2));
         atomicAdd(bsum + dst, t);
@@ -946,6 +963,25 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
         const __nv_bfloat16 hi = __float2bfloat16(v);
         dst[r * dst_ld + k_off + k] = hi;
         if (lo_col_off != 0) dst[r * dst_ld + k_off + lo_col_off + k] = __float2bfloat16(v - __bfloat162float(hi));
+    }
+}
+
+__global__ void __launch_bounds__(256) pack_weights_batch_kernel(const cb_pack_job* __restrict__ jobs, int n_jobs, long total) {
+    pdl_wait();
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+        int lo = 0, hi = n_jobs;                                         // last job with first <= i
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (jobs[mid].first <= i) lo = mid; else hi = mid; }
+        const cb_pack_job& j = jobs[lo];
+        const long e = i - j.first;
+        const long r = e / j.K;
+        const int k = (int)(e - r * j.K);
+        const long r1 = r / j.R0, r0 = r - r1 * j.R0;
+        const int k1 = k / j.K0, k0 = k - k1 * j.K0;
+        const float v = __ldg(j.src + r1 * j.s_r1 + r0 * j.s_r0 + k1 * j.s_k1 + k0 * j.s_k0);
+        __nv_bfloat16* dst = (__nv_bfloat16*)j.dst;
+        const __nv_bfloat16 hi16 = __float2bfloat16(v);
+        dst[r * j.dst_ld + j.k_off + k] = hi16;
+        if (j.lo_col_off != 0) dst[r * j.dst_ld + j.k_off + j.lo_col_off + k] = __float2bfloat16(v - __bfloat162float(hi16));
     }
 }
 
@@ -1121,15 +1157,15 @@ extern "C" int cb_warp_att_fuse_bwd(const void* feat, int in_ps, int64_t in_lo_o
     if (blocks > 148 * 8) blocks = 148 * 8;
     cudaError_t e;
     cudaStream_t st = (cudaStream_t)stream;
-    if (lpp == 8)
-        e = launch_pdl(warp_att_fuse_bwd_kernel<8>, dim3((unsigned)blocks), dim3(256), 0, st, BF(feat), (long)in_lo_off, affine,
-                       agent_off, n_scenes, max_cav, g, method, BF(d_fused_pf), (long)d_fused_lo_off, d_feat);
-    else if (lpp == 16)
-        e = launch_pdl(warp_att_fuse_bwd_kernel<16>, dim3((unsigned)blocks), dim3(256), 0, st, BF(feat), (long)in_lo_off, affine,
-                       agent_off, n_scenes, max_cav, g, method, BF(d_fused_pf), (long)d_fused_lo_off, d_feat);
-    else
-        e = launch_pdl(warp_att_fuse_bwd_kernel<32>, dim3((unsigned)blocks), dim3(256), 0, st, BF(feat), (long)in_lo_off, affine,
-                       agent_off, n_scenes, max_cav, g, method, BF(d_fused_pf), (long)d_fused_lo_off, d_feat);
+    if (blocks > 148 * 2) blocks = 148 * 2;                              // one resident wave (2 CTAs / SM)
+#define CB_FB_LAUNCH(LPP_, MAXN_)                                                                                          \
+    e = launch_pdl(warp_att_fuse_bwd_kernel<LPP_, MAXN_>, dim3((unsigned)blocks), dim3(256), 0, st, BF(feat), (long)in_lo_off, \
+                   affine, agent_off, n_scenes, max_cav, g, method, BF(d_fused_pf), (long)d_fused_lo_off, d_feat)
+    const bool small = max_cav <= 5;
+    if (lpp == 8) { if (small) CB_FB_LAUNCH(8, 5); else CB_FB_LAUNCH(8, FB_MAX_AGENTS); }
+    else if (lpp == 16) { if (small) CB_FB_LAUNCH(16, 5); else CB_FB_LAUNCH(16, FB_MAX_AGENTS); }
+    else { if (small) CB_FB_LAUNCH(32, 5); else CB_FB_LAUNCH(32, FB_MAX_AGENTS); }
+#undef CB_FB_LAUNCH
     return e == cudaSuccess ? CB_OK : (int)e;
 }
 
@@ -1208,6 +1244,13 @@ extern "C" int cb_pack_weight(const float* src, int R1, int R0, int K1, int K0, 
     const int K = K1 * K0;
     cudaError_t e = launch_pdl(pack_weight_kernel, dim3(ew_grid(rows * K)), dim3(256), 0, (cudaStream_t)stream, src, R0, K0, rows,
                                K, (long)s_r1, (long)s_r0, (long)s_k1, (long)s_k0, BFW(dst), dst_ld, k_off, lo_col_off);
+    return e == cudaSuccess ? CB_OK : (int)e;
+}
+
+extern "C" int cb_pack_weights_batch(const cb_pack_job* jobs_dev, int n_jobs, int64_t total_elems, void* stream) {
+    if (!jobs_dev || n_jobs < 1 || total_elems < 1) return CB_ERR_ARG;
+    cudaError_t e = launch_pdl(pack_weights_batch_kernel, dim3(ew_grid(total_elems / 4)), dim3(256), 0, (cudaStream_t)stream,
+                               jobs_dev, n_jobs, (long)total_elems);
     return e == cudaSuccess ? CB_OK : (int)e;
 }
 

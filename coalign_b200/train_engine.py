@@ -685,11 +685,8 @@ class TrainEngine(CoAlignEngine):
                     ck(lib.cb_permute_f32(src, ci, cu, 1, k * k, 1, ci, 0, cu * ci, 1.0, o["dst"].data_ptr(), sp),
                        "cb_permute_f32")
             elif kind == "pack_all":
-                for pk in self.packs:
-                    for (src, R1, R0, K1, K0, s1, s0, k1, k0, ro, ko) in pk.jobs:
-                        ck(lib.cb_pack_weight(src.data_ptr(), R1, R0, K1, K0, s1, s0, k1, k0,
-                                              pk.w.data_ptr() + ro * pk.k_total * 2, pk.k_total, ko,
-                                              pk.k if self.precise else 0, sp), "cb_pack_weight")
+                jobs, n_jobs, total = self._pack_job_table()
+                ck(lib.cb_pack_weights_batch(jobs.data_ptr(), n_jobs, total, sp), "cb_pack_weights_batch")
             elif kind == "head_bias":
                 c0 = 0
                 for h, cn in zip(self.head_mods, self.head_cn):
@@ -743,6 +740,24 @@ class TrainEngine(CoAlignEngine):
                     on_bucket(o["i"])
             else:
                 raise RuntimeError("unknown op " + kind)
+
+    def _pack_job_table(self):
+        """Device table of every weight-packing job (built once: parameter and pack buffers never move)."""
+        if getattr(self, "_pack_jobs", None) is None:
+            arr, total = [], 0
+            for pk in self.packs:
+                for (src, R1, R0, K1, K0, s1, s0, k1, k0, ro, ko) in pk.jobs:
+                    j = _lib.PackJob()
+                    j.src, j.dst = src.data_ptr(), pk.w.data_ptr() + ro * pk.k_total * 2
+                    j.s_r1, j.s_r0, j.s_k1, j.s_k0, j.first = s1, s0, k1, k0, total
+                    j.R0, j.K0, j.rows, j.K = R0, K0, R1 * R0, K1 * K0
+                    j.dst_ld, j.k_off, j.lo_col_off = pk.k_total, ko, (pk.k if self.precise else 0)
+                    arr.append(j)
+                    total += R1 * R0 * K1 * K0
+            buf = (_lib.PackJob * len(arr))(*arr)
+            host = torch.frombuffer(bytearray(bytes(buf)), dtype=torch.uint8)
+            self._pack_jobs = (host.to(self.device), len(arr), total)
+        return self._pack_jobs
 
     def _pfn_forward(self, n_img: int, sp: int):
         lib, ck = self.lib, _lib.check

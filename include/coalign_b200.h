@@ -472,6 +472,15 @@ int cb_pack_weight(const float* src, int R1, int R0, int K1, int K0, int64_t s_r
                    void* dst, int dst_ld, int k_off, int lo_col_off, void* stream);
 int cb_permute_f32(const float* src, int R1, int R0, int K1, int K0, int64_t s_r1, int64_t s_r0, int64_t s_k1, int64_t s_k0,
                    float alpha, float* dst, void* stream);
+/* All cb_pack_weight jobs of a model in ONE launch (a training step re-packs ~90 weight matrices; as separate launches they
+ * cost more than the 26 M elements they move).  jobs: DEVICE array; `first` = running total of rows*K of the jobs before. */
+typedef struct cb_pack_job {
+    const float* src;
+    void* dst;                   /* bf16, already offset to the job's first row */
+    int64_t s_r1, s_r0, s_k1, s_k0, first;
+    int32_t R0, K0, rows, K, dst_ld, k_off, lo_col_off, pad_;
+} cb_pack_job;
+int cb_pack_weights_batch(const cb_pack_job* jobs_dev, int n_jobs, int64_t total_elems, void* stream);
 
 /* ---- torch.optim.Adam step on flat fp32 buffers (train_utils.py:196-206: lr, eps, weight_decay from the yaml):
  *   g += wd*p;  m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g*g;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
