@@ -188,7 +188,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_co
     uint8_t* smem = smem_raw + pad;                       // 1 KiB aligned (SWIZZLE_128B atoms)
     for (int i = threadIdx.x; i < 256; i += TC_THREADS) s_bias[i] = i < p.cout_mod ? p.bias[i] : 0.f;
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = warp_idx_uniform();
     const int lane = threadIdx.x & 31;
     const int total_tiles = m_tiles * n_tiles;
     const int nk = p.n_ksteps;
@@ -222,7 +222,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_co
 
     if (warp == W_PRODUCER) {
         // ------------------------------------------------------------------ TMA producer
-        if (elect_one()) {
+        // (whole warp in the loop, elect only around the TMA instructions: see the MMA-issuer note in conv_gemm_halo64_kernel)
+        {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
@@ -231,26 +232,30 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_co
                     const int cnt = (nk - ks) < Cfg::KPS ? (nk - ks) : Cfg::KPS;
                     const uint32_t fb = full0 + stage * 8;
                     mbar_wait_a(empty0 + stage * 8, phase ^ 1);
-                    mbar_expect_tx_a(fb, (uint32_t)cnt * Cfg::KSTEP_BYTES);
+                    if (elect_one()) {
+                        mbar_expect_tx_a(fb, (uint32_t)cnt * Cfg::KSTEP_BYTES);
 #pragma unroll
-                    for (int j = 0; j < Cfg::KPS; ++j) {
-                        if (j < cnt) {
-                            const cb_kstep st = p.ksteps[ks + j];
-                            const uint32_t sa = smem_a0 + stage * Cfg::STAGE_BYTES + j * Cfg::KSTEP_BYTES;
-                            tma_load_2d_a(sa, st.a_sel ? &tmap_a1 : &tmap_a0, fb, (int)st.col, m0 + st.row_off);
-                            tma_load_2d_a(sa + A_STAGE_BYTES, &tmap_w, fb, st.w_k, n0);
+                        for (int j = 0; j < Cfg::KPS; ++j) {
+                            if (j < cnt) {
+                                const cb_kstep st = p.ksteps[ks + j];
+                                const uint32_t sa = smem_a0 + stage * Cfg::STAGE_BYTES + j * Cfg::KSTEP_BYTES;
+                                tma_load_2d_a(sa, st.a_sel ? &tmap_a1 : &tmap_a0, fb, (int)st.col, m0 + st.row_off);
+                                tma_load_2d_a(sa + A_STAGE_BYTES, &tmap_w, fb, st.w_k, n0);
+                            }
                         }
                     }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == W_MMA) {
         // ------------------------------------------------------------------ MMA issuer
-        if (elect_one()) {
+        {
             constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
-            const uint64_t adesc0 = make_sw128_desc(smem_a0);
-            const uint64_t bdesc0 = make_sw128_desc(smem_a0 + A_STAGE_BYTES);
+            const uint64_t desc_a = make_sw128_desc(smem_a0);
+            const uint32_t a_lo0 = (uint32_t)desc_a, hi = (uint32_t)(desc_a >> 32);
+            const uint32_t b_lo0 = (uint32_t)make_sw128_desc(smem_a0 + A_STAGE_BYTES);
             int stage = 0; uint32_t phase = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -261,24 +266,27 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_co
                 const uint32_t d_tmem = tmem_base + buf * BN;
                 for (int ks = 0; ks < nk; ks += Cfg::KPS) {
                     const int cnt = (nk - ks) < Cfg::KPS ? (nk - ks) : Cfg::KPS;
+                    // descriptor start-address field is (addr >> 4): stage / K-step strides and the 32-byte K advance add linearly
+                    const uint32_t a_lo = a_lo0 + (uint32_t)(stage * (Cfg::STAGE_BYTES >> 4));
+                    const uint32_t b_lo = b_lo0 + (uint32_t)(stage * (Cfg::STAGE_BYTES >> 4));
                     mbar_wait_a(full0 + stage * 8, phase);           // TMA bytes landed
                     tc_fence_after();
-                    // descriptor start-address field is (addr >> 4): stage / K-step strides and the 32-byte K advance add linearly
-                    const uint64_t adesc = adesc0 + (uint64_t)(stage * (Cfg::STAGE_BYTES >> 4));
-                    const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (Cfg::STAGE_BYTES >> 4));
+                    if (elect_one()) {
 #pragma unroll
-                    for (int j = 0; j < Cfg::KPS; ++j) {
-                        if (j < cnt) {
+                        for (int j = 0; j < Cfg::KPS; ++j) {
+                            if (j < cnt) {
 #pragma unroll
-                            for (int k = 0; k < BK / UMMA_K; ++k) {
-                                umma_bf16(d_tmem, adesc + (uint64_t)(j * (Cfg::KSTEP_BYTES >> 4) + 2 * k),
-                                          bdesc + (uint64_t)(j * (Cfg::KSTEP_BYTES >> 4) + 2 * k), idesc,
-                                          (ks > 0 || j > 0 || k > 0) ? 1u : 0u);
+                                for (int k = 0; k < BK / UMMA_K; ++k) {
+                                    umma_bf16_lh(d_tmem, a_lo + (uint32_t)(j * (Cfg::KSTEP_BYTES >> 4) + 2 * k), hi,
+                                                 b_lo + (uint32_t)(j * (Cfg::KSTEP_BYTES >> 4) + 2 * k), hi, idesc,
+                                                 (ks > 0 || j > 0 || k > 0) ? 1u : 0u);
+                                }
                             }
                         }
+                        umma_commit_a(empty0 + stage * 8);           // frees the smem slot when the MMAs retire
+                        if (ks + Cfg::KPS >= nk) umma_commit_a(tfull0 + buf * 8);
                     }
-                    umma_commit_a(empty0 + stage * 8);               // frees the smem slot when the MMAs retire
-                    if (ks + Cfg::KPS >= nk) umma_commit_a(tfull0 + buf * 8);
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -355,7 +363,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
     uint8_t* smem = smem_raw + pad;
     for (int i = threadIdx.x; i < 256; i += TC_THREADS) s_bias[i] = i < p.cout_mod ? p.bias[i] : 0.f;
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = warp_idx_uniform();
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
@@ -391,7 +399,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
 
     if (warp == W_PRODUCER) {
         // ------------------------------------------------------------------ TMA producer (both CTAs)
-        if (elect_one()) {
+        {
             int stage = 0; uint32_t phase = 0;
             for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
                 const int mp = tile / n_tiles, nt = tile - mp * n_tiles;
@@ -400,31 +408,30 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
                     const int cnt = (nk - ks) < Cfg::KPS ? (nk - ks) : Cfg::KPS;
                     const uint32_t fb = (full0 + stage * 8) & 0xFEFFFFFFu;        // leader CTA's barrier
                     mbar_wait_a(empty0 + stage * 8, phase ^ 1);
-                    if (leader) mbar_expect_tx_a(full0 + stage * 8, 2u * (uint32_t)cnt * Cfg::KSTEP_BYTES);
+                    if (elect_one()) {
+                        if (leader) mbar_expect_tx_a(full0 + stage * 8, 2u * (uint32_t)cnt * Cfg::KSTEP_BYTES);
 #pragma unroll
-                    for (int j = 0; j < Cfg::KPS; ++j) {
-                        if (j < cnt) {
-                            const cb_kstep st = p.ksteps[ks + j];
-                            const uint32_t sa = smem_a0 + stage * Cfg::STAGE_BYTES + j * Cfg::KSTEP_BYTES;
-                            tma_load_2d_2sm_a(sa, st.a_sel ? &tmap_a1 : &tmap_a0, fb, (int)st.col, m0 + st.row_off);
-                            tma_load_2d_2sm_a(sa + A_STAGE_BYTES, &tmap_w, fb, st.w_k, n0);
-                            if ((dbg & 16) && tile + n_clusters < total_tiles) {   // experiment: L2 prefetch of the next tile's A box
-                                const int m1 = (((tile + n_clusters) / n_tiles) * 2 + (int)rank) * BM;
-                                asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
-                                             ::"l"(st.a_sel ? &tmap_a1 : &tmap_a0), "r"((int)st.col), "r"(m1 + st.row_off) : "memory");
+                        for (int j = 0; j < Cfg::KPS; ++j) {
+                            if (j < cnt) {
+                                const cb_kstep st = p.ksteps[ks + j];
+                                const uint32_t sa = smem_a0 + stage * Cfg::STAGE_BYTES + j * Cfg::KSTEP_BYTES;
+                                tma_load_2d_2sm_a(sa, st.a_sel ? &tmap_a1 : &tmap_a0, fb, (int)st.col, m0 + st.row_off);
+                                tma_load_2d_2sm_a(sa + A_STAGE_BYTES, &tmap_w, fb, st.w_k, n0);
                             }
                         }
                     }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == W_MMA) {
         // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-        if (leader && elect_one()) {
+        if (leader) {
             constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
-            const uint64_t adesc0 = make_sw128_desc(smem_a0);
-            const uint64_t bdesc0 = make_sw128_desc(smem_a0 + A_STAGE_BYTES);
+            const uint64_t desc_a = make_sw128_desc(smem_a0);
+            const uint32_t a_lo0 = (uint32_t)desc_a, hi = (uint32_t)(desc_a >> 32);
+            const uint32_t b_lo0 = (uint32_t)make_sw128_desc(smem_a0 + A_STAGE_BYTES);
             int stage = 0; uint32_t phase = 0;
             int it = 0;
             for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
@@ -435,23 +442,26 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
                 const uint32_t d_tmem = tmem_base + buf * BN;
                 for (int ks = 0; ks < nk; ks += Cfg::KPS) {
                     const int cnt = (nk - ks) < Cfg::KPS ? (nk - ks) : Cfg::KPS;
+                    const uint32_t a_lo = a_lo0 + (uint32_t)(stage * (Cfg::STAGE_BYTES >> 4));
+                    const uint32_t b_lo = b_lo0 + (uint32_t)(stage * (Cfg::STAGE_BYTES >> 4));
                     mbar_wait_a(full0 + stage * 8, phase);
                     tc_fence_after();
-                    const uint64_t adesc = adesc0 + (uint64_t)(stage * (Cfg::STAGE_BYTES >> 4));
-                    const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (Cfg::STAGE_BYTES >> 4));
+                    if (elect_one()) {
 #pragma unroll
-                    for (int j = 0; j < Cfg::KPS; ++j) {
-                        if (j < cnt) {
+                        for (int j = 0; j < Cfg::KPS; ++j) {
+                            if (j < cnt) {
 #pragma unroll
-                            for (int k = 0; k < BK / UMMA_K; ++k) {
-                                umma_bf16_2sm(d_tmem, adesc + (uint64_t)(j * (Cfg::KSTEP_BYTES >> 4) + 2 * k),
-                                              bdesc + (uint64_t)(j * (Cfg::KSTEP_BYTES >> 4) + 2 * k), idesc,
-                                              (ks > 0 || j > 0 || k > 0) ? 1u : 0u);
+                                for (int k = 0; k < BK / UMMA_K; ++k) {
+                                    umma_bf16_2sm_lh(d_tmem, a_lo + (uint32_t)(j * (Cfg::KSTEP_BYTES >> 4) + 2 * k), hi,
+                                                     b_lo + (uint32_t)(j * (Cfg::KSTEP_BYTES >> 4) + 2 * k), hi, idesc,
+                                                     (ks > 0 || j > 0 || k > 0) ? 1u : 0u);
+                                }
                             }
                         }
+                        umma_commit_2sm_a(empty0 + stage * 8);
+                        if (ks + Cfg::KPS >= nk) umma_commit_2sm_a(tfull0 + buf * 8);
                     }
-                    umma_commit_2sm_a(empty0 + stage * 8);
-                    if (ks + Cfg::KPS >= nk) umma_commit_2sm_a(tfull0 + buf * 8);
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -611,7 +621,7 @@ conv_gemm_tct_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
     uint8_t* smem = smem_raw + pad;
     for (int i = threadIdx.x; i < 128; i += TC_THREADS) s_bias[i] = p.bias[i];
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = warp_idx_uniform();
     const int lane = threadIdx.x & 31;
     const int nk = p.n_ksteps;
 
@@ -641,27 +651,32 @@ conv_gemm_tct_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
     const uint32_t tfull0 = smem_u32(&tmem_full_bar[0]), tempty0 = smem_u32(&tmem_empty_bar[0]);
 
     if (warp == W_PRODUCER) {
-        if (elect_one()) {
+        // warp-uniform loops, elect only around the TMA / tcgen05 instructions (see conv_gemm_halo64_kernel)
+        {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
                 const int m0 = tile * TP;
                 for (int ks = 0; ks < nk; ++ks) {
                     const uint32_t fb = full0 + stage * 8;
                     mbar_wait_a(empty0 + stage * 8, phase ^ 1);
-                    mbar_expect_tx_a(fb, (uint32_t)Cfg::KSTEP_BYTES);
-                    const cb_kstep st = p.ksteps[ks];
-                    const uint32_t sa = smem_p0 + stage * Cfg::KSTEP_BYTES;
-                    tma_load_2d_a(sa, st.a_sel ? &tmap_a1 : &tmap_a0, fb, (int)st.col, m0 + st.row_off);
-                    tma_load_2d_a(sa + Cfg::P_BYTES, &tmap_w, fb, st.w_k, 0);
+                    if (elect_one()) {
+                        mbar_expect_tx_a(fb, (uint32_t)Cfg::KSTEP_BYTES);
+                        const cb_kstep st = p.ksteps[ks];
+                        const uint32_t sa = smem_p0 + stage * Cfg::KSTEP_BYTES;
+                        tma_load_2d_a(sa, st.a_sel ? &tmap_a1 : &tmap_a0, fb, (int)st.col, m0 + st.row_off);
+                        tma_load_2d_a(sa + Cfg::P_BYTES, &tmap_w, fb, st.w_k, 0);
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == W_MMA) {
-        if (elect_one()) {
+        {
             constexpr uint32_t idesc = make_idesc_bf16(128, TP);          // M = channels, N = pixels
-            const uint64_t pdesc0 = make_sw128_desc(smem_p0);
-            const uint64_t wdesc0 = make_sw128_desc(smem_p0 + Cfg::P_BYTES);
+            const uint64_t desc_p = make_sw128_desc(smem_p0);
+            const uint32_t p_lo0 = (uint32_t)desc_p, hi = (uint32_t)(desc_p >> 32);
+            const uint32_t w_lo0 = (uint32_t)make_sw128_desc(smem_p0 + Cfg::P_BYTES);
             int stage = 0; uint32_t phase = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
@@ -671,16 +686,19 @@ conv_gemm_tct_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * TP;
                 for (int ks = 0; ks < nk; ++ks) {
+                    const uint32_t p_lo = p_lo0 + (uint32_t)(stage * (Cfg::KSTEP_BYTES >> 4));
+                    const uint32_t w_lo = w_lo0 + (uint32_t)(stage * (Cfg::KSTEP_BYTES >> 4));
                     mbar_wait_a(full0 + stage * 8, phase);
                     tc_fence_after();
-                    const uint64_t pdesc = pdesc0 + (uint64_t)(stage * (Cfg::KSTEP_BYTES >> 4));
-                    const uint64_t wdesc = wdesc0 + (uint64_t)(stage * (Cfg::KSTEP_BYTES >> 4));
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k)
-                        umma_bf16(d_tmem, wdesc + (uint64_t)(2 * k), pdesc + (uint64_t)(2 * k), idesc,
-                                  (ks > 0 || k > 0) ? 1u : 0u);
-                    umma_commit_a(empty0 + stage * 8);
-                    if (ks + 1 >= nk) umma_commit_a(tfull0 + buf * 8);
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            umma_bf16_lh(d_tmem, w_lo + (uint32_t)(2 * k), hi, p_lo + (uint32_t)(2 * k), hi, idesc,
+                                         (ks > 0 || k > 0) ? 1u : 0u);
+                        umma_commit_a(empty0 + stage * 8);
+                        if (ks + 1 >= nk) umma_commit_a(tfull0 + buf * 8);
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -747,7 +765,7 @@ conv_gemm_halo64_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __gri
     uint8_t* smem = smem_raw + pad;
     for (int i = threadIdx.x; i < 256; i += TC_THREADS) s_bias[i] = i < p.cout_mod ? p.bias[i] : 0.f;
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = warp_idx_uniform();
     const int lane = threadIdx.x & 31;
     const int nk = p.n_ksteps;
     const int n_items = items.n;
@@ -782,11 +800,14 @@ conv_gemm_halo64_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __gri
 
     if (warp == W_PRODUCER) {
         // ------------------------------------------------------------------ TMA producer
-        if (elect_one()) {
+        {
             // resident weights: independent of the predecessor kernel, so issued before the PDL wait
-            mbar_expect_tx_a(wbar, (uint32_t)nk * Cfg::W_BYTES);
-            for (int j = 0; j < nk; ++j)
-                tma_load_2d_a(smem_w0 + j * Cfg::W_BYTES, &tmap_w, wbar, p.ksteps[j].w_k, 0);
+            if (elect_one()) {
+                mbar_expect_tx_a(wbar, (uint32_t)nk * Cfg::W_BYTES);
+                for (int j = 0; j < nk; ++j)
+                    tma_load_2d_a(smem_w0 + j * Cfg::W_BYTES, &tmap_w, wbar, p.ksteps[j].w_k, 0);
+            }
+            __syncwarp();
             pdl_wait();
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
@@ -795,19 +816,28 @@ conv_gemm_halo64_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __gri
                     const cb_kstep st = p.ksteps[items.first[ii]];
                     const uint32_t fb = full0 + stage * 8;
                     mbar_wait_a(empty0 + stage * 8, phase ^ 1);
-                    mbar_expect_tx_a(fb, (uint32_t)HALO_BYTES);
-                    tma_load_2d_a(smem_a0 + stage * HALO_STRIDE, st.a_sel ? &tmap_a1 : &tmap_a0, fb, (int)st.col,
-                                  m0 + st.row_off);
+                    if (elect_one()) {
+                        mbar_expect_tx_a(fb, (uint32_t)HALO_BYTES);
+                        tma_load_2d_a(smem_a0 + stage * HALO_STRIDE, st.a_sel ? &tmap_a1 : &tmap_a0, fb, (int)st.col,
+                                      m0 + st.row_off);
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == W_MMA) {
         // ------------------------------------------------------------------ MMA issuer
-        if (elect_one()) {
+        // The WHOLE warp runs the loop and only the tcgen05 instructions sit under elect: stage / phase / descriptors are
+        // then warp-uniform values the compiler keeps in uniform registers.  With the loop inside `if (elect_one())` the
+        // same values live in per-thread registers and every UTCHMMA operand goes through R2UR: measured 50 cycles of
+        // issue per MMA + ~290 cycles of bookkeeping per box against 32 tensor cycles per N = 64 MMA
+        // (profiles/r2_exp_halo64_issue.txt) - the level-0 layers were bound by this one thread.
+        {
             constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
-            const uint64_t adesc0 = make_sw128_desc(smem_a0);
-            const uint64_t wdesc0 = make_sw128_desc(smem_w0);
+            const uint64_t desc_a = make_sw128_desc(smem_a0), desc_w = make_sw128_desc(smem_w0);
+            const uint32_t a_lo0 = (uint32_t)desc_a, w_lo0 = (uint32_t)desc_w, hi = (uint32_t)(desc_a >> 32);
+            const uint32_t bo_shift = bo_mode ? (1u << 17) : 0u;     // matrix-base-offset field = bits 49..51
             mbar_wait_a(wbar, 0);
             int stage = 0; uint32_t phase = 0;
             int it = 0;
@@ -818,22 +848,28 @@ conv_gemm_halo64_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __gri
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * BN;
                 for (int ii = 0; ii < n_items; ++ii) {
-                    const int first = items.first[ii], ns = items.nsub[ii];
+                    const int ns = items.nsub[ii];
+                    const uint32_t a_lo = a_lo0 + (uint32_t)(stage * (HALO_STRIDE >> 4));
+                    const uint32_t w_lo = w_lo0 + (uint32_t)(items.first[ii] * (Cfg::W_BYTES >> 4));
                     mbar_wait_a(full0 + stage * 8, phase);
                     tc_fence_after();
-                    const uint64_t adesc = adesc0 + (uint64_t)(stage * (HALO_STRIDE >> 4));
-                    for (int s = 0; s < ns; ++s) {
-                        // tap s of the filter row: same box, start shifted by s rows (128 B); bo_mode 1 additionally
-                        // records the shift in the descriptor's matrix-base-offset field (bits 49..51)
-                        const uint64_t ad = adesc + (uint64_t)(s * 8) + (bo_mode ? ((uint64_t)s << 49) : 0ull);
-                        const uint64_t wd = wdesc0 + (uint64_t)((first + s) * (Cfg::W_BYTES >> 4));
+                    if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k)
-                            umma_bf16(d_tmem, ad + (uint64_t)(2 * k), wd + (uint64_t)(2 * k), idesc,
-                                      (ii > 0 || s > 0 || k > 0) ? 1u : 0u);
+                        for (int s = 0; s < 3; ++s) {
+                            // tap s of the filter row: same box, start shifted by s rows (128 B); bo_mode 1 additionally
+                            // records the shift in the descriptor's matrix-base-offset field
+                            if (s < ns) {
+#pragma unroll
+                                for (int k = 0; k < BK / UMMA_K; ++k)
+                                    umma_bf16_lh(d_tmem, a_lo + (uint32_t)(s * 8 + 2 * k), hi + (uint32_t)s * bo_shift,
+                                                 w_lo + (uint32_t)(s * (Cfg::W_BYTES >> 4) + 2 * k), hi, idesc,
+                                                 (ii > 0 || s > 0 || k > 0) ? 1u : 0u);
+                            }
+                        }
+                        umma_commit_a(empty0 + stage * 8);
+                        if (ii + 1 == n_items) umma_commit_a(tfull0 + buf * 8);
                     }
-                    umma_commit_a(empty0 + stage * 8);
-                    if (ii + 1 == n_items) umma_commit_a(tfull0 + buf * 8);
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -911,7 +947,7 @@ conv_gemm_tct_halo_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __g
     uint8_t* smem = smem_raw + pad;
     for (int i = threadIdx.x; i < 128; i += TC_THREADS) s_bias[i] = p.bias[i];
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = warp_idx_uniform();
     const int lane = threadIdx.x & 31;
     const int n_items = items.n;
 
@@ -946,7 +982,8 @@ conv_gemm_tct_halo_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __g
     const uint32_t tfull0 = smem_u32(&tmem_full_bar[0]), tempty0 = smem_u32(&tmem_empty_bar[0]);
 
     if (warp == W_PRODUCER) {
-        if (elect_one()) {
+        // warp-uniform loops, elect only around the TMA / tcgen05 instructions (see conv_gemm_halo64_kernel)
+        {
             int ps = 0, ws = 0; uint32_t pphase = 0, wphase = 0;
             for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
                 const int m0 = tile * TP;
@@ -956,25 +993,34 @@ conv_gemm_tct_halo_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __g
                     const uint32_t pb = pfull0 + ps * 8;
                     const uint32_t sa = smem_p0 + ps * Cfg::P_STRIDE;
                     mbar_wait_a(pempty0 + ps * 8, pphase ^ 1);
-                    mbar_expect_tx_a(pb, (uint32_t)Cfg::P_BYTES);
-                    tma_load_2d_a(sa, st.a_sel ? &tmap_a1 : &tmap_a0, pb, (int)st.col, m0 + st.row_off);
-                    tma_load_2d_a(sa + TP * BK * 2, st.a_sel ? &tmap_a1t : &tmap_a0t, pb, (int)st.col, m0 + st.row_off + TP);
+                    if (elect_one()) {
+                        mbar_expect_tx_a(pb, (uint32_t)Cfg::P_BYTES);
+                        tma_load_2d_a(sa, st.a_sel ? &tmap_a1 : &tmap_a0, pb, (int)st.col, m0 + st.row_off);
+                        tma_load_2d_a(sa + TP * BK * 2, st.a_sel ? &tmap_a1t : &tmap_a0t, pb, (int)st.col,
+                                      m0 + st.row_off + TP);
+                    }
+                    __syncwarp();
                     if (++ps == PST) { ps = 0; pphase ^= 1; }
                     for (int s = 0; s < ns; ++s) {
                         const uint32_t wb = wfull0 + ws * 8;
                         mbar_wait_a(wempty0 + ws * 8, wphase ^ 1);
-                        mbar_expect_tx_a(wb, (uint32_t)Cfg::W_BYTES);
-                        tma_load_2d_a(smem_w0 + ws * Cfg::W_BYTES, &tmap_w, wb, p.ksteps[first + s].w_k, 0);
+                        if (elect_one()) {
+                            mbar_expect_tx_a(wb, (uint32_t)Cfg::W_BYTES);
+                            tma_load_2d_a(smem_w0 + ws * Cfg::W_BYTES, &tmap_w, wb, p.ksteps[first + s].w_k, 0);
+                        }
+                        __syncwarp();
                         if (++ws == WST) { ws = 0; wphase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == W_MMA) {
-        if (elect_one()) {
+        {
             constexpr uint32_t idesc = make_idesc_bf16(128, TP);          // M = channels, N = pixels
-            const uint64_t pdesc0 = make_sw128_desc(smem_p0);
-            const uint64_t wdesc0 = make_sw128_desc(smem_w0);
+            const uint64_t desc_p = make_sw128_desc(smem_p0);
+            const uint32_t p_lo0 = (uint32_t)desc_p, hi = (uint32_t)(desc_p >> 32);
+            const uint32_t w_lo0 = (uint32_t)make_sw128_desc(smem_w0);
+            const uint32_t bo_shift = bo_mode ? (1u << 17) : 0u;     // matrix-base-offset field = descriptor bits 49..51
             int ps = 0, ws = 0; uint32_t pphase = 0, wphase = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
@@ -985,22 +1031,27 @@ conv_gemm_tct_halo_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __g
                 const uint32_t d_tmem = tmem_base + buf * TP;
                 for (int ii = 0; ii < n_items; ++ii) {
                     const int ns = items.nsub[ii];
+                    const uint32_t p_lo = p_lo0 + (uint32_t)(ps * (Cfg::P_STRIDE >> 4));
                     mbar_wait_a(pfull0 + ps * 8, pphase);
-                    const uint64_t pdesc = pdesc0 + (uint64_t)(ps * (Cfg::P_STRIDE >> 4));
                     for (int s = 0; s < ns; ++s) {
+                        const uint32_t pd = p_lo + (uint32_t)(s * 8), pd_hi = hi + (uint32_t)s * bo_shift;
+                        const uint32_t wd = w_lo0 + (uint32_t)(ws * (Cfg::W_BYTES >> 4));
                         mbar_wait_a(wfull0 + ws * 8, wphase);
                         tc_fence_after();
-                        const uint64_t pd = pdesc + (uint64_t)(s * 8) + (bo_mode ? ((uint64_t)s << 49) : 0ull);
-                        const uint64_t wd = wdesc0 + (uint64_t)(ws * (Cfg::W_BYTES >> 4));
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k)
-                            umma_bf16(d_tmem, wd + (uint64_t)(2 * k), pd + (uint64_t)(2 * k), idesc,
-                                      (ii > 0 || s > 0 || k > 0) ? 1u : 0u);
-                        umma_commit_a(wempty0 + ws * 8);
+                            for (int k = 0; k < BK / UMMA_K; ++k)
+                                umma_bf16_lh(d_tmem, wd + (uint32_t)(2 * k), hi, pd + (uint32_t)(2 * k), pd_hi, idesc,
+                                             (ii > 0 || s > 0 || k > 0) ? 1u : 0u);
+                            umma_commit_a(wempty0 + ws * 8);
+                            if (s + 1 == ns) {
+                                umma_commit_a(pempty0 + ps * 8);
+                                if (ii + 1 == n_items) umma_commit_a(tfull0 + buf * 8);
+                            }
+                        }
+                        __syncwarp();
                         if (++ws == WST) { ws = 0; wphase ^= 1; }
                     }
-                    umma_commit_a(pempty0 + ps * 8);
-                    if (ii + 1 == n_items) umma_commit_a(tfull0 + buf * 8);
                     if (++ps == PST) { ps = 0; pphase ^= 1; }
                 }
             }

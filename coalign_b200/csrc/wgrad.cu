@@ -77,7 +77,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_consta
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
     const uint32_t smem0 = raw_addr + pad;                     // 1 KiB aligned (SWIZZLE_128B atoms)
-    const int warp = threadIdx.x >> 5;
+    const int warp = warp_idx_uniform();
     const int lane = threadIdx.x & 31;
     const int total_items = p.n_units * p.k_splits;
 
@@ -103,8 +103,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_consta
     const uint32_t tfull0 = smem_u32(&tmem_full_bar[0]), tempty0 = smem_u32(&tmem_empty_bar[0]);
 
     // item = (K split, unit), split-major: CTAs that run at the same time work on the same pixel range (L2 reuse)
+    // Producer and MMA issuer: the whole warp runs the loop, only the TMA / tcgen05 instructions sit under elect, so the
+    // loop state stays in uniform registers (see the MMA-issuer note in conv_gemm_halo64_kernel).
     if (warp == WGW_PRODUCER) {
-        if (elect_one()) {
+        {
             int stage = 0; uint32_t phase = 0;
             for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
                 const int split = item / p.n_units, ui = item - split * p.n_units;
@@ -116,25 +118,31 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_consta
                     for (int c = 0; c < p.n_combos; ++c) {
                         const uint32_t fb = full0 + stage * 8;
                         mbar_wait_a(empty0 + stage * 8, phase ^ 1);
-                        mbar_expect_tx_a(fb, bytes);
-                        const uint32_t sa = smem0 + stage * WG_STAGE_BYTES;
-                        const int q0 = kb * WG_KB;
-                        const CUtensorMap* ta = (c == 1) ? &tmap_dz_lo : &tmap_dz;
-                        tma_load_2d_a(sa, ta, fb, u.m0, q0 + u.a_row_off);
-                        tma_load_2d_a(sa + WG_BOX_BYTES, ta, fb, u.m0 + 64, q0 + u.a_row_off);
-                        for (int j = 0; j < u.n_boxes; ++j) {
-                            const int sel = u.box[j].x_sel;
-                            const int ro = u.box[j].row_off + (c == 2 ? p.x_lo_rows[sel] : 0);
-                            tma_load_2d_a(sa + WG_A_BYTES + j * WG_BOX_BYTES, sel ? &tmap_x1 : &tmap_x0, fb, (int)u.box[j].col,
-                                          q0 + ro);
+                        if (elect_one()) {
+                            mbar_expect_tx_a(fb, bytes);
+                            const uint32_t sa = smem0 + stage * WG_STAGE_BYTES;
+                            const int q0 = kb * WG_KB;
+                            const CUtensorMap* ta = (c == 1) ? &tmap_dz_lo : &tmap_dz;
+                            tma_load_2d_a(sa, ta, fb, u.m0, q0 + u.a_row_off);
+                            tma_load_2d_a(sa + WG_BOX_BYTES, ta, fb, u.m0 + 64, q0 + u.a_row_off);
+                            for (int j = 0; j < u.n_boxes; ++j) {
+                                const int sel = u.box[j].x_sel;
+                                const int ro = u.box[j].row_off + (c == 2 ? p.x_lo_rows[sel] : 0);
+                                tma_load_2d_a(sa + WG_A_BYTES + j * WG_BOX_BYTES, sel ? &tmap_x1 : &tmap_x0, fb,
+                                              (int)u.box[j].col, q0 + ro);
+                            }
                         }
+                        __syncwarp();
                         if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == WGW_MMA) {
-        if (elect_one()) {
+        {
+            const uint64_t desc0 = make_mn_sw128_desc(smem0, WG_BOX_BYTES);
+            const uint32_t a_lo0 = (uint32_t)desc0, hi = (uint32_t)(desc0 >> 32);
+            const uint32_t b_lo0 = (uint32_t)make_mn_sw128_desc(smem0 + WG_A_BYTES, WG_BOX_BYTES);
             int stage = 0; uint32_t phase = 0;
             int it = 0;
             for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
@@ -150,21 +158,25 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_consta
                 const uint32_t d_tmem = tmem_base + buf * 256;
                 const int n_steps = (kb1 - kb0) * p.n_combos;
                 for (int s = 0; s < n_steps; ++s) {
+                    const uint32_t a_lo = a_lo0 + (uint32_t)(stage * (WG_STAGE_BYTES >> 4));
+                    const uint32_t b_lo = b_lo0 + (uint32_t)(stage * (WG_STAGE_BYTES >> 4));
                     mbar_wait_a(full0 + stage * 8, phase);
                     tc_fence_after();
-                    const uint32_t sa = smem0 + stage * WG_STAGE_BYTES;
-                    const uint64_t adesc = make_mn_sw128_desc(sa, WG_BOX_BYTES);
-                    const uint64_t bdesc = make_mn_sw128_desc(sa + WG_A_BYTES, WG_BOX_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < WG_KB / 16; ++k) {
-                        // 16 pixels further along K = 16 rows x 128 B = 2048 B (start-address field counts 16-byte units)
-                        umma_bf16(d_tmem, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (s > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < WG_KB / 16; ++k) {
+                            // 16 pixels further along K = 16 rows x 128 B = 2048 B (start-address field counts 16-byte units)
+                            umma_bf16_lh(d_tmem, a_lo + (uint32_t)(k * 128), hi, b_lo + (uint32_t)(k * 128), hi, idesc,
+                                         (s > 0 || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit_a(empty0 + stage * 8);
+                        if (s + 1 == n_steps) umma_commit_a(tfull0 + buf * 8);
                     }
-                    umma_commit_a(empty0 + stage * 8);
-                    if (s + 1 == n_steps) umma_commit_a(tfull0 + buf * 8);
+                    __syncwarp();
                     if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
                 }
-                if (n_steps == 0) umma_commit_a(tfull0 + buf * 8);       // empty K range: nothing to add (epilogue skips it)
+                if (n_steps == 0 && elect_one()) umma_commit_a(tfull0 + buf * 8);   // empty K range (epilogue skips it)
+                __syncwarp();
             }
         }
     } else if (warp < 8) {
