@@ -47,7 +47,7 @@ class BevEncoderEngine(CoAlignEngine):
         self.max_agents, self.max_scenes, self.max_cav = int(max_agents), int(max_scenes), int(max_cav)
         self.block_n_cap = int(block_n_cap)
         self.use_graph, self.simt_conv, self.pair = bool(use_graph), False, True
-        self.chan_major, self.pair_min_bn, self.halo = True, 256, True
+        self.chan_major, self.pair_min_bn, self.halo, self.chan_major_256 = True, 256, True, 0
         self.fusion, self.method = True, {"att": 0, "max": 1}[method]
         self.ny, self.nx = H, W
         self.voxel_size = [float(discrete_ratio)] * 3

@@ -521,17 +521,20 @@ struct TctCfg {
 // Epilogue of the channel-major kernels (one of the 8 epilogue warps): TMEM lane = output channel, so every 32-pixel
 // chunk is transposed back to pixel-major rows through the warp's 2 KB shared-memory stage.
 __device__ __forceinline__ void tct_epilogue(const ConvParams& p, const float* s_bias, uint4* stage, uint32_t tmem_base,
-                                             uint32_t tfull0, uint64_t* tmem_empty_bar, int m_tiles, int warp, int lane) {
-        // epilogue: warp -> channels [32*q4, +32) (TMEM lane quarter), pixel columns [128*half, +128) in 4 chunks of 32
+                                             uint32_t tfull0, uint64_t* tmem_empty_bar, int m_tiles, int n_cblk, int warp,
+                                             int lane) {
+        // epilogue: warp -> channels [32*q4, +32) of the item's 128-channel block (TMEM lane quarter), pixel columns
+        // [128*half, +128) in 4 chunks of 32
         const int q4 = warp & 3, half = warp >> 2;
-        const int ch = q4 * 32 + lane;
-        const float bias = s_bias[ch];
         const uint16_t* stage16 = reinterpret_cast<const uint16_t*>(stage);
         uint16_t* stage16w = reinterpret_cast<uint16_t*>(stage);
         const int rsub = lane >> 2, csub = lane & 3;                 // row-in-8 / 16-byte chunk for the pixel-major accesses
         const bool has_res = p.residual != nullptr;
         int it = 0;
-        for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+        for (int item = blockIdx.x; item < m_tiles * n_cblk; item += gridDim.x, ++it) {
+            const int tile = item / n_cblk;
+            const int c0 = (item - tile * n_cblk) * 128 + q4 * 32;    // first channel of this warp
+            const float bias = s_bias[c0 + lane];
             const int buf = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const long pb0 = (long)tile * TP + half * 128;
@@ -542,7 +545,7 @@ __device__ __forceinline__ void tct_epilogue(const ConvParams& p, const float* s
                 for (int i = 0; i < 4; ++i) {
                     const long q = pb0 + i * 8 + rsub;
                     if (q < p.rows_total)
-                        rcur[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + q * (long)p.res_pitch + q4 * 32) + csub);
+                        rcur[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + q * (long)p.res_pitch + c0) + csub);
                 }
             }
             mbar_wait_a(tfull0 + buf * 8, acc_phase);
@@ -556,7 +559,7 @@ __device__ __forceinline__ void tct_epilogue(const ConvParams& p, const float* s
                         const long q = pb + 32 + i * 8 + rsub;
                         rnext[i] = make_uint4(0u, 0u, 0u, 0u);
                         if (q < p.rows_total)
-                            rnext[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + q * (long)p.res_pitch + q4 * 32) + csub);
+                            rnext[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + q * (long)p.res_pitch + c0) + csub);
                     }
                 }
                 const int drow = (int)decode_row(p, pb + lane, 0).row;       // destination row of pixel (pb + lane), -1 = halo
@@ -590,7 +593,7 @@ __device__ __forceinline__ void tct_epilogue(const ConvParams& p, const float* s
                     const uint4 val = stage[R * 4 + csub];
                     const int dr = __shfl_sync(0xffffffffu, drow, R);
                     if (dr >= 0)
-                        reinterpret_cast<uint4*>(p.out + (long)dr * p.out_pitch + p.out_ch_off + q4 * 32)[csub] = val;
+                        reinterpret_cast<uint4*>(p.out + (long)dr * p.out_pitch + p.out_ch_off + c0)[csub] = val;
                 }
                 __syncwarp();
 #pragma unroll
@@ -604,7 +607,8 @@ __device__ __forceinline__ void tct_epilogue(const ConvParams& p, const float* s
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_gemm_tct_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
-                     const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ ConvParams p, int m_tiles) {
+                     const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ ConvParams p, int m_tiles,
+                     int n_cblk) {
     using Cfg = TctCfg;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -613,13 +617,13 @@ conv_gemm_tct_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
-    __shared__ __align__(16) float s_bias[128];
+    __shared__ __align__(16) float s_bias[256];
     __shared__ __align__(16) uint4 s_stage[8][128];       // per epilogue warp: 32 pixels x 64 B
 
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
     uint8_t* smem = smem_raw + pad;
-    for (int i = threadIdx.x; i < 128; i += TC_THREADS) s_bias[i] = p.bias[i];
+    for (int i = threadIdx.x; i < 128 * n_cblk; i += TC_THREADS) s_bias[i] = p.bias[i];
 
     const int warp = warp_idx_uniform();
     const int lane = threadIdx.x & 31;
@@ -654,7 +658,8 @@ conv_gemm_tct_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
         // warp-uniform loops, elect only around the TMA / tcgen05 instructions (see conv_gemm_halo64_kernel)
         {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < m_tiles * n_cblk; item += gridDim.x) {
+                const int tile = item / n_cblk, n0 = (item - tile * n_cblk) * 128;
                 const int m0 = tile * TP;
                 for (int ks = 0; ks < nk; ++ks) {
                     const uint32_t fb = full0 + stage * 8;
@@ -664,7 +669,7 @@ conv_gemm_tct_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
                         const cb_kstep st = p.ksteps[ks];
                         const uint32_t sa = smem_p0 + stage * Cfg::KSTEP_BYTES;
                         tma_load_2d_a(sa, st.a_sel ? &tmap_a1 : &tmap_a0, fb, (int)st.col, m0 + st.row_off);
-                        tma_load_2d_a(sa + Cfg::P_BYTES, &tmap_w, fb, st.w_k, 0);
+                        tma_load_2d_a(sa + Cfg::P_BYTES, &tmap_w, fb, st.w_k, n0);
                     }
                     __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -679,7 +684,7 @@ conv_gemm_tct_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
             const uint32_t w_lo0 = (uint32_t)make_sw128_desc(smem_p0 + Cfg::P_BYTES);
             int stage = 0; uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+            for (int item = blockIdx.x; item < m_tiles * n_cblk; item += gridDim.x, ++it) {
                 const int buf = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait_a(tempty0 + buf * 8, acc_phase ^ 1);
@@ -704,7 +709,7 @@ conv_gemm_tct_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_c
             }
         }
     } else if (warp < 8) {
-        tct_epilogue(p, s_bias, s_stage[warp], tmem_base, tfull0, tmem_empty_bar, m_tiles, warp, lane);
+        tct_epilogue(p, s_bias, s_stage[warp], tmem_base, tfull0, tmem_empty_bar, m_tiles, n_cblk, warp, lane);
     }
     tc_fence_before();
     __syncthreads();
@@ -928,7 +933,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_gemm_tct_halo_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
                           const __grid_constant__ CUtensorMap tmap_a0t, const __grid_constant__ CUtensorMap tmap_a1t,
                           const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ ConvParams p,
-                          const __grid_constant__ HaloItems items, int m_tiles, int bo_mode) {
+                          const __grid_constant__ HaloItems items, int m_tiles, int n_cblk, int bo_mode) {
     using Cfg = TctHaloCfg;
     constexpr int PST = Cfg::PST, WST = Cfg::WST;
     extern __shared__ uint8_t smem_raw[];
@@ -939,13 +944,13 @@ conv_gemm_tct_halo_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __g
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
-    __shared__ __align__(16) float s_bias[128];
+    __shared__ __align__(16) float s_bias[256];
     __shared__ __align__(16) uint4 s_stage[8][128];
 
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
     uint8_t* smem = smem_raw + pad;
-    for (int i = threadIdx.x; i < 128; i += TC_THREADS) s_bias[i] = p.bias[i];
+    for (int i = threadIdx.x; i < 128 * n_cblk; i += TC_THREADS) s_bias[i] = p.bias[i];
 
     const int warp = warp_idx_uniform();
     const int lane = threadIdx.x & 31;
@@ -985,7 +990,8 @@ conv_gemm_tct_halo_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __g
         // warp-uniform loops, elect only around the TMA / tcgen05 instructions (see conv_gemm_halo64_kernel)
         {
             int ps = 0, ws = 0; uint32_t pphase = 0, wphase = 0;
-            for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < m_tiles * n_cblk; item += gridDim.x) {
+                const int tile = item / n_cblk, n0 = (item - tile * n_cblk) * 128;
                 const int m0 = tile * TP;
                 for (int ii = 0; ii < n_items; ++ii) {
                     const int first = items.first[ii], ns = items.nsub[ii];
@@ -1006,7 +1012,7 @@ conv_gemm_tct_halo_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __g
                         mbar_wait_a(wempty0 + ws * 8, wphase ^ 1);
                         if (elect_one()) {
                             mbar_expect_tx_a(wb, (uint32_t)Cfg::W_BYTES);
-                            tma_load_2d_a(smem_w0 + ws * Cfg::W_BYTES, &tmap_w, wb, p.ksteps[first + s].w_k, 0);
+                            tma_load_2d_a(smem_w0 + ws * Cfg::W_BYTES, &tmap_w, wb, p.ksteps[first + s].w_k, n0);
                         }
                         __syncwarp();
                         if (++ws == WST) { ws = 0; wphase ^= 1; }
@@ -1023,7 +1029,7 @@ conv_gemm_tct_halo_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __g
             const uint32_t bo_shift = bo_mode ? (1u << 17) : 0u;     // matrix-base-offset field = descriptor bits 49..51
             int ps = 0, ws = 0; uint32_t pphase = 0, wphase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+            for (int item = blockIdx.x; item < m_tiles * n_cblk; item += gridDim.x, ++it) {
                 const int buf = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait_a(tempty0 + buf * 8, acc_phase ^ 1);
@@ -1057,7 +1063,7 @@ conv_gemm_tct_halo_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __g
             }
         }
     } else if (warp < 8) {
-        tct_epilogue(p, s_bias, s_stage[warp], tmem_base, tfull0, tmem_empty_bar, m_tiles, warp, lane);
+        tct_epilogue(p, s_bias, s_stage[warp], tmem_base, tfull0, tmem_empty_bar, m_tiles, n_cblk, warp, lane);
     }
     tc_fence_before();
     __syncthreads();
@@ -1290,7 +1296,8 @@ extern "C" int cb_conv_gemm_t(const cb_conv_desc* d, int max_ctas, void* stream)
     static thread_local ConvParams p;
     int rc = fill_params(d, p);
     if (rc) return rc;
-    if (d->n_total != 128 || d->cout_mod != 128 || d->w_rows < 128) return CB_ERR_ARG;
+    if ((d->n_total != 128 && d->n_total != 256) || d->cout_mod != d->n_total || d->w_rows < d->n_total) return CB_ERR_ARG;
+    const int n_cblk = d->n_total / 128;                      // 128-channel blocks: items = (pixel tile, block), block fastest
     if (d->out_mode != CB_OUT_PF && d->out_mode != CB_OUT_PS) return CB_ERR_ARG;
     if (d->out_lo_off != 0 || d->res_lo_off != 0) return CB_ERR_ARG;
     if (p.rows_total >= (1L << 31) - 4 * TP) return CB_ERR_ARG;
@@ -1321,11 +1328,11 @@ extern "C" int cb_conv_gemm_t(const cb_conv_desc* d, int max_ctas, void* stream)
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int m_tiles = (int)((p.rows_total + TP - 1) / TP);
-    int grid = m_tiles;
+    int grid = m_tiles * n_cblk;
     const int cap = max_ctas > 0 ? max_ctas : sms;
     if (grid > cap) grid = cap;
     cudaError_t le = launch_pdl(conv_gemm_tct_kernel, dim3(grid), dim3(TC_THREADS), TctCfg::SMEM_BYTES, (cudaStream_t)stream,
-                                ta0, ta1, tw, p, m_tiles);
+                                ta0, ta1, tw, p, m_tiles, n_cblk);
     return le == cudaSuccess ? CB_OK : (int)le;
 }
 
@@ -1395,7 +1402,8 @@ extern "C" int cb_conv_gemm_t_halo(const cb_conv_desc* d, int max_ctas, void* st
     static thread_local ConvParams p;
     int rc = fill_params(d, p);
     if (rc) return rc;
-    if (d->n_total != 128 || d->cout_mod != 128 || d->w_rows < 128) return CB_ERR_ARG;
+    if ((d->n_total != 128 && d->n_total != 256) || d->cout_mod != d->n_total || d->w_rows < d->n_total) return CB_ERR_ARG;
+    const int n_cblk = d->n_total / 128;                      // 128-channel blocks: items = (pixel tile, block), block fastest
     if (d->out_mode != CB_OUT_PF && d->out_mode != CB_OUT_PS) return CB_ERR_ARG;
     if (d->out_lo_off != 0 || d->res_lo_off != 0) return CB_ERR_ARG;
     if (p.rows_total >= (1L << 31) - 4 * TP) return CB_ERR_ARG;
@@ -1434,11 +1442,11 @@ extern "C" int cb_conv_gemm_t_halo(const cb_conv_desc* d, int max_ctas, void* st
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int m_tiles = (int)((p.rows_total + TP - 1) / TP);
-    int grid = m_tiles;
+    int grid = m_tiles * n_cblk;
     const int cap = max_ctas > 0 ? max_ctas : sms;
     if (grid > cap) grid = cap;
     const int bo_mode = cb::opt_get(CB_OPT_HALO_BO);
     cudaError_t le = launch_pdl(conv_gemm_tct_halo_kernel, dim3(grid), dim3(TC_THREADS), TctHaloCfg::SMEM_BYTES,
-                                (cudaStream_t)stream, ta0, ta1, ta0t, ta1t, tw, p, items, m_tiles, bo_mode);
+                                (cudaStream_t)stream, ta0, ta1, ta0t, ta1t, tw, p, items, m_tiles, n_cblk, bo_mode);
     return le == cudaSuccess ? CB_OK : (int)le;
 }

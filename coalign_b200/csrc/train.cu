@@ -171,6 +171,11 @@ __device__ __forceinline__ long z_off_cur(const MapP& m, const RowCur& c, const 
 // rows x up to 3 tensors of 16-byte loads in flight (raw bf16 words, converted only when consumed): ~50-100 KB per SM, what
 // HBM3e needs to stay busy (ncu of the first version: 16 KB in flight, 1.9 TB/s).  Loads are unconditional - rows past the
 // end or halo rows re-read a valid dummy row and are masked - so that they issue back to back.
+// Per-channel constants live in shared memory TRANSPOSED: channel c -> slot (c % 8) * (c_mod / 8) + c / 8, so that the 32
+// lanes of a warp (consecutive 8-channel chunks) read consecutive words.  Channel-major storage made every such load an
+// 8-way bank conflict and the kernels shared-memory bound (ncu: 9 wavefronts per 8-channel chunk in bn_bwd_apply,
+// short-scoreboard / MIO-throttle stalls; profiles/r2_ncu_bn_small.csv).
+__device__ __forceinline__ int tslot(int c, int nck) { return (c & 7) * nck + (c >> 3); }
 template <bool LO> struct Raw8 { uint4 hi, lo; };
 template <bool LO>
 __device__ __forceinline__ void ld_raw(const __nv_bfloat16* base, long off, long lo_off, Raw8<LO>& r) {
@@ -254,19 +259,21 @@ __global__ void __launch_bounds__(EW_THREADS, 2) bn_apply_kernel(
     __nv_bfloat16* __restrict__ y, long y_lo_off) {
     __shared__ float s_sc[256], s_sh[256], s_scb[256], s_shb[256];
     pdl_wait();
+    const int nck = m.c_mod >> 3;
     for (int c = threadIdx.x; c < m.c_mod; c += EW_THREADS) {
-        s_sc[c] = scale[c]; s_sh[c] = shift[c];
-        s_scb[c] = zb ? scale_b[c] : 0.f; s_shb[c] = zb ? shift_b[c] : 0.f;
+        const int t = tslot(c, nck);
+        s_sc[t] = scale[c]; s_sh[t] = shift[c];
+        s_scb[t] = zb ? scale_b[c] : 0.f; s_shb[t] = zb ? shift_b[c] : 0.f;
     }
     __syncthreads();
     const RowWalk rw = row_walk(m.c_total);
     if (rw.row0 < 0) return;
     const ColInfo ci = col_info(m, rw.chunk * 8);
     const int col = ci.col;
-    const float* sc = s_sc + ci.cb;
-    const float* sh = s_sh + ci.cb;
-    const float* scb = s_scb + ci.cb;
-    const float* shb = s_shb + ci.cb;
+    const float* sc = s_sc + (ci.cb >> 3);
+    const float* sh = s_sh + (ci.cb >> 3);
+    const float* scb = s_scb + (ci.cb >> 3);
+    const float* shb = s_shb + (ci.cb >> 3);
     RowCur c[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) c[r] = cur_init(m, rw.row0 + r * rw.row_step, R * rw.row_step);
@@ -287,11 +294,11 @@ __global__ void __launch_bounds__(EW_THREADS, 2) bn_apply_kernel(
                 float v[8], u[8];
                 cvt_raw<LO>(rz[r], v);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+                for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j * nck], sh[j * nck]);
                 if (zb) {
                     cvt_raw<LO>(rb[r], u);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] += fmaf(u[j], scb[j], shb[j]);
+                    for (int j = 0; j < 8; ++j) v[j] += fmaf(u[j], scb[j * nck], shb[j * nck]);
                 }
                 if (res) {
                     cvt_raw<LO>(rr[r], u);
@@ -324,15 +331,17 @@ __global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_reduce_kernel(
     const bool has_bn = mean != nullptr;
     const bool zmask = relu && mask_scale != nullptr && has_bn;
     const bool ymask = relu && !zmask;
+    const int nck = m.c_mod >> 3;
     for (int c = threadIdx.x; c < m.c_mod; c += EW_THREADS) {
-        s_mu[c] = has_bn ? mean[c] : 0.f;
-        s_ms[c] = zmask ? mask_scale[c] : 0.f;
-        s_mh[c] = zmask ? mask_shift[c] : 0.f;
+        const int t = tslot(c, nck);
+        s_mu[t] = has_bn ? mean[c] : 0.f;
+        s_ms[t] = zmask ? mask_scale[c] : 0.f;
+        s_mh[t] = zmask ? mask_shift[c] : 0.f;
     }
     __syncthreads();
-    const float* mu = s_mu + ci.cb;
-    const float* ms = s_ms + ci.cb;
-    const float* mh = s_mh + ci.cb;
+    const float* mu = s_mu + (ci.cb >> 3);
+    const float* ms = s_ms + (ci.cb >> 3);
+    const float* mh = s_mh + (ci.cb >> 3);
     float a0[8] = {}, a1[8] = {};
     if (rw.row0 >= 0) {
         RowCur c[R];
@@ -359,10 +368,10 @@ __global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_reduce_kernel(
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float gj = g[j];
-                        if (zmask) gj = fmaf(v[j], ms[j], mh[j]) > 0.f ? gj : 0.f;
+                        if (zmask) gj = fmaf(v[j], ms[j * nck], mh[j * nck]) > 0.f ? gj : 0.f;
                         if (ymask) gj = yv[j] > 0.f ? gj : 0.f;
                         a0[j] += gj;
-                        if (has_bn) a1[j] = fmaf(gj, v[j] - mu[j], a1[j]);       // x_hat = (z - mean) * inv_std: scaled below
+                        if (has_bn) a1[j] = fmaf(gj, v[j] - mu[j * nck], a1[j]);       // x_hat = (z - mean) * inv_std: scaled below
                     }
                 }
                 cur_next(m, c[r]);
@@ -396,6 +405,7 @@ __global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_apply_kernel(
     }
     const bool zmask = relu && mask_scale != nullptr && has_bn;
     const bool ymask = relu && !zmask;
+    const int nck = m.c_mod >> 3;
     for (int c = threadIdx.x; c < m.c_mod; c += EW_THREADS) {
         float A = 1.f, B = 0.f, Cc = 0.f;
         if (has_bn) {
@@ -405,20 +415,21 @@ __global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_apply_kernel(
             B = (float)(-gi * iv * k1);
             Cc = (float)(-gi * k0 + gi * iv * k1 * (double)mean[c]);
         }
-        s_A[c] = A; s_B[c] = B; s_C[c] = Cc;
-        s_ms[c] = zmask ? mask_scale[c] : 0.f;
-        s_mh[c] = zmask ? mask_shift[c] : 0.f;
+        const int t = tslot(c, nck);
+        s_A[t] = A; s_B[t] = B; s_C[t] = Cc;
+        s_ms[t] = zmask ? mask_scale[c] : 0.f;
+        s_mh[t] = zmask ? mask_shift[c] : 0.f;
     }
     __syncthreads();
     const RowWalk rw = row_walk(m.c_total);
     if (rw.row0 < 0) return;
     const ColInfo ci = col_info(m, rw.chunk * 8);
     const int col = ci.col;
-    const float* cA = s_A + ci.cb;
-    const float* cB = s_B + ci.cb;
-    const float* cC = s_C + ci.cb;
-    const float* ms = s_ms + ci.cb;
-    const float* mh = s_mh + ci.cb;
+    const float* cA = s_A + (ci.cb >> 3);
+    const float* cB = s_B + (ci.cb >> 3);
+    const float* cC = s_C + (ci.cb >> 3);
+    const float* ms = s_ms + (ci.cb >> 3);
+    const float* mh = s_mh + (ci.cb >> 3);
     RowCur c[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) c[r] = cur_init(m, rw.row0 + r * rw.row_step, R * rw.row_step);
@@ -442,13 +453,13 @@ __global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_apply_kernel(
                 if (ymask) cvt_raw<LO>(ry[r], yv);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    if (zmask) g[j] = fmaf(v[j], ms[j], mh[j]) > 0.f ? g[j] : 0.f;
+                    if (zmask) g[j] = fmaf(v[j], ms[j * nck], mh[j * nck]) > 0.f ? g[j] : 0.f;
                     if (ymask) g[j] = yv[j] > 0.f ? g[j] : 0.f;
                 }
                 if (dsum) store8(dsum, c[r].q * m.c_total + col, LO ? dsum_lo_off : 0, g);
                 if (has_bn) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) g[j] = fmaf(cA[j], g[j], fmaf(cB[j], v[j], cC[j]));
+                    for (int j = 0; j < 8; ++j) g[j] = fmaf(cA[j * nck], g[j], fmaf(cB[j * nck], v[j], cC[j * nck]));
                 }
                 store8(dz, c[r].q * m.c_total + col, LO ? dz_lo_off : 0, g);
             }

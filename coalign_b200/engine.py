@@ -101,6 +101,7 @@ class CoAlignEngine:
                  device="cuda", precise: bool = False, max_cav: int = 5, block_n_cap: int = 128,
                  use_graph: bool = True, simt_conv: bool = False, pair: bool = True, plan_only: bool = False,
                  backbone: str = "resnet", fusion: bool = True, chan_major: bool = True, pair_min_bn: int = 256,
+                 chan_major_256: int = 0,
                  halo: bool = True):
         # backbone "resnet": ResNetBEVBackbone (CoAlign); "plain": BaseBEVBackbone conv stacks (single-agent point_pillar,
         # /root/reference/opencood/models/sub_modules/base_bev_backbone.py).  fusion=False: every agent is its own
@@ -118,6 +119,7 @@ class CoAlignEngine:
         self.simt_conv = simt_conv            # validation only: evaluate the descriptors with the SIMT kernel
         self.pair = pair                      # CTA-pair (cta_group::2) conv kernel ...
         self.chan_major = bool(chan_major)                                # Cout=128 layers: channel-major 128x256 tiles
+        self.chan_major_256 = int(chan_major_256)                         # Cout=256: 0 CTA-pair kernel (default: equal speed, measured), 1 channel-major for 3x3, 2 for all
         self.pair_min_bn = int(pair_min_bn)                               # ... for tiles at least this wide (measured)
         self.halo = bool(halo)                                            # halo-box kernels for the Cout=64/128 layers
         nx, ny, nz = [int(v) for v in args["point_pillar_scatter"]["grid_size"]]
@@ -456,8 +458,9 @@ class CoAlignEngine:
                 elif (self.halo and not self.precise and self._has_tap_triples(o) and o.n_total == 64
                       and o.cout_mod == 64 and o.n_ksteps <= 10 and o.out_mode in (CB_OUT_PF, CB_OUT_PS)):
                     _lib.check(lib.cb_conv_gemm_halo(C.byref(o), 0, stream_ptr), "cb_conv_gemm_halo")
-                elif (self.chan_major and not self.precise and o.n_total == 128 and o.cout_mod == 128
-                      and o.out_mode in (CB_OUT_PF, CB_OUT_PS)):
+                elif (self.chan_major and not self.precise and o.cout_mod == o.n_total and o.out_mode in (CB_OUT_PF, CB_OUT_PS)
+                      and (o.n_total == 128 or (o.n_total == 256 and (self.chan_major_256 == 2 or (
+                          self.chan_major_256 == 1 and self.halo and self._has_tap_triples(o)))))):
                     if self.halo and self._has_tap_triples(o):
                         _lib.check(lib.cb_conv_gemm_t_halo(C.byref(o), 0, stream_ptr), "cb_conv_gemm_t_halo")
                     else:

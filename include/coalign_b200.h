@@ -209,9 +209,10 @@ int cb_conv_gemm(const cb_conv_desc* desc, int max_ctas, void* stream);
 /* Same GEMM on CTA pairs (tcgen05 cta_group::2, 256 x block_n tiles, cluster of 2): halves the weight-tile
  * shared-memory traffic per MAC.  max_clusters <= 0: one cluster per SM pair.  block_n 32 falls back to cb_conv_gemm. */
 int cb_conv_gemm_pair(const cb_conv_desc* desc, int max_clusters, void* stream);
-/* Channel-major variant for n_total == cout_mod == 128, bf16 PF/PS outputs: the weight tile is the UMMA A operand
+/* Channel-major variant for n_total == cout_mod == 128 or 256, bf16 PF/PS outputs: the weight tile is the UMMA A operand
  * (M = 128 output channels) and 256 pixels the N side, so one instruction does 128 x 256 x 16 MACs and the activation
- * rows are read from shared memory once per 256-wide tile.  Same descriptor; block_n is ignored.  Returns
+ * rows are read from shared memory once per 256-wide tile.  256 output channels run as two 128-channel work items per
+ * pixel tile on neighbouring CTAs (the second read of the activation box hits L2).  Same descriptor; block_n is ignored.  Returns
  * CB_ERR_ARG for descriptors outside that envelope (callers fall back to cb_conv_gemm). */
 int cb_conv_gemm_t(const cb_conv_desc* desc, int max_ctas, void* stream);
 /* Halo / resident-weight variant for n_total == cout_mod == 64 layers with at most 10 K-steps, bf16 PF/PS outputs:

@@ -209,6 +209,24 @@ def test_halo_conv_kernels_match_plain_kernels():
             assert rel_l2(g_out[k], r_out[k]) < 3e-3, (k, rel_l2(g_out[k], r_out[k]))
 
 
+def test_channel_major_256_channel_layers_match_pair_kernel():
+    """Cout = 256 layers through the channel-major kernels (two 128-channel work items per pixel tile; plain and halo
+    variants, `chan_major_256` = 2) against the default CTA-pair kernel on the same descriptors."""
+    def pair(eng):
+        eng.chan_major_256 = 0
+
+    def cm(eng):
+        eng.chan_major_256 = 2
+
+    ref = _run_small_and_big(pair)
+    got = _run_small_and_big(cm)
+    for (r_out, r_st), (g_out, g_st) in zip(ref, got):
+        for k in r_st:
+            assert rel_l2(g_st[k], r_st[k]) < 3e-3, (k, rel_l2(g_st[k], r_st[k]))
+        for k in r_out:
+            assert rel_l2(g_out[k], r_out[k]) < 3e-3, (k, rel_l2(g_out[k], r_out[k]))
+
+
 def test_voxelize_bit_exact_and_fused_path():
     """Integer pillar indices bit-exact with the serial generator restatement (oracle/voxelize.c);
     fused points->canvas == voxels->canvas."""

@@ -15,7 +15,7 @@ sp = torch.cuda.current_stream().cuda_stream
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
 
-def timeit(fn, n=6):
+def timeit(fn, n=2 if os.environ.get("EXP_BW_SIZES") else 6):
     fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tot = 0.0
@@ -29,7 +29,10 @@ def timeit(fn, n=6):
     return tot / n * 1e3
 
 
-for n, H, W, c in ((20, 100, 352, 64), (20, 50, 176, 128), (20, 25, 88, 256)):
+SIZES = ((20, 100, 352, 64), (20, 50, 176, 128), (20, 25, 88, 256))
+if os.environ.get("EXP_BW_SIZES"):
+    SIZES = tuple(SIZES[int(i)] for i in os.environ["EXP_BW_SIZES"].split(","))
+for n, H, W, c in SIZES:
     rows = n * (H + 2) * (W + 2)
     mb = rows * c * 2 / 1e6
     a, b, y = (torch.randn(rows, c, device="cuda").to(BF16) for _ in range(3))
@@ -66,4 +69,4 @@ for n, H, W, c in ((20, 100, 352, 64), (20, 50, 176, 128), (20, 25, 88, 256)):
                                                                      db.data_ptr(), sp)))
     print(f"[{n}x{H}x{W}x{c}] {mb:.1f} MB per tensor")
     for k, (nt, us) in res.items():
-        print(f"  {k:20s} {us:7.1f} us  {nt * mb / us / 1e3 * 1e3:7.0f} GB/s ({nt} tensors)", flush=True)
+        print(f"  {k:20s} {us:7.1f} us  {nt * mb / us * 1e3:7.0f} GB/s ({nt} tensors)", flush=True)

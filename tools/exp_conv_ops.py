@@ -14,7 +14,9 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 12
 args = synth.opv2v_args()
 sd = synth.random_state_dict(args, 0)
 rl = [5] * B
-eng = CoAlignEngine(args, sd, sum(rl), len(rl), precise=False, use_graph=False)
+CM = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+eng = CoAlignEngine(args, sd, sum(rl), len(rl), precise=False, use_graph=False, block_n_cap=256, chan_major_256=CM)
+print("chan_major_256 =", CM)
 scenes = [synth.make_scene(s, 5, 60000, args["lidar_range"], pose_noise=True) for s in range(B)]
 pts = torch.from_numpy(np.concatenate([p for sc in scenes for p in sc["points"]])).cuda()
 off = np.arange(0, sum(rl) + 1, dtype=np.int32) * 60000
