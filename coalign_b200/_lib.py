@@ -76,6 +76,7 @@ EXPORTS = {
     "cb_wgrad_simt": (C.c_int, [C.POINTER(WgradDesc), _P]),
     "cb_bn_stats": (C.c_int, [_P, _L, C.POINTER(Map), _P, _P]),
     "cb_bn_finalize": (C.c_int, [_P, _I, _D, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "cb_bn_stats_finalize": (C.c_int, [_P, _L, C.POINTER(Map), _P, _P, _D, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "cb_bn_apply": (C.c_int, [_P, _L, _P, _P, _P, _L, _P, _P, _P, C.c_int32, _L, _I, C.POINTER(Map), _P, _L, _P]),
     "cb_bn_bwd_reduce": (C.c_int, [_P, _L, _P, _L, _I, _P, _L, _P, _P, _P, _P, C.POINTER(Map), _P, _P]),
     "cb_bn_bwd_apply": (C.c_int, [_P, _L, _P, _L, _I, _P, _L, _P, _P, _P, _P, _P, _P, _D, C.POINTER(Map), _P, _L, _P, _L, _P,

@@ -192,10 +192,39 @@ __device__ __forceinline__ void cvt_raw(const Raw8<LO>& r, float (&v)[8]) {
     }
 }
 
+struct BnFin {                        // arguments of the BatchNorm finalize step (cb_bn_finalize)
+    int c; double count; float eps, momentum;
+    const float *gamma, *beta;
+    float *running_mean, *running_var, *scale, *shift, *mean_out, *inv_out;
+    int* counter;                     // cb_bn_stats_finalize: CTA ticket counter (zero between launches)
+};
+__device__ __forceinline__ void bn_finalize_channel(const BnFin& f, int i, double s0, double s1) {
+    if (f.gamma == nullptr) {                                            // no BatchNorm: identity + bias
+        f.scale[i] = 1.f;
+        f.shift[i] = f.beta ? f.beta[i] : 0.f;
+        return;
+    }
+    const double mean = s0 / f.count;
+    double var = s1 / f.count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double inv = 1.0 / sqrt(var + (double)f.eps);
+    const double sc = (double)f.gamma[i] * inv;
+    f.scale[i] = (float)sc;
+    f.shift[i] = (float)((double)f.beta[i] - mean * sc);
+    if (f.mean_out) f.mean_out[i] = (float)mean;
+    if (f.inv_out) f.inv_out[i] = (float)inv;
+    if (f.running_mean) f.running_mean[i] = (float)((1.0 - f.momentum) * f.running_mean[i] + f.momentum * mean);
+    if (f.running_var) {
+        const double unb = f.count > 1.0 ? var * f.count / (f.count - 1.0) : var;
+        f.running_var[i] = (float)((1.0 - f.momentum) * f.running_var[i] + f.momentum * unb);
+    }
+}
+
 template <int R, bool LO>
 __global__ void __launch_bounds__(EW_THREADS, 2) bn_stats_kernel(const __nv_bfloat16* __restrict__ z, long z_lo_off,
-                                                              const MapP m, double* __restrict__ sums) {
+                                                              const MapP m, double* __restrict__ sums, const BnFin fin) {
     __shared__ float s_part[2 * 2048];
+    __shared__ int s_last;
     pdl_wait();
     const RowWalk rw = row_walk(m.c_total);
     const ColInfo ci = col_info(m, rw.chunk * 8);
@@ -220,35 +249,23 @@ __global__ void __launch_bounds__(EW_THREADS, 2) bn_stats_kernel(const __nv_bflo
         }
     }
     block_reduce_to_global(a0, a1, m.c_total, m.c_mod, true, s_part, sums);
+    if (fin.counter == nullptr) return;
+    // cb_bn_stats_finalize: the CTA that takes the last ticket sees every CTA's sums and closes the statistics
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(fin.counter, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int i = threadIdx.x; i < fin.c; i += EW_THREADS) bn_finalize_channel(fin, i, __ldcg(sums + i), __ldcg(sums + fin.c + i));
+    if (threadIdx.x == 0) *fin.counter = 0;
 }
 
-__global__ void bn_finalize_kernel(const double* __restrict__ sums, int c, double count, float eps, float momentum,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float* __restrict__ running_mean, float* __restrict__ running_var,
-                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
-                                   float* __restrict__ inv_out) {
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, const BnFin f) {
     pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c) return;
-    if (gamma == nullptr) {                                              // no BatchNorm: identity + bias
-        scale[i] = 1.f;
-        shift[i] = beta ? beta[i] : 0.f;
-        return;
-    }
-    const double mean = sums[i] / count;
-    double var = sums[c + i] / count - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const double inv = 1.0 / sqrt(var + (double)eps);
-    const double sc = (double)gamma[i] * inv;
-    scale[i] = (float)sc;
-    shift[i] = (float)((double)beta[i] - mean * sc);
-    if (mean_out) mean_out[i] = (float)mean;
-    if (inv_out) inv_out[i] = (float)inv;
-    if (running_mean) running_mean[i] = (float)((1.0 - momentum) * running_mean[i] + momentum * mean);
-    if (running_var) {
-        const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
-        running_var[i] = (float)((1.0 - momentum) * running_var[i] + momentum * unb);
-    }
+    if (i >= f.c) return;
+    bn_finalize_channel(f, i, f.gamma ? sums[i] : 0.0, f.gamma ? sums[f.c + i] : 0.0);
 }
 
 template <int R, bool LO>
@@ -977,22 +994,42 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
     }
 }
 
+// One launch for all weight matrices.  Every CTA takes ONE contiguous range of the concatenated element space, so a thread
+// changes job at most a couple of times: the job record is looked up (binary search) only on a change and kept in
+// registers, and the index arithmetic is 32-bit.  (First version: per-element search + four 64-bit divisions, 0.42 ms for
+// 26 M elements.)
 __global__ void __launch_bounds__(256) pack_weights_batch_kernel(const cb_pack_job* __restrict__ jobs, int n_jobs, long total) {
     pdl_wait();
-    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
-        int lo = 0, hi = n_jobs;                                         // last job with first <= i
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (jobs[mid].first <= i) lo = mid; else hi = mid; }
-        const cb_pack_job& j = jobs[lo];
-        const long e = i - j.first;
-        const long r = e / j.K;
-        const int k = (int)(e - r * j.K);
-        const long r1 = r / j.R0, r0 = r - r1 * j.R0;
-        const int k1 = k / j.K0, k0 = k - k1 * j.K0;
-        const float v = __ldg(j.src + r1 * j.s_r1 + r0 * j.s_r0 + k1 * j.s_k1 + k0 * j.s_k0);
-        __nv_bfloat16* dst = (__nv_bfloat16*)j.dst;
+    long per = (total + gridDim.x - 1) / gridDim.x;
+    per = (per + 255) / 256 * 256;
+    const long beg = (long)blockIdx.x * per;
+    const long end = beg + per < total ? beg + per : total;
+    long cfirst = 0, cend = -1;
+    const float* src = nullptr;
+    __nv_bfloat16* dst = nullptr;
+    unsigned K = 1, R0 = 1, K0 = 1;
+    int s_r1 = 0, s_r0 = 0, s_k1 = 0, s_k0 = 0, dst_ld = 0, k_off = 0, lo_col = 0;
+    for (long i = beg + threadIdx.x; i < end; i += 256) {
+        if (i >= cend) {
+            int lo = 0, hi = n_jobs;                                     // last job with first <= i
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (jobs[mid].first <= i) lo = mid; else hi = mid; }
+            const cb_pack_job& j = jobs[lo];
+            cfirst = j.first;
+            cend = lo + 1 < n_jobs ? jobs[lo + 1].first : total;
+            src = j.src; dst = (__nv_bfloat16*)j.dst;
+            K = (unsigned)j.K; R0 = (unsigned)j.R0; K0 = (unsigned)j.K0;
+            s_r1 = (int)j.s_r1; s_r0 = (int)j.s_r0; s_k1 = (int)j.s_k1; s_k0 = (int)j.s_k0;
+            dst_ld = j.dst_ld; k_off = j.k_off; lo_col = j.lo_col_off;
+        }
+        const unsigned e = (unsigned)(i - cfirst);
+        const unsigned r = e / K, k = e - r * K;
+        const unsigned r1 = r / R0, r0 = r - r1 * R0;
+        const unsigned k1 = k / K0, k0 = k - k1 * K0;
+        const float v = __ldg(src + (long)((int)r1 * s_r1 + (int)r0 * s_r0 + (int)k1 * s_k1 + (int)k0 * s_k0));
         const __nv_bfloat16 hi16 = __float2bfloat16(v);
-        dst[r * j.dst_ld + j.k_off + k] = hi16;
-        if (j.lo_col_off != 0) dst[r * j.dst_ld + j.k_off + j.lo_col_off + k] = __float2bfloat16(v - __bfloat162float(hi16));
+        __nv_bfloat16* d = dst + (long)r * dst_ld + k_off + k;
+        *d = hi16;
+        if (lo_col != 0) d[lo_col] = __float2bfloat16(v - __bfloat162float(hi16));
     }
 }
 
@@ -1043,26 +1080,55 @@ using namespace cb;
 #define BF(p) ((const __nv_bfloat16*)(p))
 #define BFW(p) ((__nv_bfloat16*)(p))
 
-extern "C" int cb_bn_stats(const void* z, int64_t z_lo_off, const cb_map* map, double* sums, void* stream) {
+static int bn_stats_launch(const void* z, int64_t z_lo_off, const cb_map* map, double* sums, const BnFin& fin, void* stream) {
     MapP m;
     int rc = fill_map(map, m);
     if (rc || !z || !sums) return rc ? rc : CB_ERR_ARG;
     const int rpi = EW_THREADS / (m.c_total >> 3);
     const dim3 grid(ew_grid((m.rows_total + rpi - 1) / rpi * EW_THREADS / 8));
     cudaError_t e = z_lo_off ? launch_pdl(bn_stats_kernel<4, true>, grid, dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(z),
-                                          (long)z_lo_off, m, sums)
+                                          (long)z_lo_off, m, sums, fin)
                              : launch_pdl(bn_stats_kernel<8, false>, grid, dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(z),
-                                          (long)z_lo_off, m, sums);
+                                          (long)z_lo_off, m, sums, fin);
     return e == cudaSuccess ? CB_OK : (int)e;
+}
+
+extern "C" int cb_bn_stats(const void* z, int64_t z_lo_off, const cb_map* map, double* sums, void* stream) {
+    BnFin fin{};
+    return bn_stats_launch(z, z_lo_off, map, sums, fin, stream);
+}
+
+static int bn_fin_args(BnFin& f, const double* sums, int c, double count, float eps, float momentum, const float* gamma,
+                       const float* beta, float* running_mean, float* running_var, float* scale, float* shift, float* mean,
+                       float* inv_std) {
+    if (c < 1 || !scale || !shift || (gamma && (!sums || !beta || count <= 0))) return CB_ERR_ARG;
+    f.c = c; f.count = count; f.eps = eps; f.momentum = momentum; f.gamma = gamma; f.beta = beta;
+    f.running_mean = running_mean; f.running_var = running_var; f.scale = scale; f.shift = shift; f.mean_out = mean;
+    f.inv_out = inv_std; f.counter = nullptr;
+    return CB_OK;
 }
 
 extern "C" int cb_bn_finalize(const double* sums, int c, double count, float eps, float momentum, const float* gamma,
                               const float* beta, float* running_mean, float* running_var, float* scale, float* shift,
                               float* mean, float* inv_std, void* stream) {
-    if (c < 1 || !scale || !shift || (gamma && (!sums || !beta || count <= 0))) return CB_ERR_ARG;
-    cudaError_t e = launch_pdl(bn_finalize_kernel, dim3((c + 127) / 128), dim3(128), 0, (cudaStream_t)stream, sums, c, count, eps,
-                               momentum, gamma, beta, running_mean, running_var, scale, shift, mean, inv_std);
+    BnFin f{};
+    int rc = bn_fin_args(f, sums, c, count, eps, momentum, gamma, beta, running_mean, running_var, scale, shift, mean, inv_std);
+    if (rc) return rc;
+    cudaError_t e = launch_pdl(bn_finalize_kernel, dim3((c + 127) / 128), dim3(128), 0, (cudaStream_t)stream, sums, f);
     return e == cudaSuccess ? CB_OK : (int)e;
+}
+
+extern "C" int cb_bn_stats_finalize(const void* z, int64_t z_lo_off, const cb_map* map, double* sums, int32_t* counter,
+                                    double count, float eps, float momentum, const float* gamma, const float* beta,
+                                    float* running_mean, float* running_var, float* scale, float* shift, float* mean,
+                                    float* inv_std, void* stream) {
+    if (!map || !counter || !gamma) return CB_ERR_ARG;
+    BnFin f{};
+    int rc = bn_fin_args(f, sums, map->c_mod, count, eps, momentum, gamma, beta, running_mean, running_var, scale, shift, mean,
+                         inv_std);
+    if (rc) return rc;
+    f.counter = counter;
+    return bn_stats_launch(z, z_lo_off, map, sums, f, stream);
 }
 
 extern "C" int cb_bn_apply(const void* z, int64_t z_lo_off, const float* scale, const float* shift, const void* z_b,

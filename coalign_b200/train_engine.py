@@ -316,6 +316,7 @@ class TrainEngine(CoAlignEngine):
         self.bnf = torch.zeros(nf, dtype=torch.float32, device=dev)
         # fp64 reduction slots: forward region (per norm [2c] + the PFN's 65 feature sums) / backward region (per norm [2c]
         # + the PFN's 768 sums); each region is zeroed once at the start of its pass
+        self.bn_ticket = torch.zeros(1, dtype=torch.int32, device=dev)       # cb_bn_stats_finalize CTA counter
         self.red_f = torch.zeros(nd // 2 + 128, dtype=torch.float64, device=dev)
         self.red_b = torch.zeros(nd // 2 + 768, dtype=torch.float64, device=dev)
         self.pfn_red_off = nd // 2
@@ -638,12 +639,15 @@ class TrainEngine(CoAlignEngine):
             elif kind == "bn_fwd":
                 s = self.bn_slot[o["bn"]]
                 z = o["z"]
-                ck(lib.cb_bn_stats(z.ptr, z.lo_off, C.byref(o["map"]), self.redv(o["bn"], 0).data_ptr(), sp), "cb_bn_stats")
-                ck(lib.cb_bn_finalize(self.redv(o["bn"], 0).data_ptr(), s["c"], o["count"], o["eps"], o["mom"],
-                                      self.P[o["bn"] + ".weight"].data_ptr(), self.P[o["bn"] + ".bias"].data_ptr(),
-                                      self.R[o["bn"] + ".running_mean"].data_ptr(), self.R[o["bn"] + ".running_var"].data_ptr(),
-                                      self.bnv(o["bn"], 0).data_ptr(), self.bnv(o["bn"], 1).data_ptr(),
-                                      self.bnv(o["bn"], 2).data_ptr(), self.bnv(o["bn"], 3).data_ptr(), sp), "cb_bn_finalize")
+                # statistics + finalize in one launch (the last CTA closes them): 38 launches less per iteration
+                ck(lib.cb_bn_stats_finalize(z.ptr, z.lo_off, C.byref(o["map"]), self.redv(o["bn"], 0).data_ptr(),
+                                            self.bn_ticket.data_ptr(), o["count"], o["eps"], o["mom"],
+                                            self.P[o["bn"] + ".weight"].data_ptr(), self.P[o["bn"] + ".bias"].data_ptr(),
+                                            self.R[o["bn"] + ".running_mean"].data_ptr(),
+                                            self.R[o["bn"] + ".running_var"].data_ptr(),
+                                            self.bnv(o["bn"], 0).data_ptr(), self.bnv(o["bn"], 1).data_ptr(),
+                                            self.bnv(o["bn"], 2).data_ptr(), self.bnv(o["bn"], 3).data_ptr(), sp),
+                   "cb_bn_stats_finalize")
             elif kind == "bn_apply":
                 z, y = o["z"], o["y"]
                 zb, res = o.get("z_b"), o.get("res")

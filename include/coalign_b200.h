@@ -400,6 +400,11 @@ int cb_bn_stats(const void* z, int64_t z_lo_off, const cb_map* map, double* sums
 int cb_bn_finalize(const double* sums, int c, double count, float eps, float momentum,
                    const float* gamma, const float* beta, float* running_mean, float* running_var,
                    float* scale, float* shift, float* mean, float* inv_std, void* stream);
+/* cb_bn_stats + cb_bn_finalize in ONE launch: the CTA that draws the last ticket from `counter` (device int32, zero on
+ * entry, reset to zero by the kernel) closes the statistics.  c = map->c_mod; gamma must be non-NULL. */
+int cb_bn_stats_finalize(const void* z, int64_t z_lo_off, const cb_map* map, double* sums, int32_t* counter, double count,
+                         float eps, float momentum, const float* gamma, const float* beta, float* running_mean,
+                         float* running_var, float* scale, float* shift, float* mean, float* inv_std, void* stream);
 /* y = [relu]( z*scale + shift [+ z_b*scale_b + shift_b] [+ residual] ) written through `map` (bf16, + lo plane when
  * y_lo_off != 0).  residual: bf16 PF in z's row space, pitch res_pitch. */
 int cb_bn_apply(const void* z, int64_t z_lo_off, const float* scale, const float* shift,

@@ -120,6 +120,22 @@ def test_train_mode_batchnorm_forward_backward_pf():
     _lib.check(L.cb_bn_finalize(sums.data_ptr(), c, float(n * H * W), 1e-5, 0.1, gamma.data_ptr(), beta.data_ptr(),
                                 rm.data_ptr(), rv.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),
                                 inv.data_ptr(), sp()))
+    # the one-launch form (last CTA closes the statistics) must give the same numbers and leave its ticket counter at zero
+    sums2 = torch.zeros(2 * c, dtype=torch.float64, device="cuda")
+    ticket = torch.zeros(1, dtype=torch.int32, device="cuda")
+    rm2, rv2 = rm0.clone(), rv0.clone()
+    sc2, sh2, mean2, inv2 = (torch.empty(c, device="cuda") for _ in range(4))
+    for _ in range(2):                                                    # twice: the counter must reset itself
+        sums2.zero_()
+        rm2.copy_(rm0)
+        rv2.copy_(rv0)
+        _lib.check(L.cb_bn_stats_finalize(zp.data_ptr(), 0, C.byref(m), sums2.data_ptr(), ticket.data_ptr(), float(n * H * W),
+                                          1e-5, 0.1, gamma.data_ptr(), beta.data_ptr(), rm2.data_ptr(), rv2.data_ptr(),
+                                          sc2.data_ptr(), sh2.data_ptr(), mean2.data_ptr(), inv2.data_ptr(), sp()))
+    torch.cuda.synchronize()
+    assert int(ticket.item()) == 0
+    for a, b in ((sc2, scale), (sh2, shift), (mean2, mean), (inv2, inv), (rm2, rm), (rv2, rv)):
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-6)
     y = torch.zeros_like(zp)
     _lib.check(L.cb_bn_apply(zp.data_ptr(), 0, scale.data_ptr(), shift.data_ptr(), None, 0, None, None, rp.data_ptr(), c, 0, 1,
                              C.byref(m), y.data_ptr(), 0, sp()))
