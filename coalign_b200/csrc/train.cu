@@ -220,6 +220,9 @@ __device__ __forceinline__ void bn_finalize_channel(const BnFin& f, int i, doubl
     }
 }
 
+// One cursor per thread walks its rows (row_step apart); R rows are loaded back to back per iteration, then consumed.
+// Which tensors a launch reads is a template parameter, so a variant only holds registers for the loads it issues and the
+// two-tensor variants run with R = 8 (64-128 B in flight per thread and tensor set).
 template <int R, bool LO>
 __global__ void __launch_bounds__(EW_THREADS, 2) bn_stats_kernel(const __nv_bfloat16* __restrict__ z, long z_lo_off,
                                                               const MapP m, double* __restrict__ sums, const BnFin fin) {
@@ -230,21 +233,24 @@ __global__ void __launch_bounds__(EW_THREADS, 2) bn_stats_kernel(const __nv_bflo
     const ColInfo ci = col_info(m, rw.chunk * 8);
     float a0[8] = {}, a1[8] = {};
     if (rw.row0 >= 0) {
-        RowCur c[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) c[r] = cur_init(m, rw.row0 + r * rw.row_step, R * rw.row_step);
-        while (c[0].q < m.rows_total) {
+        RowCur c = cur_init(m, rw.row0, rw.row_step);
+        while (c.q < m.rows_total) {
             Raw8<LO> raw[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) ld_raw<LO>(z, (c[r].q < m.rows_total ? c[r].q : 0) * m.c_total + ci.col, z_lo_off, raw[r]);
+            unsigned valid = 0;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const float k = y_off_cur(m, c[r], ci) >= 0 ? 1.f : 0.f;             // halo rows hold zeros anyway
+                const bool ok = y_off_cur(m, c, ci) >= 0;                                   // halo rows hold zeros anyway
+                valid |= (unsigned)ok << r;
+                ld_raw<LO>(z, (c.q < m.rows_total ? c.q : 0) * m.c_total + ci.col, z_lo_off, raw[r]);
+                cur_next(m, c);
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float k = (valid >> r) & 1u ? 1.f : 0.f;
                 float v[8];
                 cvt_raw<LO>(raw[r], v);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { const float t = v[j] * k; a0[j] += t; a1[j] = fmaf(t, t, a1[j]); }
-                cur_next(m, c[r]);
             }
         }
     }
@@ -268,7 +274,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, const BnFin 
     bn_finalize_channel(f, i, f.gamma ? sums[i] : 0.0, f.gamma ? sums[f.c + i] : 0.0);
 }
 
-template <int R, bool LO>
+// EXTRA = a second BatchNorm branch (zb) and / or a residual is added
+template <int R, bool LO, bool EXTRA>
 __global__ void __launch_bounds__(EW_THREADS, 2) bn_apply_kernel(
     const __nv_bfloat16* __restrict__ z, long z_lo_off, const float* __restrict__ scale, const float* __restrict__ shift,
     const __nv_bfloat16* __restrict__ zb, long zb_lo_off, const float* __restrict__ scale_b, const float* __restrict__ shift_b,
@@ -280,7 +287,7 @@ __global__ void __launch_bounds__(EW_THREADS, 2) bn_apply_kernel(
     for (int c = threadIdx.x; c < m.c_mod; c += EW_THREADS) {
         const int t = tslot(c, nck);
         s_sc[t] = scale[c]; s_sh[t] = shift[c];
-        s_scb[t] = zb ? scale_b[c] : 0.f; s_shb[t] = zb ? shift_b[c] : 0.f;
+        s_scb[t] = (EXTRA && zb) ? scale_b[c] : 0.f; s_shb[t] = (EXTRA && zb) ? shift_b[c] : 0.f;
     }
     __syncthreads();
     const RowWalk rw = row_walk(m.c_total);
@@ -291,19 +298,20 @@ __global__ void __launch_bounds__(EW_THREADS, 2) bn_apply_kernel(
     const float* sh = s_sh + (ci.cb >> 3);
     const float* scb = s_scb + (ci.cb >> 3);
     const float* shb = s_shb + (ci.cb >> 3);
-    RowCur c[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) c[r] = cur_init(m, rw.row0 + r * rw.row_step, R * rw.row_step);
-    while (c[0].q < m.rows_total) {
+    RowCur c = cur_init(m, rw.row0, rw.row_step);
+    while (c.q < m.rows_total) {
         long yo[R];
-        Raw8<LO> rz[R], rb[R], rr[R];
+        Raw8<LO> rz[R], rb[EXTRA ? R : 1], rr[EXTRA ? R : 1];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            yo[r] = y_off_cur(m, c[r], ci);
-            const long qz = yo[r] >= 0 ? c[r].q : 0;
+            yo[r] = y_off_cur(m, c, ci);
+            const long qz = yo[r] >= 0 ? c.q : 0;
             ld_raw<LO>(z, qz * m.c_total + col, z_lo_off, rz[r]);
-            if (zb) ld_raw<LO>(zb, qz * m.c_total + col, zb_lo_off, rb[r]);
-            if (res) ld_raw<LO>(res, qz * (long)res_pitch + col, res_lo_off, rr[r]);
+            if (EXTRA) {
+                if (zb) ld_raw<LO>(zb, qz * m.c_total + col, zb_lo_off, rb[r]);
+                if (res) ld_raw<LO>(res, qz * (long)res_pitch + col, res_lo_off, rr[r]);
+            }
+            cur_next(m, c);
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -312,15 +320,17 @@ __global__ void __launch_bounds__(EW_THREADS, 2) bn_apply_kernel(
                 cvt_raw<LO>(rz[r], v);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j * nck], sh[j * nck]);
-                if (zb) {
-                    cvt_raw<LO>(rb[r], u);
+                if (EXTRA) {
+                    if (zb) {
+                        cvt_raw<LO>(rb[r], u);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] += fmaf(u[j], scb[j * nck], shb[j * nck]);
-                }
-                if (res) {
-                    cvt_raw<LO>(rr[r], u);
+                        for (int j = 0; j < 8; ++j) v[j] += fmaf(u[j], scb[j * nck], shb[j * nck]);
+                    }
+                    if (res) {
+                        cvt_raw<LO>(rr[r], u);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] += u[j];
+                        for (int j = 0; j < 8; ++j) v[j] += u[j];
+                    }
                 }
                 if (relu) {
 #pragma unroll
@@ -328,14 +338,13 @@ __global__ void __launch_bounds__(EW_THREADS, 2) bn_apply_kernel(
                 }
                 store8(y, yo[r], LO ? y_lo_off : 0, v);
             }
-            cur_next(m, c[r]);
         }
     }
 }
 
-// ReLU mask: from y (the stored activation) or - mask_scale != NULL, the plain conv + BN + ReLU case - recomputed from the z
-// that is loaded anyway (sign of z*scale + shift), which saves one tensor read in both backward passes.
-template <int R, bool LO>
+// ReLU mask: from y (the stored activation; YMASK) or - mask_scale != NULL, the plain conv + BN + ReLU case - recomputed from
+// the z that is loaded anyway (sign of z*scale + shift), which saves one tensor read in both backward passes.
+template <int R, bool LO, bool YMASK>
 __global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_reduce_kernel(
     const __nv_bfloat16* __restrict__ dy, long dy_lo_off, const __nv_bfloat16* __restrict__ y, long y_lo_off, int relu,
     const __nv_bfloat16* __restrict__ z, long z_lo_off, const float* __restrict__ mean, const float* __restrict__ inv_std,
@@ -346,8 +355,7 @@ __global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_reduce_kernel(
     const RowWalk rw = row_walk(m.c_total);
     const ColInfo ci = col_info(m, rw.chunk * 8);
     const bool has_bn = mean != nullptr;
-    const bool zmask = relu && mask_scale != nullptr && has_bn;
-    const bool ymask = relu && !zmask;
+    const bool zmask = !YMASK && relu && mask_scale != nullptr && has_bn;
     const int nck = m.c_mod >> 3;
     for (int c = threadIdx.x; c < m.c_mod; c += EW_THREADS) {
         const int t = tslot(c, nck);
@@ -361,37 +369,36 @@ __global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_reduce_kernel(
     const float* mh = s_mh + (ci.cb >> 3);
     float a0[8] = {}, a1[8] = {};
     if (rw.row0 >= 0) {
-        RowCur c[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) c[r] = cur_init(m, rw.row0 + r * rw.row_step, R * rw.row_step);
-        while (c[0].q < m.rows_total) {
-            long yo[R];
-            Raw8<LO> rg[R], ry[R], rz[R];
+        RowCur c = cur_init(m, rw.row0, rw.row_step);
+        while (c.q < m.rows_total) {
+            unsigned valid = 0;
+            Raw8<LO> rg[R], ry[YMASK ? R : 1], rz[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                yo[r] = y_off_cur(m, c[r], ci);
-                const long yl = yo[r] >= 0 ? yo[r] : (long)(m.y_ch_off + ci.cb);
+                const long yo = y_off_cur(m, c, ci);
+                valid |= (unsigned)(yo >= 0) << r;
+                const long yl = yo >= 0 ? yo : (long)(m.y_ch_off + ci.cb);
                 ld_raw<LO>(dy, yl, dy_lo_off, rg[r]);
-                if (ymask) ld_raw<LO>(y, yl, y_lo_off, ry[r]);
-                if (has_bn) ld_raw<LO>(z, yo[r] >= 0 ? z_off_cur(m, c[r], ci, yo[r]) : (long)ci.cb, z_lo_off, rz[r]);
+                if (YMASK) ld_raw<LO>(y, yl, y_lo_off, ry[r]);
+                if (has_bn) ld_raw<LO>(z, yo >= 0 ? z_off_cur(m, c, ci, yo) : (long)ci.cb, z_lo_off, rz[r]);
+                cur_next(m, c);
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                if (yo[r] >= 0) {
+                if ((valid >> r) & 1u) {
                     float g[8], v[8], yv[8];
                     cvt_raw<LO>(rg[r], g);
                     if (has_bn) cvt_raw<LO>(rz[r], v);
-                    if (ymask) cvt_raw<LO>(ry[r], yv);
+                    if (YMASK) cvt_raw<LO>(ry[r], yv);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float gj = g[j];
                         if (zmask) gj = fmaf(v[j], ms[j * nck], mh[j * nck]) > 0.f ? gj : 0.f;
-                        if (ymask) gj = yv[j] > 0.f ? gj : 0.f;
+                        if (YMASK) gj = yv[j] > 0.f ? gj : 0.f;
                         a0[j] += gj;
                         if (has_bn) a1[j] = fmaf(gj, v[j] - mu[j * nck], a1[j]);       // x_hat = (z - mean) * inv_std: scaled below
                     }
                 }
-                cur_next(m, c[r]);
             }
         }
     }
@@ -402,7 +409,7 @@ __global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_reduce_kernel(
     block_reduce_to_global(a0, a1, m.c_total, m.c_mod, has_bn, s_part, sums);
 }
 
-template <int R, bool LO>
+template <int R, bool LO, bool YMASK>
 __global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_apply_kernel(
     const __nv_bfloat16* __restrict__ dy, long dy_lo_off, const __nv_bfloat16* __restrict__ y, long y_lo_off, int relu,
     const __nv_bfloat16* __restrict__ z, long z_lo_off, const float* __restrict__ mean, const float* __restrict__ inv_std,
@@ -420,8 +427,7 @@ __global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_apply_kernel(
             if (d_gamma && has_bn) d_gamma[c] = (float)sums[m.c_mod + c];
         }
     }
-    const bool zmask = relu && mask_scale != nullptr && has_bn;
-    const bool ymask = relu && !zmask;
+    const bool zmask = !YMASK && relu && mask_scale != nullptr && has_bn;
     const int nck = m.c_mod >> 3;
     for (int c = threadIdx.x; c < m.c_mod; c += EW_THREADS) {
         float A = 1.f, B = 0.f, Cc = 0.f;
@@ -447,40 +453,39 @@ __global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_apply_kernel(
     const float* cC = s_C + (ci.cb >> 3);
     const float* ms = s_ms + (ci.cb >> 3);
     const float* mh = s_mh + (ci.cb >> 3);
-    RowCur c[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) c[r] = cur_init(m, rw.row0 + r * rw.row_step, R * rw.row_step);
-    while (c[0].q < m.rows_total) {
-        long yo[R];
-        Raw8<LO> rg[R], ry[R], rz[R];
+    RowCur c = cur_init(m, rw.row0, rw.row_step);
+    while (c.q < m.rows_total) {
+        int qv[R];                                        // GEMM row of each loaded row (rows_total < 2^31), -1 = masked
+        Raw8<LO> rg[R], ry[YMASK ? R : 1], rz[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            yo[r] = y_off_cur(m, c[r], ci);
-            const long yl = yo[r] >= 0 ? yo[r] : (long)(m.y_ch_off + ci.cb);
+            const long yo = y_off_cur(m, c, ci);
+            qv[r] = yo >= 0 ? (int)c.q : -1;
+            const long yl = yo >= 0 ? yo : (long)(m.y_ch_off + ci.cb);
             ld_raw<LO>(dy, yl, dy_lo_off, rg[r]);
-            if (ymask) ld_raw<LO>(y, yl, y_lo_off, ry[r]);
-            if (has_bn) ld_raw<LO>(z, yo[r] >= 0 ? z_off_cur(m, c[r], ci, yo[r]) : (long)ci.cb, z_lo_off, rz[r]);
+            if (YMASK) ld_raw<LO>(y, yl, y_lo_off, ry[r]);
+            if (has_bn) ld_raw<LO>(z, yo >= 0 ? z_off_cur(m, c, ci, yo) : (long)ci.cb, z_lo_off, rz[r]);
+            cur_next(m, c);
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            if (yo[r] >= 0) {
+            if (qv[r] >= 0) {
                 float g[8], v[8], yv[8];
                 cvt_raw<LO>(rg[r], g);
                 if (has_bn) cvt_raw<LO>(rz[r], v);
-                if (ymask) cvt_raw<LO>(ry[r], yv);
+                if (YMASK) cvt_raw<LO>(ry[r], yv);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     if (zmask) g[j] = fmaf(v[j], ms[j * nck], mh[j * nck]) > 0.f ? g[j] : 0.f;
-                    if (ymask) g[j] = yv[j] > 0.f ? g[j] : 0.f;
+                    if (YMASK) g[j] = yv[j] > 0.f ? g[j] : 0.f;
                 }
-                if (dsum) store8(dsum, c[r].q * m.c_total + col, LO ? dsum_lo_off : 0, g);
+                if (dsum) store8(dsum, (long)qv[r] * m.c_total + col, LO ? dsum_lo_off : 0, g);
                 if (has_bn) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) g[j] = fmaf(cA[j * nck], g[j], fmaf(cB[j * nck], v[j], cC[j * nck]));
                 }
-                store8(dz, c[r].q * m.c_total + col, LO ? dz_lo_off : 0, g);
+                store8(dz, (long)qv[r] * m.c_total + col, LO ? dz_lo_off : 0, g);
             }
-            cur_next(m, c[r]);
         }
     }
 }
@@ -1085,10 +1090,10 @@ static int bn_stats_launch(const void* z, int64_t z_lo_off, const cb_map* map, d
     int rc = fill_map(map, m);
     if (rc || !z || !sums) return rc ? rc : CB_ERR_ARG;
     const int rpi = EW_THREADS / (m.c_total >> 3);
-    const dim3 grid(ew_grid((m.rows_total + rpi - 1) / rpi * EW_THREADS / 8));
-    cudaError_t e = z_lo_off ? launch_pdl(bn_stats_kernel<4, true>, grid, dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(z),
+    const dim3 grid(ew_grid((m.rows_total + rpi - 1) / rpi * EW_THREADS / 16));
+    cudaError_t e = z_lo_off ? launch_pdl(bn_stats_kernel<8, true>, grid, dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(z),
                                           (long)z_lo_off, m, sums, fin)
-                             : launch_pdl(bn_stats_kernel<8, false>, grid, dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(z),
+                             : launch_pdl(bn_stats_kernel<16, false>, grid, dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(z),
                                           (long)z_lo_off, m, sums, fin);
     return e == cudaSuccess ? CB_OK : (int)e;
 }
@@ -1142,12 +1147,14 @@ extern "C" int cb_bn_apply(const void* z, int64_t z_lo_off, const float* scale, 
     const int rpi = EW_THREADS / (m.c_total >> 3);
     const dim3 grid(ew_grid((m.rows_total + rpi - 1) / rpi * EW_THREADS / 4));
     const bool lo = z_lo_off || y_lo_off || z_b_lo_off || res_lo_off;
-    cudaError_t e = lo ? launch_pdl(bn_apply_kernel<2, true>, grid, dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(z),
-                                    (long)z_lo_off, scale, shift, BF(z_b), (long)z_b_lo_off, scale_b, shift_b, BF(residual),
-                                    (int)res_pitch, (long)res_lo_off, relu, m, BFW(y), (long)y_lo_off)
-                       : launch_pdl(bn_apply_kernel<4, false>, grid, dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(z),
-                                    (long)z_lo_off, scale, shift, BF(z_b), (long)z_b_lo_off, scale_b, shift_b, BF(residual),
-                                    (int)res_pitch, (long)res_lo_off, relu, m, BFW(y), (long)y_lo_off);
+    const bool extra = z_b || residual;
+    auto go = [&](auto kern) {
+        return launch_pdl(kern, grid, dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(z), (long)z_lo_off, scale, shift, BF(z_b),
+                          (long)z_b_lo_off, scale_b, shift_b, BF(residual), (int)res_pitch, (long)res_lo_off, relu, m, BFW(y),
+                          (long)y_lo_off);
+    };
+    cudaError_t e = lo ? (extra ? go(bn_apply_kernel<2, true, true>) : go(bn_apply_kernel<4, true, false>))
+                       : (extra ? go(bn_apply_kernel<4, false, true>) : go(bn_apply_kernel<8, false, false>));
     return e == cudaSuccess ? CB_OK : (int)e;
 }
 
@@ -1163,12 +1170,13 @@ extern "C" int cb_bn_bwd_reduce(const void* dy, int64_t dy_lo_off, const void* y
     const int rpi = EW_THREADS / (m.c_total >> 3);
     const dim3 grid(ew_grid((m.rows_total + rpi - 1) / rpi * EW_THREADS / 4));
     const bool lo = dy_lo_off || y_lo_off || z_lo_off;
-    cudaError_t e = lo ? launch_pdl(bn_bwd_reduce_kernel<2, true>, grid, dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(dy),
-                                    (long)dy_lo_off, BF(y), (long)y_lo_off, relu, BF(z), (long)z_lo_off, mean, inv_std,
-                                    mask_scale, mask_shift, m, sums)
-                       : launch_pdl(bn_bwd_reduce_kernel<4, false>, grid, dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(dy),
-                                    (long)dy_lo_off, BF(y), (long)y_lo_off, relu, BF(z), (long)z_lo_off, mean, inv_std,
-                                    mask_scale, mask_shift, m, sums);
+    const bool ymask = relu && !zmask;
+    auto go = [&](auto kern) {
+        return launch_pdl(kern, grid, dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(dy), (long)dy_lo_off, BF(y), (long)y_lo_off,
+                          relu, BF(z), (long)z_lo_off, mean, inv_std, mask_scale, mask_shift, m, sums);
+    };
+    cudaError_t e = lo ? (ymask ? go(bn_bwd_reduce_kernel<2, true, true>) : go(bn_bwd_reduce_kernel<4, true, false>))
+                       : (ymask ? go(bn_bwd_reduce_kernel<4, false, true>) : go(bn_bwd_reduce_kernel<6, false, false>));
     return e == cudaSuccess ? CB_OK : (int)e;
 }
 
@@ -1186,14 +1194,14 @@ extern "C" int cb_bn_bwd_apply(const void* dy, int64_t dy_lo_off, const void* y,
     const int rpi = EW_THREADS / (m.c_total >> 3);
     const dim3 grid(ew_grid((m.rows_total + rpi - 1) / rpi * EW_THREADS / 4));
     const bool lo = dy_lo_off || y_lo_off || z_lo_off || dz_lo_off || dsum_lo_off;
-    cudaError_t e = lo ? launch_pdl(bn_bwd_apply_kernel<2, true>, grid, dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(dy),
-                                    (long)dy_lo_off, BF(y), (long)y_lo_off, relu, BF(z), (long)z_lo_off, mean, inv_std, gamma,
-                                    mask_scale, mask_shift, sums, count, m, BFW(dz), (long)dz_lo_off, BFW(dsum_pf),
-                                    (long)dsum_lo_off, d_gamma, d_beta)
-                       : launch_pdl(bn_bwd_apply_kernel<4, false>, grid, dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(dy),
-                                    (long)dy_lo_off, BF(y), (long)y_lo_off, relu, BF(z), (long)z_lo_off, mean, inv_std, gamma,
-                                    mask_scale, mask_shift, sums, count, m, BFW(dz), (long)dz_lo_off, BFW(dsum_pf),
-                                    (long)dsum_lo_off, d_gamma, d_beta);
+    const bool ymask = relu && !zmask;
+    auto go = [&](auto kern) {
+        return launch_pdl(kern, grid, dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(dy), (long)dy_lo_off, BF(y), (long)y_lo_off,
+                          relu, BF(z), (long)z_lo_off, mean, inv_std, gamma, mask_scale, mask_shift, sums, count, m, BFW(dz),
+                          (long)dz_lo_off, BFW(dsum_pf), (long)dsum_lo_off, d_gamma, d_beta);
+    };
+    cudaError_t e = lo ? (ymask ? go(bn_bwd_apply_kernel<2, true, true>) : go(bn_bwd_apply_kernel<3, true, false>))
+                       : (ymask ? go(bn_bwd_apply_kernel<4, false, true>) : go(bn_bwd_apply_kernel<6, false, false>));
     return e == cudaSuccess ? CB_OK : (int)e;
 }
 
