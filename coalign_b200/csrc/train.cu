@@ -1090,10 +1090,10 @@ static int bn_stats_launch(const void* z, int64_t z_lo_off, const cb_map* map, d
     int rc = fill_map(map, m);
     if (rc || !z || !sums) return rc ? rc : CB_ERR_ARG;
     const int rpi = EW_THREADS / (m.c_total >> 3);
-    const dim3 grid(ew_grid((m.rows_total + rpi - 1) / rpi * EW_THREADS / 16));
-    cudaError_t e = z_lo_off ? launch_pdl(bn_stats_kernel<8, true>, grid, dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(z),
+    const dim3 grid(ew_grid((m.rows_total + rpi - 1) / rpi * EW_THREADS / 8));
+    cudaError_t e = z_lo_off ? launch_pdl(bn_stats_kernel<4, true>, grid, dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(z),
                                           (long)z_lo_off, m, sums, fin)
-                             : launch_pdl(bn_stats_kernel<16, false>, grid, dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(z),
+                             : launch_pdl(bn_stats_kernel<8, false>, grid, dim3(EW_THREADS), 0, (cudaStream_t)stream, BF(z),
                                           (long)z_lo_off, m, sums, fin);
     return e == cudaSuccess ? CB_OK : (int)e;
 }

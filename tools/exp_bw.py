@@ -46,6 +46,7 @@ for n, H, W, c in SIZES:
     res["copy"] = (2, timeit(lambda: o.copy_(a)))
     res["add"] = (3, timeit(lambda: torch.add(a, b, out=o)))
     res["colsum(f32 acc)"] = (1, timeit(lambda: a.sum(0, dtype=torch.float32)))
+    res["sum(all) torch"] = (1, timeit(lambda: a.sum(dtype=torch.float32)))      # read-only reference (same dirty-L2 start)
     res["bn_stats"] = (1, timeit(lambda: L.cb_bn_stats(a.data_ptr(), 0, C.byref(m), sums.data_ptr(), sp)))
     res["bn_apply"] = (2, timeit(lambda: L.cb_bn_apply(a.data_ptr(), 0, scale.data_ptr(), shift.data_ptr(), None, 0, None,
                                                        None, None, c, 0, 1, C.byref(m), o.data_ptr(), 0, sp)))
