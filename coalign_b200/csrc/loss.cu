@@ -36,16 +36,19 @@ __device__ __forceinline__ double block_sum(double v, double* s_red) {
     return t;
 }
 
-// positives per sample: pos_normalizer (point_pillar_loss.py:54), one CTA per sample
+// positives per sample: pos_normalizer (point_pillar_loss.py:54).  grid = (chunks, samples); the counts are integers, so
+// the fp64 atomics are exact in any order (pos_norm zeroed by the caller).
+constexpr int POS_CHUNKS = 32;
 __global__ void __launch_bounds__(256) loss_pos_count_kernel(const void* __restrict__ pos, const LossGeom g,
                                                              double* __restrict__ pos_norm) {
     __shared__ double s_red[8];
-    const int b = blockIdx.x;
+    const int b = blockIdx.y;
     const size_t per = (size_t)g.HW * g.A;
     double c = 0.0;
-    for (size_t i = threadIdx.x; i < per; i += blockDim.x) c += ld_label(pos, b * per + i, g.labels_f64) > 0.0 ? 1.0 : 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (size_t)gridDim.x * blockDim.x)
+        c += ld_label(pos, b * per + i, g.labels_f64) > 0.0 ? 1.0 : 0.0;
     c = block_sum(c, s_red);
-    if (threadIdx.x == 0) pos_norm[b] = c;
+    if (threadIdx.x == 0 && c != 0.0) atomicAdd(pos_norm + b, c);
 }
 
 // one thread per (sample, pixel, anchor); partial sums {cls, reg, dir} per CTA
@@ -201,7 +204,9 @@ extern "C" int cb_pointpillar_loss(const float* cls_preds, const float* reg_pred
     const int n_blocks = (int)((total + 255) / 256);
     if ((size_t)((char*)(partial + (size_t)n_blocks * 3) - (char*)workspace) > workspace_bytes) return CB_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    loss_pos_count_kernel<<<n, 256, 0, st>>>(pos_equal_one, g, pos_norm);
+    cudaError_t me = cudaMemsetAsync(pos_norm, 0, sizeof(double) * (size_t)n, st);
+    if (me != cudaSuccess) return (int)me;
+    loss_pos_count_kernel<<<dim3(POS_CHUNKS, n), 256, 0, st>>>(pos_equal_one, g, pos_norm);
     CB_CHECK_LAUNCH();
     loss_main_kernel<<<n_blocks, 256, 0, st>>>(cls_preds, reg_preds, dir_preds, pos_equal_one, neg_equal_one, targets, g,
                                                pos_norm, grad_cls, grad_reg, grad_dir, partial);

@@ -14,6 +14,7 @@
 //   K4   8 lanes per voxel: emit reference-format tensors.
 // The hot path (cb_points_to_canvas) does not need the voxel ORDER and uses the v2 pipeline further down.
 #include <limits.h>
+#include <mutex>
 #include "common.cuh"
 #include "../../include/coalign_b200.h"
 
@@ -273,7 +274,10 @@ __global__ void pfn_coef_kernel(const float* __restrict__ w, const float* __rest
 #pragma unroll
     for (int j = 0; j < PFN_NCOEF; ++j) out[j * 64 + c] = pfn_coef(j, wc, scale[c], shift[c]);
 }
-__constant__ float2 c_pfn_k[PFN_NCOEF][32];
+// One table per SLOT: concurrently active engines (different workspaces / streams / captured graphs) each get their own
+// copy, so one engine's upload cannot change the coefficients under another engine's running kernel (pfn_slot_for below).
+constexpr int PFN_SLOTS = 4;
+__constant__ float2 c_pfn_k[PFN_SLOTS][PFN_NCOEF][32];
 
 __device__ __forceinline__ void pillar_centre(const PfnParams& pp, int cz, int cy, int cx, float& ctrx, float& ctry,
                                               float& ctrz) {
@@ -377,27 +381,27 @@ __device__ __forceinline__ void pfn_group_store(PointFn pt, int n, int max_pts, 
 // Fused path: ONE THREAD per pillar and channel group of 2*NP channels (group index GRP); the coefficients live in
 // constant memory, so every FFMA2 takes them as a uniform-register operand (no weight registers, no shared-memory
 // traffic).  Pillars are visited class by class (same point count inside a warp) so warps do not diverge on n.
-template <int NP, int GRP, class PointFn>
+template <int NP, int GRP, int SLOT, class PointFn>
 __device__ __forceinline__ void pfn_thread_store(PointFn pt, const float4 p0, int n, int max_pts, int a, int cz,
                                                  int cy, int cx, const PfnParams& pp, const CanvasGeom& cg,
                                                  __nv_bfloat16* canvas, long lo_off, long* dirty_slot) {
     float ctrx, ctry, ctrz;
     pillar_centre(pp, cz, cy, cx, ctrx, ctry, ctrz);
     f2 best[NP];
-    pfn_eval<NP>([&](int j, int c) { const float2 v = c_pfn_k[j][GRP * NP + c]; return f2{v.x, v.y}; }, pt, p0, n,
+    pfn_eval<NP>([&](int j, int c) { const float2 v = c_pfn_k[SLOT][j][GRP * NP + c]; return f2{v.x, v.y}; }, pt, p0, n,
                  max_pts, ctrx, ctry, ctrz, best);
     const long row = canvas_row(cg, a, cy, cx);
     pfn_store<NP>(best, canvas + row * 64 + GRP * 2 * NP, lo_off);
     if (dirty_slot && GRP == 0) *dirty_slot = row;
 }
 // grp (warp-uniform: even / odd warps) -> compile-time channel half, so the constant-bank addresses are immediates
-template <int NP, class PointFn>
+template <int NP, int SLOT, class PointFn>
 __device__ __forceinline__ void pfn_thread_dispatch(int grp, PointFn pt, const float4 p0, int n, int max_pts, int a,
                                                     int cz, int cy, int cx, const PfnParams& pp, const CanvasGeom& cg,
                                                     __nv_bfloat16* canvas, long lo_off, long* dirty_slot) {
     static_assert(NP == 16, "two 32-channel halves per pillar");
-    if (grp == 0) pfn_thread_store<NP, 0>(pt, p0, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dirty_slot);
-    else          pfn_thread_store<NP, 1>(pt, p0, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dirty_slot);
+    if (grp == 0) pfn_thread_store<NP, 0, SLOT>(pt, p0, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dirty_slot);
+    else          pfn_thread_store<NP, 1, SLOT>(pt, p0, n, max_pts, a, cz, cy, cx, pp, cg, canvas, lo_off, dirty_slot);
 }
 
 // K4a: emit reference-format voxel tensors (8 lanes per voxel, voxels of all agents flattened) ---------
@@ -662,7 +666,7 @@ __global__ void __launch_bounds__(256) vox2_big_rank_kernel(const float4* __rest
 
 // V5: PFN + scatter, thread per (pillar, channel group of 2*NP channels); the 64/(2*NP) groups of a pillar are
 // consecutive warps of one CTA.  Work items are taken class-major so the pillars of a warp share a point-count class.
-template <int NP>
+template <int NP, int SLOT>
 __global__ void __launch_bounds__(256, 2) vox2_pfn_kernel(const Vox2Ws ws, int max_pts,
                                                                           const PfnParams pp, const CanvasGeom cg,
                                                                           __nv_bfloat16* canvas, long lo_off,
@@ -707,7 +711,7 @@ __global__ void __launch_bounds__(256, 2) vox2_pfn_kernel(const Vox2Ws ws, int m
         const int n = word & 63, cx = (word >> 6) & 0xFFF, cy = (word >> 18) & 0xFFF;
         const int a = gcell / ws.ncell;
         long* dslot = dirty_rows ? dirty_rows + gidx : nullptr;
-        pfn_thread_dispatch<NP>(grp, [&](int k) { return *slot_ptr(ws, gcell, k); }, p_cur, n, max_pts, a, 0, cy, cx, pp, cg,
+        pfn_thread_dispatch<NP, SLOT>(grp, [&](int k) { return *slot_ptr(ws, gcell, k); }, p_cur, n, max_pts, a, 0, cy, cx, pp, cg,
                                     canvas, lo_off, dslot);
         it_cur = it_nxt; it_nxt = it_nn; p_cur = p_nxt;
     }
@@ -883,7 +887,7 @@ static int carve2(Vox2Ws& ws, void* base, size_t bytes, int n_agents, int sum_po
 static int run_front2(const float* points, const int32_t* pt_offset, const int32_t* off_dev, int total_cap, int agent_cap,
                       int n_agents, const float* range,
                       const float* vsize, const int32_t* grid, int max_pts, int max_voxels, void* workspace,
-                      size_t workspace_bytes, cudaStream_t st, Vox2Ws& ws, const PfnParams& pp) {
+                      size_t workspace_bytes, cudaStream_t st, Vox2Ws& ws, const PfnParams& pp, int pfn_slot) {
     if (n_agents < 1 || n_agents > CB_MAX_AGENTS || max_pts < 1 || max_pts > 32 || max_voxels < 1) return CB_ERR_ARG;
     if (!workspace || ((uintptr_t)points & 15)) return CB_ERR_ARG;
     if (grid[0] > 4096 || grid[1] > 4096 || grid[2] != 1) return CB_ERR_ARG;          // packed work items; nz == 1
@@ -918,7 +922,8 @@ static int run_front2(const float* points, const int32_t* pt_offset, const int32
     cudaError_t e;
     pfn_coef_kernel<<<1, 64, 0, st>>>(pp.w, pp.scale, pp.shift, ws.coef);
     CB_CHECK_LAUNCH();
-    e = cudaMemcpyToSymbolAsync(c_pfn_k, ws.coef, sizeof(float) * PFN_NCOEF * 64, 0, cudaMemcpyDeviceToDevice, st);
+    e = cudaMemcpyToSymbolAsync(c_pfn_k, ws.coef, sizeof(float) * PFN_NCOEF * 64,
+                                sizeof(float) * PFN_NCOEF * 64 * (size_t)pfn_slot, cudaMemcpyDeviceToDevice, st);
     if (e) return (int)e;
     e = cudaMemsetAsync(ws.count, 0, clr[0], st);                 if (e) return (int)e;
     if (may_cap) { e = cudaMemsetAsync(ws.first, 0x7f, clr[1], st); if (e) return (int)e; }
@@ -988,6 +993,26 @@ extern "C" int cb_voxelize(const float* points, const int32_t* pt_offset, int n_
     return CB_OK;
 }
 
+// Constant-table slot of a caller, keyed by its workspace (one per engine): the same workspace always gets the same slot;
+// a new workspace takes a free slot or, when all PFN_SLOTS are owned, the least recently used one.  Up to PFN_SLOTS engines
+// can therefore run (or replay captured graphs) concurrently on different streams without sharing a table; within one
+// stream the upload and the kernel are ordered, so sequential use is always safe.
+static int pfn_slot_for(const void* workspace) {
+    static std::mutex mu;
+    static const void* owner[cb::PFN_SLOTS] = {};
+    static unsigned long stamp[cb::PFN_SLOTS] = {};
+    static unsigned long tick = 0;
+    std::lock_guard<std::mutex> lock(mu);
+    int lru = 0;
+    for (int i = 0; i < cb::PFN_SLOTS; ++i) {
+        if (owner[i] == workspace) { stamp[i] = ++tick; return i; }
+        if (stamp[i] < stamp[lru]) lru = i;
+    }
+    owner[lru] = workspace;
+    stamp[lru] = ++tick;
+    return lru;
+}
+
 static int points_to_canvas_impl(const float* points, const int32_t* pt_offset, const int32_t* off_dev, int total_cap,
                                  int agent_cap, int n_agents, const float* range,
                                  const float* vsize, const int32_t* grid, int max_pts, int max_voxels,
@@ -1003,11 +1028,21 @@ static int points_to_canvas_impl(const float* points, const int32_t* pt_offset, 
     const PfnParams pp = make_pfn(w, scale, shift, vsize, center_off);
     cudaError_t ce;
     Vox2Ws ws2;
+    const int pfn_slot = pfn_slot_for(workspace);
     int rc2 = run_front2(points, pt_offset, off_dev, total_cap, agent_cap, n_agents, range, vsize, grid, max_pts, max_voxels,
-                         workspace, workspace_bytes, st, ws2, pp);
+                         workspace, workspace_bytes, st, ws2, pp, pfn_slot);
     if (rc2) return rc2;
-    ce = launch_pdl(vox2_pfn_kernel<16>, dim3(148 * 2), dim3(256), 0, st, ws2, max_pts, pp, cg, (__nv_bfloat16*)canvas_ps,
-                    (long)lo_off, (long*)dirty_rows, (int*)dirty_count);
+    auto go = [&](auto kern) {
+        return launch_pdl(kern, dim3(148 * 2), dim3(256), 0, st, ws2, max_pts, pp, cg, (__nv_bfloat16*)canvas_ps, (long)lo_off,
+                          (long*)dirty_rows, (int*)dirty_count);
+    };
+    static_assert(PFN_SLOTS == 4, "one instantiation per slot below");
+    switch (pfn_slot) {
+        case 0: ce = go(vox2_pfn_kernel<16, 0>); break;
+        case 1: ce = go(vox2_pfn_kernel<16, 1>); break;
+        case 2: ce = go(vox2_pfn_kernel<16, 2>); break;
+        default: ce = go(vox2_pfn_kernel<16, 3>); break;
+    }
     if (ce) return (int)ce;
     return CB_OK;
 }

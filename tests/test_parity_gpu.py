@@ -565,6 +565,36 @@ def test_varying_cloud_sizes_reuse_one_graph():
             assert torch.equal(out[k], want[k]), (frame, k)
 
 
+def test_two_engines_with_different_pfn_weights_on_concurrent_streams():
+    """The fused points -> canvas path keeps its PFN coefficients in a constant-memory table; each engine (workspace) has its
+    own table slot, so two engines with different weights replaying their graphs on different streams at the same time
+    must each reproduce their own single-stream result, every time."""
+    args = G.small_args("att")
+    scenes = G.small_case_scenes([3, 2], 900, n_points=1800)
+    clouds = [p for sc in scenes for p in sc["points"]]
+    off = np.concatenate([[0], np.cumsum([c.shape[0] for c in clouds])]).astype(np.int32)
+    pts = torch.from_numpy(np.concatenate(clouds).astype(np.float32)).cuda()
+    pw = torch.from_numpy(np.stack([sc["pairwise_t_matrix"] for sc in scenes])).cuda()
+    engs, want, streams = [], [], []
+    for seed in (11, 12):
+        eng = make_engine(args, synth.random_state_dict(args, seed), 5, 2, precise=False)
+        eng.forward_points(pts, off, [3, 2], pw)                       # captures the graph
+        want.append({k: v.clone() for k, v in eng.forward_points(pts, off, [3, 2], pw).items()})
+        engs.append(eng)
+        streams.append(torch.cuda.Stream())
+    torch.cuda.synchronize()
+    assert not torch.equal(want[0]["cls_preds"], want[1]["cls_preds"])
+    for _ in range(20):
+        got = []
+        for eng, st in zip(engs, streams):
+            with torch.cuda.stream(st):
+                got.append({k: v.clone() for k, v in eng.forward_points(pts, off, [3, 2], pw).items()})
+        torch.cuda.synchronize()
+        for g, w in zip(got, want):
+            for k in w:
+                assert torch.equal(g[k], w[k]), k
+
+
 def test_single_agent_pointpillar_matches_reference_golden():
     """BASELINE configs[0]: single-agent `point_pillar` (BaseBEVBackbone, no fusion) through the nn.Module twin:
     precise mode within rtol 1e-3 of the unmodified reference's outputs; bf16 mode at bf16-level drift; raw-point entry

@@ -1,5 +1,5 @@
 #!/bin/bash
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_train_ops_gpu.py -q -x > gpurun_out/r2_pytest_g.txt 2>&1; tail -3 gpurun_out/r2_pytest_g.txt
-timeout 600 python tools/exp_bw.py > gpurun_out/exp_bw5.txt 2>&1; grep "bn_stats\|MB per\|torch" gpurun_out/exp_bw5.txt
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r2_pytest_full.txt 2>&1; tail -5 gpurun_out/r2_pytest_full.txt
+timeout 900 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/r2_bench_d.json 2> gpurun_out/r2_bench_d.err; tail -3 gpurun_out/r2_bench_d.err
