@@ -464,6 +464,55 @@ def _full_size_case(args, n_agents, seed, pose_noise):
         assert_close(res[True][k], ref[k].numpy(), 1e-3, 2.5e-3, f"precise {k}")
         assert rel_l2(res[True][k], ref[k].numpy()) < 2e-4, (k, rel_l2(res[True][k], ref[k].numpy()))
         assert rel_l2(res[False][k], ref[k].numpy()) < 3e-2, (k, rel_l2(res[False][k], ref[k].numpy()))
+    if tuple(res[True]["cls_preds"].shape[1:]) == (2, 100, 352):
+        _detection_level_agreement(res, ref)
+
+
+def _detection_level_agreement(res, ref):
+    """What the bf16 head maps mean for detections: decode + NMS (cb_postprocess, voxel_postprocessor.py:292-400) of the
+    reference's, the precise and the bf16 head maps with the same score offset (random weights give no confident anchors by
+    themselves: the offset puts the 300 best reference anchors above the score threshold).  Every box kept from the
+    reference maps must have a partner in the GPU result: centre within 0.3 m (the two anchors of a cell share a centre),
+    score within 0.05; and the GPU result may not invent more than a tenth more boxes."""
+    from coalign_b200.postprocess import VoxelPostprocessorB200
+    params = G.post_params()
+    pp = VoxelPostprocessorB200(params, train=False)
+    anchors = pp.generate_anchor_box()
+    thr = float(params["target_args"]["score_threshold"])
+    # random-weight head maps are not on the scale of a trained head (logit std of tens): the same scale for all three
+    # brings the logits to std 2 and - below - the regression deltas to std 0.3
+    cscale = np.float32(2.0 / float(ref["cls_preds"].numpy().std()))
+    ref_cls = ref["cls_preds"].numpy() * cscale
+    kth = np.sort(ref_cls.reshape(-1))[-300]
+    shift = float(np.log(thr / (1.0 - thr)) - kth)
+    rscale = np.float32(0.3 / float(ref["reg_preds"].numpy().std()))
+    tfm = torch.eye(4)
+
+    def run(o):
+        cls = torch.from_numpy(np.asarray(o["cls_preds"]) * cscale + shift).cuda()
+        out = pp.post_process_batch(cls, torch.from_numpy(np.asarray(o["reg_preds"]) * rscale).cuda(),
+                                    torch.from_numpy(np.asarray(o["dir_preds"])).cuda(), anchors, tfm)[0]
+        assert out[0] is not None
+        return out[0].cpu().numpy().mean(axis=1), out[1].cpu().numpy()       # box centres (K,3), scores (K,)
+
+    want_c, want_s = run({k: v.numpy() for k, v in ref.items()})
+    assert want_c.shape[0] >= 5, want_c.shape
+    stats = {}
+    for mode in (True, False):
+        got_c, got_s = run(res[mode])
+        d = np.linalg.norm(want_c[:, None, :2] - got_c[None, :, :2], axis=2)
+        j = d.argmin(axis=1)
+        ok = (d[np.arange(len(j)), j] < 0.3) & (np.abs(got_s[j] - want_s) < 0.05)
+        stats["precise" if mode else "bf16"] = (int((~ok).sum()), len(want_s), len(got_s))
+        # measured: the only reference boxes without a partner sit on the score threshold (scores 0.200-0.208 at 0.20)
+        assert all(want_s[i] < thr + 0.02 for i in np.where(~ok)[0]), [float(want_s[i]) for i in np.where(~ok)[0]]
+    # an anchor sitting exactly on the score threshold may flip in any arithmetic: allow 2 boxes in precise mode;
+    # bf16 mode (head logits rel-L2 1-2e-2): at least 90 % of the reference's boxes, at most 10 % + 2 extra ones
+    assert stats["precise"][0] <= 2, stats
+    assert stats["bf16"][0] <= max(2, 0.1 * stats["bf16"][1]), stats
+    for k in stats:
+        assert stats[k][2] <= 1.1 * stats[k][1] + 2, stats
+    print("detection-level agreement (missed, reference boxes, ours):", stats)
 
 
 def test_full_size_opv2v_two_agents_vs_oracle():
