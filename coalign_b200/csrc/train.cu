@@ -1031,6 +1031,10 @@ __global__ void __launch_bounds__(256) pack_weights_batch_kernel(const cb_pack_j
         const unsigned r1 = r / R0, r0 = r - r1 * R0;
         const unsigned k1 = k / K0, k0 = k - k1 * K0;
         const float v = __ldg(src + (long)((int)r1 * s_r1 + (int)r0 * s_r0 + (int)k1 * s_k1 + (int)k0 * s_k0));
+        if (lo_col < 0) {                                                // fp32 destination (gradient permutation jobs)
+            reinterpret_cast<float*>(dst)[(long)r * dst_ld + k_off + k] = v;
+            continue;
+        }
         const __nv_bfloat16 hi16 = __float2bfloat16(v);
         __nv_bfloat16* d = dst + (long)r * dst_ld + k_off + k;
         *d = hi16;

@@ -613,7 +613,20 @@ class TrainEngine(CoAlignEngine):
             bwd.append(("bucket", {"i": len(self.levels) - li}))
         bwd.append(("pfn_bwd", {"n_img": n_img}))
         bwd.append(("bucket", {"i": len(self.levels) + 1}))
-        return {"fwd": fwd, "bwd": bwd}
+        # the gradient permutations (packed GEMM order -> the parameter's layout in gflat) only have to be done before the
+        # bucket's all-reduce: one table-driven launch per bucket instead of one launch per weight tensor
+        merged: List[Tuple[str, dict]] = []
+        pend: List[dict] = []
+        for kind, o in bwd:
+            if kind == "permute":
+                pend.append(o)
+                continue
+            if kind == "bucket" and pend:
+                merged.append(("permute_batch", {"jobs": pend}))
+                pend = []
+            merged.append((kind, o))
+        assert not pend
+        return {"fwd": fwd, "bwd": merged}
 
     def _alloc_dx_in(self):
         """Input-gradient buffers of the first block of levels 1.. (PS layout of the previous level's output)."""
@@ -688,6 +701,27 @@ class TrainEngine(CoAlignEngine):
                     ci, cu, k = o["cin"], o["cu"], o["k"]
                     ck(lib.cb_permute_f32(src, ci, cu, 1, k * k, 1, ci, 0, cu * ci, 1.0, o["dst"].data_ptr(), sp),
                        "cb_permute_f32")
+            elif kind == "permute_batch":         # all gradient permutations of one all-reduce bucket in one launch
+                if "_tab" not in o:
+                    arr, total = [], 0
+                    for q in o["jobs"]:
+                        j = _lib.PackJob()
+                        j.src, j.dst = q["src"].data_ptr() + q["src_off"] * 4, q["dst"].data_ptr()
+                        if q["kind"] == "conv":       # packed [co][tap][ci] -> OIHW
+                            co, ci, t = q["cout"], q["cin"], q["taps"]
+                            R1, R0, K0, st = co, ci, t, (t * ci, 1, 0, ci)
+                        else:                         # packed [(ab, co)][ci] -> [ci][co][ab]
+                            ci, cu, k = q["cin"], q["cu"], q["k"]
+                            R1, R0, K0, st = ci, cu, k * k, (1, ci, 0, cu * ci)
+                        j.s_r1, j.s_r0, j.s_k1, j.s_k0, j.first = st[0], st[1], st[2], st[3], total
+                        j.R0, j.K0, j.rows, j.K = R0, K0, R1 * R0, K0
+                        j.dst_ld, j.k_off, j.lo_col_off = K0, 0, -1
+                        arr.append(j)
+                        total += R1 * R0 * K0
+                    buf = (_lib.PackJob * len(arr))(*arr)
+                    o["_tab"] = (torch.frombuffer(bytearray(bytes(buf)), dtype=torch.uint8).to(self.device), len(arr), total)
+                tab, n_jobs, total = o["_tab"]
+                ck(lib.cb_pack_weights_batch(tab.data_ptr(), n_jobs, total, sp), "cb_pack_weights_batch")
             elif kind == "pack_all":
                 jobs, n_jobs, total = self._pack_job_table()
                 ck(lib.cb_pack_weights_batch(jobs.data_ptr(), n_jobs, total, sp), "cb_pack_weights_batch")

@@ -484,7 +484,7 @@ typedef struct cb_pack_job {
     const float* src;
     void* dst;                   /* bf16, already offset to the job's first row */
     int64_t s_r1, s_r0, s_k1, s_k0, first;
-    int32_t R0, K0, rows, K, dst_ld, k_off, lo_col_off, pad_;
+    int32_t R0, K0, rows, K, dst_ld, k_off, lo_col_off, pad_;   /* lo_col_off < 0: dst is fp32 (a cb_permute_f32 job, alpha 1) */
 } cb_pack_job;
 int cb_pack_weights_batch(const cb_pack_job* jobs_dev, int n_jobs, int64_t total_elems, void* stream);
 

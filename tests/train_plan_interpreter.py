@@ -334,6 +334,9 @@ def run_train_plan(eng, args, batch, loss_grad_fn):
                 emu_bn_bwd(eng, o)
             elif kind == "permute":
                 emu_permute(eng, o)
+            elif kind == "permute_batch":
+                for q in o["jobs"]:
+                    emu_permute(eng, q)
             elif kind == "pack_all":
                 emu_pack_all(eng)
             elif kind == "head_bias":
