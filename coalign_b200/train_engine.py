@@ -419,6 +419,16 @@ class TrainEngine(CoAlignEngine):
             ops.append(("wgrad", {"desc": d, "dz": dz, "xs": list(xs), "dst": dst_t, "dst_off": dst_off, "units": grp, "ld": ld}))
         return ops
 
+    @staticmethod
+    def permute_job_shape(q: dict):
+        """(R1, R0, K0, (s_r1, s_r0, s_k1, s_k0)) of a gradient permutation: dst[(r1, r0)][k0] = src[r1*s_r1 + r0*s_r0 + k0*s_k0]
+        (the cb_permute_f32 / cb_pack_job convention with K1 = 1)."""
+        if q["kind"] == "conv":                       # packed [co][tap][ci] -> OIHW: dst[(co, ci)][tap]
+            co, ci, t = q["cout"], q["cin"], q["taps"]
+            return co, ci, t, (t * ci, 1, 0, ci)
+        ci, cu, k = q["cin"], q["cu"], q["k"]         # packed [(ab, co)][ci] -> [ci][co][ab]: dst[(ci, co)][ab]
+        return ci, cu, k * k, (1, ci, 0, cu * ci)
+
     def _unpack(self, slot: str, kind: str, **kw) -> Tuple[str, dict]:
         """packed-order gradient -> the parameter's own layout in gflat (cb_permute_f32)."""
         off, rows, ld = self.wg_slots[slot]
@@ -694,25 +704,16 @@ class TrainEngine(CoAlignEngine):
                                        o["d_beta"].data_ptr() if o["d_beta"] is not None else None, sp), "cb_bn_bwd_apply")
             elif kind == "permute":
                 src = o["src"].data_ptr() + o["src_off"] * 4
-                if o["kind"] == "conv":           # packed [co][tap][ci] -> OIHW: dst[(co, ci)][tap]
-                    co, ci, t = o["cout"], o["cin"], o["taps"]
-                    ck(lib.cb_permute_f32(src, co, ci, 1, t, t * ci, 1, 0, ci, 1.0, o["dst"].data_ptr(), sp), "cb_permute_f32")
-                else:                             # packed [(ab, co)][ci] -> [ci][co][ab]: dst[(ci, co)][ab]
-                    ci, cu, k = o["cin"], o["cu"], o["k"]
-                    ck(lib.cb_permute_f32(src, ci, cu, 1, k * k, 1, ci, 0, cu * ci, 1.0, o["dst"].data_ptr(), sp),
-                       "cb_permute_f32")
+                R1, R0, K0, st = self.permute_job_shape(o)
+                ck(lib.cb_permute_f32(src, R1, R0, 1, K0, st[0], st[1], st[2], st[3], 1.0, o["dst"].data_ptr(), sp),
+                   "cb_permute_f32")
             elif kind == "permute_batch":         # all gradient permutations of one all-reduce bucket in one launch
                 if "_tab" not in o:
                     arr, total = [], 0
                     for q in o["jobs"]:
                         j = _lib.PackJob()
                         j.src, j.dst = q["src"].data_ptr() + q["src_off"] * 4, q["dst"].data_ptr()
-                        if q["kind"] == "conv":       # packed [co][tap][ci] -> OIHW
-                            co, ci, t = q["cout"], q["cin"], q["taps"]
-                            R1, R0, K0, st = co, ci, t, (t * ci, 1, 0, ci)
-                        else:                         # packed [(ab, co)][ci] -> [ci][co][ab]
-                            ci, cu, k = q["cin"], q["cu"], q["k"]
-                            R1, R0, K0, st = ci, cu, k * k, (1, ci, 0, cu * ci)
+                        R1, R0, K0, st = self.permute_job_shape(q)
                         j.s_r1, j.s_r0, j.s_k1, j.s_k0, j.first = st[0], st[1], st[2], st[3], total
                         j.R0, j.K0, j.rows, j.K = R0, K0, R1 * R0, K0
                         j.dst_ld, j.k_off, j.lo_col_off = K0, 0, -1

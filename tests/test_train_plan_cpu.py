@@ -78,3 +78,27 @@ def test_training_plan_max_fusion_matches_hand_written_backward():
         b = b.double()
         rel = float((a - b).norm() / (b.norm() + 1e-30))
         assert rel < 3e-2, (name, rel)
+
+
+def test_permute_job_strides_match_the_layout_semantics():
+    """The (rows, K, strides) records handed to cb_permute_f32 / the batched cb_pack_job table reproduce the permutation the
+    plan interpreter applies by layout (packed GEMM order -> the parameter's own layout), for both job kinds."""
+    import torch
+    from coalign_b200.train_engine import TrainEngine
+    from tests.train_plan_interpreter import emu_permute
+    rng = torch.Generator().manual_seed(0)
+    for q in ({"kind": "conv", "cout": 6, "cin": 5, "taps": 9}, {"kind": "deconv", "cin": 7, "cu": 4, "k": 2},
+              {"kind": "conv", "cout": 3, "cin": 8, "taps": 1}):
+        n = (q["cout"] * q["cin"] * q["taps"]) if q["kind"] == "conv" else (q["cin"] * q["cu"] * q["k"] ** 2)
+        src = torch.randn(n + 11, generator=rng)
+        shape = (q["cout"], q["cin"], 3, 3) if q.get("taps") == 9 else (
+            (q["cout"], q["cin"], 1, 1) if q["kind"] == "conv" else (q["cin"], q["cu"], q["k"], q["k"]))
+        want = torch.zeros(shape)
+        emu_permute(None, dict(q, src=src, src_off=11, dst=want))
+        R1, R0, K0, (s_r1, s_r0, s_k1, s_k0) = TrainEngine.permute_job_shape(q)
+        got = torch.empty(R1 * R0 * K0)
+        for r1 in range(R1):
+            for r0 in range(R0):
+                for k0 in range(K0):
+                    got[(r1 * R0 + r0) * K0 + k0] = src[11 + r1 * s_r1 + r0 * s_r0 + k0 * s_k0]
+        assert torch.equal(got.view(shape), want), q
