@@ -114,7 +114,7 @@ __device__ __forceinline__ void block_reduce_to_global(float (&a0)[8], float (&a
 }
 
 // Thread layout shared by the row-wise kernels: a thread owns one 8-channel chunk (fixed) and walks rows with a
-// division-free cursor (n, hp, wp advance by the decomposed row step); two rows are in flight per iteration.
+// division-free cursor (n, hp, wp advance by the decomposed row step); R rows are loaded back to back per iteration.
 struct RowWalk { int chunk, cpr, row0, row_step; };
 __device__ __forceinline__ RowWalk row_walk(int c_total) {
     RowWalk r;
